@@ -1,0 +1,233 @@
+// TEST INFRASTRUCTURE ONLY -- white-box driver around the UNMODIFIED reference engine.
+//
+// Built by oracle/Makefile against the reference sources where they lie under
+// /root/reference (never copied into this repository); the binary lands in
+// oracle/_ref/ (git-ignored, travels to the GPU box).  It exposes three modes:
+//
+//   refdump static <config.json> <out.bin>
+//       static tables the hot path consumes (lane / laneLink lengths, cross
+//       ordering and distances) -> used to validate our host loader bit-for-bit.
+//   refdump run <config.json> <steps> <threads> <out.bin> [every]
+//       per-step dynamic state of every running vehicle (raw IEEE-754 bits) ->
+//       the parity oracle for tests/ and for generating tests/golden/.
+//   refdump bench <config.json> <steps> <threads> [warmup]
+//       timing loop in the shape of tools/debug/simple_run.cpp:42-57, prints one
+//       JSON line -> the `--impl reference` arm of bench.py.
+//
+// Access to Engine internals uses the access-specifier trick described in
+// SURVEY.md Appendix A (class layout is unaffected).
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <iostream>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <random>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <condition_variable>
+#include <vector>
+
+#define private public
+#define protected public
+#include "engine/engine.h"
+#undef private
+#undef protected
+
+using namespace CityFlow;
+
+namespace {
+
+struct Out {
+    FILE *fp;
+    explicit Out(const char *path) : fp(fopen(path, "wb")) {
+        if (!fp) { perror(path); exit(2); }
+    }
+    ~Out() { fclose(fp); }
+    void i32(int32_t v) { fwrite(&v, 4, 1, fp); }
+    void i64(int64_t v) { fwrite(&v, 8, 1, fp); }
+    void f64(double v) { fwrite(&v, 8, 1, fp); }
+};
+
+struct Index {
+    std::map<const Drivable *, int> drivable;
+    std::map<const RoadLink *, int> roadLink;
+    std::map<const Cross *, int> cross;
+    std::map<const Road *, int> road;
+    std::map<const Intersection *, int> inter;
+    explicit Index(Engine &e) {
+        int k = 0;
+        for (Lane *l : e.roadnet.getLanes()) drivable[l] = k++;
+        for (LaneLink *l : e.roadnet.getLaneLinks()) drivable[l] = k++;
+        int r = 0, c = 0, rd = 0, it = 0;
+        for (Road &road_ : e.roadnet.getRoads()) road[&road_] = rd++;
+        for (Intersection &in : e.roadnet.getIntersections()) {
+            inter[&in] = it++;
+            for (RoadLink &rl : in.getRoadLinks()) roadLink[&rl] = r++;
+            for (Cross &cr : in.getCrosses()) cross[&cr] = c++;
+        }
+    }
+};
+
+// "flow_<k>_<n>" -> (k, n); anything else -> (-1, hash-free -1)
+void parseId(const std::string &id, int32_t &flow, int32_t &cnt) {
+    flow = -1; cnt = -1;
+    if (id.compare(0, 5, "flow_") == 0) {
+        size_t us = id.find('_', 5);
+        if (us != std::string::npos) {
+            flow = atoi(id.substr(5, us - 5).c_str());
+            cnt = atoi(id.substr(us + 1).c_str());
+        }
+    } else if (id.compare(0, 16, "manually_pushed_") == 0) {
+        flow = -2;
+        cnt = atoi(id.substr(16).c_str());
+    }
+}
+
+int dumpStatic(const char *cfg, const char *outPath) {
+    Engine e(cfg, 1);
+    Index ix(e);
+    Out o(outPath);
+    const auto &lanes = e.roadnet.getLanes();
+    const auto &links = e.roadnet.getLaneLinks();
+    o.i32(0x43465331);  // 'CFS1'
+    o.i32((int32_t) e.roadnet.getRoads().size());
+    o.i32((int32_t) e.roadnet.getIntersections().size());
+    o.i32((int32_t) lanes.size());
+    o.i32((int32_t) links.size());
+    o.i32((int32_t) ix.roadLink.size());
+    o.i32((int32_t) ix.cross.size());
+    for (Lane *l : lanes) {
+        o.f64(l->getLength());
+        o.f64(l->getMaxSpeed());
+        o.i32(ix.road[l->getBelongRoad()]);
+        o.i32((int32_t) l->getLaneIndex());
+        o.i32((int32_t) l->getLaneLinks().size());
+        for (LaneLink *ll : l->getLaneLinks()) o.i32(ix.drivable[ll]);
+    }
+    for (LaneLink *l : links) {
+        o.f64(l->getLength());
+        o.i32(ix.drivable[l->getStartLane()]);
+        o.i32(ix.drivable[l->getEndLane()]);
+        o.i32(ix.roadLink[l->getRoadLink()]);
+        o.i32((int32_t) l->getRoadLinkType());
+        o.i32((int32_t) l->getCrosses().size());
+        for (Cross *c : l->getCrosses()) {
+            int side = (c->getLaneLink(0) == l) ? 0 : 1;
+            o.i32(ix.cross[c]);
+            o.i32(side);
+            o.i32(ix.drivable[c->getLaneLink(1 - side)]);
+            o.f64(c->distanceOnLane[side]);
+            o.f64(c->distanceOnLane[1 - side]);
+        }
+    }
+    // traffic lights: per intersection, phases (time, availability per roadLink)
+    for (Intersection &in : e.roadnet.getIntersections()) {
+        o.i32(in.isVirtualIntersection() ? 1 : 0);
+        o.i32((int32_t) in.getRoadLinks().size());
+        auto &phases = in.getTrafficLight().getPhases();
+        o.i32((int32_t) phases.size());
+        for (auto &ph : phases) {
+            o.f64(ph.time);
+            for (size_t k = 0; k < in.getRoadLinks().size(); ++k) o.i32(ph.roadLinkAvailable[k] ? 1 : 0);
+        }
+    }
+    return 0;
+}
+
+int dumpRun(const char *cfg, int steps, int threads, const char *outPath, int every) {
+    Engine e(cfg, threads);
+    Index ix(e);
+    Out o(outPath);
+    const auto &lanes = e.roadnet.getLanes();
+    o.i32(0x43464431);  // 'CFD1'
+    o.i32((int32_t) lanes.size());
+    for (int s = 0; s < steps; ++s) {
+        e.nextStep();
+        if ((s + 1) % every != 0 && s + 1 != steps) continue;
+        std::vector<const Vehicle *> run = e.getRunningVehicles(false);
+        o.i32(s + 1);
+        o.i32((int32_t) e.getVehicleCount());
+        o.i32((int32_t) run.size());
+        o.i32((int32_t) e.vehiclePool.size());
+        o.i32(e.finishedVehicleCnt);
+        o.f64(e.cumulativeTravelTime);
+        for (Lane *l : lanes) o.i32((int32_t) l->getVehicleCount());
+        for (Lane *l : lanes) {
+            int c = 0;
+            for (Vehicle *v : l->getVehicles()) c += v->getSpeed() < 0.1;
+            o.i32(c);
+        }
+        for (Lane *l : lanes) o.i32((int32_t) l->getWaitingBuffer().size());
+        for (Intersection &in : e.roadnet.getIntersections()) {
+            o.i32(in.isVirtualIntersection() ? -1 : in.getTrafficLight().getCurrentPhaseIndex());
+        }
+        for (const Vehicle *v : run) {
+            int32_t f, c, lf = -1, lc = -1, bf = -1, bc = -1;
+            parseId(v->getId(), f, c);
+            if (v->getLeader()) parseId(v->getLeader()->getId(), lf, lc);
+            if (v->getBlocker()) parseId(v->getBlocker()->getId(), bf, bc);
+            o.i32(f); o.i32(c);
+            o.i32(v->getPriority());
+            o.i32(ix.drivable[v->getCurDrivable()]);
+            o.i32(lf); o.i32(lc);
+            o.i32(bf); o.i32(bc);
+            o.f64(v->getDistance());
+            o.f64(v->getSpeed());
+            o.f64(v->getLeader() ? v->getGap() : 0.0);
+            o.i64((int64_t) v->controllerInfo.enterLaneLinkTime);
+        }
+        // order inside every drivable (front -> back) as (flow,cnt) pairs
+        for (Drivable *d : e.roadnet.getDrivables()) {
+            o.i32((int32_t) d->getVehicles().size());
+            for (Vehicle *v : d->getVehicles()) {
+                int32_t f, c;
+                parseId(v->getId(), f, c);
+                o.i32(f); o.i32(c);
+            }
+        }
+    }
+    return 0;
+}
+
+int bench(const char *cfg, int steps, int threads, int warmup) {
+    auto t0 = std::chrono::steady_clock::now();
+    Engine e(cfg, threads);
+    auto t1 = std::chrono::steady_clock::now();
+    for (int s = 0; s < warmup; ++s) e.nextStep();
+    long long vs = 0;
+    auto t2 = std::chrono::steady_clock::now();
+    for (int s = 0; s < steps; ++s) {
+        e.nextStep();
+        vs += (long long) e.getVehicleCount();
+    }
+    auto t3 = std::chrono::steady_clock::now();
+    double load = std::chrono::duration<double>(t1 - t0).count();
+    double sec = std::chrono::duration<double>(t3 - t2).count();
+    printf("{\"steps\": %d, \"warmup\": %d, \"threads\": %d, \"load_s\": %.6f, \"seconds\": %.6f, "
+           "\"vehicle_steps\": %lld, \"final_vehicles\": %zu, \"vehicle_steps_per_s\": %.3f}\n",
+           steps, warmup, threads, load, sec, vs, e.getVehicleCount(), sec > 0 ? vs / sec : 0.0);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc >= 4 && !strcmp(argv[1], "static")) return dumpStatic(argv[2], argv[3]);
+    if (argc >= 6 && !strcmp(argv[1], "run"))
+        return dumpRun(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
+    if (argc >= 5 && !strcmp(argv[1], "bench"))
+        return bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0);
+    fprintf(stderr, "usage: refdump static|run|bench ...\n");
+    return 64;
+}
