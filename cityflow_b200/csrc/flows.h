@@ -1,0 +1,80 @@
+// Host-side demand description: flow file parsing (engine.cpp:106-164), route resolution
+// (Router::updateShortestPath / dijkstra, router.cpp:160-243) and the per-(route, start lane)
+// drivable sequences ("plans") that replace the reference's lazy per-vehicle lookahead deque
+// (Router::getNextDrivable, router.cpp:39-76) on the device.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+
+#include "roadnet.h"
+
+namespace cfb {
+
+// VehicleInfo defaults, vehicle.h:31-45
+struct VehicleTemplate {
+    double speed = 0;
+    double len = 5;
+    double width = 2;
+    double maxPosAcc = 4.5;
+    double maxNegAcc = 4.5;
+    double usualPosAcc = 2.5;
+    double usualNegAcc = 2.5;
+    double minGap = 2;
+    double maxSpeed = 16.66667;
+    double headwayTime = 1;
+    double yieldDistance = 5;
+    double turnSpeed = 8.3333;
+    bool operator<(const VehicleTemplate &o) const;
+};
+
+struct FlowDef {
+    VehicleTemplate tmpl;
+    std::vector<int> anchors;   // road ids as listed in "route"
+    double interval = 0;
+    int startTime = 0, endTime = -1;
+    std::string id;             // "flow_<i>"
+};
+
+// A resolved road-level route (after Dijkstra between anchors) plus, for every admissible
+// start lane, the full drivable sequence lane,link,lane,...  Drivable ids: lane l -> l,
+// laneLink k -> nLanes + k.  PLAN_END terminates a sequence; PLAN_DEAD marks "lane cannot reach
+// the next road" (the reference asserts there, vehicle.cpp:60).
+constexpr int PLAN_END = -1;
+constexpr int PLAN_DEAD = -2;
+
+struct Route {
+    bool valid = false;
+    std::vector<int> roads;
+    std::vector<int> startLanes;          // candidate first lanes (Router::getFirstDrivable, router.cpp:23-37)
+    std::vector<int> planOfStartLane;     // plan id per candidate
+};
+
+class Routing {
+public:
+    explicit Routing(const RoadNet &net) : net_(net) {}
+    // Shortest road path between consecutive anchors (LENGTH metric); false = invalid route.
+    bool resolve(const std::vector<int> &anchors, std::vector<int> &roads) const;
+    // Interns the route; builds plans for every candidate start lane. Returns route id.
+    int intern(const std::vector<int> &anchors);
+    const Route &route(int id) const { return routes_[id]; }
+    // plan storage (flat, PLAN_END terminated)
+    const std::vector<int> &planData() const { return planData_; }
+    const std::vector<int> &planBeg() const { return planBeg_; }
+    int numPlans() const { return (int) planBeg_.size(); }
+    // next laneLink for a vehicle on `lane` whose route continues with roads[r+1] (, roads[r+2])
+    int chooseLink(int lane, const std::vector<int> &roads, int r) const;
+
+private:
+    bool dijkstra(int start, int end, std::vector<int> &buffer) const;
+    int buildPlan(const std::vector<int> &roads, int startLane);
+    const RoadNet &net_;
+    std::vector<Route> routes_;
+    std::map<std::vector<int>, int> byAnchors_;
+    std::vector<int> planData_, planBeg_;
+};
+
+// Parses the flow file; returns false with a message on stderr on format errors.
+bool loadFlows(const std::string &path, const RoadNet &net, std::vector<FlowDef> &out);
+
+}  // namespace cfb
