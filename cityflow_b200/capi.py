@@ -1,0 +1,140 @@
+"""ctypes binding of the C-ABI (include/cityflow_b200.h) -- what a foreign-language host would
+bind.  Used by the parity tests so they exercise the exported symbols directly."""
+from __future__ import annotations
+
+import ctypes
+import re
+import os
+
+import numpy as np
+
+from . import LIB_PATH
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "cityflow_b200.h")
+
+VEH_DTYPE = np.dtype([
+    ("flow", "<i4"), ("cnt", "<i4"), ("priority", "<i4"), ("drivable", "<i4"),
+    ("leader_flow", "<i4"), ("leader_cnt", "<i4"), ("blocker_flow", "<i4"), ("blocker_cnt", "<i4"),
+    ("dis", "<f8"), ("speed", "<f8"), ("gap", "<f8"), ("enter_ll_time", "<i8"),
+])
+REF_DTYPE = np.dtype([("flow", "<i4"), ("index", "<i4")])
+
+
+def declared_symbols() -> list:
+    """Every function name the header declares."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def load_library() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("cityflow_b200: %s is missing -- build it first (__graft_entry__.build())" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, i64, dbl, cp = c.c_void_p, c.c_int, c.c_int64, c.c_double, c.c_char_p
+    sig = {
+        "cfb_engine_create": (vp, [cp, i32, i32]),
+        "cfb_engine_destroy": (None, [vp]),
+        "cfb_last_error": (cp, [vp]),
+        "cfb_next_step": (i32, [vp]),
+        "cfb_next_steps": (i32, [vp, i32]),
+        "cfb_get_vehicle_count": (i64, [vp]),
+        "cfb_get_current_time": (dbl, [vp]),
+        "cfb_get_average_travel_time": (dbl, [vp]),
+        "cfb_num_lanes": (i32, [vp]),
+        "cfb_lane_id": (cp, [vp, i32]),
+        "cfb_num_intersections": (i32, [vp]),
+        "cfb_intersection_id": (cp, [vp, i32]),
+        "cfb_get_lane_vehicle_count": (i32, [vp, vp, i32]),
+        "cfb_get_lane_waiting_vehicle_count": (i32, [vp, vp, i32]),
+        "cfb_get_vehicle_speed": (i64, [vp, vp, vp, vp, i64]),
+        "cfb_get_vehicles": (i64, [vp, i32, vp, i64]),
+        "cfb_get_lane_vehicles": (i64, [vp, vp, i32, vp, i64]),
+        "cfb_set_tl_phase": (i32, [vp, cp, i32]),
+        "cfb_set_tl_phase_index": (i32, [vp, i32, i32]),
+        "cfb_set_random_seed": (i32, [vp, i32]),
+        "cfb_reset": (i32, [vp, i32]),
+        "cfb_debug_vehicles": (i64, [vp, vp, i64]),
+        "cfb_gpu_launches": (i64, [vp]),
+        "cfb_enable_kernel_timing": (i32, [vp, i32]),
+        "cfb_kernel_times": (i32, [vp, vp, vp]),
+        "cfb_synchronize": (i32, [vp]),
+        "cfb_num_drivables": (i64, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+class CEngine:
+    """Minimal object wrapper over the raw C calls (numpy in / out)."""
+
+    def __init__(self, config: str, device: int = 0):
+        self.lib = load_library()
+        self.h = self.lib.cfb_engine_create(config.encode(), 1, device)
+        if not self.h:
+            raise RuntimeError("cfb_engine_create failed: %s" % self.lib.cfb_last_error(None).decode())
+        self.n_lanes = self.lib.cfb_num_lanes(self.h)
+        self.n_inter = self.lib.cfb_num_intersections(self.h)
+        self.n_drivables = int(self.lib.cfb_num_drivables(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cfb_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(self.lib.cfb_last_error(self.h).decode())
+        return rc
+
+    def next_step(self, n: int = 1):
+        self._check(self.lib.cfb_next_steps(self.h, n))
+
+    def vehicle_count(self) -> int:
+        return int(self._check(self.lib.cfb_get_vehicle_count(self.h)))
+
+    def lane_ids(self):
+        return [self.lib.cfb_lane_id(self.h, i).decode() for i in range(self.n_lanes)]
+
+    def lane_vehicle_count(self):
+        a = np.zeros(self.n_lanes, np.int32)
+        self._check(self.lib.cfb_get_lane_vehicle_count(self.h, a.ctypes.data, self.n_lanes))
+        return a
+
+    def lane_waiting_count(self):
+        a = np.zeros(self.n_lanes, np.int32)
+        self._check(self.lib.cfb_get_lane_waiting_vehicle_count(self.h, a.ctypes.data, self.n_lanes))
+        return a
+
+    def vehicle_speed(self):
+        n = self._check(self.lib.cfb_get_vehicle_speed(self.h, None, None, None, 0))
+        ids = np.zeros(n, REF_DTYPE)
+        sp = np.zeros(n)
+        ds = np.zeros(n)
+        self._check(self.lib.cfb_get_vehicle_speed(self.h, ids.ctypes.data, sp.ctypes.data, ds.ctypes.data, n))
+        return ids, sp, ds
+
+    def debug_vehicles(self):
+        n = self._check(self.lib.cfb_debug_vehicles(self.h, None, 0))
+        a = np.zeros(n, VEH_DTYPE)
+        if n:
+            self._check(self.lib.cfb_debug_vehicles(self.h, a.ctypes.data, n))
+        return a
+
+    def set_tl_phase(self, inter: int, phase: int):
+        self._check(self.lib.cfb_set_tl_phase_index(self.h, inter, phase))
+
+    def reset(self, seed: bool = False):
+        self._check(self.lib.cfb_reset(self.h, int(seed)))
+
+    def average_travel_time(self) -> float:
+        return float(self.lib.cfb_get_average_travel_time(self.h))
+
+    def gpu_launches(self) -> int:
+        return int(self.lib.cfb_gpu_launches(self.h))

@@ -1,0 +1,1249 @@
+// B200 (sm_100a) step engine: device-resident vehicle state + the kernel sequence that replaces
+// the reference's barrier-delimited thread phases (Engine::nextStep, engine.cpp:566-594).
+//
+// Data layout.  Vehicles do not live in a slot-indexed pool; they live in
+// *lane buckets*: every drivable (lane or laneLink) owns a fixed-capacity, contiguous range of
+// "positions" [off[d], off[d+1]) in a set of structure-of-arrays, and the vehicles on it occupy
+// the first count[d] positions in the reference's list order (front -> back, FIFO with
+// mid-list removal).  A vehicle's list predecessor -- its leader -- is therefore the previous
+// position, every per-vehicle phase reads and writes its fields with unit stride inside a
+// warp, and the reference's std::list erase / std::sort+append (engine.cpp:282-315, :477-494)
+// becomes a warp-scan compaction plus a per-bucket rank sort of the few entrants.
+//
+//   kin[p]   double2 {dis, speed}            gap[p] double      leader[p] int (position, -1)
+//   ids[p]   int4 {slot, tmpl, priority, plan}
+//   nav[p]   int4 {planPos, prevDrivable, blocker(slot), enterLaneLinkTime}
+//
+// Kernel sequence per step (all FP64, -fmad=false so every operation rounds exactly like the
+// reference's SSE2 build; expression shapes follow vehicle.cpp verbatim):
+//   k_ingest   P0-P2  waiting-queue append, Lane::available admission, light -> roadLink mask
+//   k_notify   P3     Cross::notify per laneLink (+ leader search of vehicles admitted to an empty lane)
+//   k_control  P4     getNextSpeed / vehicleControl / setDeltaDistance per vehicle (warp per bucket)
+//   k_move     P5-P6  bucket compaction, entrant rank-sort + append, commit, finished ring
+//   k_leader   P7-P8  leader/gap rebuild (warp shuffle), cross-drivable head search, blocker drop,
+//                     TrafficLight::passTime
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "device_sim.h"
+
+namespace cfb {
+
+#define CFB_CUDA(x)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess)                                                                       \
+            throw std::runtime_error(std::string("cityflow_b200 CUDA error: ") + cudaGetErrorString(e_) + \
+                                     " at " + __FILE__ + ":" + std::to_string(__LINE__));           \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Device-side tables
+struct DTmpl {  // 16 doubles
+    double len, maxPosAcc, maxNegAcc, usualPosAcc, usualNegAcc, minGap, maxSpeed, headwayTime;
+    double yieldDistance, turnSpeed, approachDist, speed0, pad[4];
+};
+
+struct __align__(16) Notify {  // one side of one Cross (roadnet.h:122-124), epoch-stamped
+    double dist;
+    int pos;
+    int epoch;
+};
+
+struct Ctrl {
+    int step;        // Engine::step
+    int active;      // activeVehicleCount
+    int moverCount;
+    int finCount;
+    int error;
+    int spawnCount;
+    int pad[2];
+};
+
+constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
+constexpr int PLAN_LOOKAHEAD_END = -1;
+
+struct View {
+    int nLanes, nLinks, nDrv, nInter, nRL, nCross;
+    int moverCap, finCap;
+    double dt;
+    int rl;
+    // static topology
+    const double *drvLength, *drvMaxSpeed;
+    const int *off;
+    const int *laneOutBeg, *laneOutLinks;
+    const int *llStartLane, *llEndLane, *llRoadLink;
+    const unsigned char *llTurn, *llType;
+    const int *llCrossBeg, *lcIdx;
+    const double *lcDist;
+    const int *csLink;
+    const int *interPhaseBeg, *interRLBeg, *phaseAvailBeg, *rlInter;
+    const double *phaseTime;
+    const unsigned char *phaseAvail, *interVirtual;
+    const DTmpl *tmpl;
+    const int *planBeg, *planData;
+    // dynamic, per position
+    double2 *kin, *nkin;
+    double *gap;
+    int *leader;
+    int4 *ids, *nav;
+    int2 *nbuf;
+    // dynamic, per drivable / slot / cross / intersection
+    int *count, *pos;
+    int *waitHead, *waitTail, *waitNext;
+    int4 *slotInfo;
+    unsigned char *inserted;
+    Notify *notify;
+    int *curPhase;
+    double *remain;
+    unsigned char *rlAvail;
+    // movers
+    int *entCnt, *ent;
+    double2 *mkin;
+    int4 *mids, *mnav;
+    int2 *finSlots;
+    Ctrl *ctrl;
+    const SpawnRec *spawn;
+};
+
+// ------------------------------------------------------------------------------------------
+// Scalar helpers.  The reference is compiled for x86-64 without FMA; conversions double->int
+// use cvttsd2si, which yields INT_MIN when out of range (CUDA would saturate).
+__device__ __forceinline__ double min2(double x, double y) { return x < y ? x : y; }  // utility.h:70
+__device__ __forceinline__ double max2(double x, double y) { return x > y ? x : y; }  // utility.h:66
+__device__ __forceinline__ int x86int(double x) {
+    return (x > -2147483649.0 && x < 2147483648.0) ? (int) x : INT_MIN;
+}
+constexpr double kEps = 1e-8;
+
+// Vehicle::getNoCollisionSpeed vehicle.cpp:200-209
+__device__ __forceinline__ double noCollisionSpeed(double vL, double dL, double vF, double dF, double gap, double dt,
+                                                   double targetGap) {
+    double c = vF * dt / 2 + targetGap - 0.5 * vL * vL / dL - gap;
+    double a = 0.5 / dF;
+    double b = 0.5 * dt;
+    if (b * b < 4 * a * c) return -100;
+    double v1 = 0.5 / a * (sqrt(b * b - 4 * a * c) - b);
+    double v2 = 2 * vL - dL * dt + 2 * (gap - targetGap) / dt;
+    return min2(v1, v2);
+}
+// Vehicle::getBrakeDistanceAfterAccel vehicle.cpp:302-306 + getStopBeforeSpeed :240-250
+__device__ __forceinline__ double stopBeforeSpeed(const DTmpl &T, double speed, double distance, double dt) {
+    double nextSpeed = speed + T.usualPosAcc * dt;
+    double brake = (speed + nextSpeed) * dt / 2 + (nextSpeed * nextSpeed / T.usualNegAcc / 2);
+    if (brake < distance) return speed + T.usualPosAcc * dt;
+    double takeInterval = 2 * distance / (speed + kEps) / dt;
+    if (takeInterval >= 1) return speed - speed / x86int(takeInterval);
+    return speed - speed / takeInterval;
+}
+// Vehicle::getDistanceUntilSpeed vehicle.cpp:275-282
+__device__ __forceinline__ double distanceUntilSpeed(double mySpeed, double speed, double acc, double dt) {
+    if (speed <= mySpeed) return 0;
+    int stage1steps = x86int(floor((speed - mySpeed) / acc / dt));
+    double stage1speed = mySpeed + stage1steps * acc / dt;
+    double stage1dis = (mySpeed + stage1speed) * (stage1steps * dt) / 2;
+    return stage1dis + (stage1speed < speed ? ((stage1speed + speed) * dt / 2) : 0);
+}
+// Vehicle::getReachSteps vehicle.cpp:252-268
+__device__ __forceinline__ int reachSteps(double mySpeed, double distance, double targetSpeed, double acc, double dt) {
+    if (distance <= 0) return 0;
+    if (mySpeed > targetSpeed) return x86int(ceil(distance / mySpeed));
+    double du = distanceUntilSpeed(mySpeed, targetSpeed, acc, dt);
+    if (du > distance) return x86int(ceil((sqrt(mySpeed * mySpeed + 2 * acc * distance) - mySpeed) / acc / dt));
+    return x86int(ceil((targetSpeed - mySpeed) / acc / dt) + ceil((distance - du) / targetSpeed / dt));
+}
+// Vehicle::canYield vehicle.cpp:284-287
+__device__ __forceinline__ bool canYield(const DTmpl &T, double speed, double dist) {
+    return (dist > 0 && 0.5 * speed * speed / T.maxNegAcc < dist - T.yieldDistance) || (dist < 0 && dist + T.len < 0);
+}
+
+__device__ __forceinline__ int planAt(const View &V, int plan, int idx) { return V.planData[V.planBeg[plan] + idx]; }
+
+// Cross-drivable leader search for the head of a list (Vehicle::updateLeaderAndGap, else-branch,
+// vehicle.cpp:162-195).  `myLane >= 0` enables the handleWaiting ordering rule: lanes later in
+// roadnet order have not been served yet when the reference inserts into `myLane` (engine.cpp:503).
+__device__ void headSearch(const View &V, int d, double dis, int plan, int planPos, const DTmpl &T, int myLane,
+                           int &outLeader, double &outGap) {
+    int leader = -1;
+    double gap = 0;
+    double x = V.drvLength[d] - dis;
+    for (int i = 0;; ++i) {
+        int nd = planAt(V, plan, planPos + 1 + i);
+        if (nd < 0) break;
+        if (nd >= V.nLanes) {
+            int sl = V.llStartLane[nd - V.nLanes];
+            for (int q = V.laneOutBeg[sl]; q < V.laneOutBeg[sl + 1]; ++q) {
+                int dl = V.nLanes + V.laneOutLinks[q];
+                int c = V.count[dl];
+                if (c > 0) {
+                    int tp = V.off[dl] + c - 1;
+                    double candGap = x + V.kin[tp].x - V.tmpl[V.ids[tp].y].len;
+                    if (leader < 0 || candGap < gap) {
+                        leader = tp;
+                        gap = candGap;
+                    }
+                }
+            }
+            if (leader >= 0) break;
+        } else {
+            int c = V.count[nd];
+            if (myLane >= 0 && nd > myLane && (V.inserted[nd] & 1)) c -= 1;
+            if (c > 0) {
+                int tp = V.off[nd] + c - 1;
+                leader = tp;
+                gap = x + V.kin[tp].x - V.tmpl[V.ids[tp].y].len;
+                break;
+            }
+        }
+        x += V.drvLength[nd];
+        if (x > T.approachDist) break;  // same expression as the look-ahead bound, vehicle.cpp:190-191
+    }
+    outLeader = leader;
+    if (leader >= 0) outGap = gap;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_ingest: thread i serves lane i (queue append + admission) and roadLink i (light mask).
+// Flow::nextStep / planRoute stay on the host (serial mt19937 order); their result arrives as
+// lane-sorted SpawnRec's.  handleWaiting: engine.cpp:502-516, Lane::available roadnet.cpp:428-435.
+__global__ void __launch_bounds__(256) k_ingest(View V) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V.nRL) {
+        int in = V.rlInter[i];
+        int ph = V.interPhaseBeg[in] + V.curPhase[in];
+        V.rlAvail[i] = V.phaseAvail[V.phaseAvailBeg[ph] + (i - V.interRLBeg[in])];
+    }
+    if (i == 0) V.ctrl->moverCount = 0;
+    if (i >= V.nLanes) return;
+    const int nSpawn = V.ctrl->spawnCount;
+    if (nSpawn > 0) {
+        int lo = 0, hi = nSpawn;  // lower bound of lane i
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (V.spawn[mid].lane < i) lo = mid + 1; else hi = mid;
+        }
+        int tail = V.waitTail[i];
+        for (int r = lo; r < nSpawn && V.spawn[r].lane == i; ++r) {
+            SpawnRec s = V.spawn[r];
+            V.slotInfo[s.slot] = make_int4(s.tmpl, s.priority, s.plan, 0);
+            V.waitNext[s.slot] = -1;
+            if (tail < 0) V.waitHead[i] = s.slot; else V.waitNext[tail] = s.slot;
+            tail = s.slot;
+        }
+        V.waitTail[i] = tail;
+    }
+    unsigned char ins = 0;
+    const int h = V.waitHead[i];
+    if (h >= 0) {
+        const int n = V.count[i], base = V.off[i];
+        const int4 info = V.slotInfo[h];
+        const DTmpl &T = V.tmpl[info.x];
+        bool avail = true;
+        double2 tk = make_double2(0, 0);
+        double tlen = 0;
+        if (n > 0) {
+            tk = V.kin[base + n - 1];
+            tlen = V.tmpl[V.ids[base + n - 1].y].len;
+            avail = tk.x > tlen + T.minGap;
+        }
+        if (avail) {
+            if (n >= V.off[i + 1] - base) {
+                atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW);
+            } else {
+                const int p = base + n;
+                V.kin[p] = make_double2(0.0, T.speed0);
+                V.ids[p] = make_int4(h, info.x, info.y, info.z);
+                V.nav[p] = make_int4(0, -1, -1, INT_MAX);
+                if (n > 0) {
+                    V.leader[p] = p - 1;
+                    V.gap[p] = tk.x - tlen - 0.0;
+                    ins = 1;
+                } else {
+                    V.leader[p] = -1;
+                    ins = 3;  // admitted to an empty lane: leader search runs in k_notify
+                }
+                V.count[i] = n + 1;
+                V.pos[h] = p;
+                atomicAdd(&V.ctrl->active, 1);
+                int nx = V.waitNext[h];
+                V.waitHead[i] = nx;
+                if (nx < 0) V.waitTail[i] = -1;
+            }
+        }
+    }
+    V.inserted[i] = ins;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_notify: thread per laneLink (Engine::threadNotifyCross, engine.cpp:317-372).  Notify slots
+// are epoch-stamped instead of cleared (Cross::clearNotify would sweep every cross every step).
+__global__ void __launch_bounds__(256) k_notify(View V) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V.nLanes && (V.inserted[i] & 2)) {  // vehicle admitted to an empty lane this step
+        const int p = V.off[i];
+        const int4 idv = V.ids[p];
+        int ld = -1;
+        double g = 0;
+        headSearch(V, i, 0.0, idv.w, 0, V.tmpl[idv.y], i, ld, g);
+        V.leader[p] = ld;
+        if (ld >= 0) V.gap[p] = g;
+    }
+    if (i >= V.nLinks) return;
+    const int cb = V.llCrossBeg[i], ce = V.llCrossBeg[i + 1];
+    if (cb == ce) return;
+    const int epoch = V.ctrl->step + 1;
+    const int linkDrv = V.nLanes + i;
+    int ri = ce - 1;
+    auto put = [&](int k, int pos, double dist) {
+        Notify n;
+        n.dist = dist;
+        n.pos = pos;
+        n.epoch = epoch;
+        V.notify[V.lcIdx[k]] = n;
+    };
+    // (1) the last vehicle on the end lane if it came out of this link
+    {
+        const int el = V.llEndLane[i];
+        const int c = V.count[el];
+        if (c > 0) {
+            const int tp = V.off[el] + c - 1;
+            if (V.nav[tp].y == linkDrv) {
+                const double tdis = V.kin[tp].x;
+                const double vehDistance = tdis - V.tmpl[V.ids[tp].y].len;
+                const double L = V.drvLength[linkDrv];
+                while (ri >= cb) {
+                    double crossDistance = L - V.lcDist[ri];
+                    if (crossDistance + vehDistance < 0) {
+                        put(ri, tp, -(tdis + crossDistance));
+                        --ri;
+                    } else break;
+                }
+            }
+        }
+    }
+    // (2) vehicles on the link, front to back
+    {
+        const int c = V.count[linkDrv], base = V.off[linkDrv];
+        for (int j = 0; j < c && ri >= cb; ++j) {
+            const double vehDistance = V.kin[base + j].x;
+            const double len = V.tmpl[V.ids[base + j].y].len;
+            while (ri >= cb) {
+                double crossDistance = V.lcDist[ri];
+                if (vehDistance > crossDistance) {
+                    if (vehDistance - crossDistance - len <= 0) put(ri, base + j, crossDistance - vehDistance);
+                    else break;
+                } else {
+                    put(ri, base + j, crossDistance - vehDistance);
+                }
+                --ri;
+            }
+        }
+    }
+    // (3) the first vehicle of the start lane if it heads for this link and the link is green
+    if (ri >= cb) {
+        const int sl = V.llStartLane[i];
+        if (V.count[sl] > 0) {
+            const int hp = V.off[sl];
+            const int4 idv = V.ids[hp];
+            if (planAt(V, idv.w, V.nav[hp].x + 1) == linkDrv && V.rlAvail[V.llRoadLink[i]]) {
+                const double vehDistance = V.drvLength[sl] - V.kin[hp].x;
+                while (ri >= cb) {
+                    put(ri, hp, vehDistance + V.lcDist[ri]);
+                    --ri;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Cross::canPass roadnet.cpp:603-676.  `cs` = 2*cross + side of the asking vehicle's laneLink.
+__device__ bool canPass(const View &V, int cs, int epoch, const DTmpl &T, double mySpeed, int myEnterLL, int myPriority,
+                        double distanceToLaneLinkStart, double distOnLane, int &foeSlot) {
+    const Notify f = V.notify[cs ^ 1];
+    foeSlot = -1;
+    if (f.epoch != epoch) return true;  // foeVehicle == nullptr
+    const int fp = f.pos;
+    const int4 fid = V.ids[fp];
+    foeSlot = fid.x;
+    const int myLink = V.csLink[cs], foeLink = V.csLink[cs ^ 1];
+    const int t1 = V.llType[myLink], t2 = V.llType[foeLink];
+    const double d1 = distOnLane - distanceToLaneLinkStart, d2 = f.dist;
+    if (!canYield(T, mySpeed, d1)) return true;
+    const DTmpl &FT = V.tmpl[fid.y];
+    const double foeSpeed = V.kin[fp].y;
+    int yield = 0;
+    if (!canYield(FT, foeSpeed, d2)) yield = 1;
+    if (yield == 0) {
+        if (t1 > t2) {
+            yield = -1;
+        } else {
+            const double dt = V.dt;
+            if (d2 > 0) {
+                int foeSteps = reachSteps(foeSpeed, d2, V.llTurn[foeLink] ? FT.turnSpeed : FT.maxSpeed, FT.usualPosAcc, dt);
+                int mySteps = reachSteps(mySpeed, d1, V.llTurn[myLink] ? T.turnSpeed : T.maxSpeed, T.usualPosAcc, dt);
+                if (foeSteps > mySteps) yield = -1;
+                else if (t1 < t2) yield = 1;
+                else if (foeSteps < mySteps) yield = 1;
+                else {
+                    // enterLaneLinkTime is a size_t compared as double (vehicle.h:262)
+                    const int foeEnter = V.nav[fp].w;
+                    if (myEnterLL == foeEnter) {
+                        if (d1 == d2) yield = myPriority > fid.z ? -1 : 1;
+                        else yield = d1 < d2 ? -1 : 1;
+                    } else {
+                        yield = myEnterLL < foeEnter ? -1 : 1;
+                    }
+                }
+            } else {
+                yield = d2 + FT.len < 0 ? -1 : 1;
+            }
+        }
+    }
+    if (yield == 1) {
+        // deadlock detection over the committed blocker chain (Floyd), roadnet.cpp:662-674
+        auto blockerOf = [&](int p) -> int {
+            int b = V.nav[p].z;
+            return b < 0 ? -1 : V.pos[b];
+        };
+        int fast = fp, slow = fp;
+        while (fast >= 0) {
+            int fb = blockerOf(fast);
+            if (fb < 0) break;
+            slow = blockerOf(slow);
+            fast = blockerOf(fb);
+            if (slow == fast) {
+                yield = -1;
+                break;
+            }
+        }
+    }
+    return yield == -1;
+}
+
+// k_control: one warp per drivable bucket, one lane per vehicle (strided by 32).
+// Vehicle::getNextSpeed vehicle.cpp:308-335, getCarFollowSpeed :212-238, getIntersectionRelatedSpeed
+// :337-376, Engine::vehicleControl engine.cpp:188-251, Vehicle::setDeltaDistance vehicle.cpp:49-68.
+__global__ void __launch_bounds__(256) k_control(View V) {
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= V.nDrv) return;
+    const int n = V.count[d];
+    if (n == 0) return;
+    const int base = V.off[d];
+    const double dt = V.dt;
+    const double dLen = V.drvLength[d], dMax = V.drvMaxSpeed[d];
+    const bool onLink = d >= V.nLanes;
+    const int epoch = V.ctrl->step + 1;
+    for (int k = lane; k < n; k += 32) {
+        const int p = base + k;
+        const double2 kk = V.kin[p];
+        const double dis = kk.x, speed = kk.y;
+        const int4 idv = V.ids[p];
+        const int4 nv = V.nav[p];
+        const DTmpl &T = V.tmpl[idv.y];
+        const int planBase = V.planBeg[idv.w] + nv.x + 1;
+
+        double v = T.maxSpeed;
+        v = min2(v, speed + T.maxPosAcc * dt);
+        v = min2(v, dMax);
+        // ---- car following ----
+        {
+            const int lp = V.leader[p];
+            double cf;
+            if (lp < 0) {
+                cf = T.maxSpeed;
+            } else {
+                const double leaderSpeed = V.kin[lp].y;
+                const DTmpl &LT = V.tmpl[V.ids[lp].y];
+                const double g = V.gap[p];
+                cf = noCollisionSpeed(leaderSpeed, LT.maxNegAcc, speed, T.maxNegAcc, g, dt, 0);
+                double assumeDecel = 0;
+                if (speed > leaderSpeed) assumeDecel = speed - leaderSpeed;
+                cf = min2(cf, noCollisionSpeed(leaderSpeed, LT.usualNegAcc, speed, T.usualNegAcc, g, dt, T.minGap));
+                cf = min2(cf, (g + (leaderSpeed + assumeDecel / 2) * dt - speed * dt / 2) / (T.headwayTime + dt / 2));
+            }
+            v = min2(v, cf);
+        }
+        // ---- intersection logic ----
+        int newBlocker = -1;
+        const int nd0 = V.planData[planBase];
+        if (onLink || (nd0 >= V.nLanes && dLen - dis <= T.approachDist)) {
+            double s = T.maxSpeed;
+            int ll = -1;
+            bool done = false;
+            if (nd0 >= V.nLanes) {
+                ll = nd0 - V.nLanes;
+                bool blocked = !V.rlAvail[V.llRoadLink[ll]];
+                if (!blocked) {  // Lane::canEnter roadnet.cpp:437-445
+                    const int el = V.llEndLane[ll];
+                    const int c = V.count[el];
+                    if (c > 0) {
+                        const int tp = V.off[el] + c - 1;
+                        const double2 tk = V.kin[tp];
+                        blocked = !(tk.x > V.tmpl[V.ids[tp].y].len + T.len || tk.y >= 2);
+                    }
+                }
+                if (blocked) {
+                    if (0.5 * speed * speed / T.maxNegAcc > dLen - dis) {
+                        // cannot stop before the line any more
+                    } else {
+                        s = min2(s, stopBeforeSpeed(T, speed, dLen - dis, dt));
+                        done = true;
+                    }
+                }
+                if (!done && V.llTurn[ll]) s = min2(s, T.turnSpeed);
+            }
+            if (!done) {
+                if (ll < 0 && onLink) ll = d - V.nLanes;
+                const double toStart = onLink ? dis : -(dLen - dis);
+                const int cb = V.llCrossBeg[ll], ce = V.llCrossBeg[ll + 1];
+                for (int q = cb; q < ce; ++q) {
+                    const double dOn = V.lcDist[q];
+                    if (dOn < toStart) continue;
+                    int foeSlot;
+                    if (!canPass(V, V.lcIdx[q], epoch, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
+                        s = min2(s, stopBeforeSpeed(T, speed, dOn - toStart - T.yieldDistance, dt));
+                        newBlocker = foeSlot;
+                        break;
+                    }
+                }
+            }
+            v = min2(v, s);
+        }
+        v = max2(v, speed - T.maxNegAcc * dt);
+        // ---- Engine::vehicleControl ----
+        double deltaDis;
+        if (v < 0) {
+            deltaDis = 0.5 * speed * speed / T.maxNegAcc;
+            v = 0;
+        } else {
+            deltaDis = (speed + v) * dt / 2;
+        }
+        // ---- setDeltaDistance: walk over the planned drivables ----
+        double nd = deltaDis + dis;
+        int cur = d, hops = 0, newDrv = -1;
+        double curLen = dLen;
+        while (cur >= 0 && nd > curLen) {
+            nd -= curLen;
+            int nx = V.planData[planBase + hops];
+            ++hops;
+            if (nx < 0) {
+                if (nx != PLAN_LOOKAHEAD_END) atomicOr(&V.ctrl->error, ERR_ROUTE_DEAD_END);
+                newDrv = -2;  // ran off the last road: end
+                cur = -1;
+            } else {
+                cur = nx;
+                newDrv = nx;
+                curLen = V.drvLength[nx];
+            }
+        }
+        V.nkin[p] = make_double2(nd, v);
+        V.nbuf[p] = make_int2(newDrv, newBlocker);
+        if (newDrv >= 0) {  // Engine::pushBuffer (engine.cpp:247-249)
+            const int m = atomicAdd(&V.ctrl->moverCount, 1);
+            if (m >= V.moverCap) {
+                atomicOr(&V.ctrl->error, ERR_MOVER_OVERFLOW);
+            } else {
+                V.mkin[m] = make_double2(nd, v);
+                V.mids[m] = idv;
+                // enterLaneLinkTime: step for links, INT_MAX for lanes (engine.cpp:486-490)
+                V.mnav[m] = make_int4(nv.x + hops, d, newBlocker, newDrv >= V.nLanes ? epoch - 1 : INT_MAX);
+                const int e = atomicAdd(&V.entCnt[newDrv], 1);
+                if (e >= ENT_CAP) atomicOr(&V.ctrl->error, ERR_ENTRANT_OVERFLOW);
+                else V.ent[newDrv * ENT_CAP + e] = m;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_move: warp per drivable.  Survivors are compacted in place with a ballot/popc scan (stable,
+// so list order is preserved); the few entrants are rank-sorted by (new distance desc, priority
+// asc) -- the reference's global std::sort on distance (engine.cpp:480) restricted to one target --
+// and appended.  Commits Buffer -> state (Vehicle::update, vehicle.cpp:107-143).
+__global__ void __launch_bounds__(256) k_move(View V) {
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= V.nDrv) return;
+    const int n = V.count[d];
+    int m = V.entCnt[d];
+    if (n == 0 && m == 0) return;
+    const int base = V.off[d], cap = V.off[d + 1] - base;
+    int nsurv = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int k = c0 + lane;
+        const bool valid = k < n;
+        double2 nk = make_double2(0, 0);
+        int2 nb = make_int2(0, 0);
+        int4 idv = make_int4(0, 0, 0, 0), nv = make_int4(0, 0, 0, 0);
+        if (valid) {
+            const int p = base + k;
+            nk = V.nkin[p];
+            nb = V.nbuf[p];
+            idv = V.ids[p];
+            nv = V.nav[p];
+        }
+        const bool keep = valid && nb.x == -1;
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        const int dst = nsurv + __popc(mask & ((1u << lane) - 1));
+        __syncwarp();
+        if (keep) {
+            const int q = base + dst;
+            V.kin[q] = nk;                                     // dis, speed
+            nv.z = nb.y;                                       // blocker := buffer.blocker or null
+            V.nav[q] = nv;
+            if (dst != k) {
+                V.ids[q] = idv;
+                V.pos[idv.x] = q;
+            }
+        } else if (valid && nb.x == -2) {                      // finished (engine.cpp:296-310)
+            V.pos[idv.x] = -1;
+            const int f = atomicAdd(&V.ctrl->finCount, 1);
+            if (f < V.finCap) V.finSlots[f] = make_int2(idv.x, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
+            atomicSub(&V.ctrl->active, 1);
+        }
+        nsurv += __popc(mask);
+    }
+    if (m > 0) {
+        if (m > ENT_CAP) m = ENT_CAP;
+        if (nsurv + m > cap) {
+            if (lane == 0) atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW);
+            m = max(0, cap - nsurv);
+        }
+        int mi = -1;
+        double myDis = 0;
+        int myPrio = 0;
+        if (lane < m) {
+            mi = V.ent[d * ENT_CAP + lane];
+            myDis = V.mkin[mi].x;
+            myPrio = V.mids[mi].z;
+        }
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+            const double od = __shfl_sync(0xffffffffu, myDis, j);
+            const int op = __shfl_sync(0xffffffffu, myPrio, j);
+            if (lane < m && j != lane && (od > myDis || (od == myDis && op < myPrio))) ++rank;
+        }
+        if (lane < m) {
+            const int q = base + nsurv + rank;
+            const int4 idv = V.mids[mi];
+            V.kin[q] = V.mkin[mi];
+            V.ids[q] = idv;
+            V.nav[q] = V.mnav[mi];
+            V.pos[idv.x] = q;
+        }
+        if (lane == 0) V.entCnt[d] = 0;
+    }
+    if (lane == 0) V.count[d] = nsurv + m;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_leader: warp per drivable.  Non-heads: leader = list predecessor, gap = leader.dis -
+// leader.len - dis (vehicle.cpp:158-160), predecessor values arrive by warp shuffle.  Heads:
+// cross-drivable search.  Also drops blockers that left the network this step
+// (engine.cpp:419-421) and, in the tail threads, advances the traffic lights
+// (TrafficLight::passTime, trafficlight.cpp:29-37) and the step counter.
+__global__ void __launch_bounds__(256) k_leader(View V) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = gtid >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gtid == 0) V.ctrl->step += 1;  // Engine::step (engine.cpp:593); nothing in this kernel reads it
+    if (gtid < V.nInter && !V.rl && !V.interVirtual[gtid]) {
+        double rem = V.remain[gtid] - V.dt;
+        int cur = V.curPhase[gtid];
+        const int pb = V.interPhaseBeg[gtid], nph = V.interPhaseBeg[gtid + 1] - pb;
+        while (rem <= 0.0) {
+            cur = (cur + 1) % nph;
+            rem += V.phaseTime[pb + cur];
+        }
+        V.remain[gtid] = rem;
+        V.curPhase[gtid] = cur;
+    }
+    if (d >= V.nDrv) return;
+    const int n = V.count[d];
+    if (n == 0) return;
+    const int base = V.off[d];
+    double carryDis = 0, carryLen = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int k = c0 + lane;
+        const bool valid = k < n;
+        const int p = base + k;
+        double dis = 0, len = 0;
+        int4 idv = make_int4(0, 0, 0, 0);
+        if (valid) {
+            dis = V.kin[p].x;
+            idv = V.ids[p];
+            len = V.tmpl[idv.y].len;
+        }
+        double pd = __shfl_up_sync(0xffffffffu, dis, 1);
+        double pl = __shfl_up_sync(0xffffffffu, len, 1);
+        if (lane == 0) {
+            pd = carryDis;
+            pl = carryLen;
+        }
+        carryDis = __shfl_sync(0xffffffffu, dis, 31);
+        carryLen = __shfl_sync(0xffffffffu, len, 31);
+        if (valid) {
+            if (k > 0) {
+                V.leader[p] = p - 1;
+                V.gap[p] = pd - pl - dis;
+            } else {
+                int ld = -1;
+                double g = 0;
+                headSearch(V, d, dis, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
+                V.leader[p] = ld;
+                if (ld >= 0) V.gap[p] = g;
+            }
+            const int b = V.nav[p].z;
+            if (b >= 0 && V.pos[b] < 0) V.nav[p].z = -1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Observation kernels
+__global__ void __launch_bounds__(256) k_lane_waiting(View V, int *out) {  // engine.cpp:636-648
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= V.nLanes) return;
+    const int n = V.count[d], base = V.off[d];
+    int c = 0;
+    for (int k = lane; k < n; k += 32) c += V.kin[base + k].y < 0.1;
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) out[d] = c;
+}
+
+__global__ void __launch_bounds__(256) k_gather_running(View V, SpeedRec *out, int *cursor, int cap) {
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= V.nDrv) return;
+    const int n = V.count[d], base = V.off[d];
+    if (n == 0) return;
+    int start = 0;
+    if (lane == 0) start = atomicAdd(cursor, n);
+    start = __shfl_sync(0xffffffffu, start, 0);
+    for (int k = lane; k < n; k += 32) {
+        if (start + k < cap) {
+            SpeedRec r;
+            r.slot = V.ids[base + k].x;
+            r.drivable = d;
+            const double2 kk = V.kin[base + k];
+            r.speed = kk.y;
+            r.dis = kk.x;
+            out[start + k] = r;
+        }
+    }
+}
+
+__global__ void k_lane_slots(View V, int *out, const int *laneBeg) {
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= V.nLanes) return;
+    const int n = V.count[d], base = V.off[d], o = laneBeg[d];
+    for (int k = lane; k < n; k += 32) out[o + k] = V.ids[base + k].x;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CFB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T> &v) {
+        alloc(v.size());
+        if (!v.empty()) CFB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void fill(int byte) {
+        if (n) CFB_CUDA(cudaMemset(p, byte, n * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+};
+
+struct DeviceSim::Impl {
+    DeviceSimOptions opt;
+    View V{};
+    cudaStream_t stream = nullptr;
+    int P = 0;
+    std::vector<int> offHost;
+    std::vector<double> phase0Time;   // remainDuration after TrafficLight::init(0)
+    // static
+    DevBuf<double> drvLength, drvMaxSpeed, lcDist, phaseTime;
+    DevBuf<int> off, laneOutBeg, laneOutLinks, llStartLane, llEndLane, llRoadLink, llCrossBeg, lcIdx, csLink,
+        interPhaseBeg, interRLBeg, phaseAvailBeg, rlInter, planBeg, planData;
+    DevBuf<unsigned char> llTurn, llType, phaseAvail, interVirtual;
+    DevBuf<DTmpl> tmpl;
+    // dynamic
+    DevBuf<double2> kin, nkin, mkin;
+    DevBuf<double> gap, remain;
+    DevBuf<int> leader, count, pos, waitHead, waitTail, waitNext, curPhase, entCnt, ent, scratchI;
+    DevBuf<int2> finSlots;
+    DevBuf<int4> ids, nav, slotInfo, mids, mnav;
+    DevBuf<int2> nbuf;
+    DevBuf<unsigned char> inserted, rlAvail;
+    DevBuf<Notify> notify;
+    DevBuf<Ctrl> ctrl;
+    DevBuf<SpawnRec> spawn;
+    DevBuf<SpeedRec> speedOut;
+    int spawnCap = 0;
+    // pinned staging
+    static constexpr int RING = 16;
+    SpawnRec *hSpawn[RING] = {};
+    int hSpawnCap[RING] = {};
+    cudaEvent_t spawnDone[RING] = {};
+    int ringIdx = 0;
+    int *hCounts = nullptr; // pinned, RING ints
+    Ctrl *hCtrl = nullptr;  // pinned readback
+    int *hInts = nullptr;   // pinned readback (lanes)
+    size_t hIntsCap = 0;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[6] = {};
+    KernelTimes times;
+
+    int slotCap = 0;
+
+    void ensureHostInts(size_t n) {
+        if (n <= hIntsCap) return;
+        if (hInts) cudaFreeHost(hInts);
+        CFB_CUDA(cudaMallocHost(&hInts, n * sizeof(int)));
+        hIntsCap = n;
+    }
+};
+
+static DTmpl toDevice(const VehicleTemplate &t, double interval) {
+    DTmpl d{};
+    d.len = t.len;
+    d.maxPosAcc = t.maxPosAcc;
+    d.maxNegAcc = t.maxNegAcc;
+    d.usualPosAcc = t.usualPosAcc;
+    d.usualNegAcc = t.usualNegAcc;
+    d.minGap = t.minGap;
+    d.maxSpeed = t.maxSpeed;
+    d.headwayTime = t.headwayTime;
+    d.yieldDistance = t.yieldDistance;
+    d.turnSpeed = t.turnSpeed;
+    // vehicle.cpp:42-44 (and the identical look-ahead bound at :190-191)
+    d.approachDist = t.maxSpeed * t.maxSpeed / t.usualNegAcc / 2 + t.maxSpeed * interval * 2;
+    d.speed0 = t.speed;
+    return d;
+}
+
+DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &templates, const Routing &routing,
+                     const DeviceSimOptions &opt)
+    : impl_(new Impl()) {
+    Impl &I = *impl_;
+    I.opt = opt;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        delete impl_;
+        impl_ = nullptr;
+        throw std::runtime_error(std::string("cityflow_b200: no CUDA device available (") +
+                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                 "); this engine has no CPU fallback");
+    }
+    CFB_CUDA(cudaSetDevice(opt.device));
+    CFB_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
+    View &V = I.V;
+    const int nL = net.nLanes(), nK = net.nLinks(), nD = nL + nK;
+    V.nLanes = nL; V.nLinks = nK; V.nDrv = nD; V.nInter = net.nInter(); V.nRL = net.nRoadLinks(); V.nCross = net.nCross();
+    V.dt = opt.interval;
+    V.rl = opt.rlTrafficLight ? 1 : 0;
+
+    // ---- static tables ----
+    std::vector<double> len(nD), maxs(nD);
+    std::vector<int> off(nD + 1, 0);
+    for (int d = 0; d < nD; ++d) {
+        len[d] = d < nL ? net.laneLength[d] : net.llLength[d - nL];
+        maxs[d] = d < nL ? net.laneMaxSpeed[d] : 10000.0;  // LaneLink::maxSpeed, roadnet.h:456
+        // bucket capacity: room for bumper-to-bumper traffic of 2.5 m vehicles plus slack
+        int cap = (int) (len[d] / 2.5) + 8;
+        cap = (cap + 3) & ~3;
+        off[d + 1] = off[d] + cap;
+    }
+    I.P = off[nD];
+    I.offHost = off;
+    I.drvLength.upload(len); I.drvMaxSpeed.upload(maxs); I.off.upload(off);
+    std::vector<int> lob(nL + 1, 0), lol;
+    for (int l = 0; l < nL; ++l) {
+        for (int ll : net.laneOutLinks[l]) lol.push_back(ll);
+        lob[l + 1] = (int) lol.size();
+    }
+    if (lol.empty()) lol.push_back(0);
+    I.laneOutBeg.upload(lob); I.laneOutLinks.upload(lol);
+    std::vector<unsigned char> turn(std::max(nK, 1)), type(std::max(nK, 1));
+    std::vector<int> lcb(nK + 1, 0), lcIdx, csLink(std::max(2 * net.nCross(), 1), 0), llRL(net.llRoadLink);
+    std::vector<double> lcDist;
+    for (int k = 0; k < nK; ++k) {
+        turn[k] = net.linkIsTurn(k) ? 1 : 0;
+        type[k] = (unsigned char) net.rlType[net.llRoadLink[k]];
+        for (const CrossRef &c : net.llCrosses[k]) {
+            lcIdx.push_back(c.cross * 2 + c.side);
+            lcDist.push_back(net.crossDist[c.side][c.cross]);
+        }
+        lcb[k + 1] = (int) lcIdx.size();
+    }
+    for (int c = 0; c < net.nCross(); ++c) {
+        csLink[2 * c] = net.crossLink[0][c];
+        csLink[2 * c + 1] = net.crossLink[1][c];
+    }
+    if (lcIdx.empty()) { lcIdx.push_back(0); lcDist.push_back(0); }
+    auto nz = [](std::vector<int> v) { if (v.empty()) v.push_back(0); return v; };
+    I.llStartLane.upload(nz(net.llStartLane)); I.llEndLane.upload(nz(net.llEndLane)); I.llRoadLink.upload(nz(llRL));
+    I.llTurn.upload(turn); I.llType.upload(type);
+    I.llCrossBeg.upload(lcb); I.lcIdx.upload(lcIdx); I.lcDist.upload(lcDist); I.csLink.upload(csLink);
+    I.interPhaseBeg.upload(net.interPhaseBeg); I.interRLBeg.upload(net.interRoadLinkBeg);
+    I.phaseAvailBeg.upload(nz(net.phaseAvailBeg)); I.rlInter.upload(nz(net.rlInter));
+    std::vector<double> pt = net.phaseTime; if (pt.empty()) pt.push_back(0);
+    I.phaseTime.upload(pt);
+    std::vector<unsigned char> pa = net.phaseAvail; if (pa.empty()) pa.push_back(0);
+    I.phaseAvail.upload(pa);
+    std::vector<unsigned char> iv(net.interVirtual.begin(), net.interVirtual.end());
+    I.interVirtual.upload(iv);
+    I.phase0Time.assign(net.nInter(), 0.0);
+    for (int i = 0; i < net.nInter(); ++i)
+        if (!net.interVirtual[i]) I.phase0Time[i] = net.phaseTime[net.interPhaseBeg[i]];
+
+    V.drvLength = I.drvLength.p; V.drvMaxSpeed = I.drvMaxSpeed.p; V.off = I.off.p;
+    V.laneOutBeg = I.laneOutBeg.p; V.laneOutLinks = I.laneOutLinks.p;
+    V.llStartLane = I.llStartLane.p; V.llEndLane = I.llEndLane.p; V.llRoadLink = I.llRoadLink.p;
+    V.llTurn = I.llTurn.p; V.llType = I.llType.p;
+    V.llCrossBeg = I.llCrossBeg.p; V.lcIdx = I.lcIdx.p; V.lcDist = I.lcDist.p; V.csLink = I.csLink.p;
+    V.interPhaseBeg = I.interPhaseBeg.p; V.interRLBeg = I.interRLBeg.p; V.phaseAvailBeg = I.phaseAvailBeg.p;
+    V.rlInter = I.rlInter.p; V.phaseTime = I.phaseTime.p; V.phaseAvail = I.phaseAvail.p; V.interVirtual = I.interVirtual.p;
+
+    uploadTemplates(templates);
+    uploadPlans(routing);
+
+    // ---- dynamic state ----
+    const size_t P = (size_t) I.P;
+    I.kin.alloc(P); I.nkin.alloc(P); I.gap.alloc(P); I.leader.alloc(P); I.ids.alloc(P); I.nav.alloc(P); I.nbuf.alloc(P);
+    I.count.alloc(nD); I.entCnt.alloc(nD); I.ent.alloc((size_t) nD * ENT_CAP);
+    I.waitHead.alloc(std::max(nL, 1)); I.waitTail.alloc(std::max(nL, 1)); I.inserted.alloc(std::max(nL, 1));
+    I.notify.alloc(std::max(2 * net.nCross(), 1));
+    I.curPhase.alloc(net.nInter()); I.remain.alloc(net.nInter()); I.rlAvail.alloc(std::max(net.nRoadLinks(), 1));
+    V.moverCap = (int) std::min<size_t>(P, (size_t) 1 << 22);
+    I.mkin.alloc(V.moverCap); I.mids.alloc(V.moverCap); I.mnav.alloc(V.moverCap);
+    V.finCap = 1 << 20;
+    I.finSlots.alloc(V.finCap);
+    I.ctrl.alloc(1);
+    CFB_CUDA(cudaMallocHost(&I.hCtrl, sizeof(Ctrl)));
+    CFB_CUDA(cudaMallocHost(&I.hCounts, Impl::RING * sizeof(int)));
+    V.kin = I.kin.p; V.nkin = I.nkin.p; V.gap = I.gap.p; V.leader = I.leader.p; V.ids = I.ids.p; V.nav = I.nav.p;
+    V.nbuf = I.nbuf.p; V.count = I.count.p; V.entCnt = I.entCnt.p; V.ent = I.ent.p;
+    V.waitHead = I.waitHead.p; V.waitTail = I.waitTail.p; V.inserted = I.inserted.p; V.notify = I.notify.p;
+    V.curPhase = I.curPhase.p; V.remain = I.remain.p; V.rlAvail = I.rlAvail.p;
+    V.mkin = I.mkin.p; V.mids = I.mids.p; V.mnav = I.mnav.p; V.finSlots = I.finSlots.p; V.ctrl = I.ctrl.p;
+    ensureSlotCapacity(opt.slotCapacity);
+    for (int r = 0; r < Impl::RING; ++r) CFB_CUDA(cudaEventCreateWithFlags(&I.spawnDone[r], cudaEventDisableTiming));
+    for (auto &ev : I.ev) CFB_CUDA(cudaEventCreate(&ev));
+    reset();
+}
+
+DeviceSim::~DeviceSim() {
+    if (!impl_) return;
+    Impl &I = *impl_;
+    cudaStreamSynchronize(I.stream);
+    for (int r = 0; r < Impl::RING; ++r) {
+        if (I.hSpawn[r]) cudaFreeHost(I.hSpawn[r]);
+        if (I.spawnDone[r]) cudaEventDestroy(I.spawnDone[r]);
+    }
+    for (auto &ev : I.ev) if (ev) cudaEventDestroy(ev);
+    if (I.hCtrl) cudaFreeHost(I.hCtrl);
+    if (I.hCounts) cudaFreeHost(I.hCounts);
+    if (I.hInts) cudaFreeHost(I.hInts);
+    if (I.stream) cudaStreamDestroy(I.stream);
+    delete impl_;
+}
+
+void DeviceSim::uploadTemplates(const std::vector<VehicleTemplate> &templates) {
+    Impl &I = *impl_;
+    std::vector<DTmpl> t;
+    for (const auto &x : templates) t.push_back(toDevice(x, I.opt.interval));
+    if (t.empty()) t.push_back(DTmpl{});
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    I.tmpl.upload(t);
+    I.V.tmpl = I.tmpl.p;
+}
+
+void DeviceSim::uploadPlans(const Routing &routing) {
+    Impl &I = *impl_;
+    std::vector<int> pb = routing.planBeg(), pd = routing.planData();
+    if (pb.empty()) pb.push_back(0);
+    if (pd.empty()) pd.push_back(PLAN_END);
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    I.planBeg.upload(pb);
+    I.planData.upload(pd);
+    I.V.planBeg = I.planBeg.p;
+    I.V.planData = I.planData.p;
+}
+
+void DeviceSim::ensureSlotCapacity(int slots) {
+    Impl &I = *impl_;
+    if (slots <= I.slotCap) return;
+    int cap = std::max(I.slotCap, 1024);
+    while (cap < slots) cap *= 2;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    DevBuf<int> npos, nnext;
+    DevBuf<int4> ninfo;
+    npos.alloc(cap); nnext.alloc(cap); ninfo.alloc(cap);
+    npos.fill(0xff); nnext.fill(0xff); ninfo.fill(0);
+    if (I.slotCap) {
+        CFB_CUDA(cudaMemcpy(npos.p, I.pos.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
+        CFB_CUDA(cudaMemcpy(nnext.p, I.waitNext.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
+        CFB_CUDA(cudaMemcpy(ninfo.p, I.slotInfo.p, I.slotCap * sizeof(int4), cudaMemcpyDeviceToDevice));
+    }
+    std::swap(I.pos.p, npos.p); std::swap(I.pos.n, npos.n);
+    std::swap(I.waitNext.p, nnext.p); std::swap(I.waitNext.n, nnext.n);
+    std::swap(I.slotInfo.p, ninfo.p); std::swap(I.slotInfo.n, ninfo.n);
+    I.slotCap = cap;
+    I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p;
+}
+
+void DeviceSim::reset() {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    I.count.fill(0); I.entCnt.fill(0);
+    I.waitHead.fill(0xff); I.waitTail.fill(0xff); I.inserted.fill(0);
+    I.pos.fill(0xff); I.waitNext.fill(0xff);
+    I.notify.fill(0);
+    I.curPhase.fill(0);
+    CFB_CUDA(cudaMemcpy(I.remain.p, I.phase0Time.data(), I.phase0Time.size() * sizeof(double), cudaMemcpyHostToDevice));
+    I.rlAvail.fill(0);
+    I.ctrl.fill(0);
+    // leader = -1 everywhere is not required (only occupied positions are read)
+    steps_ = 0;
+}
+
+int DeviceSim::numPositions() const { return impl_->P; }
+int DeviceSim::numDrivables() const { return impl_->V.nDrv; }
+
+void DeviceSim::step(const SpawnRec *recs, int n) {
+    Impl &I = *impl_;
+    View &V = I.V;
+    cudaStream_t s = I.stream;
+    // ---- stage this step's spawn records (pinned ring -> device) ----
+    if (n > I.spawnCap) {
+        CFB_CUDA(cudaStreamSynchronize(s));
+        I.spawnCap = std::max(1024, n * 2);
+        I.spawn.alloc(I.spawnCap);
+    }
+    V.spawn = I.spawn.p;
+    const int r = I.ringIdx;
+    I.ringIdx = (I.ringIdx + 1) % Impl::RING;
+    CFB_CUDA(cudaEventSynchronize(I.spawnDone[r]));  // ring slot r free again (RING steps in flight at most)
+    if (n > 0) {
+        if (n > I.hSpawnCap[r]) {
+            if (I.hSpawn[r]) cudaFreeHost(I.hSpawn[r]);
+            I.hSpawnCap[r] = std::max(1024, n * 2);
+            CFB_CUDA(cudaMallocHost(&I.hSpawn[r], I.hSpawnCap[r] * sizeof(SpawnRec)));
+        }
+        memcpy(I.hSpawn[r], recs, n * sizeof(SpawnRec));
+        CFB_CUDA(cudaMemcpyAsync(I.spawn.p, I.hSpawn[r], n * sizeof(SpawnRec), cudaMemcpyHostToDevice, s));
+    }
+    I.hCounts[r] = n;
+    CFB_CUDA(cudaMemcpyAsync(&V.ctrl->spawnCount, &I.hCounts[r], sizeof(int), cudaMemcpyHostToDevice, s));
+    CFB_CUDA(cudaEventRecord(I.spawnDone[r], s));
+    const int TPB = 256;
+    const int gLaneRL = (std::max(V.nLanes, V.nRL) + TPB - 1) / TPB;
+    const int gLinkLane = (std::max(V.nLinks, V.nLanes) + TPB - 1) / TPB;
+    const int gWarpDrv = (int) (((size_t) V.nDrv * 32 + TPB - 1) / TPB);
+    const int gLeader = std::max(gWarpDrv, (V.nInter + TPB - 1) / TPB);
+    const bool tm = I.timing;
+    if (tm) cudaEventRecord(I.ev[0], s);
+    k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
+    if (tm) cudaEventRecord(I.ev[1], s);
+    k_notify<<<std::max(gLinkLane, 1), TPB, 0, s>>>(V);
+    if (tm) cudaEventRecord(I.ev[2], s);
+    k_control<<<std::max(gWarpDrv, 1), TPB, 0, s>>>(V);
+    if (tm) cudaEventRecord(I.ev[3], s);
+    k_move<<<std::max(gWarpDrv, 1), TPB, 0, s>>>(V);
+    if (tm) cudaEventRecord(I.ev[4], s);
+    k_leader<<<std::max(gLeader, 1), TPB, 0, s>>>(V);
+    if (tm) cudaEventRecord(I.ev[5], s);
+    CFB_CUDA(cudaGetLastError());
+    launches_ += 5;
+    steps_ += 1;
+    if (tm) {
+        CFB_CUDA(cudaEventSynchronize(I.ev[5]));
+        float ms[5];
+        for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&ms[k], I.ev[k], I.ev[k + 1]);
+        I.times.ingest += ms[0]; I.times.notify += ms[1]; I.times.control += ms[2]; I.times.move += ms[3];
+        I.times.leader += ms[4];
+        I.times.launches += 1;
+    }
+}
+
+void DeviceSim::synchronize() { CFB_CUDA(cudaStreamSynchronize(impl_->stream)); }
+
+void DeviceSim::enableKernelTiming(bool on) {
+    impl_->timing = on;
+    impl_->times = KernelTimes();
+}
+DeviceSim::KernelTimes DeviceSim::kernelTimes() { return impl_->times; }
+
+static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src) {
+    CFB_CUDA(cudaMemcpyAsync(dst, src, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaStreamSynchronize(s));
+}
+
+int DeviceSim::vehicleCount() {
+    readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
+    return impl_->hCtrl->active;
+}
+
+int DeviceSim::errorFlags() {
+    readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
+    return impl_->hCtrl->error;
+}
+
+void DeviceSim::laneVehicleCount(int32_t *out) {
+    Impl &I = *impl_;
+    I.ensureHostInts(I.V.nLanes);
+    CFB_CUDA(cudaMemcpyAsync(I.hInts, I.V.count, I.V.nLanes * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    memcpy(out, I.hInts, I.V.nLanes * sizeof(int));
+}
+
+void DeviceSim::laneWaitingVehicleCount(int32_t *out) {
+    Impl &I = *impl_;
+    if (I.scratchI.n < (size_t) I.V.nLanes) I.scratchI.alloc(I.V.nLanes);
+    I.ensureHostInts(I.V.nLanes);
+    const int TPB = 256;
+    k_lane_waiting<<<(I.V.nLanes * 32 + TPB - 1) / TPB, TPB, 0, I.stream>>>(I.V, I.scratchI.p);
+    CFB_CUDA(cudaMemcpyAsync(I.hInts, I.scratchI.p, I.V.nLanes * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    memcpy(out, I.hInts, I.V.nLanes * sizeof(int));
+    launches_ += 1;
+}
+
+int DeviceSim::runningVehicles(std::vector<SpeedRec> &out) {
+    Impl &I = *impl_;
+    readCtrlImpl(I.stream, I.hCtrl, I.V.ctrl);
+    const int n = I.hCtrl->active;
+    out.resize(n);
+    if (n == 0) return 0;
+    if (I.speedOut.n < (size_t) n) I.speedOut.alloc((size_t) n * 2);
+    if (I.scratchI.n < 1) I.scratchI.alloc(std::max(I.V.nLanes, 1));
+    CFB_CUDA(cudaMemsetAsync(I.scratchI.p, 0, sizeof(int), I.stream));
+    const int TPB = 256;
+    k_gather_running<<<(int) (((size_t) I.V.nDrv * 32 + TPB - 1) / TPB), TPB, 0, I.stream>>>(I.V, I.speedOut.p, I.scratchI.p, n);
+    CFB_CUDA(cudaMemcpyAsync(out.data(), I.speedOut.p, (size_t) n * sizeof(SpeedRec), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    launches_ += 1;
+    return n;
+}
+
+int DeviceSim::drainFinished(std::vector<FinRec> &slots) {
+    Impl &I = *impl_;
+    readCtrlImpl(I.stream, I.hCtrl, I.V.ctrl);
+    const int n = std::min(I.hCtrl->finCount, I.V.finCap);
+    slots.resize(n);
+    if (n > 0) {
+        CFB_CUDA(cudaMemcpyAsync(slots.data(), I.finSlots.p, n * sizeof(int2), cudaMemcpyDeviceToHost, I.stream));
+        CFB_CUDA(cudaMemsetAsync(&I.V.ctrl->finCount, 0, sizeof(int), I.stream));
+        CFB_CUDA(cudaStreamSynchronize(I.stream));
+    }
+    return n;
+}
+
+void DeviceSim::phases(int32_t *out) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaMemcpyAsync(out, I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+}
+
+int DeviceSim::leaderSlotOf(int slot) {
+    Impl &I = *impl_;
+    if (slot < 0 || slot >= I.slotCap) return -2;
+    int p = -1;
+    CFB_CUDA(cudaMemcpyAsync(&p, I.V.pos + slot, sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    if (p < 0) return -2;
+    int lp = -1;
+    CFB_CUDA(cudaMemcpy(&lp, I.V.leader + p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (lp < 0) return -1;
+    int4 idv;
+    CFB_CUDA(cudaMemcpy(&idv, I.V.ids + lp, sizeof(int4), cudaMemcpyDeviceToHost));
+    return idv.x;
+}
+
+void DeviceSim::laneVehicleSlots(std::vector<int32_t> &slots, std::vector<int32_t> &laneBeg) {
+    Impl &I = *impl_;
+    const int nL = I.V.nLanes;
+    std::vector<int32_t> cnt(nL);
+    laneVehicleCount(cnt.data());
+    laneBeg.assign(nL + 1, 0);
+    for (int l = 0; l < nL; ++l) laneBeg[l + 1] = laneBeg[l] + cnt[l];
+    slots.resize(laneBeg[nL]);
+    if (slots.empty()) return;
+    DevBuf<int> dBeg, dOut;
+    dBeg.upload(std::vector<int>(laneBeg.begin(), laneBeg.end()));
+    dOut.alloc(slots.size());
+    const int TPB = 256;
+    k_lane_slots<<<(nL * 32 + TPB - 1) / TPB, TPB, 0, I.stream>>>(I.V, dOut.p, dBeg.p);
+    CFB_CUDA(cudaMemcpyAsync(slots.data(), dOut.p, slots.size() * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    launches_ += 1;
+}
+
+void DeviceSim::debugDump(std::vector<DebugRec> &out) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    const size_t P = (size_t) I.P;
+    std::vector<int> count(I.V.nDrv), leader(P);
+    std::vector<double2> kin(P);
+    std::vector<double> gap(P);
+    std::vector<int4> ids(P), nav(P);
+    CFB_CUDA(cudaMemcpy(count.data(), I.V.count, count.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(leader.data(), I.V.leader, P * sizeof(int), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(kin.data(), I.V.kin, P * sizeof(double2), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(gap.data(), I.V.gap, P * sizeof(double), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(ids.data(), I.V.ids, P * sizeof(int4), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(nav.data(), I.V.nav, P * sizeof(int4), cudaMemcpyDeviceToHost));
+    out.clear();
+    for (int d = 0; d < I.V.nDrv; ++d) {
+        for (int k = 0; k < count[d]; ++k) {
+            const int p = I.offHost[d] + k;
+            DebugRec r{};
+            r.slot = ids[p].x;
+            r.drivable = d;
+            r.leaderSlot = leader[p] >= 0 ? ids[leader[p]].x : -1;
+            r.blockerSlot = nav[p].z;
+            r.priority = ids[p].z;
+            r.enterLaneLinkTime = nav[p].w;
+            r.listIndex = k;
+            r.dis = kin[p].x;
+            r.speed = kin[p].y;
+            r.gap = leader[p] >= 0 ? gap[p] : 0.0;
+            out.push_back(r);
+        }
+    }
+}
+
+void DeviceSim::setPhase(int intersection, int phase) {
+    Impl &I = *impl_;
+    // TrafficLight::setPhase only changes curPhaseIndex (trafficlight.cpp:39-41)
+    CFB_CUDA(cudaMemcpyAsync(I.V.curPhase + intersection, &phase, sizeof(int), cudaMemcpyHostToDevice, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+}
+
+}  // namespace cfb

@@ -1,0 +1,111 @@
+// Device-resident simulation state + the per-step kernel sequence (implemented in
+// device_sim.cu).  This is the internal C++ seam between the host engine (flows, RNG, ids; see
+// host_engine.cpp) and the CUDA path; the public boundary is the C-ABI in
+// include/cityflow_b200.h.  No CUDA types appear here so host-only translation units can
+// include it.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "flows.h"
+#include "roadnet.h"
+
+namespace cfb {
+
+// One vehicle handed to the device this step: it is appended to `lane`'s waiting queue
+// (Lane::pushWaitingVehicle, roadnet.h:365).  Records of one step must be sorted by lane,
+// stable in spawn order.
+struct SpawnRec {
+    int32_t slot;      // host-allocated stable vehicle handle
+    int32_t lane;      // first drivable
+    int32_t tmpl;      // index into the template table
+    int32_t priority;  // Vehicle::priority (vehicle.cpp:45)
+    int32_t plan;      // index into the plan table (route x start lane)
+    int32_t pad[3];
+};
+
+struct FinRec {        // a vehicle that ran off its last road during step `step` (0-based)
+    int32_t slot;
+    int32_t step;
+};
+
+struct SpeedRec {      // one running vehicle for get_vehicle_speed / get_vehicle_distance
+    int32_t slot;
+    int32_t drivable;
+    double speed;
+    double dis;
+};
+
+struct DebugRec {      // full per-vehicle state for parity tests (cfb_debug_vehicles)
+    int32_t slot, drivable, leaderSlot, blockerSlot, priority, enterLaneLinkTime, listIndex, pad;
+    double dis, speed, gap;
+};
+
+enum DeviceError : int {
+    ERR_BUCKET_OVERFLOW = 1,    // more vehicles on a drivable than its bucket holds
+    ERR_ENTRANT_OVERFLOW = 2,   // more vehicles entering one drivable in one step than staged
+    ERR_MOVER_OVERFLOW = 4,
+    ERR_ROUTE_DEAD_END = 8,     // lane cannot reach the next road of the route (reference asserts)
+    ERR_FINISHED_OVERFLOW = 16,
+};
+
+struct DeviceSimOptions {
+    int device = 0;
+    double interval = 1.0;
+    bool rlTrafficLight = false;
+    int slotCapacity = 1 << 18;
+    int replicas = 1;           // bench only: K independent copies of the scenario in one engine
+};
+
+class DeviceSim {
+public:
+    // Throws std::runtime_error when no CUDA device / extension is usable (no CPU fallback).
+    DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &templates, const Routing &routing,
+              const DeviceSimOptions &opt);
+    ~DeviceSim();
+    DeviceSim(const DeviceSim &) = delete;
+    DeviceSim &operator=(const DeviceSim &) = delete;
+
+    // Re-upload the (grown) template / plan tables.
+    void uploadTemplates(const std::vector<VehicleTemplate> &templates);
+    void uploadPlans(const Routing &routing);
+    void ensureSlotCapacity(int slots);
+
+    // Enqueue one simulation step (asynchronous). `recs` must stay valid until the call returns.
+    void step(const SpawnRec *recs, int n);
+    void synchronize();
+
+    // Observations (synchronise the stream).
+    int vehicleCount();
+    int errorFlags();
+    long long stepsDone() const { return steps_; }
+    void laneVehicleCount(int32_t *out);          // nLanes * replicas
+    void laneWaitingVehicleCount(int32_t *out);   // speed < 0.1
+    int runningVehicles(std::vector<SpeedRec> &out);
+    int drainFinished(std::vector<FinRec> &out);     // vehicles that left the network since the last drain
+    void phases(int32_t *out);
+    int leaderSlotOf(int slot);                   // -1 none, -2 unknown/not running
+    void laneVehicleSlots(std::vector<int32_t> &slots, std::vector<int32_t> &laneBeg);
+    void debugDump(std::vector<DebugRec> &out);   // every running vehicle, drivable-major, list order
+
+    // Control.
+    void setPhase(int intersection, int phase);
+    void reset();
+
+    // Measurement support for bench.py / profiles (CUDA-event timing of one kernel across launches).
+    struct KernelTimes { double ingest = 0, notify = 0, control = 0, move = 0, leader = 0; long long launches = 0; };
+    void enableKernelTiming(bool on);
+    KernelTimes kernelTimes();
+    long long launchesDone() const { return launches_; }
+    int numPositions() const;
+    int numDrivables() const;
+
+private:
+    struct Impl;
+    Impl *impl_;
+    long long steps_ = 0;
+    long long launches_ = 0;
+};
+
+}  // namespace cfb

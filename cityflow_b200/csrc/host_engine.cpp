@@ -1,0 +1,561 @@
+// Host side of the engine + the C-ABI of include/cityflow_b200.h.
+//
+// What stays on the host (and why): config / roadnet / flow loading; Flow::nextStep spawning
+// and the first-lane draw, because they consume one serial std::mt19937 in a fixed order
+// (flow.cpp:6-22, vehicle.cpp:45, engine.cpp:606, router.cpp:99 via engine.cpp:453-457) that the
+// results depend on; vehicle id <-> slot tables; travel-time statistics.  Everything per
+// vehicle / lane / intersection per step runs in device_sim.cu.  There is no CPU path for the
+// simulation: without a CUDA device cfb_engine_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <random>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cityflow_b200.h"
+#include "device_sim.h"
+#include "flows.h"
+#include "json_min.h"
+#include "roadnet.h"
+
+namespace cfb {
+
+struct FlowRun {            // Flow, flow.h:17-53
+    FlowDef def;
+    double nowTime = 0, currentTime = 0;
+    int cnt = 0;
+    bool valid = true;
+    int routeId = -1;
+    int tmplId = -1;
+};
+
+struct SlotInfo {
+    int32_t flow = -1, index = -1;   // id: flow_<flow>_<index> / manually_pushed_<index> (flow == -2)
+    int32_t priority = 0;
+    double enterTime = 0;
+    bool live = false;
+};
+
+struct Pending {            // a vehicle created this step, waiting for planRoute (engine.cpp:450-470)
+    int slot, road, routeId, tmplId, flow;
+};
+
+class HostEngine {
+public:
+    std::string error;
+    RoadNet net;
+    std::vector<FlowRun> flows;
+    std::unique_ptr<Routing> routing;
+    std::vector<VehicleTemplate> templates;
+    std::map<VehicleTemplate, int> templateIndex;
+    std::unique_ptr<DeviceSim> dev;
+    double interval = 1.0;
+    int seed = 0;
+    bool rlTrafficLight = false, laneChange = false, saveReplay = false;
+    std::mt19937 rnd;
+    size_t step = 0;
+    int manuallyPushCnt = 0;
+    int finishedCnt = 0;
+    double cumulativeTravelTime = 0;
+    std::vector<SlotInfo> slots;
+    std::vector<int> freeSlots;
+    std::map<int, int> pool;                                 // priority -> slot (vehiclePool, engine.h:25)
+    std::unordered_map<uint64_t, int> idToSlot;
+    std::vector<Pending> pending;
+    std::vector<SpawnRec> batch;
+    std::vector<std::string> laneIds;
+    size_t uploadedPlans = 0, uploadedTemplates = 0;
+    bool finishedDirty = false;                              // steps enqueued since the last drain
+
+    static uint64_t key(int flow, int index) { return ((uint64_t) (uint32_t) flow << 32) | (uint32_t) index; }
+
+    int internTemplate(const VehicleTemplate &t) {
+        auto it = templateIndex.find(t);
+        if (it != templateIndex.end()) return it->second;
+        int id = (int) templates.size();
+        templates.push_back(t);
+        templateIndex[t] = id;
+        return id;
+    }
+
+    // Engine::loadConfig engine.cpp:37-84
+    bool load(const std::string &configFile, int device) {
+        bool opened = false;
+        Json doc = Json::parseFile(configFile, &opened);
+        if (!opened) { error = "cannot open config file!"; return false; }
+        if (!doc.isObject()) { error = "wrong format of config file"; return false; }
+        auto need = [&](const char *k) -> const Json & {
+            const Json *v = doc.find(k);
+            if (!v) throw JsonError(std::string(k) + " is required but missing in json file");
+            return *v;
+        };
+        std::string dir, roadnetFile, flowFile;
+        try {
+            const Json &iv = need("interval");
+            if (!iv.isNumber()) throw JsonError("interval: expected type d");
+            interval = iv.asDouble();
+            const Json &rl = need("rlTrafficLight");
+            if (!rl.isBool()) throw JsonError("rlTrafficLight: expected type b");
+            rlTrafficLight = rl.asBool();
+            const Json *lc = doc.find("laneChange");
+            laneChange = lc && lc->isBool() ? lc->asBool() : false;
+            const Json &sd = need("seed");
+            if (!sd.isInt()) throw JsonError("seed: expected type i");
+            seed = sd.asInt();
+            rnd.seed(seed);
+            auto str = [&](const char *k) -> std::string {
+                const Json &v = need(k);
+                if (!v.isString()) throw JsonError(std::string(k) + ": expected type PKc");
+                return v.s;
+            };
+            dir = str("dir");
+            roadnetFile = str("roadnetFile");
+            flowFile = str("flowFile");
+            const Json &sr = need("saveReplay");
+            if (!sr.isBool()) throw JsonError("saveReplay: expected type b");
+            saveReplay = sr.asBool();
+        } catch (const JsonError &e) {
+            error = e.what();
+            return false;
+        }
+        if (laneChange) {
+            error = "laneChange=true is not supported by the B200 engine yet";
+            return false;
+        }
+        if (!net.load(dir + roadnetFile)) { error = "loading roadnet file error!"; return false; }
+        std::vector<FlowDef> defs;
+        if (!loadFlows(dir + flowFile, net, defs)) { error = "loading flow file error!"; return false; }
+        routing.reset(new Routing(net));
+        for (auto &d : defs) {
+            FlowRun f;
+            f.def = d;
+            f.nowTime = d.interval;  // flow.h:35
+            f.routeId = routing->intern(d.anchors);
+            f.tmplId = internTemplate(d.tmpl);
+            flows.push_back(std::move(f));
+        }
+        if (saveReplay)
+            std::cerr << "[cityflow_b200] saveReplay is not implemented by the GPU engine; no replay is written" << std::endl;
+        laneIds.resize(net.nLanes());
+        for (int l = 0; l < net.nLanes(); ++l) laneIds[l] = net.laneName(l);
+        DeviceSimOptions opt;
+        opt.device = device;
+        opt.interval = interval;
+        opt.rlTrafficLight = rlTrafficLight;
+        dev.reset(new DeviceSim(net, templates, *routing, opt));
+        uploadedPlans = routing->numPlans();
+        uploadedTemplates = templates.size();
+        return true;
+    }
+
+    double currentTime() const { return step * interval; }  // engine.cpp:678
+
+    void checkDevice() {
+        int err = dev->errorFlags();
+        if (err) {
+            std::string m = "device capacity/route error:";
+            if (err & ERR_BUCKET_OVERFLOW) m += " lane bucket overflow;";
+            if (err & ERR_ENTRANT_OVERFLOW) m += " too many vehicles entering one drivable in one step;";
+            if (err & ERR_MOVER_OVERFLOW) m += " mover staging overflow;";
+            if (err & ERR_ROUTE_DEAD_END) m += " a vehicle reached a lane that cannot continue its route (the reference asserts here, vehicle.cpp:60);";
+            if (err & ERR_FINISHED_OVERFLOW) m += " finished ring overflow;";
+            throw std::runtime_error(m);
+        }
+    }
+
+    // Bring host bookkeeping up to date with the device (vehicles that left the network):
+    // the tail of Engine::threadUpdateLocation (engine.cpp:296-310).
+    void drain() {
+        if (!finishedDirty) return;
+        std::vector<FinRec> fin;
+        dev->drainFinished(fin);
+        for (const FinRec &f : fin) {
+            SlotInfo &s = slots[f.slot];
+            if (!s.live) continue;
+            finishedCnt += 1;
+            cumulativeTravelTime += f.step * interval - s.enterTime;
+            pool.erase(s.priority);
+            idToSlot.erase(key(s.flow, s.index));
+            s.live = false;
+            freeSlots.push_back(f.slot);
+        }
+        finishedDirty = false;
+        checkDevice();
+    }
+
+    int allocSlot() {
+        if (!freeSlots.empty()) {
+            int s = freeSlots.back();
+            freeSlots.pop_back();
+            return s;
+        }
+        slots.emplace_back();
+        return (int) slots.size() - 1;
+    }
+
+    // Vehicle ctor (vehicle.cpp:38-47) + Engine::pushVehicle (engine.cpp:605-613)
+    int createVehicle(int flow, int index, int routeId, int tmplId, int firstRoad) {
+        int priority;
+        for (;;) {
+            priority = (int) rnd();
+            if (!pool.count(priority)) break;
+            // the candidate may belong to a vehicle that already left the network on the device
+            drain();
+            if (!pool.count(priority)) break;
+        }
+        (void) rnd();  // threadIndex = rnd() % threadNum (engine.cpp:606): drawn, not needed here
+        const int slot = allocSlot();
+        SlotInfo &s = slots[slot];
+        s.flow = flow;
+        s.index = index;
+        s.priority = priority;
+        s.enterTime = currentTime();
+        s.live = true;
+        pool.emplace(priority, slot);
+        idToSlot[key(flow, index)] = slot;
+        pending.push_back({slot, firstRoad, routeId, tmplId, flow});
+        return slot;
+    }
+
+    // Engine::nextStep engine.cpp:566-594 (host part: P0 spawn, P1 planRoute; the rest is device work)
+    void nextStep() {
+        for (size_t i = 0; i < flows.size(); ++i) {  // Flow::nextStep flow.cpp:6-22
+            FlowRun &f = flows[i];
+            if (!f.valid) continue;
+            if (f.def.endTime != -1 && f.currentTime > f.def.endTime) continue;
+            if (f.currentTime >= f.def.startTime) {
+                while (f.nowTime >= f.def.interval) {
+                    createVehicle((int) i, f.cnt++, f.routeId, f.tmplId, f.def.anchors[0]);
+                    f.nowTime -= f.def.interval;
+                }
+                f.nowTime += interval;
+            }
+            f.currentTime += interval;
+        }
+        batch.clear();
+        if (!pending.empty()) {
+            // Engine::planRoute walks roads in file order, each road's buffer in spawn order
+            std::stable_sort(pending.begin(), pending.end(), [](const Pending &a, const Pending &b) { return a.road < b.road; });
+            for (const Pending &p : pending) {
+                const Route &rt = routing->route(p.routeId);
+                if (rt.valid) {
+                    const size_t pick = rnd() % rt.startLanes.size();  // Router::selectLaneIndex router.cpp:99
+                    SpawnRec r{};
+                    r.slot = p.slot;
+                    r.lane = rt.startLanes[pick];
+                    r.tmpl = p.tmplId;
+                    r.priority = slots[p.slot].priority;
+                    r.plan = rt.planOfStartLane[pick];
+                    batch.push_back(r);
+                } else {
+                    if (p.flow >= 0) {
+                        if (flows[p.flow].valid)
+                            std::cerr << "[warning] Invalid route '" << flows[p.flow].def.id << "'. Omitted by default." << std::endl;
+                        flows[p.flow].valid = false;
+                    }
+                    SlotInfo &s = slots[p.slot];
+                    pool.erase(s.priority);
+                    idToSlot.erase(key(s.flow, s.index));
+                    s.live = false;
+                    freeSlots.push_back(p.slot);
+                }
+            }
+            pending.clear();
+            std::stable_sort(batch.begin(), batch.end(), [](const SpawnRec &a, const SpawnRec &b) { return a.lane < b.lane; });
+        }
+        if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
+        if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
+        dev->ensureSlotCapacity((int) slots.size());
+        dev->step(batch.data(), (int) batch.size());
+        finishedDirty = true;
+        step += 1;
+        if ((step & 255) == 0) drain();  // bound the finished ring / free slots in long unobserved runs
+    }
+
+    // Engine::reset engine.cpp:744-760
+    void reset(bool resetRnd) {
+        dev->synchronize();
+        dev->reset();
+        slots.clear();
+        freeSlots.clear();
+        pool.clear();
+        idToSlot.clear();
+        pending.clear();
+        finishedCnt = 0;
+        cumulativeTravelTime = 0;
+        for (auto &f : flows) {  // Flow::reset flow.cpp:28-32 (valid / manuallyPushCnt are not reset)
+            f.nowTime = f.def.interval;
+            f.currentTime = 0;
+            f.cnt = 0;
+        }
+        step = 0;
+        finishedDirty = false;
+        if (resetRnd) rnd.seed(seed);
+    }
+
+    cfb_vehicle_ref refOf(int slot) const { return cfb_vehicle_ref{slots[slot].flow, slots[slot].index}; }
+};
+
+}  // namespace cfb
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+struct cfb_engine {
+    cfb::HostEngine h;
+    std::string lastError;
+    std::vector<cfb::SpeedRec> recs;
+};
+
+static thread_local std::string g_createError;
+
+#define CFB_TRY(e, ...)                                    \
+    try {                                                  \
+        __VA_ARGS__                                        \
+    } catch (const std::exception &ex) {                   \
+        (e)->lastError = ex.what();                        \
+        const char *w = ex.what();                         \
+        if (strstr(w, "CUDA")) return CFB_ERR_DEVICE;      \
+        if (strstr(w, "capacity")) return CFB_ERR_CAPACITY;\
+        return CFB_ERR_ARGUMENT;                           \
+    }
+
+extern "C" {
+
+cfb_engine *cfb_engine_create(const char *config_file, int thread_num, int device) {
+    (void) thread_num;
+    cfb_engine *e = nullptr;
+    try {
+        e = new cfb_engine();
+        int dev = device;
+        if (dev < 0) dev = 0;
+        if (!e->h.load(config_file ? config_file : "", dev)) {
+            g_createError = e->h.error.empty() ? "load config failed!" : e->h.error;
+            std::cerr << g_createError << std::endl << "load config failed!" << std::endl;
+            delete e;
+            return nullptr;
+        }
+        return e;
+    } catch (const std::exception &ex) {
+        g_createError = ex.what();
+        delete e;
+        return nullptr;
+    }
+}
+
+void cfb_engine_destroy(cfb_engine *e) { delete e; }
+
+const char *cfb_last_error(const cfb_engine *e) { return e ? e->lastError.c_str() : g_createError.c_str(); }
+
+int cfb_next_step(cfb_engine *e) {
+    CFB_TRY(e, e->h.nextStep();)
+    return CFB_OK;
+}
+
+int cfb_next_steps(cfb_engine *e, int n) {
+    CFB_TRY(e, for (int i = 0; i < n; ++i) e->h.nextStep();)
+    return CFB_OK;
+}
+
+int64_t cfb_get_vehicle_count(cfb_engine *e) {
+    CFB_TRY(e, int c = e->h.dev->vehicleCount(); e->h.checkDevice(); return c;)
+}
+
+double cfb_get_current_time(const cfb_engine *e) { return e->h.currentTime(); }
+
+double cfb_get_average_travel_time(cfb_engine *e) {
+    try {
+        cfb::HostEngine &h = e->h;
+        h.drain();
+        double tt = h.cumulativeTravelTime;
+        int n = h.finishedCnt;
+        for (auto &kv : h.pool) {  // priority order, like vehiclePool (engine.cpp:685-689)
+            tt += h.currentTime() - h.slots[kv.second].enterTime;
+            n++;
+        }
+        return n == 0 ? 0 : tt / n;
+    } catch (const std::exception &ex) {
+        e->lastError = ex.what();
+        return std::nan("");
+    }
+}
+
+int cfb_num_lanes(const cfb_engine *e) { return e->h.net.nLanes(); }
+const char *cfb_lane_id(const cfb_engine *e, int lane) {
+    return lane >= 0 && lane < e->h.net.nLanes() ? e->h.laneIds[lane].c_str() : nullptr;
+}
+int cfb_num_intersections(const cfb_engine *e) { return e->h.net.nInter(); }
+const char *cfb_intersection_id(const cfb_engine *e, int i) {
+    return i >= 0 && i < e->h.net.nInter() ? e->h.net.interId[i].c_str() : nullptr;
+}
+
+int cfb_get_lane_vehicle_count(cfb_engine *e, int32_t *out, int n) {
+    if (n < e->h.net.nLanes()) { e->lastError = "output buffer too small"; return CFB_ERR_ARGUMENT; }
+    CFB_TRY(e, e->h.dev->laneVehicleCount(out);)
+    return CFB_OK;
+}
+
+int cfb_get_lane_waiting_vehicle_count(cfb_engine *e, int32_t *out, int n) {
+    if (n < e->h.net.nLanes()) { e->lastError = "output buffer too small"; return CFB_ERR_ARGUMENT; }
+    CFB_TRY(e, e->h.dev->laneWaitingVehicleCount(out);)
+    return CFB_OK;
+}
+
+int64_t cfb_get_vehicle_speed(cfb_engine *e, cfb_vehicle_ref *ids, double *speed, double *distance, int64_t cap) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        int n = h.dev->runningVehicles(e->recs);
+        // vehiclePool order = ascending priority (engine.cpp:780-790)
+        std::sort(e->recs.begin(), e->recs.end(), [&h](const cfb::SpeedRec &a, const cfb::SpeedRec &b) {
+            return h.slots[a.slot].priority < h.slots[b.slot].priority;
+        });
+        for (int64_t i = 0; i < n && i < cap; ++i) {
+            if (ids) ids[i] = h.refOf(e->recs[i].slot);
+            if (speed) speed[i] = e->recs[i].speed;
+            if (distance) distance[i] = e->recs[i].dis;
+        }
+        return n;
+    )
+}
+
+int64_t cfb_get_vehicles(cfb_engine *e, int include_waiting, cfb_vehicle_ref *ids, int64_t cap) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        if (!include_waiting) return cfb_get_vehicle_speed(e, ids, nullptr, nullptr, cap);
+        h.drain();
+        int64_t n = 0;
+        for (auto &kv : h.pool) {
+            if (n < cap && ids) ids[n] = h.refOf(kv.second);
+            ++n;
+        }
+        return n;
+    )
+}
+
+int64_t cfb_get_lane_vehicles(cfb_engine *e, int64_t *lane_begin, int n_lanes_plus1, cfb_vehicle_ref *ids, int64_t cap) {
+    if (n_lanes_plus1 < e->h.net.nLanes() + 1) { e->lastError = "output buffer too small"; return CFB_ERR_ARGUMENT; }
+    CFB_TRY(e,
+        std::vector<int32_t> slots; std::vector<int32_t> beg;
+        e->h.dev->laneVehicleSlots(slots, beg);
+        for (size_t l = 0; l < beg.size(); ++l) lane_begin[l] = beg[l];
+        for (size_t i = 0; i < slots.size() && (int64_t) i < cap; ++i) ids[i] = e->h.refOf(slots[i]);
+        return (int64_t) slots.size();
+    )
+}
+
+int cfb_get_leader(cfb_engine *e, cfb_vehicle_ref v, cfb_vehicle_ref *leader, int *found) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        h.drain();
+        auto it = h.idToSlot.find(cfb::HostEngine::key(v.flow, v.index));
+        if (it == h.idToSlot.end()) throw std::runtime_error("Vehicle not found");
+        int ls = h.dev->leaderSlotOf(it->second);
+        *found = ls >= 0;
+        if (ls >= 0) *leader = h.refOf(ls);
+    )
+    return CFB_OK;
+}
+
+int cfb_set_tl_phase_index(cfb_engine *e, int intersection, int phase) {
+    cfb::HostEngine &h = e->h;
+    if (!h.rlTrafficLight) {  // engine.cpp:720-723
+        std::cerr << "please set rlTrafficLight to true to enable traffic light control" << std::endl;
+        return CFB_OK;
+    }
+    if (intersection < 0 || intersection >= h.net.nInter()) { e->lastError = "no such intersection"; return CFB_ERR_ARGUMENT; }
+    const int nph = h.net.interPhaseBeg[intersection + 1] - h.net.interPhaseBeg[intersection];
+    if (phase < 0 || phase >= nph) {
+        // the reference stores the index unchecked and throws later from phases.at() inside a worker
+        e->lastError = "phase index out of range";
+        return CFB_ERR_ARGUMENT;
+    }
+    CFB_TRY(e, h.dev->setPhase(intersection, phase);)
+    return CFB_OK;
+}
+
+int cfb_set_tl_phase(cfb_engine *e, const char *id, int phase) {
+    auto it = e->h.net.interIndex.find(id ? id : "");
+    if (it == e->h.net.interIndex.end()) {
+        if (!e->h.rlTrafficLight) return cfb_set_tl_phase_index(e, -1, phase);
+        e->lastError = std::string("no such intersection: ") + (id ? id : "");
+        return CFB_ERR_ARGUMENT;
+    }
+    return cfb_set_tl_phase_index(e, it->second, phase);
+}
+
+int cfb_set_random_seed(cfb_engine *e, int seed) {
+    e->h.rnd.seed(seed);
+    return CFB_OK;
+}
+
+int cfb_reset(cfb_engine *e, int reset_rnd) {
+    CFB_TRY(e, e->h.reset(reset_rnd != 0);)
+    return CFB_OK;
+}
+
+int cfb_push_vehicle(cfb_engine *e, const double v[10], const char *const *roads, int n_roads) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        cfb::VehicleTemplate t;
+        double *f[10] = {&t.speed, &t.len, &t.width, &t.maxPosAcc, &t.maxNegAcc, &t.usualPosAcc, &t.usualNegAcc,
+                         &t.minGap, &t.maxSpeed, &t.headwayTime};
+        for (int k = 0; k < 10; ++k) if (!std::isnan(v[k])) *f[k] = v[k];
+        std::vector<int> anchors;
+        for (int k = 0; k < n_roads; ++k) {
+            auto it = h.net.roadIndex.find(roads[k]);
+            if (it == h.net.roadIndex.end()) throw std::runtime_error(std::string("No such road: ") + roads[k]);
+            anchors.push_back(it->second);
+        }
+        if (anchors.empty()) throw std::runtime_error("push_vehicle needs at least one road");
+        int routeId = h.routing->intern(anchors);
+        int tmplId = h.internTemplate(t);
+        h.createVehicle(-2, h.manuallyPushCnt++, routeId, tmplId, anchors[0]);
+    )
+    return CFB_OK;
+}
+
+// Full dynamic state of every running vehicle (tests only), same record layout as
+// oracle/refdump's per-vehicle dump: 8 x int32, 3 x double, 1 x int64.
+int64_t cfb_debug_vehicles(cfb_engine *e, void *out, int64_t cap) {
+    struct Rec { int32_t flow, cnt, priority, drivable, lf, lc, bf, bc; double dis, speed, gap; int64_t enter; };
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        std::vector<cfb::DebugRec> recs;
+        h.dev->debugDump(recs);
+        Rec *o = (Rec *) out;
+        for (size_t i = 0; i < recs.size() && (int64_t) i < cap; ++i) {
+            const cfb::DebugRec &r = recs[i];
+            Rec x;
+            x.flow = h.slots[r.slot].flow; x.cnt = h.slots[r.slot].index; x.priority = r.priority; x.drivable = r.drivable;
+            x.lf = r.leaderSlot >= 0 ? h.slots[r.leaderSlot].flow : -1;
+            x.lc = r.leaderSlot >= 0 ? h.slots[r.leaderSlot].index : -1;
+            x.bf = r.blockerSlot >= 0 ? h.slots[r.blockerSlot].flow : -1;
+            x.bc = r.blockerSlot >= 0 ? h.slots[r.blockerSlot].index : -1;
+            x.dis = r.dis; x.speed = r.speed; x.gap = r.gap; x.enter = r.enterLaneLinkTime;
+            o[i] = x;
+        }
+        return (int64_t) recs.size();
+    )
+}
+
+int64_t cfb_gpu_launches(const cfb_engine *e) { return e->h.dev->launchesDone(); }
+int cfb_enable_kernel_timing(cfb_engine *e, int on) { e->h.dev->enableKernelTiming(on != 0); return CFB_OK; }
+int cfb_kernel_times(cfb_engine *e, double ms[5], int64_t *steps) {
+    auto t = e->h.dev->kernelTimes();
+    ms[0] = t.ingest; ms[1] = t.notify; ms[2] = t.control; ms[3] = t.move; ms[4] = t.leader;
+    if (steps) *steps = t.launches;
+    return CFB_OK;
+}
+int cfb_synchronize(cfb_engine *e) {
+    CFB_TRY(e, e->h.dev->synchronize();)
+    return CFB_OK;
+}
+int64_t cfb_num_drivables(const cfb_engine *e) { return e->h.dev->numDrivables(); }
+
+}  // extern "C"

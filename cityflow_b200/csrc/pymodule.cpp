@@ -1,0 +1,246 @@
+// pybind11 module: the `cityflow.Engine` Python surface of the reference (src/cityflow.cpp:10-48),
+// same method names, keyword names and defaults, implemented as a thin wrapper over the C-ABI in
+// include/cityflow_b200.h.  Dict results are built in std::map key order (sorted by id), as
+// pybind11's stl caster does for the reference's std::map return values.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/cityflow_b200.h"
+
+namespace py = pybind11;
+using namespace py::literals;
+
+namespace {
+
+std::string vehicleName(const cfb_vehicle_ref &r) {
+    if (r.flow == -2) return "manually_pushed_" + std::to_string(r.index);
+    return "flow_" + std::to_string(r.flow) + "_" + std::to_string(r.index);
+}
+
+bool parseVehicleName(const std::string &id, cfb_vehicle_ref &out) {
+    try {
+        if (id.compare(0, 16, "manually_pushed_") == 0) {
+            out.flow = -2;
+            out.index = std::stoi(id.substr(16));
+            return true;
+        }
+        if (id.compare(0, 5, "flow_") == 0) {
+            size_t us = id.find('_', 5);
+            if (us == std::string::npos) return false;
+            out.flow = std::stoi(id.substr(5, us - 5));
+            out.index = std::stoi(id.substr(us + 1));
+            return vehicleName(out) == id;
+        }
+    } catch (...) {
+    }
+    return false;
+}
+
+class Engine {
+public:
+    Engine(const std::string &configFile, int threadNum, int device) {
+        if (device < 0) {
+            const char *env = std::getenv("CITYFLOW_B200_DEVICE");
+            device = env ? std::atoi(env) : 0;
+        }
+        {
+            py::gil_scoped_release rel;
+            e_ = cfb_engine_create(configFile.c_str(), threadNum, device);
+        }
+        if (!e_) throw std::runtime_error(std::string("load config failed! ") + cfb_last_error(nullptr));
+        const int n = cfb_num_lanes(e_);
+        std::vector<std::string> ids(n);
+        for (int i = 0; i < n; ++i) ids[i] = cfb_lane_id(e_, i);
+        laneOrder_.resize(n);
+        std::iota(laneOrder_.begin(), laneOrder_.end(), 0);
+        std::sort(laneOrder_.begin(), laneOrder_.end(), [&](int a, int b) { return ids[a] < ids[b]; });
+        laneKeys_.reserve(n);
+        for (int i = 0; i < n; ++i) laneKeys_.push_back(py::str(ids[laneOrder_[i]]));
+        laneBuf_.resize(n);
+    }
+    ~Engine() {
+        if (e_) cfb_engine_destroy(e_);
+    }
+    Engine(const Engine &) = delete;
+
+    void check(int rc) const {
+        if (rc < 0) throw std::runtime_error(cfb_last_error(e_));
+    }
+    void nextStep() {
+        py::gil_scoped_release rel;
+        int rc = cfb_next_step(e_);
+        if (rc < 0) {
+            py::gil_scoped_acquire acq;
+            check(rc);
+        }
+    }
+    void nextSteps(int n) {
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = cfb_next_steps(e_, n);
+        }
+        check(rc);
+    }
+    size_t getVehicleCount() {
+        int64_t c = cfb_get_vehicle_count(e_);
+        if (c < 0) check((int) c);
+        return (size_t) c;
+    }
+    py::dict laneDict(bool waiting) {
+        int rc = waiting ? cfb_get_lane_waiting_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size())
+                         : cfb_get_lane_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size());
+        check(rc);
+        py::dict d;
+        for (size_t i = 0; i < laneOrder_.size(); ++i) d[laneKeys_[i]] = py::int_(laneBuf_[laneOrder_[i]]);
+        return d;
+    }
+    py::dict getLaneVehicleCount() { return laneDict(false); }
+    py::dict getLaneWaitingVehicleCount() { return laneDict(true); }
+
+    py::dict vehicleDict(bool distance) {
+        int64_t n = cfb_get_vehicle_speed(e_, nullptr, nullptr, nullptr, 0);
+        if (n < 0) check((int) n);
+        std::vector<cfb_vehicle_ref> ids(n);
+        std::vector<double> val(n);
+        n = cfb_get_vehicle_speed(e_, ids.data(), distance ? nullptr : val.data(), distance ? val.data() : nullptr, n);
+        if (n < 0) check((int) n);
+        std::vector<std::pair<std::string, double>> items(n);
+        for (int64_t i = 0; i < n; ++i) items[i] = {vehicleName(ids[i]), val[i]};
+        std::sort(items.begin(), items.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        py::dict d;
+        for (auto &kv : items) d[py::str(kv.first)] = py::float_(kv.second);
+        return d;
+    }
+    py::dict getVehicleSpeed() { return vehicleDict(false); }
+    py::dict getVehicleDistance() { return vehicleDict(true); }
+
+    std::vector<std::string> getVehicles(bool includeWaiting) {
+        int64_t n = cfb_get_vehicles(e_, includeWaiting, nullptr, 0);
+        if (n < 0) check((int) n);
+        std::vector<cfb_vehicle_ref> ids(n);
+        n = cfb_get_vehicles(e_, includeWaiting, ids.data(), n);
+        if (n < 0) check((int) n);
+        std::vector<std::string> out(n);
+        for (int64_t i = 0; i < n; ++i) out[i] = vehicleName(ids[i]);
+        return out;
+    }
+    py::dict getLaneVehicles() {
+        const int nl = (int) laneOrder_.size();
+        std::vector<int64_t> beg(nl + 1);
+        int64_t n = cfb_get_lane_vehicles(e_, beg.data(), nl + 1, nullptr, 0);
+        if (n < 0) check((int) n);
+        std::vector<cfb_vehicle_ref> ids(n);
+        n = cfb_get_lane_vehicles(e_, beg.data(), nl + 1, ids.data(), n);
+        if (n < 0) check((int) n);
+        py::dict d;
+        for (int i = 0; i < nl; ++i) {
+            const int l = laneOrder_[i];
+            py::list lst;
+            for (int64_t k = beg[l]; k < beg[l + 1] && k < n; ++k) lst.append(py::str(vehicleName(ids[k])));
+            d[laneKeys_[i]] = lst;
+        }
+        return d;
+    }
+    std::string getLeader(const std::string &id) {
+        cfb_vehicle_ref v, l{};
+        int found = 0;
+        if (!parseVehicleName(id, v) || cfb_get_leader(e_, v, &l, &found) < 0)
+            throw std::runtime_error("Vehicle '" + id + "' not found");  // engine.cpp:839
+        return found ? vehicleName(l) : "";
+    }
+    double getCurrentTime() const { return cfb_get_current_time(e_); }
+    double getAverageTravelTime() { return cfb_get_average_travel_time(e_); }
+    void setTrafficLightPhase(const std::string &id, int phase) { check(cfb_set_tl_phase(e_, id.c_str(), phase)); }
+    void setRandomSeed(int seed) { check(cfb_set_random_seed(e_, seed)); }
+    void reset(bool seed) { check(cfb_reset(e_, seed)); }
+    void pushVehicle(const std::map<std::string, double> &info, const std::vector<std::string> &roads) {
+        static const char *names[10] = {"speed", "length", "width", "maxPosAcc", "maxNegAcc", "usualPosAcc",
+                                        "usualNegAcc", "minGap", "maxSpeed", "headwayTime"};
+        double v[10];
+        for (int k = 0; k < 10; ++k) {
+            auto it = info.find(names[k]);
+            v[k] = it == info.end() ? std::numeric_limits<double>::quiet_NaN() : it->second;
+        }
+        std::vector<const char *> r;
+        for (auto &s : roads) r.push_back(s.c_str());
+        check(cfb_push_vehicle(e_, v, r.data(), (int) r.size()));
+    }
+    void setReplayLogFile(const std::string &) {  // engine.cpp:727-734
+        py::print("saveReplay is not set to true in config file!", "file"_a = py::module_::import("sys").attr("stderr"));
+    }
+    void setSaveReplay(bool) {  // engine.cpp:736-742
+        py::print("saveReplay is not set to true in config file!", "file"_a = py::module_::import("sys").attr("stderr"));
+    }
+    [[noreturn]] void unsupported(const char *what) const {
+        throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
+    }
+    // measurement helpers (not part of the reference surface)
+    int64_t gpuLaunches() const { return cfb_gpu_launches(e_); }
+    void enableKernelTiming(bool on) { cfb_enable_kernel_timing(e_, on); }
+    py::tuple kernelTimes() {
+        double ms[5];
+        int64_t n = 0;
+        cfb_kernel_times(e_, ms, &n);
+        return py::make_tuple(py::make_tuple(ms[0], ms[1], ms[2], ms[3], ms[4]), n);
+    }
+    void synchronize() {
+        py::gil_scoped_release rel;
+        cfb_synchronize(e_);
+    }
+
+private:
+    cfb_engine *e_ = nullptr;
+    std::vector<int> laneOrder_;
+    std::vector<py::str> laneKeys_;
+    std::vector<int32_t> laneBuf_;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_cityflow_b200, m) {
+    m.doc() = "B200-native CityFlow step engine (drop-in for cityflow.Engine)";
+    py::class_<Engine>(m, "Engine")
+        .def(py::init<const std::string &, int, int>(), "config_file"_a, "thread_num"_a = 1, "device"_a = -1)
+        .def("next_step", &Engine::nextStep)
+        .def("get_vehicle_count", &Engine::getVehicleCount)
+        .def("get_vehicles", &Engine::getVehicles, "include_waiting"_a = false)
+        .def("get_lane_vehicle_count", &Engine::getLaneVehicleCount)
+        .def("get_lane_waiting_vehicle_count", &Engine::getLaneWaitingVehicleCount)
+        .def("get_lane_vehicles", &Engine::getLaneVehicles)
+        .def("get_vehicle_speed", &Engine::getVehicleSpeed)
+        .def("get_vehicle_info", [](Engine &e, const std::string &) { e.unsupported("get_vehicle_info"); }, "vehicle_id"_a)
+        .def("get_vehicle_distance", &Engine::getVehicleDistance)
+        .def("get_leader", &Engine::getLeader, "vehicle_id"_a)
+        .def("get_current_time", &Engine::getCurrentTime)
+        .def("get_average_travel_time", &Engine::getAverageTravelTime)
+        .def("set_tl_phase", &Engine::setTrafficLightPhase, "intersection_id"_a, "phase_id"_a)
+        .def("set_vehicle_speed", [](Engine &e, const std::string &, double) { e.unsupported("set_vehicle_speed"); },
+             "vehicle_id"_a, "speed"_a)
+        .def("set_replay_file", &Engine::setReplayLogFile, "replay_file"_a)
+        .def("set_random_seed", &Engine::setRandomSeed, "seed"_a)
+        .def("set_save_replay", &Engine::setSaveReplay, "open"_a)
+        .def("push_vehicle", &Engine::pushVehicle)
+        .def("reset", &Engine::reset, "seed"_a = false)
+        .def("load", [](Engine &e, py::object) { e.unsupported("load"); }, "archive"_a)
+        .def("snapshot", [](Engine &e) { e.unsupported("snapshot"); })
+        .def("load_from_file", [](Engine &e, const std::string &) { e.unsupported("load_from_file"); }, "path"_a)
+        .def("set_vehicle_route", [](Engine &e, const std::string &, const std::vector<std::string> &) { e.unsupported("set_vehicle_route"); },
+             "vehicle_id"_a, "route"_a)
+        // extras
+        .def("next_steps", &Engine::nextSteps, "n"_a)
+        .def("gpu_launches", &Engine::gpuLaunches)
+        .def("enable_kernel_timing", &Engine::enableKernelTiming, "on"_a = true)
+        .def("kernel_times", &Engine::kernelTimes)
+        .def("synchronize", &Engine::synchronize);
+    m.attr("__version__") = "b200-dev";
+}

@@ -1,0 +1,116 @@
+/* cityflow_b200 -- C ABI of the B200-native CityFlow step engine.
+ *
+ * The reference has no C interface: its boundary is the C++ class CityFlow::Engine
+ * (src/engine/engine.h:114-183) exposed to Python by pybind11 (src/cityflow.cpp:10-48).  This
+ * header is the C-ABI a binding for that class would call: one function per public Engine
+ * method on the hot path, plain pointers and sizes, caller-allocated output buffers, no C++ or
+ * torch types.  Every entry cites the reference method it replaces.  The pybind11 module shipped
+ * in cityflow_b200/ (class `Engine`, same signatures as src/cityflow.cpp) is a thin wrapper over
+ * exactly these functions; INTEGRATION.md shows the equivalent binding a reference maintainer
+ * would add.
+ *
+ * Conventions: functions returning int return 0 on success and a negative code on failure, the
+ * message is available from cfb_last_error().  An engine is not thread-safe; distinct engines
+ * may be driven from distinct threads.  All simulation state lives in GPU memory; there is no
+ * CPU fallback: cfb_engine_create fails when no CUDA device is usable.
+ */
+#ifndef CITYFLOW_B200_H
+#define CITYFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cfb_engine cfb_engine;
+
+/* A vehicle as the reference names it: "flow_<flow>_<index>" (flow.cpp:11) or, for vehicles
+ * added with push_vehicle, "manually_pushed_<index>" (engine.cpp:714; flow == -2). */
+typedef struct cfb_vehicle_ref {
+    int32_t flow;
+    int32_t index;
+} cfb_vehicle_ref;
+
+enum {
+    CFB_OK = 0,
+    CFB_ERR_LOAD = -1,        /* config / roadnet / flow could not be loaded (engine.cpp:21-24) */
+    CFB_ERR_DEVICE = -2,      /* CUDA error or no device */
+    CFB_ERR_ARGUMENT = -3,    /* unknown id, buffer too small, ... */
+    CFB_ERR_CAPACITY = -4,    /* a device-side bucket / ring overflowed */
+    CFB_ERR_UNSUPPORTED = -5  /* feature of the reference not built here (laneChange, archive) */
+};
+
+/* Engine::Engine(configFile, threadNum)  engine.cpp:13-34.  thread_num is accepted for signature
+ * compatibility and ignored (the kernel sequence is the thread pool).  `device` < 0 selects the
+ * current CUDA device (LOCAL_RANK-aware callers pass their rank).  Returns NULL on failure; the
+ * reason is then available from cfb_last_error(NULL). */
+cfb_engine *cfb_engine_create(const char *config_file, int thread_num, int device);
+/* Engine::~Engine  engine.cpp:762-771 */
+void cfb_engine_destroy(cfb_engine *e);
+/* message of the last failure on `e` (or of the last failed create when e == NULL) */
+const char *cfb_last_error(const cfb_engine *e);
+
+/* Engine::nextStep  engine.cpp:566-594.  Enqueues the kernel sequence for one step and returns
+ * without waiting for the GPU; observations synchronise. */
+int cfb_next_step(cfb_engine *e);
+/* n consecutive steps (no reference counterpart; saves n-1 host round trips) */
+int cfb_next_steps(cfb_engine *e, int n);
+/* Engine::getVehicleCount  engine.cpp:615 */
+int64_t cfb_get_vehicle_count(cfb_engine *e);
+/* Engine::getCurrentTime  engine.cpp:678 */
+double cfb_get_current_time(const cfb_engine *e);
+/* Engine::getAverageTravelTime  engine.cpp:682-691 */
+double cfb_get_average_travel_time(cfb_engine *e);
+
+/* Static id tables.  Lanes are indexed in roadnet order (RoadNet::getLanes, roadnet.cpp:314-318);
+ * lane ids are "<roadId>_<laneIndex>" (roadnet.h:323-325). */
+int cfb_num_lanes(const cfb_engine *e);
+const char *cfb_lane_id(const cfb_engine *e, int lane);
+int cfb_num_intersections(const cfb_engine *e);
+const char *cfb_intersection_id(const cfb_engine *e, int intersection);
+
+/* Engine::getLaneVehicleCount  engine.cpp:628-634: out[lane] for all cfb_num_lanes() lanes */
+int cfb_get_lane_vehicle_count(cfb_engine *e, int32_t *out, int n);
+/* Engine::getLaneWaitingVehicleCount  engine.cpp:636-648 (speed < 0.1) */
+int cfb_get_lane_waiting_vehicle_count(cfb_engine *e, int32_t *out, int n);
+/* Engine::getVehicleSpeed  engine.cpp:662-668 / getVehicleDistance :670-676: running vehicles in
+ * vehiclePool (priority) order.  Returns the number of running vehicles (may exceed cap; only
+ * cap entries are written); any of the three output pointers may be NULL. */
+int64_t cfb_get_vehicle_speed(cfb_engine *e, cfb_vehicle_ref *ids, double *speed, double *distance, int64_t cap);
+/* Engine::getVehicles(includeWaiting)  engine.cpp:619-626 */
+int64_t cfb_get_vehicles(cfb_engine *e, int include_waiting, cfb_vehicle_ref *ids, int64_t cap);
+/* Engine::getLaneVehicles  engine.cpp:650-660: CSR over lanes, lane_begin has n_lanes+1 entries */
+int64_t cfb_get_lane_vehicles(cfb_engine *e, int64_t *lane_begin, int n_lanes_plus1, cfb_vehicle_ref *ids, int64_t cap);
+/* Engine::getLeader  engine.cpp:836-850: found=0 -> no leader.  Unknown vehicle -> CFB_ERR_ARGUMENT */
+int cfb_get_leader(cfb_engine *e, cfb_vehicle_ref vehicle, cfb_vehicle_ref *leader, int *found);
+
+/* Engine::setTrafficLightPhase  engine.cpp:719-725 (no-op with a message unless rlTrafficLight) */
+int cfb_set_tl_phase(cfb_engine *e, const char *intersection_id, int phase);
+int cfb_set_tl_phase_index(cfb_engine *e, int intersection, int phase);
+/* Engine::setRandomSeed  engine.h:170 */
+int cfb_set_random_seed(cfb_engine *e, int seed);
+/* Engine::reset(resetRnd)  engine.cpp:744-760 */
+int cfb_reset(cfb_engine *e, int reset_rnd);
+/* Engine::pushVehicle(info, roads)  engine.cpp:693-717.  `values` hold, in this order: speed,
+ * length, width, maxPosAcc, maxNegAcc, usualPosAcc, usualNegAcc, minGap, maxSpeed, headwayTime;
+ * NaN = "not given" (struct default, vehicle.h:31-45). */
+int cfb_push_vehicle(cfb_engine *e, const double values[10], const char *const *roads, int n_roads);
+
+/* Test support: full dynamic state of every running vehicle, drivable-major in list order.
+ * Record = 8 x int32 {flow, index, priority, drivable, leader flow, leader index, blocker flow,
+ * blocker index}, 3 x double {distance, speed, gap}, 1 x int64 {enterLaneLinkTime}; 64 bytes. */
+int64_t cfb_debug_vehicles(cfb_engine *e, void *out, int64_t cap);
+
+/* Measurement support (bench.py): number of our kernels launched so far, per-kernel CUDA-event
+ * time accumulators (ms) when enabled, and device-side size figures. */
+int64_t cfb_gpu_launches(const cfb_engine *e);
+int cfb_enable_kernel_timing(cfb_engine *e, int on);
+int cfb_kernel_times(cfb_engine *e, double ms_out[5], int64_t *steps_timed);
+int cfb_synchronize(cfb_engine *e);
+int64_t cfb_num_drivables(const cfb_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITYFLOW_B200_H */
