@@ -64,7 +64,7 @@ struct Ctrl {
     int finCount;
     int error;
     int spawnCount;
-    int pad[2];
+    unsigned long long vehicleSteps;  // sum over steps of activeVehicleCount after the step (the bench metric)
 };
 
 constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
@@ -655,7 +655,10 @@ __global__ void __launch_bounds__(256) k_leader(View V) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int d = gtid >> 5;
     const int lane = threadIdx.x & 31;
-    if (gtid == 0) V.ctrl->step += 1;  // Engine::step (engine.cpp:593); nothing in this kernel reads it
+    if (gtid == 0) {  // Engine::step (engine.cpp:593); nothing in this kernel reads these
+        V.ctrl->step += 1;
+        V.ctrl->vehicleSteps += (unsigned long long) V.ctrl->active;  // k_move (all finishes) is complete
+    }
     if (gtid < V.nInter && !V.rl && !V.interVirtual[gtid]) {
         double rem = V.remain[gtid] - V.dt;
         int cur = V.curPhase[gtid];
@@ -816,6 +819,9 @@ struct DeviceSim::Impl {
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {};
+    std::vector<cudaEvent_t> stepEv;   // timed-step brackets (bench)
+    size_t stepEvUsed = 0;
+    DevBuf<unsigned char> flushBuf;
     KernelTimes times;
 
     int slotCap = 0;
@@ -967,6 +973,7 @@ DeviceSim::~DeviceSim() {
         if (I.spawnDone[r]) cudaEventDestroy(I.spawnDone[r]);
     }
     for (auto &ev : I.ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : I.stepEv) cudaEventDestroy(ev);
     if (I.hCtrl) cudaFreeHost(I.hCtrl);
     if (I.hCounts) cudaFreeHost(I.hCounts);
     if (I.hInts) cudaFreeHost(I.hInts);
@@ -1092,7 +1099,41 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     }
 }
 
+static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src);
 void DeviceSim::synchronize() { CFB_CUDA(cudaStreamSynchronize(impl_->stream)); }
+
+// ---- measurement support: CUDA-event brackets on the engine's own stream ----
+void DeviceSim::flushL2() {
+    Impl &I = *impl_;
+    const size_t bytes = (size_t) 256 << 20;  // > 126 MB L2
+    if (I.flushBuf.n < bytes) I.flushBuf.alloc(bytes);
+    CFB_CUDA(cudaMemsetAsync(I.flushBuf.p, (int) (steps_ & 0xff), bytes, I.stream));
+}
+void DeviceSim::markTimed() {
+    Impl &I = *impl_;
+    if (I.stepEvUsed == I.stepEv.size()) {
+        cudaEvent_t e;
+        CFB_CUDA(cudaEventCreate(&e));
+        I.stepEv.push_back(e);
+    }
+    CFB_CUDA(cudaEventRecord(I.stepEv[I.stepEvUsed++], I.stream));
+}
+double DeviceSim::collectTimedMs() {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    double total = 0;
+    for (size_t k = 0; k + 1 < I.stepEvUsed; k += 2) {
+        float ms = 0;
+        CFB_CUDA(cudaEventElapsedTime(&ms, I.stepEv[k], I.stepEv[k + 1]));
+        total += ms;
+    }
+    I.stepEvUsed = 0;
+    return total;
+}
+unsigned long long DeviceSim::vehicleSteps() {
+    readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
+    return impl_->hCtrl->vehicleSteps;
+}
 
 void DeviceSim::enableKernelTiming(bool on) {
     impl_->timing = on;
@@ -1100,6 +1141,7 @@ void DeviceSim::enableKernelTiming(bool on) {
 }
 DeviceSim::KernelTimes DeviceSim::kernelTimes() { return impl_->times; }
 
+static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src);
 static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src) {
     CFB_CUDA(cudaMemcpyAsync(dst, src, sizeof(Ctrl), cudaMemcpyDeviceToHost, s));
     CFB_CUDA(cudaStreamSynchronize(s));

@@ -96,6 +96,10 @@ public:
     // Measurement support for bench.py / profiles (CUDA-event timing of one kernel across launches).
     struct KernelTimes { double ingest = 0, notify = 0, control = 0, move = 0, leader = 0; long long launches = 0; };
     void enableKernelTiming(bool on);
+    void flushL2();                 // 256 MiB memset on the engine stream
+    void markTimed();               // record an event; brackets are (even, odd) pairs
+    double collectTimedMs();        // sync; sum of bracket durations; clears the brackets
+    unsigned long long vehicleSteps();  // device-side sum of the vehicle count after every step
     KernelTimes kernelTimes();
     long long launchesDone() const { return launches_; }
     int numPositions() const;

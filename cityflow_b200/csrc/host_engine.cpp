@@ -73,6 +73,7 @@ public:
     std::vector<std::string> laneIds;
     size_t uploadedPlans = 0, uploadedTemplates = 0;
     bool finishedDirty = false;                              // steps enqueued since the last drain
+    long long h2dBytes = 0, d2hBytes = 0;                    // host<->device traffic of the public calls (bench e2e)
 
     static uint64_t key(int flow, int index) { return ((uint64_t) (uint32_t) flow << 32) | (uint32_t) index; }
 
@@ -274,6 +275,7 @@ public:
         if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
         dev->ensureSlotCapacity((int) slots.size());
         dev->step(batch.data(), (int) batch.size());
+        h2dBytes += (long long) batch.size() * sizeof(SpawnRec) + sizeof(int);
         finishedDirty = true;
         step += 1;
         if ((step & 255) == 0) drain();  // bound the finished ring / free slots in long unobserved runs
@@ -364,7 +366,7 @@ int cfb_next_steps(cfb_engine *e, int n) {
 }
 
 int64_t cfb_get_vehicle_count(cfb_engine *e) {
-    CFB_TRY(e, int c = e->h.dev->vehicleCount(); e->h.checkDevice(); return c;)
+    CFB_TRY(e, int c = e->h.dev->vehicleCount(); e->h.checkDevice(); e->h.d2hBytes += 64; return c;)
 }
 
 double cfb_get_current_time(const cfb_engine *e) { return e->h.currentTime(); }
@@ -544,6 +546,29 @@ int64_t cfb_debug_vehicles(cfb_engine *e, void *out, int64_t cap) {
     )
 }
 
+// n steps, each bracketed by CUDA events on the engine stream; optional L2 flush between steps
+// (outside the brackets).  Returns the summed device time in ms and the vehicle-steps done.
+int cfb_timed_steps(cfb_engine *e, int n, int flush_l2, double *ms, int64_t *vehicle_steps) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        h.dev->synchronize();
+        const unsigned long long v0 = h.dev->vehicleSteps();
+        for (int i = 0; i < n; ++i) {
+            if (flush_l2) h.dev->flushL2();
+            h.dev->markTimed();
+            h.nextStep();
+            h.dev->markTimed();
+        }
+        *ms = h.dev->collectTimedMs();
+        *vehicle_steps = (int64_t) (h.dev->vehicleSteps() - v0);
+        h.checkDevice();
+    )
+    return CFB_OK;
+}
+int64_t cfb_vehicle_steps(cfb_engine *e) {
+    CFB_TRY(e, return (int64_t) e->h.dev->vehicleSteps();)
+}
+
 int64_t cfb_gpu_launches(const cfb_engine *e) { return e->h.dev->launchesDone(); }
 int cfb_enable_kernel_timing(cfb_engine *e, int on) { e->h.dev->enableKernelTiming(on != 0); return CFB_OK; }
 int cfb_kernel_times(cfb_engine *e, double ms[5], int64_t *steps) {
@@ -559,3 +584,9 @@ int cfb_synchronize(cfb_engine *e) {
 int64_t cfb_num_drivables(const cfb_engine *e) { return e->h.dev->numDrivables(); }
 
 }  // extern "C"
+
+extern "C" int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2h) {
+    if (h2d) *h2d = e->h.h2dBytes;
+    if (d2h) *d2h = e->h.d2hBytes;
+    return CFB_OK;
+}

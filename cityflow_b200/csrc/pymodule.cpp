@@ -193,6 +193,20 @@ public:
         cfb_kernel_times(e_, ms, &n);
         return py::make_tuple(py::make_tuple(ms[0], ms[1], ms[2], ms[3], ms[4]), n);
     }
+    py::tuple timedSteps(int n, bool flushL2) {
+        double ms = 0;
+        int64_t vs = 0;
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = cfb_timed_steps(e_, n, flushL2, &ms, &vs);
+        }
+        check(rc);
+        return py::make_tuple(ms, vs);
+    }
+    int64_t vehicleSteps() { return cfb_vehicle_steps(e_); }
+    int64_t numDrivables() const { return cfb_num_drivables(e_); }
+    py::tuple transferBytes() { int64_t a = 0, b = 0; cfb_transfer_bytes(e_, &a, &b); return py::make_tuple(a, b); }
     void synchronize() {
         py::gil_scoped_release rel;
         cfb_synchronize(e_);
@@ -241,6 +255,10 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("gpu_launches", &Engine::gpuLaunches)
         .def("enable_kernel_timing", &Engine::enableKernelTiming, "on"_a = true)
         .def("kernel_times", &Engine::kernelTimes)
+        .def("timed_steps", &Engine::timedSteps, "n"_a, "flush_l2"_a = false)
+        .def("vehicle_steps", &Engine::vehicleSteps)
+        .def("transfer_bytes", &Engine::transferBytes)
+        .def("num_drivables", [](Engine &e) { return e.numDrivables(); })
         .def("synchronize", &Engine::synchronize);
     m.attr("__version__") = "b200-dev";
 }

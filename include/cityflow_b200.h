@@ -105,6 +105,13 @@ int64_t cfb_debug_vehicles(cfb_engine *e, void *out, int64_t cap);
 /* Measurement support (bench.py): number of our kernels launched so far, per-kernel CUDA-event
  * time accumulators (ms) when enabled, and device-side size figures. */
 int64_t cfb_gpu_launches(const cfb_engine *e);
+/* n steps, each bracketed by CUDA events on the engine's stream (optionally with a 256 MiB L2
+ * flush before each bracket); *ms = summed device time, *vehicle_steps = sum of vehicle counts */
+int cfb_timed_steps(cfb_engine *e, int n, int flush_l2, double *ms, int64_t *vehicle_steps);
+/* device-side running sum of get_vehicle_count() after every step since creation / reset */
+int64_t cfb_vehicle_steps(cfb_engine *e);
+/* bytes copied host->device (spawn records) and device->host (control block reads) so far */
+int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2h);
 int cfb_enable_kernel_timing(cfb_engine *e, int on);
 int cfb_kernel_times(cfb_engine *e, double ms_out[5], int64_t *steps_timed);
 int cfb_synchronize(cfb_engine *e);

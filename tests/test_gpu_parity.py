@@ -130,3 +130,21 @@ def test_reset_determinism(cfg_3x3_dense):
     assert a[0] == b[0]
     assert np.array_equal(a[1], b[1])
     assert np.array_equal(np.sort(a[2], order=["flow", "cnt"]), np.sort(b[2], order=["flow", "cnt"]))
+
+
+def test_30x30_dense_lane_counts_vs_port(scenario_dir):
+    """BASELINE.json configs[2] shape (30x30, dense demand): per-lane counts bit-exact and all
+    speeds bit-equal against the CPU restatement while the network fills up."""
+    from cityflow_b200 import scenario
+    from cityflow_b200.capi import CEngine
+    cfg = scenario.make_grid_scenario(scenario_dir, 30, 30, name="g30d", dense=dict(frac=0.5, interval=10.0, seed=1))
+    eng = CEngine(cfg)
+    ora = H.PortOracle(cfg)
+    for s in (100, 250, 400):
+        eng.next_step(s - ora.steps)
+        ora.next_step(s - ora.steps)
+        assert np.array_equal(eng.lane_vehicle_count(), ora.lane_vehicle_count()), "lane counts differ at step %d" % s
+        assert np.array_equal(eng.lane_waiting_count(), ora.lane_waiting_count())
+        bad = H.compare_states(_relax(ora.snapshot()), _gpu_state(eng, s))
+        assert not bad, "step %d: %s" % (s, "; ".join(bad[:6]))
+    assert ora.vehicle_count() > 50000
