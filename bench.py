@@ -45,6 +45,10 @@ def parse_args():
     p.add_argument("--threads", type=int, default=0, help="reference arm: thread_num (default nproc)")
     p.add_argument("--cpu-steps", type=int, default=100, help="cpu_baseline sample: timed steps after the prefill")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--clock-ms", type=int, default=200, help="nvidia-smi sampling period (0 = off)")
+    p.add_argument("--profile-steps", type=int, default=0,
+                   help="ncu mode: after prefill+warmup run this many steps between cudaProfilerStart/Stop and exit "
+                        "(use with ncu --profile-from-start off)")
     return p.parse_args()
 
 
@@ -66,8 +70,9 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, period_ms=50):
         self.device = device
+        self.period_ms = period_ms
         self.proc = None
         self.path = None
 
@@ -76,7 +81,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -207,13 +212,22 @@ def run_ours(args):
         return float(t.item())
 
     # ---- scenario preparation + warm-up (clock sampling starts here: the timed regions are sub-second) ----
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(local, args.clock_ms)
+    if rank == 0 and args.clock_ms > 0:
         sampler.start()
     eng.next_steps(args.prefill)
     eng.synchronize()
     eng.timed_steps(max(args.warmup, 3), True)
     n_start = eng.get_vehicle_count()
+    if args.profile_steps > 0:  # profiling run: numbers printed under a profiler are never bench values
+        cudart = torch.cuda.cudart()
+        cudart.cudaProfilerStart()
+        eng.timed_steps(args.profile_steps, True)
+        cudart.cudaProfilerStop()
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"profiled_steps": args.profile_steps, "vehicles": n_start}))
+        return
 
     # ---- value: K steps, device time (CUDA events on the engine stream), L2 flushed between steps ----
     barrier()

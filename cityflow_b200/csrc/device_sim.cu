@@ -14,12 +14,19 @@
 //   ids[p]   int4 {slot, tmpl, priority, plan}
 //   nav[p]   int4 {planPos, prevDrivable, blocker(slot), enterLaneLinkTime}
 //
+// Work lists.  At ~1e5 vehicles only ~8 k of the 43 k drivables of the 30x30 grid are occupied,
+// so no kernel sweeps the topology: k_move leaves behind the list of occupied drivables and the
+// list of occupied positions (double-buffered on step parity), k_ingest appends what it admits,
+// and every phase is a grid-stride loop over one of those lists with a fixed, SM-count-sized
+// grid (CUDA-graph friendly, no host knowledge of the population needed).
+//
 // Kernel sequence per step (all FP64, -fmad=false so every operation rounds exactly like the
 // reference's SSE2 build; expression shapes follow vehicle.cpp verbatim):
 //   k_ingest   P0-P2  waiting-queue append, Lane::available admission, light -> roadLink mask
-//   k_notify   P3     Cross::notify per laneLink (+ leader search of vehicles admitted to an empty lane)
-//   k_control  P4     getNextSpeed / vehicleControl / setDeltaDistance per vehicle (warp per bucket)
-//   k_move     P5-P6  bucket compaction, entrant rank-sort + append, commit, finished ring
+//   k_notify   P3     Cross::notify, warp per occupied drivable, one lane per cross
+//   k_control  P4     getNextSpeed / vehicleControl / setDeltaDistance, thread per vehicle
+//   k_move     P5-P6  bucket compaction (ballot scan), entrant rank-sort + append, commit,
+//                     finished ring, next step's work lists
 //   k_leader   P7-P8  leader/gap rebuild (warp shuffle), cross-drivable head search, blocker drop,
 //                     TrafficLight::passTime
 #include <cuda_runtime.h>
@@ -27,6 +34,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -64,17 +72,23 @@ struct Ctrl {
     int finCount;
     int error;
     int spawnCount;
+    int nVeh[2];     // work lists, double-buffered on step parity
+    int nAct[2];
+    int nExtra;
+    int pad;
     unsigned long long vehicleSteps;  // sum over steps of activeVehicleCount after the step (the bench metric)
 };
 
 constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
 constexpr int PLAN_LOOKAHEAD_END = -1;
+constexpr int SPAWN_SMEM = 2048;
 
 struct View {
     int nLanes, nLinks, nDrv, nInter, nRL, nCross;
-    int moverCap, finCap;
+    int moverCap, finCap, vehCap;
     double dt;
     int rl;
+    int par;   // step parity (host-provided; equals ctrl->step & 1): selects the live work lists
     // static topology
     const double *drvLength, *drvMaxSpeed;
     const int *off;
@@ -109,6 +123,10 @@ struct View {
     double2 *mkin;
     int4 *mids, *mnav;
     int2 *finSlots;
+    // work lists
+    int2 *vehList[2];   // {position, drivable} of every running vehicle
+    int *actList[2];    // occupied drivables
+    int *extraList;     // empty drivables that receive entrants this step
     Ctrl *ctrl;
     const SpawnRec *spawn;
 };
@@ -212,32 +230,47 @@ __device__ void headSearch(const View &V, int d, double dis, int plan, int planP
 // ------------------------------------------------------------------------------------------
 // k_ingest: thread i serves lane i (queue append + admission) and roadLink i (light mask).
 // Flow::nextStep / planRoute stay on the host (serial mt19937 order); their result arrives as
-// lane-sorted SpawnRec's.  handleWaiting: engine.cpp:502-516, Lane::available roadnet.cpp:428-435.
+// lane-sorted SpawnRec's whose lane keys are staged in shared memory for the per-lane lookup.
+// handleWaiting: engine.cpp:502-516, Lane::available roadnet.cpp:428-435.
 __global__ void __launch_bounds__(256) k_ingest(View V) {
+    __shared__ int sLane[SPAWN_SMEM];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nSpawn = V.ctrl->spawnCount;
+    const int cpar = V.par;
+    const bool staged = nSpawn <= SPAWN_SMEM;
+    if (staged)
+        for (int k = threadIdx.x; k < nSpawn; k += blockDim.x) sLane[k] = V.spawn[k].lane;
+    __syncthreads();
     if (i < V.nRL) {
         int in = V.rlInter[i];
         int ph = V.interPhaseBeg[in] + V.curPhase[in];
         V.rlAvail[i] = V.phaseAvail[V.phaseAvailBeg[ph] + (i - V.interRLBeg[in])];
     }
-    if (i == 0) V.ctrl->moverCount = 0;
+    if (i == 0) {  // lists of the other parity are rebuilt by this step's k_move
+        V.ctrl->moverCount = 0;
+        V.ctrl->nVeh[cpar ^ 1] = 0;
+        V.ctrl->nAct[cpar ^ 1] = 0;
+        V.ctrl->nExtra = 0;
+    }
     if (i >= V.nLanes) return;
-    const int nSpawn = V.ctrl->spawnCount;
     if (nSpawn > 0) {
         int lo = 0, hi = nSpawn;  // lower bound of lane i
         while (lo < hi) {
             int mid = (lo + hi) >> 1;
-            if (V.spawn[mid].lane < i) lo = mid + 1; else hi = mid;
+            int key = staged ? sLane[mid] : V.spawn[mid].lane;
+            if (key < i) lo = mid + 1; else hi = mid;
         }
-        int tail = V.waitTail[i];
-        for (int r = lo; r < nSpawn && V.spawn[r].lane == i; ++r) {
-            SpawnRec s = V.spawn[r];
-            V.slotInfo[s.slot] = make_int4(s.tmpl, s.priority, s.plan, 0);
-            V.waitNext[s.slot] = -1;
-            if (tail < 0) V.waitHead[i] = s.slot; else V.waitNext[tail] = s.slot;
-            tail = s.slot;
+        if (lo < nSpawn && (staged ? sLane[lo] : V.spawn[lo].lane) == i) {
+            int tail = V.waitTail[i];
+            for (int r = lo; r < nSpawn && (staged ? sLane[r] : V.spawn[r].lane) == i; ++r) {
+                SpawnRec s = V.spawn[r];
+                V.slotInfo[s.slot] = make_int4(s.tmpl, s.priority, s.plan, 0);
+                V.waitNext[s.slot] = -1;
+                if (tail < 0) V.waitHead[i] = s.slot; else V.waitNext[tail] = s.slot;
+                tail = s.slot;
+            }
+            V.waitTail[i] = tail;
         }
-        V.waitTail[i] = tail;
     }
     unsigned char ins = 0;
     const int h = V.waitHead[i];
@@ -268,10 +301,13 @@ __global__ void __launch_bounds__(256) k_ingest(View V) {
                 } else {
                     V.leader[p] = -1;
                     ins = 3;  // admitted to an empty lane: leader search runs in k_notify
+                    V.actList[cpar][atomicAdd(&V.ctrl->nAct[cpar], 1)] = i;
                 }
                 V.count[i] = n + 1;
                 V.pos[h] = p;
                 atomicAdd(&V.ctrl->active, 1);
+                const int vi = atomicAdd(&V.ctrl->nVeh[cpar], 1);
+                if (vi < V.vehCap) V.vehList[cpar][vi] = make_int2(p, i);
                 int nx = V.waitNext[h];
                 V.waitHead[i] = nx;
                 if (nx < 0) V.waitTail[i] = -1;
@@ -282,94 +318,141 @@ __global__ void __launch_bounds__(256) k_ingest(View V) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_notify: thread per laneLink (Engine::threadNotifyCross, engine.cpp:317-372).  Notify slots
-// are epoch-stamped instead of cleared (Cross::clearNotify would sweep every cross every step).
-__global__ void __launch_bounds__(256) k_notify(View V) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V.nLanes && (V.inserted[i] & 2)) {  // vehicle admitted to an empty lane this step
-        const int p = V.off[i];
-        const int4 idv = V.ids[p];
-        int ld = -1;
-        double g = 0;
-        headSearch(V, i, 0.0, idv.w, 0, V.tmpl[idv.y], i, ld, g);
-        V.leader[p] = ld;
-        if (ld >= 0) V.gap[p] = g;
-    }
-    if (i >= V.nLinks) return;
-    const int cb = V.llCrossBeg[i], ce = V.llCrossBeg[i + 1];
-    if (cb == ce) return;
-    const int epoch = V.ctrl->step + 1;
-    const int linkDrv = V.nLanes + i;
-    int ri = ce - 1;
-    auto put = [&](int k, int pos, double dist) {
-        Notify n;
-        n.dist = dist;
-        n.pos = pos;
-        n.epoch = epoch;
-        V.notify[V.lcIdx[k]] = n;
-    };
-    // (1) the last vehicle on the end lane if it came out of this link
+// Cross::notify for one laneLink, executed by a whole warp: one lane per cross.
+// Engine::threadNotifyCross (engine.cpp:317-372) walks the link's crosses from the far end with
+// one cursor shared by three sources in order -- (1) the end lane's last vehicle if it came out
+// of this link, (2) the vehicles on the link front to back, (3) the start lane's first vehicle
+// if it heads for this link and the link is green.  Every source keeps taking crosses while a
+// condition that is monotone along the link holds, so the owner of a cross is simply the first
+// source whose condition (same FP64 expression as the reference) holds for it.  Notify slots are
+// epoch-stamped instead of cleared (Cross::clearNotify would sweep every cross every step).
+__device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
+    const int cb = V.llCrossBeg[ll], nc = V.llCrossBeg[ll + 1] - cb;
+    if (nc == 0) return;
+    const int linkDrv = V.nLanes + ll;
+    // source 1
+    bool has1 = false;
+    int tp = -1;
+    double tdis = 0, vehDistance1 = 0;
     {
-        const int el = V.llEndLane[i];
+        const int el = V.llEndLane[ll];
         const int c = V.count[el];
         if (c > 0) {
-            const int tp = V.off[el] + c - 1;
+            tp = V.off[el] + c - 1;
             if (V.nav[tp].y == linkDrv) {
-                const double tdis = V.kin[tp].x;
-                const double vehDistance = tdis - V.tmpl[V.ids[tp].y].len;
-                const double L = V.drvLength[linkDrv];
-                while (ri >= cb) {
-                    double crossDistance = L - V.lcDist[ri];
-                    if (crossDistance + vehDistance < 0) {
-                        put(ri, tp, -(tdis + crossDistance));
-                        --ri;
-                    } else break;
-                }
+                has1 = true;
+                tdis = V.kin[tp].x;
+                vehDistance1 = tdis - V.tmpl[V.ids[tp].y].len;
             }
         }
     }
-    // (2) vehicles on the link, front to back
+    // source 3
+    bool has3 = false;
+    int hp = -1;
+    double vehDistance3 = 0;
     {
-        const int c = V.count[linkDrv], base = V.off[linkDrv];
-        for (int j = 0; j < c && ri >= cb; ++j) {
-            const double vehDistance = V.kin[base + j].x;
-            const double len = V.tmpl[V.ids[base + j].y].len;
-            while (ri >= cb) {
-                double crossDistance = V.lcDist[ri];
-                if (vehDistance > crossDistance) {
-                    if (vehDistance - crossDistance - len <= 0) put(ri, base + j, crossDistance - vehDistance);
-                    else break;
-                } else {
-                    put(ri, base + j, crossDistance - vehDistance);
-                }
-                --ri;
+        const int sl = V.llStartLane[ll];
+        if (V.count[sl] > 0) {
+            hp = V.off[sl];
+            if (planAt(V, V.ids[hp].w, V.nav[hp].x + 1) == linkDrv && V.rlAvail[V.llRoadLink[ll]]) {
+                has3 = true;
+                vehDistance3 = V.drvLength[sl] - V.kin[hp].x;
             }
         }
     }
-    // (3) the first vehicle of the start lane if it heads for this link and the link is green
-    if (ri >= cb) {
-        const int sl = V.llStartLane[i];
-        if (V.count[sl] > 0) {
-            const int hp = V.off[sl];
-            const int4 idv = V.ids[hp];
-            if (planAt(V, idv.w, V.nav[hp].x + 1) == linkDrv && V.rlAvail[V.llRoadLink[i]]) {
-                const double vehDistance = V.drvLength[sl] - V.kin[hp].x;
-                while (ri >= cb) {
-                    put(ri, hp, vehDistance + V.lcDist[ri]);
-                    --ri;
+    const int c2 = V.count[linkDrv], base2 = V.off[linkDrv];
+    if (!has1 && !has3 && c2 == 0) return;
+    const double L = V.drvLength[linkDrv];
+    for (int k0 = 0; k0 < nc; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < nc;
+        const double dk = valid ? V.lcDist[cb + k] : 0.0;
+        int owner = -1;
+        double ndist = 0;
+        if (valid && has1) {
+            const double crossDistance = L - dk;
+            if (crossDistance + vehDistance1 < 0) {
+                owner = tp;
+                ndist = -(tdis + crossDistance);
+            }
+        }
+        for (int j0 = 0; j0 < c2; j0 += 32) {  // vehicles on the link, front to back
+            double vj = 0, lj = 0;
+            if (j0 + lane < c2) {
+                vj = V.kin[base2 + j0 + lane].x;
+                lj = V.tmpl[V.ids[base2 + j0 + lane].y].len;
+            }
+            const int m = min(32, c2 - j0);
+            for (int j = 0; j < m; ++j) {
+                const double v = __shfl_sync(0xffffffffu, vj, j);
+                const double l = __shfl_sync(0xffffffffu, lj, j);
+                if (valid && owner < 0) {
+                    bool take = true;
+                    if (v > dk) take = (v - dk - l <= 0);
+                    if (take) {
+                        owner = base2 + j0 + j;
+                        ndist = dk - v;
+                    }
                 }
             }
         }
+        if (valid && owner < 0 && has3) {
+            owner = hp;
+            ndist = vehDistance3 + dk;
+        }
+        if (valid && owner >= 0) {
+            Notify n;
+            n.dist = ndist;
+            n.pos = owner;
+            n.epoch = epoch;
+            V.notify[V.lcIdx[cb + k]] = n;
+        }
+    }
+}
+
+// k_notify: warp per occupied drivable.  A link handles itself; a lane triggers the (empty)
+// links its tail vehicle came out of / its head vehicle heads for, so no empty link is swept.
+// Also runs the leader search of a vehicle admitted to an empty lane this step.
+__global__ void __launch_bounds__(256) k_notify(View V) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int cpar = V.par;
+    const int nAct = V.ctrl->nAct[cpar];
+    const int epoch = V.ctrl->step + 1;
+    for (int w = warp; w < nAct; w += nWarps) {
+        const int d = V.actList[cpar][w];
+        if (d >= V.nLanes) {
+            notifyLink(V, d - V.nLanes, lane, epoch);
+            continue;
+        }
+        const int c = V.count[d], base = V.off[d];
+        if (c == 0) continue;
+        if ((V.inserted[d] & 2) && lane == 0) {  // vehicle admitted to an empty lane this step
+            const int4 idv = V.ids[base];
+            int ld = -1;
+            double g = 0;
+            headSearch(V, d, 0.0, idv.w, 0, V.tmpl[idv.y], d, ld, g);
+            V.leader[base] = ld;
+            if (ld >= 0) V.gap[base] = g;
+        }
+        // the link the tail came out of, if it is empty now (otherwise it is on the list itself)
+        const int prev = V.nav[base + c - 1].y;
+        int l1 = -1;
+        if (prev >= V.nLanes && V.count[prev] == 0) {
+            l1 = prev - V.nLanes;
+            notifyLink(V, l1, lane, epoch);
+        }
+        // the link the head is about to take, if empty
+        const int nx = planAt(V, V.ids[base].w, V.nav[base].x + 1);
+        if (nx >= V.nLanes && V.count[nx] == 0 && nx - V.nLanes != l1) notifyLink(V, nx - V.nLanes, lane, epoch);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // Cross::canPass roadnet.cpp:603-676.  `cs` = 2*cross + side of the asking vehicle's laneLink.
-__device__ bool canPass(const View &V, int cs, int epoch, const DTmpl &T, double mySpeed, int myEnterLL, int myPriority,
-                        double distanceToLaneLinkStart, double distOnLane, int &foeSlot) {
-    const Notify f = V.notify[cs ^ 1];
-    foeSlot = -1;
-    if (f.epoch != epoch) return true;  // foeVehicle == nullptr
+__device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, double mySpeed, int myEnterLL,
+                        int myPriority, double distanceToLaneLinkStart, double distOnLane, int &foeSlot) {
     const int fp = f.pos;
     const int4 fid = V.ids[fp];
     foeSlot = fid.x;
@@ -428,22 +511,19 @@ __device__ bool canPass(const View &V, int cs, int epoch, const DTmpl &T, double
     return yield == -1;
 }
 
-// k_control: one warp per drivable bucket, one lane per vehicle (strided by 32).
+// k_control: one thread per running vehicle (grid-stride over the position list).
 // Vehicle::getNextSpeed vehicle.cpp:308-335, getCarFollowSpeed :212-238, getIntersectionRelatedSpeed
 // :337-376, Engine::vehicleControl engine.cpp:188-251, Vehicle::setDeltaDistance vehicle.cpp:49-68.
-__global__ void __launch_bounds__(256) k_control(View V) {
-    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (d >= V.nDrv) return;
-    const int n = V.count[d];
-    if (n == 0) return;
-    const int base = V.off[d];
+__global__ void __launch_bounds__(128) k_control(View V) {
+    const int cpar = V.par;
+    const int nVeh = min(V.ctrl->nVeh[cpar], V.vehCap);
     const double dt = V.dt;
-    const double dLen = V.drvLength[d], dMax = V.drvMaxSpeed[d];
-    const bool onLink = d >= V.nLanes;
     const int epoch = V.ctrl->step + 1;
-    for (int k = lane; k < n; k += 32) {
-        const int p = base + k;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nVeh; it += gridDim.x * blockDim.x) {
+        const int2 vd = V.vehList[cpar][it];
+        const int p = vd.x, d = vd.y;
+        const double dLen = V.drvLength[d], dMax = V.drvMaxSpeed[d];
+        const bool onLink = d >= V.nLanes;
         const double2 kk = V.kin[p];
         const double dis = kk.x, speed = kk.y;
         const int4 idv = V.ids[p];
@@ -508,8 +588,11 @@ __global__ void __launch_bounds__(256) k_control(View V) {
                 for (int q = cb; q < ce; ++q) {
                     const double dOn = V.lcDist[q];
                     if (dOn < toStart) continue;
+                    const int cs = V.lcIdx[q];
+                    const Notify f = V.notify[cs ^ 1];
+                    if (f.epoch != epoch) continue;  // foeVehicle == nullptr: can pass
                     int foeSlot;
-                    if (!canPass(V, V.lcIdx[q], epoch, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
+                    if (!canPass(V, cs, f, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
                         s = min2(s, stopBeforeSpeed(T, speed, dOn - toStart - T.yieldDistance, dt));
                         newBlocker = foeSlot;
                         break;
@@ -559,154 +642,180 @@ __global__ void __launch_bounds__(256) k_control(View V) {
                 const int e = atomicAdd(&V.entCnt[newDrv], 1);
                 if (e >= ENT_CAP) atomicOr(&V.ctrl->error, ERR_ENTRANT_OVERFLOW);
                 else V.ent[newDrv * ENT_CAP + e] = m;
+                // an empty target is on no work list yet: queue it for k_move
+                if (e == 0 && V.count[newDrv] == 0) V.extraList[atomicAdd(&V.ctrl->nExtra, 1)] = newDrv;
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// k_move: warp per drivable.  Survivors are compacted in place with a ballot/popc scan (stable,
-// so list order is preserved); the few entrants are rank-sorted by (new distance desc, priority
-// asc) -- the reference's global std::sort on distance (engine.cpp:480) restricted to one target --
-// and appended.  Commits Buffer -> state (Vehicle::update, vehicle.cpp:107-143).
+// k_move: warp per drivable that is occupied or receives entrants.  Survivors are compacted in
+// place with a ballot/popc scan (stable, so list order is preserved); the few entrants are
+// rank-sorted by (new distance desc, priority asc) -- the reference's global std::sort on distance
+// (engine.cpp:480) restricted to one target -- and appended.  Commits Buffer -> state
+// (Vehicle::update, vehicle.cpp:107-143) and emits the next step's work lists.
 __global__ void __launch_bounds__(256) k_move(View V) {
-    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (d >= V.nDrv) return;
-    const int n = V.count[d];
-    int m = V.entCnt[d];
-    if (n == 0 && m == 0) return;
-    const int base = V.off[d], cap = V.off[d + 1] - base;
-    int nsurv = 0;
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        const int k = c0 + lane;
-        const bool valid = k < n;
-        double2 nk = make_double2(0, 0);
-        int2 nb = make_int2(0, 0);
-        int4 idv = make_int4(0, 0, 0, 0), nv = make_int4(0, 0, 0, 0);
-        if (valid) {
-            const int p = base + k;
-            nk = V.nkin[p];
-            nb = V.nbuf[p];
-            idv = V.ids[p];
-            nv = V.nav[p];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int cpar = V.par, npar = cpar ^ 1;
+    const int nAct = V.ctrl->nAct[cpar];
+    const int nTot = nAct + V.ctrl->nExtra;
+    for (int w = warp; w < nTot; w += nWarps) {
+        const int d = w < nAct ? V.actList[cpar][w] : V.extraList[w - nAct];
+        const int n = V.count[d];
+        int m = V.entCnt[d];
+        const int base = V.off[d], cap = V.off[d + 1] - base;
+        int nsurv = 0;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int k = c0 + lane;
+            const bool valid = k < n;
+            double2 nk = make_double2(0, 0);
+            int2 nb = make_int2(0, 0);
+            int4 idv = make_int4(0, 0, 0, 0), nv = make_int4(0, 0, 0, 0);
+            if (valid) {
+                const int p = base + k;
+                nk = V.nkin[p];
+                nb = V.nbuf[p];
+                idv = V.ids[p];
+                nv = V.nav[p];
+            }
+            const bool keep = valid && nb.x == -1;
+            const unsigned mask = __ballot_sync(0xffffffffu, keep);
+            const int dst = nsurv + __popc(mask & ((1u << lane) - 1));
+            __syncwarp();
+            if (keep) {
+                const int q = base + dst;
+                V.kin[q] = nk;                                     // dis, speed
+                nv.z = nb.y;                                       // blocker := buffer.blocker or null
+                V.nav[q] = nv;
+                if (dst != k) {
+                    V.ids[q] = idv;
+                    V.pos[idv.x] = q;
+                }
+            } else if (valid && nb.x == -2) {                      // finished (engine.cpp:296-310)
+                V.pos[idv.x] = -1;
+                const int f = atomicAdd(&V.ctrl->finCount, 1);
+                if (f < V.finCap) V.finSlots[f] = make_int2(idv.x, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
+                atomicSub(&V.ctrl->active, 1);
+            }
+            nsurv += __popc(mask);
         }
-        const bool keep = valid && nb.x == -1;
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        const int dst = nsurv + __popc(mask & ((1u << lane) - 1));
-        __syncwarp();
-        if (keep) {
-            const int q = base + dst;
-            V.kin[q] = nk;                                     // dis, speed
-            nv.z = nb.y;                                       // blocker := buffer.blocker or null
-            V.nav[q] = nv;
-            if (dst != k) {
+        if (m > 0) {
+            if (m > ENT_CAP) m = ENT_CAP;
+            if (nsurv + m > cap) {
+                if (lane == 0) atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW);
+                m = max(0, cap - nsurv);
+            }
+            int mi = -1;
+            double myDis = 0;
+            int myPrio = 0;
+            if (lane < m) {
+                mi = V.ent[d * ENT_CAP + lane];
+                myDis = V.mkin[mi].x;
+                myPrio = V.mids[mi].z;
+            }
+            int rank = 0;
+            for (int j = 0; j < m; ++j) {
+                const double od = __shfl_sync(0xffffffffu, myDis, j);
+                const int op = __shfl_sync(0xffffffffu, myPrio, j);
+                if (lane < m && j != lane && (od > myDis || (od == myDis && op < myPrio))) ++rank;
+            }
+            if (lane < m) {
+                const int q = base + nsurv + rank;
+                const int4 idv = V.mids[mi];
+                V.kin[q] = V.mkin[mi];
                 V.ids[q] = idv;
+                V.nav[q] = V.mnav[mi];
                 V.pos[idv.x] = q;
             }
-        } else if (valid && nb.x == -2) {                      // finished (engine.cpp:296-310)
-            V.pos[idv.x] = -1;
-            const int f = atomicAdd(&V.ctrl->finCount, 1);
-            if (f < V.finCap) V.finSlots[f] = make_int2(idv.x, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
-            atomicSub(&V.ctrl->active, 1);
+            if (lane == 0) V.entCnt[d] = 0;
         }
-        nsurv += __popc(mask);
+        const int total = nsurv + m;
+        if (lane == 0) V.count[d] = total;
+        if (total > 0) {  // next step's work lists
+            int start = 0;
+            if (lane == 0) {
+                V.actList[npar][atomicAdd(&V.ctrl->nAct[npar], 1)] = d;
+                start = atomicAdd(&V.ctrl->nVeh[npar], total);
+            }
+            start = __shfl_sync(0xffffffffu, start, 0);
+            for (int k = lane; k < total; k += 32)
+                if (start + k < V.vehCap) V.vehList[npar][start + k] = make_int2(base + k, d);
+        }
     }
-    if (m > 0) {
-        if (m > ENT_CAP) m = ENT_CAP;
-        if (nsurv + m > cap) {
-            if (lane == 0) atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW);
-            m = max(0, cap - nsurv);
-        }
-        int mi = -1;
-        double myDis = 0;
-        int myPrio = 0;
-        if (lane < m) {
-            mi = V.ent[d * ENT_CAP + lane];
-            myDis = V.mkin[mi].x;
-            myPrio = V.mids[mi].z;
-        }
-        int rank = 0;
-        for (int j = 0; j < m; ++j) {
-            const double od = __shfl_sync(0xffffffffu, myDis, j);
-            const int op = __shfl_sync(0xffffffffu, myPrio, j);
-            if (lane < m && j != lane && (od > myDis || (od == myDis && op < myPrio))) ++rank;
-        }
-        if (lane < m) {
-            const int q = base + nsurv + rank;
-            const int4 idv = V.mids[mi];
-            V.kin[q] = V.mkin[mi];
-            V.ids[q] = idv;
-            V.nav[q] = V.mnav[mi];
-            V.pos[idv.x] = q;
-        }
-        if (lane == 0) V.entCnt[d] = 0;
-    }
-    if (lane == 0) V.count[d] = nsurv + m;
 }
 
 // ------------------------------------------------------------------------------------------
-// k_leader: warp per drivable.  Non-heads: leader = list predecessor, gap = leader.dis -
-// leader.len - dis (vehicle.cpp:158-160), predecessor values arrive by warp shuffle.  Heads:
-// cross-drivable search.  Also drops blockers that left the network this step
-// (engine.cpp:419-421) and, in the tail threads, advances the traffic lights
-// (TrafficLight::passTime, trafficlight.cpp:29-37) and the step counter.
+// k_leader: warp per occupied drivable (the list k_move just wrote).  Non-heads: leader = list
+// predecessor, gap = leader.dis - leader.len - dis (vehicle.cpp:158-160), predecessor values
+// arrive by warp shuffle.  Heads: cross-drivable search.  Also drops blockers that left the
+// network this step (engine.cpp:419-421) and, in the leading threads, advances the traffic
+// lights (TrafficLight::passTime, trafficlight.cpp:29-37) and the step counter.
 __global__ void __launch_bounds__(256) k_leader(View V) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = gtid >> 5;
     const int lane = threadIdx.x & 31;
-    if (gtid == 0) {  // Engine::step (engine.cpp:593); nothing in this kernel reads these
-        V.ctrl->step += 1;
-        V.ctrl->vehicleSteps += (unsigned long long) V.ctrl->active;  // k_move (all finishes) is complete
+    const int warp = gtid >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int npar = V.par ^ 1;
+    const int nAct = V.ctrl->nAct[npar];
+    if (gtid == 0) {  // nothing in this kernel reads these (list parity is the host-provided V.par)
+        V.ctrl->step += 1;                                             // Engine::step (engine.cpp:593)
+        V.ctrl->vehicleSteps += (unsigned long long) V.ctrl->active;  // all finishes of this step are in
     }
-    if (gtid < V.nInter && !V.rl && !V.interVirtual[gtid]) {
-        double rem = V.remain[gtid] - V.dt;
-        int cur = V.curPhase[gtid];
-        const int pb = V.interPhaseBeg[gtid], nph = V.interPhaseBeg[gtid + 1] - pb;
-        while (rem <= 0.0) {
-            cur = (cur + 1) % nph;
-            rem += V.phaseTime[pb + cur];
-        }
-        V.remain[gtid] = rem;
-        V.curPhase[gtid] = cur;
-    }
-    if (d >= V.nDrv) return;
-    const int n = V.count[d];
-    if (n == 0) return;
-    const int base = V.off[d];
-    double carryDis = 0, carryLen = 0;
-    for (int c0 = 0; c0 < n; c0 += 32) {
-        const int k = c0 + lane;
-        const bool valid = k < n;
-        const int p = base + k;
-        double dis = 0, len = 0;
-        int4 idv = make_int4(0, 0, 0, 0);
-        if (valid) {
-            dis = V.kin[p].x;
-            idv = V.ids[p];
-            len = V.tmpl[idv.y].len;
-        }
-        double pd = __shfl_up_sync(0xffffffffu, dis, 1);
-        double pl = __shfl_up_sync(0xffffffffu, len, 1);
-        if (lane == 0) {
-            pd = carryDis;
-            pl = carryLen;
-        }
-        carryDis = __shfl_sync(0xffffffffu, dis, 31);
-        carryLen = __shfl_sync(0xffffffffu, len, 31);
-        if (valid) {
-            if (k > 0) {
-                V.leader[p] = p - 1;
-                V.gap[p] = pd - pl - dis;
-            } else {
-                int ld = -1;
-                double g = 0;
-                headSearch(V, d, dis, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
-                V.leader[p] = ld;
-                if (ld >= 0) V.gap[p] = g;
+    if (!V.rl) {
+        for (int in = gtid; in < V.nInter; in += gridDim.x * blockDim.x) {
+            if (V.interVirtual[in]) continue;
+            double rem = V.remain[in] - V.dt;
+            int cur = V.curPhase[in];
+            const int pb = V.interPhaseBeg[in], nph = V.interPhaseBeg[in + 1] - pb;
+            while (rem <= 0.0) {
+                cur = (cur + 1) % nph;
+                rem += V.phaseTime[pb + cur];
             }
-            const int b = V.nav[p].z;
-            if (b >= 0 && V.pos[b] < 0) V.nav[p].z = -1;
+            V.remain[in] = rem;
+            V.curPhase[in] = cur;
+        }
+    }
+    for (int w = warp; w < nAct; w += nWarps) {
+        const int d = V.actList[npar][w];
+        const int n = V.count[d];
+        const int base = V.off[d];
+        double carryDis = 0, carryLen = 0;
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int k = c0 + lane;
+            const bool valid = k < n;
+            const int p = base + k;
+            double dis = 0, len = 0;
+            int4 idv = make_int4(0, 0, 0, 0);
+            if (valid) {
+                dis = V.kin[p].x;
+                idv = V.ids[p];
+                len = V.tmpl[idv.y].len;
+            }
+            double pd = __shfl_up_sync(0xffffffffu, dis, 1);
+            double pl = __shfl_up_sync(0xffffffffu, len, 1);
+            if (lane == 0) {
+                pd = carryDis;
+                pl = carryLen;
+            }
+            carryDis = __shfl_sync(0xffffffffu, dis, 31);
+            carryLen = __shfl_sync(0xffffffffu, len, 31);
+            if (valid) {
+                if (k > 0) {
+                    V.leader[p] = p - 1;
+                    V.gap[p] = pd - pl - dis;
+                } else {
+                    int ld = -1;
+                    double g = 0;
+                    headSearch(V, d, dis, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
+                    V.leader[p] = ld;
+                    if (ld >= 0) V.gap[p] = g;
+                }
+                const int b = V.nav[p].z;
+                if (b >= 0 && V.pos[b] < 0) V.nav[p].z = -1;
+            }
         }
     }
 }
@@ -797,7 +906,8 @@ struct DeviceSim::Impl {
     DevBuf<double2> kin, nkin, mkin;
     DevBuf<double> gap, remain;
     DevBuf<int> leader, count, pos, waitHead, waitTail, waitNext, curPhase, entCnt, ent, scratchI;
-    DevBuf<int2> finSlots;
+    DevBuf<int2> finSlots, vehList0, vehList1;
+    DevBuf<int> act0, act1, extra;
     DevBuf<int4> ids, nav, slotInfo, mids, mnav;
     DevBuf<int2> nbuf;
     DevBuf<unsigned char> inserted, rlAvail;
@@ -825,6 +935,9 @@ struct DeviceSim::Impl {
     KernelTimes times;
 
     int slotCap = 0;
+    int numSMs = 148;
+    bool useGraph = true, graphDirty = false;
+    cudaGraphExec_t graphExec[2] = {nullptr, nullptr};
 
     void ensureHostInts(size_t n) {
         if (n <= hIntsCap) return;
@@ -868,6 +981,8 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     }
     CFB_CUDA(cudaSetDevice(opt.device));
     CFB_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
+    CFB_CUDA(cudaDeviceGetAttribute(&I.numSMs, cudaDevAttrMultiProcessorCount, opt.device));
+    if (const char *g = getenv("CITYFLOW_B200_NO_GRAPH")) I.useGraph = !(g[0] == '1');
     View &V = I.V;
     const int nL = net.nLanes(), nK = net.nLinks(), nD = nL + nK;
     V.nLanes = nL; V.nLinks = nK; V.nDrv = nD; V.nInter = net.nInter(); V.nRL = net.nRoadLinks(); V.nCross = net.nCross();
@@ -948,6 +1063,10 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.curPhase.alloc(net.nInter()); I.remain.alloc(net.nInter()); I.rlAvail.alloc(std::max(net.nRoadLinks(), 1));
     V.moverCap = (int) std::min<size_t>(P, (size_t) 1 << 22);
     I.mkin.alloc(V.moverCap); I.mids.alloc(V.moverCap); I.mnav.alloc(V.moverCap);
+    V.vehCap = I.P;
+    I.vehList0.alloc(P); I.vehList1.alloc(P); I.act0.alloc(nD); I.act1.alloc(nD); I.extra.alloc(nD);
+    V.vehList[0] = I.vehList0.p; V.vehList[1] = I.vehList1.p; V.actList[0] = I.act0.p; V.actList[1] = I.act1.p;
+    V.extraList = I.extra.p;
     V.finCap = 1 << 20;
     I.finSlots.alloc(V.finCap);
     I.ctrl.alloc(1);
@@ -974,6 +1093,7 @@ DeviceSim::~DeviceSim() {
     }
     for (auto &ev : I.ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : I.stepEv) cudaEventDestroy(ev);
+    for (int k = 0; k < 2; ++k) if (I.graphExec[k]) cudaGraphExecDestroy(I.graphExec[k]);
     if (I.hCtrl) cudaFreeHost(I.hCtrl);
     if (I.hCounts) cudaFreeHost(I.hCounts);
     if (I.hInts) cudaFreeHost(I.hInts);
@@ -989,6 +1109,7 @@ void DeviceSim::uploadTemplates(const std::vector<VehicleTemplate> &templates) {
     CFB_CUDA(cudaStreamSynchronize(I.stream));
     I.tmpl.upload(t);
     I.V.tmpl = I.tmpl.p;
+    I.graphDirty = true;
 }
 
 void DeviceSim::uploadPlans(const Routing &routing) {
@@ -1001,6 +1122,7 @@ void DeviceSim::uploadPlans(const Routing &routing) {
     I.planData.upload(pd);
     I.V.planBeg = I.planBeg.p;
     I.V.planData = I.planData.p;
+    I.graphDirty = true;
 }
 
 void DeviceSim::ensureSlotCapacity(int slots) {
@@ -1023,6 +1145,7 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     std::swap(I.slotInfo.p, ninfo.p); std::swap(I.slotInfo.n, ninfo.n);
     I.slotCap = cap;
     I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p;
+    I.graphDirty = true;
 }
 
 void DeviceSim::reset() {
@@ -1052,6 +1175,7 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
         CFB_CUDA(cudaStreamSynchronize(s));
         I.spawnCap = std::max(1024, n * 2);
         I.spawn.alloc(I.spawnCap);
+        I.graphDirty = true;
     }
     V.spawn = I.spawn.p;
     const int r = I.ringIdx;
@@ -1069,23 +1193,47 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     I.hCounts[r] = n;
     CFB_CUDA(cudaMemcpyAsync(&V.ctrl->spawnCount, &I.hCounts[r], sizeof(int), cudaMemcpyHostToDevice, s));
     CFB_CUDA(cudaEventRecord(I.spawnDone[r], s));
+    V.par = (int) (steps_ & 1);
     const int TPB = 256;
     const int gLaneRL = (std::max(V.nLanes, V.nRL) + TPB - 1) / TPB;
-    const int gLinkLane = (std::max(V.nLinks, V.nLanes) + TPB - 1) / TPB;
-    const int gWarpDrv = (int) (((size_t) V.nDrv * 32 + TPB - 1) / TPB);
-    const int gLeader = std::max(gWarpDrv, (V.nInter + TPB - 1) / TPB);
+    // list-driven kernels: fixed grids sized to the machine (grid-stride loops inside)
+    const int gWarp = I.numSMs * 8;        // 8 warps per block -> 64 warps per SM
+    const int gVeh = I.numSMs * 8;         // x128 threads
     const bool tm = I.timing;
-    if (tm) cudaEventRecord(I.ev[0], s);
-    k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
-    if (tm) cudaEventRecord(I.ev[1], s);
-    k_notify<<<std::max(gLinkLane, 1), TPB, 0, s>>>(V);
-    if (tm) cudaEventRecord(I.ev[2], s);
-    k_control<<<std::max(gWarpDrv, 1), TPB, 0, s>>>(V);
-    if (tm) cudaEventRecord(I.ev[3], s);
-    k_move<<<std::max(gWarpDrv, 1), TPB, 0, s>>>(V);
-    if (tm) cudaEventRecord(I.ev[4], s);
-    k_leader<<<std::max(gLeader, 1), TPB, 0, s>>>(V);
-    if (tm) cudaEventRecord(I.ev[5], s);
+    auto launchAll = [&](bool withEvents) {
+        if (withEvents) cudaEventRecord(I.ev[0], s);
+        k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
+        if (withEvents) cudaEventRecord(I.ev[1], s);
+        k_notify<<<gWarp, TPB, 0, s>>>(V);
+        if (withEvents) cudaEventRecord(I.ev[2], s);
+        k_control<<<gVeh, 128, 0, s>>>(V);
+        if (withEvents) cudaEventRecord(I.ev[3], s);
+        k_move<<<gWarp, TPB, 0, s>>>(V);
+        if (withEvents) cudaEventRecord(I.ev[4], s);
+        k_leader<<<gWarp, TPB, 0, s>>>(V);
+        if (withEvents) cudaEventRecord(I.ev[5], s);
+    };
+    if (tm || !I.useGraph) {
+        launchAll(tm);
+    } else {
+        // The five kernels of one step are replayed as one CUDA graph per list parity: one launch
+        // call per step instead of five, and no host-paced gaps between the kernels.
+        if (I.graphDirty) {
+            for (int k = 0; k < 2; ++k)
+                if (I.graphExec[k]) { cudaGraphExecDestroy(I.graphExec[k]); I.graphExec[k] = nullptr; }
+            I.graphDirty = false;
+        }
+        cudaGraphExec_t &ge = I.graphExec[V.par];
+        if (!ge) {
+            cudaGraph_t g = nullptr;
+            CFB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            launchAll(false);
+            CFB_CUDA(cudaStreamEndCapture(s, &g));
+            CFB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+            cudaGraphDestroy(g);
+        }
+        CFB_CUDA(cudaGraphLaunch(ge, s));
+    }
     CFB_CUDA(cudaGetLastError());
     launches_ += 5;
     steps_ += 1;
