@@ -256,9 +256,11 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     barrier()
     h2d1, d2h1 = eng.transfer_bytes()
+    host_gen_ms, host_enq_ms = eng.host_times()
     e2e_value = reduce_sum(acc) / reduce_max(e2e_s)
     clocks = sampler.stop() if rank == 0 else {}
 
+    eng_steps_total = args.prefill + max(args.warmup, 3) + 3 * args.steps
     # ---- per-kernel device time (CUDA events around every kernel; separate pass, serialised) ----
     eng.enable_kernel_timing(True)
     ksteps = min(args.steps, 50)
@@ -308,6 +310,7 @@ def run_ours(args):
                     "api": "cityflow.Engine.next_step() + get_vehicle_count() every step"},
             "gpu_launches": int(launches),
             "kernel_ms": kms,
+            "host_ms_per_step": {"spawn_generation": host_gen_ms / max(eng_steps_total, 1), "enqueue": host_enq_ms / max(eng_steps_total, 1)},
             "roofline": roof(dominant),
             "roofline_leader_scan": roof("k_leader"),
             "clocks": clocks,

@@ -11,8 +11,10 @@
 // becomes a warp-scan compaction plus a per-bucket rank sort of the few entrants.
 //
 //   kin[p]   double2 {dis, speed}            gap[p] double      leader[p] int (position, -1)
-//   ids[p]   int4 {slot, tmpl, priority, plan}
-//   nav[p]   int4 {planPos, prevDrivable, blocker(slot), enterLaneLinkTime}
+//   ids[p]   int4 {slot, tmpl, priority, nextDrivable}      (next drivable on the plan, cached)
+//   nav[p]   int4 {planIdx, prevDrivable, blocker(slot), enterLaneLinkTime}   (planIdx: absolute index into planData)
+//   tail[d]  {dis, len, speed, position, prevDrivable} of the last vehicle of every drivable (position -1 = empty):
+//            the one record other drivables' vehicles look at (leader search, Lane::canEnter, notify source 1)
 //
 // Work lists.  At ~1e5 vehicles only ~8 k of the 43 k drivables of the 30x30 grid are occupied,
 // so no kernel sweeps the topology: k_move leaves behind the list of occupied drivables and the
@@ -30,6 +32,7 @@
 //   k_leader   P7-P8  leader/gap rebuild (warp shuffle), cross-drivable head search, blocker drop,
 //                     TrafficLight::passTime
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <climits>
@@ -43,6 +46,7 @@
 #include "device_sim.h"
 
 namespace cfb {
+namespace cg = cooperative_groups;
 
 #define CFB_CUDA(x)                                                                                  \
     do {                                                                                             \
@@ -63,6 +67,11 @@ struct __align__(16) Notify {  // one side of one Cross (roadnet.h:122-124), epo
     double dist;
     int pos;
     int epoch;
+};
+
+struct __align__(16) Tail {  // last vehicle of a drivable (Drivable::getLastVehicle), pos < 0 when empty
+    double dis, len, speed;
+    int pos, prev;
 };
 
 struct Ctrl {
@@ -115,6 +124,10 @@ struct View {
     int4 *slotInfo;
     unsigned char *inserted;
     Notify *notify;
+    Tail *tail;
+    unsigned *foeMask;   // per laneLink, maskWords words: crosses of the link whose foe side was notified this step
+    const int *lcPeer;   // flat index of the same cross in the other laneLink's cross list
+    int maskWords;
     int *curPhase;
     double *remain;
     unsigned char *rlAvail;
@@ -128,7 +141,7 @@ struct View {
     int *actList[2];    // occupied drivables
     int *extraList;     // empty drivables that receive entrants this step
     Ctrl *ctrl;
-    const SpawnRec *spawn;
+    const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
 };
 
 // ------------------------------------------------------------------------------------------
@@ -185,38 +198,47 @@ __device__ __forceinline__ bool canYield(const DTmpl &T, double speed, double di
 __device__ __forceinline__ int planAt(const View &V, int plan, int idx) { return V.planData[V.planBeg[plan] + idx]; }
 
 // Cross-drivable leader search for the head of a list (Vehicle::updateLeaderAndGap, else-branch,
-// vehicle.cpp:162-195).  `myLane >= 0` enables the handleWaiting ordering rule: lanes later in
-// roadnet order have not been served yet when the reference inserts into `myLane` (engine.cpp:503).
-__device__ void headSearch(const View &V, int d, double dis, int plan, int planPos, const DTmpl &T, int myLane,
+// vehicle.cpp:162-195).  Candidates are read from the per-drivable tail records.  `myLane >= 0`
+// enables the handleWaiting ordering rule: lanes later in roadnet order have not been served yet
+// when the reference inserts into `myLane` (engine.cpp:503), so their admission is ignored.
+__device__ void headSearch(const View &V, int d, double dis, int nextDrv, int planIdx, const DTmpl &T, int myLane,
                            int &outLeader, double &outGap) {
     int leader = -1;
     double gap = 0;
     double x = V.drvLength[d] - dis;
+    int nd = nextDrv;
     for (int i = 0;; ++i) {
-        int nd = planAt(V, plan, planPos + 1 + i);
+        if (i > 0) nd = V.planData[planIdx + 1 + i];
         if (nd < 0) break;
         if (nd >= V.nLanes) {
-            int sl = V.llStartLane[nd - V.nLanes];
+            const int sl = V.llStartLane[nd - V.nLanes];
             for (int q = V.laneOutBeg[sl]; q < V.laneOutBeg[sl + 1]; ++q) {
-                int dl = V.nLanes + V.laneOutLinks[q];
-                int c = V.count[dl];
-                if (c > 0) {
-                    int tp = V.off[dl] + c - 1;
-                    double candGap = x + V.kin[tp].x - V.tmpl[V.ids[tp].y].len;
+                const Tail t = V.tail[V.nLanes + V.laneOutLinks[q]];
+                if (t.pos >= 0) {
+                    double candGap = x + t.dis - t.len;
                     if (leader < 0 || candGap < gap) {
-                        leader = tp;
+                        leader = t.pos;
                         gap = candGap;
                     }
                 }
             }
             if (leader >= 0) break;
         } else {
-            int c = V.count[nd];
-            if (myLane >= 0 && nd > myLane && (V.inserted[nd] & 1)) c -= 1;
-            if (c > 0) {
-                int tp = V.off[nd] + c - 1;
-                leader = tp;
-                gap = x + V.kin[tp].x - V.tmpl[V.ids[tp].y].len;
+            Tail t = V.tail[nd];
+            if (myLane >= 0 && nd > myLane && (V.inserted[nd] & 1)) {  // undo the later lane's admission
+                const int c = V.count[nd] - 1;
+                if (c > 0) {
+                    const int tp = V.off[nd] + c - 1;
+                    t.pos = tp;
+                    t.dis = V.kin[tp].x;
+                    t.len = V.tmpl[V.ids[tp].y].len;
+                } else {
+                    t.pos = -1;
+                }
+            }
+            if (t.pos >= 0) {
+                leader = t.pos;
+                gap = x + t.dis - t.len;
                 break;
             }
         }
@@ -235,7 +257,7 @@ __device__ void headSearch(const View &V, int d, double dis, int plan, int planP
 __global__ void __launch_bounds__(256) k_ingest(View V) {
     __shared__ int sLane[SPAWN_SMEM];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nSpawn = V.ctrl->spawnCount;
+    const int nSpawn = V.spawn[-1].slot;
     const int cpar = V.par;
     const bool staged = nSpawn <= SPAWN_SMEM;
     if (staged)
@@ -246,6 +268,7 @@ __global__ void __launch_bounds__(256) k_ingest(View V) {
         int ph = V.interPhaseBeg[in] + V.curPhase[in];
         V.rlAvail[i] = V.phaseAvail[V.phaseAvailBeg[ph] + (i - V.interRLBeg[in])];
     }
+    for (int k = i; k < V.nLinks * V.maskWords; k += gridDim.x * blockDim.x) V.foeMask[k] = 0u;
     if (i == 0) {  // lists of the other parity are rebuilt by this step's k_move
         V.ctrl->moverCount = 0;
         V.ctrl->nVeh[cpar ^ 1] = 0;
@@ -279,24 +302,23 @@ __global__ void __launch_bounds__(256) k_ingest(View V) {
         const int4 info = V.slotInfo[h];
         const DTmpl &T = V.tmpl[info.x];
         bool avail = true;
-        double2 tk = make_double2(0, 0);
-        double tlen = 0;
-        if (n > 0) {
-            tk = V.kin[base + n - 1];
-            tlen = V.tmpl[V.ids[base + n - 1].y].len;
-            avail = tk.x > tlen + T.minGap;
-        }
+        const Tail tl = V.tail[i];
+        if (n > 0) avail = tl.dis > tl.len + T.minGap;
         if (avail) {
             if (n >= V.off[i + 1] - base) {
                 atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW);
             } else {
                 const int p = base + n;
                 V.kin[p] = make_double2(0.0, T.speed0);
-                V.ids[p] = make_int4(h, info.x, info.y, info.z);
-                V.nav[p] = make_int4(0, -1, -1, INT_MAX);
+                const int planIdx = V.planBeg[info.z];
+                V.ids[p] = make_int4(h, info.x, info.y, V.planData[planIdx + 1]);
+                V.nav[p] = make_int4(planIdx, -1, -1, INT_MAX);
+                Tail nt;
+                nt.dis = 0.0; nt.len = T.len; nt.speed = T.speed0; nt.pos = p; nt.prev = -1;
+                V.tail[i] = nt;
                 if (n > 0) {
                     V.leader[p] = p - 1;
-                    V.gap[p] = tk.x - tlen - 0.0;
+                    V.gap[p] = tl.dis - tl.len - 0.0;
                     ins = 1;
                 } else {
                     V.leader[p] = -1;
@@ -335,15 +357,12 @@ __device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
     int tp = -1;
     double tdis = 0, vehDistance1 = 0;
     {
-        const int el = V.llEndLane[ll];
-        const int c = V.count[el];
-        if (c > 0) {
-            tp = V.off[el] + c - 1;
-            if (V.nav[tp].y == linkDrv) {
-                has1 = true;
-                tdis = V.kin[tp].x;
-                vehDistance1 = tdis - V.tmpl[V.ids[tp].y].len;
-            }
+        const Tail t = V.tail[V.llEndLane[ll]];
+        if (t.pos >= 0 && t.prev == linkDrv) {
+            has1 = true;
+            tp = t.pos;
+            tdis = t.dis;
+            vehDistance1 = tdis - t.len;
         }
     }
     // source 3
@@ -354,7 +373,7 @@ __device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
         const int sl = V.llStartLane[ll];
         if (V.count[sl] > 0) {
             hp = V.off[sl];
-            if (planAt(V, V.ids[hp].w, V.nav[hp].x + 1) == linkDrv && V.rlAvail[V.llRoadLink[ll]]) {
+            if (V.ids[hp].w == linkDrv && V.rlAvail[V.llRoadLink[ll]]) {
                 has3 = true;
                 vehDistance3 = V.drvLength[sl] - V.kin[hp].x;
             }
@@ -406,6 +425,11 @@ __device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
             n.pos = owner;
             n.epoch = epoch;
             V.notify[V.lcIdx[cb + k]] = n;
+            // tell the crossing link which of ITS crosses now has a foe (k_control visits only those)
+            const int peer = V.lcPeer[cb + k];
+            const int foeLink = V.csLink[V.lcIdx[cb + k] ^ 1];
+            const int bit = peer - V.llCrossBeg[foeLink];
+            atomicOr(&V.foeMask[foeLink * V.maskWords + (bit >> 5)], 1u << (bit & 31));
         }
     }
 }
@@ -432,7 +456,7 @@ __global__ void __launch_bounds__(256) k_notify(View V) {
             const int4 idv = V.ids[base];
             int ld = -1;
             double g = 0;
-            headSearch(V, d, 0.0, idv.w, 0, V.tmpl[idv.y], d, ld, g);
+            headSearch(V, d, 0.0, idv.w, V.nav[base].x, V.tmpl[idv.y], d, ld, g);
             V.leader[base] = ld;
             if (ld >= 0) V.gap[base] = g;
         }
@@ -444,7 +468,7 @@ __global__ void __launch_bounds__(256) k_notify(View V) {
             notifyLink(V, l1, lane, epoch);
         }
         // the link the head is about to take, if empty
-        const int nx = planAt(V, V.ids[base].w, V.nav[base].x + 1);
+        const int nx = V.ids[base].w;
         if (nx >= V.nLanes && V.count[nx] == 0 && nx - V.nLanes != l1) notifyLink(V, nx - V.nLanes, lane, epoch);
     }
 }
@@ -529,7 +553,7 @@ __global__ void __launch_bounds__(128) k_control(View V) {
         const int4 idv = V.ids[p];
         const int4 nv = V.nav[p];
         const DTmpl &T = V.tmpl[idv.y];
-        const int planBase = V.planBeg[idv.w] + nv.x + 1;
+        const int planBase = nv.x + 1;
 
         double v = T.maxSpeed;
         v = min2(v, speed + T.maxPosAcc * dt);
@@ -554,7 +578,7 @@ __global__ void __launch_bounds__(128) k_control(View V) {
         }
         // ---- intersection logic ----
         int newBlocker = -1;
-        const int nd0 = V.planData[planBase];
+        const int nd0 = idv.w;
         if (onLink || (nd0 >= V.nLanes && dLen - dis <= T.approachDist)) {
             double s = T.maxSpeed;
             int ll = -1;
@@ -563,13 +587,8 @@ __global__ void __launch_bounds__(128) k_control(View V) {
                 ll = nd0 - V.nLanes;
                 bool blocked = !V.rlAvail[V.llRoadLink[ll]];
                 if (!blocked) {  // Lane::canEnter roadnet.cpp:437-445
-                    const int el = V.llEndLane[ll];
-                    const int c = V.count[el];
-                    if (c > 0) {
-                        const int tp = V.off[el] + c - 1;
-                        const double2 tk = V.kin[tp];
-                        blocked = !(tk.x > V.tmpl[V.ids[tp].y].len + T.len || tk.y >= 2);
-                    }
+                    const Tail t = V.tail[V.llEndLane[ll]];
+                    if (t.pos >= 0) blocked = !(t.dis > t.len + T.len || t.speed >= 2);
                 }
                 if (blocked) {
                     if (0.5 * speed * speed / T.maxNegAcc > dLen - dis) {
@@ -584,18 +603,28 @@ __global__ void __launch_bounds__(128) k_control(View V) {
             if (!done) {
                 if (ll < 0 && onLink) ll = d - V.nLanes;
                 const double toStart = onLink ? dis : -(dLen - dis);
-                const int cb = V.llCrossBeg[ll], ce = V.llCrossBeg[ll + 1];
-                for (int q = cb; q < ce; ++q) {
-                    const double dOn = V.lcDist[q];
-                    if (dOn < toStart) continue;
-                    const int cs = V.lcIdx[q];
-                    const Notify f = V.notify[cs ^ 1];
-                    if (f.epoch != epoch) continue;  // foeVehicle == nullptr: can pass
-                    int foeSlot;
-                    if (!canPass(V, cs, f, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
-                        s = min2(s, stopBeforeSpeed(T, speed, dOn - toStart - T.yieldDistance, dt));
-                        newBlocker = foeSlot;
-                        break;
+                // crosses of the link in ascending distance; only those with a notified foe matter
+                // (a cross without foe passes, roadnet.cpp:613), and k_notify marked exactly those
+                const int cb = V.llCrossBeg[ll];
+                bool stop = false;
+                for (int wd = 0; wd < V.maskWords && !stop; ++wd) {
+                    unsigned bits = V.foeMask[ll * V.maskWords + wd];
+                    while (bits) {
+                        const int b = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int q = cb + wd * 32 + b;
+                        const double dOn = V.lcDist[q];
+                        if (dOn < toStart) continue;
+                        const int cs = V.lcIdx[q];
+                        const Notify f = V.notify[cs ^ 1];
+                        if (f.epoch != epoch) continue;
+                        int foeSlot;
+                        if (!canPass(V, cs, f, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
+                            s = min2(s, stopBeforeSpeed(T, speed, dOn - toStart - T.yieldDistance, dt));
+                            newBlocker = foeSlot;
+                            stop = true;
+                            break;
+                        }
                     }
                 }
             }
@@ -631,12 +660,18 @@ __global__ void __launch_bounds__(128) k_control(View V) {
         V.nkin[p] = make_double2(nd, v);
         V.nbuf[p] = make_int2(newDrv, newBlocker);
         if (newDrv >= 0) {  // Engine::pushBuffer (engine.cpp:247-249)
-            const int m = atomicAdd(&V.ctrl->moverCount, 1);
+            int m;
+            {  // one atomic per warp for the movers of this warp
+                auto g = cg::coalesced_threads();
+                int b = 0;
+                if (g.thread_rank() == 0) b = atomicAdd(&V.ctrl->moverCount, (int) g.size());
+                m = g.shfl(b, 0) + (int) g.thread_rank();
+            }
             if (m >= V.moverCap) {
                 atomicOr(&V.ctrl->error, ERR_MOVER_OVERFLOW);
             } else {
                 V.mkin[m] = make_double2(nd, v);
-                V.mids[m] = idv;
+                V.mids[m] = make_int4(idv.x, idv.y, idv.z, V.planData[planBase + hops]);  // next drivable after the new one
                 // enterLaneLinkTime: step for links, INT_MAX for lanes (engine.cpp:486-490)
                 V.mnav[m] = make_int4(nv.x + hops, d, newBlocker, newDrv >= V.nLanes ? epoch - 1 : INT_MAX);
                 const int e = atomicAdd(&V.entCnt[newDrv], 1);
@@ -662,11 +697,19 @@ __global__ void __launch_bounds__(256) k_move(View V) {
     const int cpar = V.par, npar = cpar ^ 1;
     const int nAct = V.ctrl->nAct[cpar];
     const int nTot = nAct + V.ctrl->nExtra;
-    for (int w = warp; w < nTot; w += nWarps) {
-        const int d = w < nAct ? V.actList[cpar][w] : V.extraList[w - nAct];
+    __shared__ int sTot[8];
+    __shared__ int sBaseVeh, sBaseAct;
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    (void) warp; (void) nWarps;
+    for (int w0 = blockIdx.x * wpb; w0 < nTot; w0 += gridDim.x * wpb) {  // trip count uniform per block
+        const int w = w0 + wib;
+        int total = 0, d = -1, base = 0;
+        if (w < nTot) {
+        d = w < nAct ? V.actList[cpar][w] : V.extraList[w - nAct];
         const int n = V.count[d];
         int m = V.entCnt[d];
-        const int base = V.off[d], cap = V.off[d + 1] - base;
+        base = V.off[d];
+        const int cap = V.off[d + 1] - base;
         int nsurv = 0;
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int k = c0 + lane;
@@ -732,18 +775,38 @@ __global__ void __launch_bounds__(256) k_move(View V) {
             }
             if (lane == 0) V.entCnt[d] = 0;
         }
-        const int total = nsurv + m;
-        if (lane == 0) V.count[d] = total;
-        if (total > 0) {  // next step's work lists
-            int start = 0;
-            if (lane == 0) {
-                V.actList[npar][atomicAdd(&V.ctrl->nAct[npar], 1)] = d;
-                start = atomicAdd(&V.ctrl->nVeh[npar], total);
+        total = nsurv + m;
+        __syncwarp();  // the committed records written above are read back by lane 0
+        if (lane == 0) {
+            V.count[d] = total;
+            Tail t;
+            t.dis = 0; t.len = 0; t.speed = 0; t.pos = -1; t.prev = -1;
+            if (total > 0) {  // re-read the committed last vehicle (written by this warp just above)
+                const int q = base + total - 1;
+                const double2 kq = V.kin[q];
+                t.dis = kq.x; t.speed = kq.y; t.len = V.tmpl[V.ids[q].y].len; t.pos = q; t.prev = V.nav[q].y;
             }
-            start = __shfl_sync(0xffffffffu, start, 0);
-            for (int k = lane; k < total; k += 32)
-                if (start + k < V.vehCap) V.vehList[npar][start + k] = make_int2(base + k, d);
+            V.tail[d] = t;
         }
+        }  // w < nTot
+        // next step's work lists: one pair of atomics per block, offsets by a scan over its warps
+        if (lane == 0) sTot[wib] = total;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int sv = 0, sa = 0;
+            for (int k = 0; k < wpb; ++k) { sv += sTot[k]; sa += sTot[k] > 0; }
+            sBaseVeh = sv ? atomicAdd(&V.ctrl->nVeh[npar], sv) : 0;
+            sBaseAct = sa ? atomicAdd(&V.ctrl->nAct[npar], sa) : 0;
+        }
+        __syncthreads();
+        if (total > 0) {
+            int offV = sBaseVeh, offA = sBaseAct;
+            for (int k = 0; k < wib; ++k) { offV += sTot[k]; offA += sTot[k] > 0; }
+            if (lane == 0) V.actList[npar][offA] = d;
+            for (int k = lane; k < total; k += 32)
+                if (offV + k < V.vehCap) V.vehList[npar][offV + k] = make_int2(base + k, d);
+        }
+        __syncthreads();
     }
 }
 
@@ -907,7 +970,9 @@ struct DeviceSim::Impl {
     DevBuf<double> gap, remain;
     DevBuf<int> leader, count, pos, waitHead, waitTail, waitNext, curPhase, entCnt, ent, scratchI;
     DevBuf<int2> finSlots, vehList0, vehList1;
-    DevBuf<int> act0, act1, extra;
+    DevBuf<int> act0, act1, extra, lcPeer;
+    DevBuf<Tail> tail;
+    DevBuf<unsigned> foeMask;
     DevBuf<int4> ids, nav, slotInfo, mids, mnav;
     DevBuf<int2> nbuf;
     DevBuf<unsigned char> inserted, rlAvail;
@@ -917,7 +982,7 @@ struct DeviceSim::Impl {
     DevBuf<SpeedRec> speedOut;
     int spawnCap = 0;
     // pinned staging
-    static constexpr int RING = 16;
+    static constexpr int RING = 64;
     SpawnRec *hSpawn[RING] = {};
     int hSpawnCap[RING] = {};
     cudaEvent_t spawnDone[RING] = {};
@@ -1026,7 +1091,18 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
         csLink[2 * c] = net.crossLink[0][c];
         csLink[2 * c + 1] = net.crossLink[1][c];
     }
-    if (lcIdx.empty()) { lcIdx.push_back(0); lcDist.push_back(0); }
+    // peer index: where the same cross sits in the crossing link's list; mask width
+    std::vector<int> lcPeer(lcIdx.size(), 0), flatOf(std::max(2 * net.nCross(), 1), 0);
+    int maxCross = 1;
+    for (int k = 0; k < nK; ++k) {
+        maxCross = std::max(maxCross, lcb[k + 1] - lcb[k]);
+        for (int q = lcb[k]; q < lcb[k + 1]; ++q) flatOf[lcIdx[q]] = q;
+    }
+    for (size_t q = 0; q < lcIdx.size(); ++q) lcPeer[q] = flatOf[lcIdx[q] ^ 1];
+    V.maskWords = (maxCross + 31) / 32;
+    if (lcIdx.empty()) { lcIdx.push_back(0); lcDist.push_back(0); lcPeer.push_back(0); }
+    I.lcPeer.upload(lcPeer);
+    V.lcPeer = I.lcPeer.p;
     auto nz = [](std::vector<int> v) { if (v.empty()) v.push_back(0); return v; };
     I.llStartLane.upload(nz(net.llStartLane)); I.llEndLane.upload(nz(net.llEndLane)); I.llRoadLink.upload(nz(llRL));
     I.llTurn.upload(turn); I.llType.upload(type);
@@ -1063,6 +1139,8 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.curPhase.alloc(net.nInter()); I.remain.alloc(net.nInter()); I.rlAvail.alloc(std::max(net.nRoadLinks(), 1));
     V.moverCap = (int) std::min<size_t>(P, (size_t) 1 << 22);
     I.mkin.alloc(V.moverCap); I.mids.alloc(V.moverCap); I.mnav.alloc(V.moverCap);
+    I.tail.alloc(nD); I.foeMask.alloc((size_t) std::max(nK, 1) * V.maskWords);
+    V.tail = I.tail.p; V.foeMask = I.foeMask.p;
     V.vehCap = I.P;
     I.vehList0.alloc(P); I.vehList1.alloc(P); I.act0.alloc(nD); I.act1.alloc(nD); I.extra.alloc(nD);
     V.vehList[0] = I.vehList0.p; V.vehList[1] = I.vehList1.p; V.actList[0] = I.act0.p; V.actList[1] = I.act1.p;
@@ -1155,6 +1233,8 @@ void DeviceSim::reset() {
     I.waitHead.fill(0xff); I.waitTail.fill(0xff); I.inserted.fill(0);
     I.pos.fill(0xff); I.waitNext.fill(0xff);
     I.notify.fill(0);
+    I.tail.fill(0xff);   // pos = -1: every drivable empty
+    I.foeMask.fill(0);
     I.curPhase.fill(0);
     CFB_CUDA(cudaMemcpy(I.remain.p, I.phase0Time.data(), I.phase0Time.size() * sizeof(double), cudaMemcpyHostToDevice));
     I.rlAvail.fill(0);
@@ -1170,28 +1250,25 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     Impl &I = *impl_;
     View &V = I.V;
     cudaStream_t s = I.stream;
-    // ---- stage this step's spawn records (pinned ring -> device) ----
-    if (n > I.spawnCap) {
+    // ---- stage this step's spawn records: one H2D copy of [header | records] from a pinned ring ----
+    if (n + 1 > I.spawnCap) {
         CFB_CUDA(cudaStreamSynchronize(s));
-        I.spawnCap = std::max(1024, n * 2);
+        I.spawnCap = std::max(1024, (n + 1) * 2);
         I.spawn.alloc(I.spawnCap);
         I.graphDirty = true;
     }
-    V.spawn = I.spawn.p;
+    V.spawn = I.spawn.p + 1;
     const int r = I.ringIdx;
     I.ringIdx = (I.ringIdx + 1) % Impl::RING;
     CFB_CUDA(cudaEventSynchronize(I.spawnDone[r]));  // ring slot r free again (RING steps in flight at most)
-    if (n > 0) {
-        if (n > I.hSpawnCap[r]) {
-            if (I.hSpawn[r]) cudaFreeHost(I.hSpawn[r]);
-            I.hSpawnCap[r] = std::max(1024, n * 2);
-            CFB_CUDA(cudaMallocHost(&I.hSpawn[r], I.hSpawnCap[r] * sizeof(SpawnRec)));
-        }
-        memcpy(I.hSpawn[r], recs, n * sizeof(SpawnRec));
-        CFB_CUDA(cudaMemcpyAsync(I.spawn.p, I.hSpawn[r], n * sizeof(SpawnRec), cudaMemcpyHostToDevice, s));
+    if (n + 1 > I.hSpawnCap[r]) {
+        if (I.hSpawn[r]) cudaFreeHost(I.hSpawn[r]);
+        I.hSpawnCap[r] = std::max(1024, (n + 1) * 2);
+        CFB_CUDA(cudaMallocHost(&I.hSpawn[r], I.hSpawnCap[r] * sizeof(SpawnRec)));
     }
-    I.hCounts[r] = n;
-    CFB_CUDA(cudaMemcpyAsync(&V.ctrl->spawnCount, &I.hCounts[r], sizeof(int), cudaMemcpyHostToDevice, s));
+    I.hSpawn[r][0].slot = n;
+    if (n > 0) memcpy(I.hSpawn[r] + 1, recs, n * sizeof(SpawnRec));
+    CFB_CUDA(cudaMemcpyAsync(I.spawn.p, I.hSpawn[r], (size_t) (n + 1) * sizeof(SpawnRec), cudaMemcpyHostToDevice, s));
     CFB_CUDA(cudaEventRecord(I.spawnDone[r], s));
     V.par = (int) (steps_ & 1);
     const int TPB = 256;

@@ -7,6 +7,7 @@
 // vehicle / lane / intersection per step runs in device_sim.cu.  There is no CPU path for the
 // simulation: without a CUDA device cfb_engine_create fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <iostream>
@@ -47,6 +48,55 @@ struct Pending {            // a vehicle created this step, waiting for planRout
     int slot, road, routeId, tmplId, flow;
 };
 
+// Open-addressing hash map priority -> slot: Engine::checkPriority (engine.cpp:601) is on the
+// per-spawn path; the reference's ordered std::map is only materialised (sorted) when an API call
+// needs vehiclePool order.
+class PriorityMap {
+public:
+    PriorityMap() { rehash(1 << 12); }
+    bool contains(int k) const { return find(k) >= 0; }
+    void insert(int k, int v) {
+        if ((used_ + 1) * 2 > cap_) rehash(cap_ * 2);
+        size_t i = hash(k);
+        while (state_[i] == 1) i = (i + 1) & (cap_ - 1);
+        if (state_[i] == 0) ++used_;
+        state_[i] = 1; key_[i] = k; val_[i] = v; ++size_;
+    }
+    void erase(int k) {
+        long i = find(k);
+        if (i >= 0) { state_[i] = 2; --size_; }
+    }
+    void clear() { std::fill(state_.begin(), state_.end(), 0); used_ = size_ = 0; }
+    size_t size() const { return size_; }
+    // (priority, slot) pairs in ascending priority = vehiclePool iteration order
+    std::vector<std::pair<int, int>> sorted() const {
+        std::vector<std::pair<int, int>> out;
+        out.reserve(size_);
+        for (size_t i = 0; i < cap_; ++i) if (state_[i] == 1) out.emplace_back(key_[i], val_[i]);
+        std::sort(out.begin(), out.end());
+        return out;
+    }
+private:
+    size_t hash(int k) const { return ((uint32_t) k * 2654435761u) & (cap_ - 1); }
+    long find(int k) const {
+        size_t i = hash(k);
+        while (state_[i] != 0) {
+            if (state_[i] == 1 && key_[i] == k) return (long) i;
+            i = (i + 1) & (cap_ - 1);
+        }
+        return -1;
+    }
+    void rehash(size_t n) {
+        std::vector<int> ok = std::move(key_), ov = std::move(val_);
+        std::vector<uint8_t> os = std::move(state_);
+        cap_ = n; key_.assign(n, 0); val_.assign(n, 0); state_.assign(n, 0); used_ = size_ = 0;
+        for (size_t i = 0; i < os.size(); ++i) if (os[i] == 1) insert(ok[i], ov[i]);
+    }
+    std::vector<int> key_, val_;
+    std::vector<uint8_t> state_;
+    size_t cap_ = 0, used_ = 0, size_ = 0;
+};
+
 class HostEngine {
 public:
     std::string error;
@@ -66,8 +116,10 @@ public:
     double cumulativeTravelTime = 0;
     std::vector<SlotInfo> slots;
     std::vector<int> freeSlots;
-    std::map<int, int> pool;                                 // priority -> slot (vehiclePool, engine.h:25)
-    std::unordered_map<uint64_t, int> idToSlot;
+    PriorityMap pool;                                        // priority -> slot (vehiclePool, engine.h:25)
+    std::unordered_map<uint64_t, int> idToSlot;              // built lazily (get_leader)
+    bool idMapValid = false;
+    long long hostGenNs = 0, hostEnqueueNs = 0;              // host time spent generating spawns / enqueuing
     std::vector<Pending> pending;
     std::vector<SpawnRec> batch;
     std::vector<std::string> laneIds;
@@ -177,16 +229,20 @@ public:
         if (!finishedDirty) return;
         std::vector<FinRec> fin;
         dev->drainFinished(fin);
+        // deterministic accumulation order for the travel-time sum (ring order is atomics order)
+        std::sort(fin.begin(), fin.end(), [this](const FinRec &a, const FinRec &b) {
+            return a.step != b.step ? a.step < b.step : slots[a.slot].priority < slots[b.slot].priority;
+        });
         for (const FinRec &f : fin) {
             SlotInfo &s = slots[f.slot];
             if (!s.live) continue;
             finishedCnt += 1;
             cumulativeTravelTime += f.step * interval - s.enterTime;
             pool.erase(s.priority);
-            idToSlot.erase(key(s.flow, s.index));
             s.live = false;
             freeSlots.push_back(f.slot);
         }
+        if (!fin.empty()) idMapValid = false;
         finishedDirty = false;
         checkDevice();
     }
@@ -206,10 +262,10 @@ public:
         int priority;
         for (;;) {
             priority = (int) rnd();
-            if (!pool.count(priority)) break;
+            if (!pool.contains(priority)) break;
             // the candidate may belong to a vehicle that already left the network on the device
             drain();
-            if (!pool.count(priority)) break;
+            if (!pool.contains(priority)) break;
         }
         (void) rnd();  // threadIndex = rnd() % threadNum (engine.cpp:606): drawn, not needed here
         const int slot = allocSlot();
@@ -219,14 +275,15 @@ public:
         s.priority = priority;
         s.enterTime = currentTime();
         s.live = true;
-        pool.emplace(priority, slot);
-        idToSlot[key(flow, index)] = slot;
+        pool.insert(priority, slot);
+        idMapValid = false;
         pending.push_back({slot, firstRoad, routeId, tmplId, flow});
         return slot;
     }
 
     // Engine::nextStep engine.cpp:566-594 (host part: P0 spawn, P1 planRoute; the rest is device work)
     void nextStep() {
+        const auto t0 = std::chrono::steady_clock::now();
         for (size_t i = 0; i < flows.size(); ++i) {  // Flow::nextStep flow.cpp:6-22
             FlowRun &f = flows[i];
             if (!f.valid) continue;
@@ -263,7 +320,7 @@ public:
                     }
                     SlotInfo &s = slots[p.slot];
                     pool.erase(s.priority);
-                    idToSlot.erase(key(s.flow, s.index));
+                    idMapValid = false;
                     s.live = false;
                     freeSlots.push_back(p.slot);
                 }
@@ -274,7 +331,11 @@ public:
         if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
         if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
         dev->ensureSlotCapacity((int) slots.size());
+        const auto t1 = std::chrono::steady_clock::now();
         dev->step(batch.data(), (int) batch.size());
+        const auto t2 = std::chrono::steady_clock::now();
+        hostGenNs += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+        hostEnqueueNs += std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
         h2dBytes += (long long) batch.size() * sizeof(SpawnRec) + sizeof(int);
         finishedDirty = true;
         step += 1;
@@ -289,6 +350,7 @@ public:
         freeSlots.clear();
         pool.clear();
         idToSlot.clear();
+        idMapValid = false;
         pending.clear();
         finishedCnt = 0;
         cumulativeTravelTime = 0;
@@ -300,6 +362,17 @@ public:
         step = 0;
         finishedDirty = false;
         if (resetRnd) rnd.seed(seed);
+    }
+
+    int slotOfId(int flow, int index) {
+        if (!idMapValid) {
+            idToSlot.clear();
+            for (size_t s = 0; s < slots.size(); ++s)
+                if (slots[s].live) idToSlot[key(slots[s].flow, slots[s].index)] = (int) s;
+            idMapValid = true;
+        }
+        auto it = idToSlot.find(key(flow, index));
+        return it == idToSlot.end() ? -1 : it->second;
     }
 
     cfb_vehicle_ref refOf(int slot) const { return cfb_vehicle_ref{slots[slot].flow, slots[slot].index}; }
@@ -377,7 +450,7 @@ double cfb_get_average_travel_time(cfb_engine *e) {
         h.drain();
         double tt = h.cumulativeTravelTime;
         int n = h.finishedCnt;
-        for (auto &kv : h.pool) {  // priority order, like vehiclePool (engine.cpp:685-689)
+        for (auto &kv : h.pool.sorted()) {  // priority order, like vehiclePool (engine.cpp:685-689)
             tt += h.currentTime() - h.slots[kv.second].enterTime;
             n++;
         }
@@ -432,7 +505,7 @@ int64_t cfb_get_vehicles(cfb_engine *e, int include_waiting, cfb_vehicle_ref *id
         if (!include_waiting) return cfb_get_vehicle_speed(e, ids, nullptr, nullptr, cap);
         h.drain();
         int64_t n = 0;
-        for (auto &kv : h.pool) {
+        for (auto &kv : h.pool.sorted()) {
             if (n < cap && ids) ids[n] = h.refOf(kv.second);
             ++n;
         }
@@ -455,9 +528,9 @@ int cfb_get_leader(cfb_engine *e, cfb_vehicle_ref v, cfb_vehicle_ref *leader, in
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
         h.drain();
-        auto it = h.idToSlot.find(cfb::HostEngine::key(v.flow, v.index));
-        if (it == h.idToSlot.end()) throw std::runtime_error("Vehicle not found");
-        int ls = h.dev->leaderSlotOf(it->second);
+        const int vs = h.slotOfId(v.flow, v.index);
+        if (vs < 0) throw std::runtime_error("Vehicle not found");
+        int ls = h.dev->leaderSlotOf(vs);
         *found = ls >= 0;
         if (ls >= 0) *leader = h.refOf(ls);
     )
@@ -588,5 +661,11 @@ int64_t cfb_num_drivables(const cfb_engine *e) { return e->h.dev->numDrivables()
 extern "C" int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2h) {
     if (h2d) *h2d = e->h.h2dBytes;
     if (d2h) *d2h = e->h.d2hBytes;
+    return CFB_OK;
+}
+
+extern "C" int cfb_host_times(const cfb_engine *e, double *gen_ms, double *enqueue_ms) {
+    if (gen_ms) *gen_ms = e->h.hostGenNs * 1e-6;
+    if (enqueue_ms) *enqueue_ms = e->h.hostEnqueueNs * 1e-6;
     return CFB_OK;
 }

@@ -206,6 +206,7 @@ public:
     }
     int64_t vehicleSteps() { return cfb_vehicle_steps(e_); }
     int64_t numDrivables() const { return cfb_num_drivables(e_); }
+    py::tuple hostTimes() { double a = 0, b = 0; cfb_host_times(e_, &a, &b); return py::make_tuple(a, b); }
     py::tuple transferBytes() { int64_t a = 0, b = 0; cfb_transfer_bytes(e_, &a, &b); return py::make_tuple(a, b); }
     void synchronize() {
         py::gil_scoped_release rel;
@@ -259,6 +260,7 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("vehicle_steps", &Engine::vehicleSteps)
         .def("transfer_bytes", &Engine::transferBytes)
         .def("num_drivables", [](Engine &e) { return e.numDrivables(); })
+        .def("host_times", &Engine::hostTimes)
         .def("synchronize", &Engine::synchronize);
     m.attr("__version__") = "b200-dev";
 }

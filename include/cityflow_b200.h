@@ -112,6 +112,8 @@ int cfb_timed_steps(cfb_engine *e, int n, int flush_l2, double *ms, int64_t *veh
 int64_t cfb_vehicle_steps(cfb_engine *e);
 /* bytes copied host->device (spawn records) and device->host (control block reads) so far */
 int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2h);
+/* cumulative host time (ms) spent generating spawn records / enqueuing GPU work in cfb_next_step */
+int cfb_host_times(const cfb_engine *e, double *gen_ms, double *enqueue_ms);
 int cfb_enable_kernel_timing(cfb_engine *e, int on);
 int cfb_kernel_times(cfb_engine *e, double ms_out[5], int64_t *steps_timed);
 int cfb_synchronize(cfb_engine *e);
