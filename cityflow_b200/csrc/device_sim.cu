@@ -86,7 +86,16 @@ struct Ctrl {
     int nExtra;
     int pad;
     unsigned long long vehicleSteps;  // sum over steps of activeVehicleCount after the step (the bench metric)
+    unsigned long long dbg[8];        // CFB_DEBUG_COUNTERS builds: in-kernel cycle / trip-count maxima
 };
+
+#ifdef CFB_DEBUG_COUNTERS
+#define CFB_DBG_MAX(i, v) atomicMax(&V.ctrl->dbg[i], (unsigned long long) (v))
+#define CFB_DBG_ADD(i, v) atomicAdd(&V.ctrl->dbg[i], (unsigned long long) (v))
+#else
+#define CFB_DBG_MAX(i, v)
+#define CFB_DBG_ADD(i, v)
+#endif
 
 constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
 constexpr int PLAN_LOOKAHEAD_END = -1;
@@ -104,6 +113,7 @@ struct View {
     const int *laneOutBeg, *laneOutLinks;
     const int *llStartLane, *llEndLane, *llRoadLink;
     const unsigned char *llTurn, *llType;
+    const int4 *linkInfo;   // per laneLink {roadLink, endLane, crossBeg, turn | type << 8}
     const int *llCrossBeg, *lcIdx;
     const double *lcDist;
     const int *csLink;
@@ -140,6 +150,7 @@ struct View {
     int2 *vehList[2];   // {position, drivable} of every running vehicle
     int *actList[2];    // occupied drivables
     int *extraList;     // empty drivables that receive entrants this step
+    unsigned *dbgCyc, *dbgPath;   // CFB_DEBUG_COUNTERS builds: per-position cycles / path bits of k_control
     Ctrl *ctrl;
     const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
 };
@@ -481,7 +492,8 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
     const int4 fid = V.ids[fp];
     foeSlot = fid.x;
     const int myLink = V.csLink[cs], foeLink = V.csLink[cs ^ 1];
-    const int t1 = V.llType[myLink], t2 = V.llType[foeLink];
+    const int f1 = V.linkInfo[myLink].w, f2 = V.linkInfo[foeLink].w;
+    const int t1 = f1 >> 8, t2 = f2 >> 8;
     const double d1 = distOnLane - distanceToLaneLinkStart, d2 = f.dist;
     if (!canYield(T, mySpeed, d1)) return true;
     const DTmpl &FT = V.tmpl[fid.y];
@@ -494,8 +506,8 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
         } else {
             const double dt = V.dt;
             if (d2 > 0) {
-                int foeSteps = reachSteps(foeSpeed, d2, V.llTurn[foeLink] ? FT.turnSpeed : FT.maxSpeed, FT.usualPosAcc, dt);
-                int mySteps = reachSteps(mySpeed, d1, V.llTurn[myLink] ? T.turnSpeed : T.maxSpeed, T.usualPosAcc, dt);
+                int foeSteps = reachSteps(foeSpeed, d2, (f2 & 1) ? FT.turnSpeed : FT.maxSpeed, FT.usualPosAcc, dt);
+                int mySteps = reachSteps(mySpeed, d1, (f1 & 1) ? T.turnSpeed : T.maxSpeed, T.usualPosAcc, dt);
                 if (foeSteps > mySteps) yield = -1;
                 else if (t1 < t2) yield = 1;
                 else if (foeSteps < mySteps) yield = 1;
@@ -521,7 +533,9 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
             return b < 0 ? -1 : V.pos[b];
         };
         int fast = fp, slow = fp;
+        int trips = 0;
         while (fast >= 0) {
+            ++trips;
             int fb = blockerOf(fast);
             if (fb < 0) break;
             slow = blockerOf(slow);
@@ -538,21 +552,36 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
 // k_control: one thread per running vehicle (grid-stride over the position list).
 // Vehicle::getNextSpeed vehicle.cpp:308-335, getCarFollowSpeed :212-238, getIntersectionRelatedSpeed
 // :337-376, Engine::vehicleControl engine.cpp:188-251, Vehicle::setDeltaDistance vehicle.cpp:49-68.
-__global__ void __launch_bounds__(128) k_control(View V) {
+__global__ void __launch_bounds__(512, 2) k_control(View V) {
     const int cpar = V.par;
     const int nVeh = min(V.ctrl->nVeh[cpar], V.vehCap);
     const double dt = V.dt;
     const int epoch = V.ctrl->step + 1;
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nVeh; it += gridDim.x * blockDim.x) {
+        const long long tStart = clock64();
         const int2 vd = V.vehList[cpar][it];
         const int p = vd.x, d = vd.y;
-        const double dLen = V.drvLength[d], dMax = V.drvMaxSpeed[d];
-        const bool onLink = d >= V.nLanes;
+        // ---- load phase: everything the branches below may need is requested up front with
+        // clamped (always valid) indices, so the dependent-load depth is 3 levels, not one
+        // round trip per branch ----
         const double2 kk = V.kin[p];
-        const double dis = kk.x, speed = kk.y;
         const int4 idv = V.ids[p];
         const int4 nv = V.nav[p];
+        const int lp = V.leader[p];
+        const double g = V.gap[p];
+        const double dLen = V.drvLength[d], dMax = V.drvMaxSpeed[d];
+        const bool onLink = d >= V.nLanes;
+        const double dis = kk.x, speed = kk.y;
+        const int lpc = lp >= 0 ? lp : p;
+        const double leaderSpeed = V.kin[lpc].y;
+        const int leaderTmpl = V.ids[lpc].y;
+        const int llc = idv.w >= V.nLanes ? idv.w - V.nLanes : (onLink ? d - V.nLanes : 0);  // the laneLink of interest
+        const int4 li = V.linkInfo[llc];          // {roadLink, endLane, crossBeg, turn | type << 8}
+        const unsigned mask0 = V.foeMask[llc * V.maskWords];
         const DTmpl &T = V.tmpl[idv.y];
+        const DTmpl &LT = V.tmpl[leaderTmpl];
+        const unsigned char linkGreen = V.rlAvail[li.x];
+        const Tail endTail = V.tail[li.y];
         const int planBase = nv.x + 1;
 
         double v = T.maxSpeed;
@@ -560,14 +589,10 @@ __global__ void __launch_bounds__(128) k_control(View V) {
         v = min2(v, dMax);
         // ---- car following ----
         {
-            const int lp = V.leader[p];
             double cf;
             if (lp < 0) {
                 cf = T.maxSpeed;
             } else {
-                const double leaderSpeed = V.kin[lp].y;
-                const DTmpl &LT = V.tmpl[V.ids[lp].y];
-                const double g = V.gap[p];
                 cf = noCollisionSpeed(leaderSpeed, LT.maxNegAcc, speed, T.maxNegAcc, g, dt, 0);
                 double assumeDecel = 0;
                 if (speed > leaderSpeed) assumeDecel = speed - leaderSpeed;
@@ -576,19 +601,21 @@ __global__ void __launch_bounds__(128) k_control(View V) {
             }
             v = min2(v, cf);
         }
+        const long long tCf = clock64(); (void) tCf;
+        unsigned pathBits = (lp >= 0 ? 1u : 0u); (void) pathBits;
         // ---- intersection logic ----
         int newBlocker = -1;
         const int nd0 = idv.w;
         if (onLink || (nd0 >= V.nLanes && dLen - dis <= T.approachDist)) {
+            pathBits |= 2u;
             double s = T.maxSpeed;
             int ll = -1;
             bool done = false;
             if (nd0 >= V.nLanes) {
                 ll = nd0 - V.nLanes;
-                bool blocked = !V.rlAvail[V.llRoadLink[ll]];
+                bool blocked = !linkGreen;
                 if (!blocked) {  // Lane::canEnter roadnet.cpp:437-445
-                    const Tail t = V.tail[V.llEndLane[ll]];
-                    if (t.pos >= 0) blocked = !(t.dis > t.len + T.len || t.speed >= 2);
+                    if (endTail.pos >= 0) blocked = !(endTail.dis > endTail.len + T.len || endTail.speed >= 2);
                 }
                 if (blocked) {
                     if (0.5 * speed * speed / T.maxNegAcc > dLen - dis) {
@@ -598,17 +625,17 @@ __global__ void __launch_bounds__(128) k_control(View V) {
                         done = true;
                     }
                 }
-                if (!done && V.llTurn[ll]) s = min2(s, T.turnSpeed);
+                if (!done && (li.w & 1)) s = min2(s, T.turnSpeed);
             }
             if (!done) {
                 if (ll < 0 && onLink) ll = d - V.nLanes;
                 const double toStart = onLink ? dis : -(dLen - dis);
                 // crosses of the link in ascending distance; only those with a notified foe matter
                 // (a cross without foe passes, roadnet.cpp:613), and k_notify marked exactly those
-                const int cb = V.llCrossBeg[ll];
+                const int cb = li.z;
                 bool stop = false;
                 for (int wd = 0; wd < V.maskWords && !stop; ++wd) {
-                    unsigned bits = V.foeMask[ll * V.maskWords + wd];
+                    unsigned bits = wd == 0 ? mask0 : V.foeMask[ll * V.maskWords + wd];
                     while (bits) {
                         const int b = __ffs(bits) - 1;
                         bits &= bits - 1;
@@ -618,6 +645,7 @@ __global__ void __launch_bounds__(128) k_control(View V) {
                         const int cs = V.lcIdx[q];
                         const Notify f = V.notify[cs ^ 1];
                         if (f.epoch != epoch) continue;
+                        pathBits |= 4u;
                         int foeSlot;
                         if (!canPass(V, cs, f, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
                             s = min2(s, stopBeforeSpeed(T, speed, dOn - toStart - T.yieldDistance, dt));
@@ -659,6 +687,12 @@ __global__ void __launch_bounds__(128) k_control(View V) {
         }
         V.nkin[p] = make_double2(nd, v);
         V.nbuf[p] = make_int2(newDrv, newBlocker);
+#ifdef CFB_DEBUG_COUNTERS
+        V.dbgCyc[p] = (unsigned) (clock64() - tStart);
+        V.dbgPath[p] = pathBits | ((unsigned) (tCf - tStart) >> 6 << 8);
+#endif
+        (void) tStart;
+        if (newDrv >= 0) pathBits |= 8u;
         if (newDrv >= 0) {  // Engine::pushBuffer (engine.cpp:247-249)
             int m;
             {  // one atomic per warp for the movers of this warp
@@ -972,6 +1006,8 @@ struct DeviceSim::Impl {
     DevBuf<int2> finSlots, vehList0, vehList1;
     DevBuf<int> act0, act1, extra, lcPeer;
     DevBuf<Tail> tail;
+    DevBuf<unsigned> dbgCyc, dbgPath;
+    DevBuf<int4> linkInfo;
     DevBuf<unsigned> foeMask;
     DevBuf<int4> ids, nav, slotInfo, mids, mnav;
     DevBuf<int2> nbuf;
@@ -1001,6 +1037,7 @@ struct DeviceSim::Impl {
 
     int slotCap = 0;
     int numSMs = 148;
+    int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
     bool useGraph = true, graphDirty = false;
     cudaGraphExec_t graphExec[2] = {nullptr, nullptr};
 
@@ -1106,6 +1143,12 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     auto nz = [](std::vector<int> v) { if (v.empty()) v.push_back(0); return v; };
     I.llStartLane.upload(nz(net.llStartLane)); I.llEndLane.upload(nz(net.llEndLane)); I.llRoadLink.upload(nz(llRL));
     I.llTurn.upload(turn); I.llType.upload(type);
+    {
+        std::vector<int4> li(std::max(nK, 1), make_int4(0, 0, 0, 0));
+        for (int k = 0; k < nK; ++k) li[k] = make_int4(net.llRoadLink[k], net.llEndLane[k], lcb[k], (int) turn[k] | ((int) type[k] << 8));
+        I.linkInfo.upload(li);
+        V.linkInfo = I.linkInfo.p;
+    }
     I.llCrossBeg.upload(lcb); I.lcIdx.upload(lcIdx); I.lcDist.upload(lcDist); I.csLink.upload(csLink);
     I.interPhaseBeg.upload(net.interPhaseBeg); I.interRLBeg.upload(net.interRoadLinkBeg);
     I.phaseAvailBeg.upload(nz(net.phaseAvailBeg)); I.rlInter.upload(nz(net.rlInter));
@@ -1141,6 +1184,8 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.mkin.alloc(V.moverCap); I.mids.alloc(V.moverCap); I.mnav.alloc(V.moverCap);
     I.tail.alloc(nD); I.foeMask.alloc((size_t) std::max(nK, 1) * V.maskWords);
     V.tail = I.tail.p; V.foeMask = I.foeMask.p;
+    I.dbgCyc.alloc(P); I.dbgPath.alloc(P); I.dbgCyc.fill(0); I.dbgPath.fill(0);
+    V.dbgCyc = I.dbgCyc.p; V.dbgPath = I.dbgPath.p;
     V.vehCap = I.P;
     I.vehList0.alloc(P); I.vehList1.alloc(P); I.act0.alloc(nD); I.act1.alloc(nD); I.extra.alloc(nD);
     V.vehList[0] = I.vehList0.p; V.vehList[1] = I.vehList1.p; V.actList[0] = I.act0.p; V.actList[1] = I.act1.p;
@@ -1274,20 +1319,27 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     const int TPB = 256;
     const int gLaneRL = (std::max(V.nLanes, V.nRL) + TPB - 1) / TPB;
     // list-driven kernels: fixed grids sized to the machine (grid-stride loops inside)
-    const int gWarp = I.numSMs * 8;        // 8 warps per block -> 64 warps per SM
-    const int gVeh = I.numSMs * 8;         // x128 threads
+    // exactly one resident wave per kernel (occupancy x #SM blocks): a second, partial wave would
+    // double the latency of these dependent-load-bound kernels
+    if (!I.gridNotify) {
+        int b = 0;
+        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_notify, TPB, 0)); I.gridNotify = std::max(b, 1) * I.numSMs;
+        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move, TPB, 0)); I.gridMove = std::max(b, 1) * I.numSMs;
+        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_leader, TPB, 0)); I.gridLeader = std::max(b, 1) * I.numSMs;
+        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_control, 512, 0)); I.gridControl = std::max(b, 1) * I.numSMs;
+    }
     const bool tm = I.timing;
     auto launchAll = [&](bool withEvents) {
         if (withEvents) cudaEventRecord(I.ev[0], s);
         k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[1], s);
-        k_notify<<<gWarp, TPB, 0, s>>>(V);
+        k_notify<<<I.gridNotify, TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[2], s);
-        k_control<<<gVeh, 128, 0, s>>>(V);
+        k_control<<<I.gridControl, 512, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[3], s);
-        k_move<<<gWarp, TPB, 0, s>>>(V);
+        k_move<<<I.gridMove, TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[4], s);
-        k_leader<<<gWarp, TPB, 0, s>>>(V);
+        k_leader<<<I.gridLeader, TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[5], s);
     };
     if (tm || !I.useGraph) {
@@ -1354,6 +1406,19 @@ double DeviceSim::collectTimedMs() {
     }
     I.stepEvUsed = 0;
     return total;
+}
+int DeviceSim::debugArrays(unsigned *cyc, unsigned *path) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    CFB_CUDA(cudaMemcpy(cyc, I.dbgCyc.p, (size_t) I.P * 4, cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(path, I.dbgPath.p, (size_t) I.P * 4, cudaMemcpyDeviceToHost));
+    I.dbgCyc.fill(0); I.dbgPath.fill(0);
+    return I.P;
+}
+void DeviceSim::debugCounters(unsigned long long out[8], bool clear) {
+    readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
+    for (int k = 0; k < 8; ++k) out[k] = impl_->hCtrl->dbg[k];
+    if (clear) CFB_CUDA(cudaMemsetAsync(impl_->V.ctrl->dbg, 0, sizeof(unsigned long long) * 8, impl_->stream));
 }
 unsigned long long DeviceSim::vehicleSteps() {
     readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);

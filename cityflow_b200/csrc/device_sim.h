@@ -99,7 +99,9 @@ public:
     void flushL2();                 // 256 MiB memset on the engine stream
     void markTimed();               // record an event; brackets are (even, odd) pairs
     double collectTimedMs();        // sync; sum of bracket durations; clears the brackets
-    unsigned long long vehicleSteps();  // device-side sum of the vehicle count after every step
+    unsigned long long vehicleSteps();
+    void debugCounters(unsigned long long out[8], bool clear);
+    int debugArrays(unsigned *cyc, unsigned *path);   // numPositions() entries each  // CFB_DEBUG_COUNTERS builds only  // device-side sum of the vehicle count after every step
     KernelTimes kernelTimes();
     long long launchesDone() const { return launches_; }
     int numPositions() const;

@@ -669,3 +669,15 @@ extern "C" int cfb_host_times(const cfb_engine *e, double *gen_ms, double *enque
     if (enqueue_ms) *enqueue_ms = e->h.hostEnqueueNs * 1e-6;
     return CFB_OK;
 }
+
+extern "C" int cfb_debug_counters(cfb_engine *e, uint64_t out[8], int clear) {
+    unsigned long long t[8];
+    e->h.dev->debugCounters(t, clear != 0);
+    for (int k = 0; k < 8; ++k) out[k] = t[k];
+    return CFB_OK;
+}
+
+extern "C" int64_t cfb_debug_arrays(cfb_engine *e, uint32_t *cyc, uint32_t *path, int64_t cap) {
+    if (cap < e->h.dev->numPositions()) return e->h.dev->numPositions();
+    return e->h.dev->debugArrays(cyc, path);
+}

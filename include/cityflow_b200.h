@@ -114,6 +114,10 @@ int64_t cfb_vehicle_steps(cfb_engine *e);
 int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2h);
 /* cumulative host time (ms) spent generating spawn records / enqueuing GPU work in cfb_next_step */
 int cfb_host_times(const cfb_engine *e, double *gen_ms, double *enqueue_ms);
+/* in-kernel debug maxima (all zero unless the library was built with -DCFB_DEBUG_COUNTERS) */
+int cfb_debug_counters(cfb_engine *e, uint64_t out[8], int clear);
+/* per-position cycle / path-bit samples of the control kernel (debug builds); returns #positions */
+int64_t cfb_debug_arrays(cfb_engine *e, uint32_t *cyc, uint32_t *path, int64_t cap);
 int cfb_enable_kernel_timing(cfb_engine *e, int on);
 int cfb_kernel_times(cfb_engine *e, double ms_out[5], int64_t *steps_timed);
 int cfb_synchronize(cfb_engine *e);
