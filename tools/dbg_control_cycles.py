@@ -1,5 +1,5 @@
 import sys, ctypes, tempfile, numpy as np
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cityflow_b200 import scenario
 from cityflow_b200.capi import CEngine
 d=tempfile.mkdtemp()
