@@ -21,7 +21,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -171,18 +170,13 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    from cityflow_b200.distutil import Ranks
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    ranks = Ranks("nccl", torch.device("cuda", local))
+    world, rank, dist = ranks.world, ranks.rank, ranks.dist
 
     import cityflow  # our drop-in module (repo root)
     tmp = tempfile.TemporaryDirectory()
@@ -192,24 +186,11 @@ def run_ours(args):
     load_s = time.perf_counter() - t0
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        ranks.barrier()
         torch.cuda.synchronize()
         eng.synchronize()
 
-    def reduce_max(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def reduce_sum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    reduce_max, reduce_sum = ranks.max, ranks.sum
 
     # ---- scenario preparation + warm-up (clock sampling starts here: the timed regions are sub-second) ----
     sampler = ClockSampler(local, args.clock_ms)
@@ -332,8 +313,7 @@ def run_ours(args):
         print(json.dumps(line))
     del eng
     tmp.cleanup()
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 def main():

@@ -11,7 +11,7 @@ _HERE = _os.path.dirname(_os.path.abspath(__file__))
 LIB_PATH = _os.path.join(_HERE, "libcityflow_b200.so")
 
 try:
-    from ._cityflow_b200 import Engine, __version__  # noqa: F401
+    from ._cityflow_b200 import Archive, Engine, __version__  # noqa: F401
 except ImportError as _e:  # extension not built: fail loudly at use, not silently
     _IMPORT_ERROR = _e
 
@@ -23,9 +23,6 @@ except ImportError as _e:  # extension not built: fail loudly at use, not silent
 
     __version__ = "unbuilt"
 
-
-class Archive:
-    """Placeholder for ``cityflow.Archive`` (snapshot/restore is a SURVEY.md §8f 'next' row)."""
-
-    def __init__(self, *a, **k):
-        raise RuntimeError("cityflow_b200: Archive (snapshot/load/dump) is not implemented yet")
+    class Archive:  # type: ignore
+        def __init__(self, *a, **k):
+            raise RuntimeError("cityflow_b200: the CUDA extension is not built")

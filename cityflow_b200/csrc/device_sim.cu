@@ -84,7 +84,7 @@ struct Ctrl {
     int nVeh[2];     // work lists, double-buffered on step parity
     int nAct[2];
     int nExtra;
-    int pad;
+    int nCustom;     // outstanding set_vehicle_speed requests (Vehicle::setCustomSpeed, vehicle.h:128)
     unsigned long long vehicleSteps;  // sum over steps of activeVehicleCount after the step (the bench metric)
     unsigned long long dbg[8];        // CFB_DEBUG_COUNTERS builds: in-kernel cycle / trip-count maxima
 };
@@ -150,6 +150,8 @@ struct View {
     int2 *vehList[2];   // {position, drivable} of every running vehicle
     int *actList[2];    // occupied drivables
     int *extraList;     // empty drivables that receive entrants this step
+    double *cust;        // per position: custom speed for the coming step (NaN = none)
+    double *slotCust;    // per slot: custom speed of a vehicle still in a waiting queue
     unsigned *dbgCyc, *dbgPath;   // CFB_DEBUG_COUNTERS builds: per-position cycles / path bits of k_control
     Ctrl *ctrl;
     const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
@@ -335,6 +337,10 @@ __global__ void __launch_bounds__(256) k_ingest(View V) {
                     V.leader[p] = -1;
                     ins = 3;  // admitted to an empty lane: leader search runs in k_notify
                     V.actList[cpar][atomicAdd(&V.ctrl->nAct[cpar], 1)] = i;
+                }
+                if (V.ctrl->nCustom > 0) {
+                    const double cs = V.slotCust[h];
+                    if (cs == cs) { V.cust[p] = cs; V.slotCust[h] = __longlong_as_double(-1LL); }
                 }
                 V.count[i] = n + 1;
                 V.pos[h] = p;
@@ -583,6 +589,16 @@ __global__ void __launch_bounds__(512, 2) k_control(View V) {
         const unsigned char linkGreen = V.rlAvail[li.x];
         const Tail endTail = V.tail[li.y];
         const int planBase = nv.x + 1;
+        double custom = 0;
+        bool hasCustom = false;
+        if (V.ctrl->nCustom > 0) {  // uniform; zero cost when set_vehicle_speed is not in use
+            custom = V.cust[p];
+            hasCustom = custom == custom;
+            if (hasCustom) {  // consumed this step (Vehicle::update clears it, vehicle.cpp:120-122)
+                V.cust[p] = __longlong_as_double(-1LL);
+                atomicSub(&V.ctrl->nCustom, 1);
+            }
+        }
 
         double v = T.maxSpeed;
         v = min2(v, speed + T.maxPosAcc * dt);
@@ -591,7 +607,9 @@ __global__ void __launch_bounds__(512, 2) k_control(View V) {
         {
             double cf;
             if (lp < 0) {
-                cf = T.maxSpeed;
+                cf = hasCustom ? custom : T.maxSpeed;
+            } else if (hasCustom) {
+                cf = min2(custom, noCollisionSpeed(leaderSpeed, LT.maxNegAcc, speed, T.maxNegAcc, g, dt, 0));
             } else {
                 cf = noCollisionSpeed(leaderSpeed, LT.maxNegAcc, speed, T.maxNegAcc, g, dt, 0);
                 double assumeDecel = 0;
@@ -1001,7 +1019,7 @@ struct DeviceSim::Impl {
     DevBuf<DTmpl> tmpl;
     // dynamic
     DevBuf<double2> kin, nkin, mkin;
-    DevBuf<double> gap, remain;
+    DevBuf<double> gap, remain, cust, slotCust;
     DevBuf<int> leader, count, pos, waitHead, waitTail, waitNext, curPhase, entCnt, ent, scratchI;
     DevBuf<int2> finSlots, vehList0, vehList1;
     DevBuf<int> act0, act1, extra, lcPeer;
@@ -1182,6 +1200,7 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.curPhase.alloc(net.nInter()); I.remain.alloc(net.nInter()); I.rlAvail.alloc(std::max(net.nRoadLinks(), 1));
     V.moverCap = (int) std::min<size_t>(P, (size_t) 1 << 22);
     I.mkin.alloc(V.moverCap); I.mids.alloc(V.moverCap); I.mnav.alloc(V.moverCap);
+    I.cust.alloc(P); I.cust.fill(0xff); V.cust = I.cust.p;
     I.tail.alloc(nD); I.foeMask.alloc((size_t) std::max(nK, 1) * V.maskWords);
     V.tail = I.tail.p; V.foeMask = I.foeMask.p;
     I.dbgCyc.alloc(P); I.dbgPath.alloc(P); I.dbgCyc.fill(0); I.dbgPath.fill(0);
@@ -1256,18 +1275,21 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     CFB_CUDA(cudaStreamSynchronize(I.stream));
     DevBuf<int> npos, nnext;
     DevBuf<int4> ninfo;
-    npos.alloc(cap); nnext.alloc(cap); ninfo.alloc(cap);
-    npos.fill(0xff); nnext.fill(0xff); ninfo.fill(0);
+    DevBuf<double> ncust;
+    npos.alloc(cap); nnext.alloc(cap); ninfo.alloc(cap); ncust.alloc(cap);
+    npos.fill(0xff); nnext.fill(0xff); ninfo.fill(0); ncust.fill(0xff);
     if (I.slotCap) {
         CFB_CUDA(cudaMemcpy(npos.p, I.pos.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
         CFB_CUDA(cudaMemcpy(nnext.p, I.waitNext.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
         CFB_CUDA(cudaMemcpy(ninfo.p, I.slotInfo.p, I.slotCap * sizeof(int4), cudaMemcpyDeviceToDevice));
+        CFB_CUDA(cudaMemcpy(ncust.p, I.slotCust.p, I.slotCap * sizeof(double), cudaMemcpyDeviceToDevice));
     }
     std::swap(I.pos.p, npos.p); std::swap(I.pos.n, npos.n);
     std::swap(I.waitNext.p, nnext.p); std::swap(I.waitNext.n, nnext.n);
     std::swap(I.slotInfo.p, ninfo.p); std::swap(I.slotInfo.n, ninfo.n);
+    std::swap(I.slotCust.p, ncust.p); std::swap(I.slotCust.n, ncust.n);
     I.slotCap = cap;
-    I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p;
+    I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p;
     I.graphDirty = true;
 }
 
@@ -1276,7 +1298,7 @@ void DeviceSim::reset() {
     CFB_CUDA(cudaStreamSynchronize(I.stream));
     I.count.fill(0); I.entCnt.fill(0);
     I.waitHead.fill(0xff); I.waitTail.fill(0xff); I.inserted.fill(0);
-    I.pos.fill(0xff); I.waitNext.fill(0xff);
+    I.pos.fill(0xff); I.waitNext.fill(0xff); I.cust.fill(0xff); I.slotCust.fill(0xff);
     I.notify.fill(0);
     I.tail.fill(0xff);   // pos = -1: every drivable empty
     I.foeMask.fill(0);
@@ -1568,6 +1590,155 @@ void DeviceSim::debugDump(std::vector<DebugRec> &out) {
             r.gap = leader[p] >= 0 ? gap[p] : 0.0;
             out.push_back(r);
         }
+    }
+}
+
+// ---- snapshot / restore of the whole dynamic state (Archive, archive.cpp:9-151) ----
+// The image stays in device memory (a D2D copy at HBM speed); toHost()/fromHost() serialise it.
+struct DeviceSim::Snapshot {
+    struct Region { size_t bytes; };
+    std::vector<Region> regions;
+    DevBuf<unsigned char> blob;
+    long long steps = 0;
+    int slotCap = 0;
+    size_t total = 0;
+};
+
+static std::vector<std::pair<void *, size_t>> snapshotRegions(DeviceSim::Impl &I) {
+    const View &V = I.V;
+    const size_t P = (size_t) I.P, S = (size_t) I.slotCap;
+    return {
+        {V.kin, P * sizeof(double2)}, {V.gap, P * sizeof(double)}, {V.leader, P * sizeof(int)},
+        {V.ids, P * sizeof(int4)}, {V.nav, P * sizeof(int4)}, {V.cust, P * sizeof(double)},
+        {V.count, (size_t) V.nDrv * sizeof(int)}, {V.entCnt, (size_t) V.nDrv * sizeof(int)},
+        {V.tail, (size_t) V.nDrv * sizeof(Tail)},
+        {V.waitHead, (size_t) std::max(V.nLanes, 1) * sizeof(int)}, {V.waitTail, (size_t) std::max(V.nLanes, 1) * sizeof(int)},
+        {V.inserted, (size_t) std::max(V.nLanes, 1)},
+        {V.curPhase, (size_t) V.nInter * sizeof(int)}, {V.remain, (size_t) V.nInter * sizeof(double)},
+        {V.vehList[0], P * sizeof(int2)}, {V.vehList[1], P * sizeof(int2)},
+        {V.actList[0], (size_t) V.nDrv * sizeof(int)}, {V.actList[1], (size_t) V.nDrv * sizeof(int)},
+        {V.ctrl, sizeof(Ctrl)},
+        // slot-indexed arrays last (their size may differ between snapshot and restore time)
+        {V.pos, S * sizeof(int)}, {V.waitNext, S * sizeof(int)}, {V.slotInfo, S * sizeof(int4)}, {V.slotCust, S * sizeof(double)},
+    };
+}
+
+DeviceSim::Snapshot *DeviceSim::snapshot() {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    auto regs = snapshotRegions(I);
+    Snapshot *s = new Snapshot();
+    for (auto &r : regs) { s->regions.push_back({r.second}); s->total += (r.second + 255) & ~(size_t) 255; }
+    s->blob.alloc(s->total);
+    size_t off = 0;
+    for (auto &r : regs) {
+        if (r.second) CFB_CUDA(cudaMemcpyAsync(s->blob.p + off, r.first, r.second, cudaMemcpyDeviceToDevice, I.stream));
+        off += (r.second + 255) & ~(size_t) 255;
+    }
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    s->steps = steps_;
+    s->slotCap = I.slotCap;
+    return s;
+}
+
+void DeviceSim::restore(const Snapshot *s) {
+    Impl &I = *impl_;
+    ensureSlotCapacity(s->slotCap);
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    auto regs = snapshotRegions(I);
+    if (regs.size() != s->regions.size()) throw std::runtime_error("cityflow_b200: archive does not match this engine");
+    // slots beyond the archive's capacity: unused
+    I.pos.fill(0xff); I.waitNext.fill(0xff); I.slotCust.fill(0xff);
+    size_t off = 0;
+    for (size_t k = 0; k < regs.size(); ++k) {
+        const size_t bytes = s->regions[k].bytes;
+        if (bytes > regs[k].second) throw std::runtime_error("cityflow_b200: archive does not match this engine (region size)");
+        if (k + 4 < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
+        if (bytes) CFB_CUDA(cudaMemcpyAsync(regs[k].first, s->blob.p + off, bytes, cudaMemcpyDeviceToDevice, I.stream));
+        off += (bytes + 255) & ~(size_t) 255;
+    }
+    I.notify.fill(0);      // epoch-stamped scratch: nothing of an older timeline may match
+    I.foeMask.fill(0);
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    steps_ = s->steps;
+}
+
+void DeviceSim::freeSnapshot(Snapshot *s) { delete s; }
+
+void DeviceSim::snapshotToHost(const Snapshot *s, std::vector<unsigned char> &out) {
+    // header: magic, steps, slotCap, #regions, region sizes; then the blob
+    std::vector<long long> hdr = {0x43464241LL, s->steps, (long long) s->slotCap, (long long) s->regions.size()};
+    for (auto &r : s->regions) hdr.push_back((long long) r.bytes);
+    out.resize(hdr.size() * sizeof(long long) + s->total);
+    memcpy(out.data(), hdr.data(), hdr.size() * sizeof(long long));
+    if (s->total) CFB_CUDA(cudaMemcpy(out.data() + hdr.size() * sizeof(long long), s->blob.p, s->total, cudaMemcpyDeviceToHost));
+}
+
+DeviceSim::Snapshot *DeviceSim::snapshotFromHost(const unsigned char *data, size_t n) {
+    if (n < 4 * sizeof(long long)) throw std::runtime_error("cityflow_b200: truncated archive");
+    const long long *h = reinterpret_cast<const long long *>(data);
+    if (h[0] != 0x43464241LL) throw std::runtime_error("cityflow_b200: not an archive of this engine");
+    Snapshot *s = new Snapshot();
+    s->steps = h[1];
+    s->slotCap = (int) h[2];
+    const size_t nr = (size_t) h[3];
+    if (n < (4 + nr) * sizeof(long long)) { delete s; throw std::runtime_error("cityflow_b200: truncated archive"); }
+    for (size_t k = 0; k < nr; ++k) { s->regions.push_back({(size_t) h[4 + k]}); s->total += ((size_t) h[4 + k] + 255) & ~(size_t) 255; }
+    const size_t hb = (4 + nr) * sizeof(long long);
+    if (n < hb + s->total) { delete s; throw std::runtime_error("cityflow_b200: truncated archive"); }
+    s->blob.alloc(s->total);
+    if (s->total) CFB_CUDA(cudaMemcpy(s->blob.p, data + hb, s->total, cudaMemcpyHostToDevice));
+    return s;
+}
+
+bool DeviceSim::vehicleState(int slot, VehState &out) {
+    Impl &I = *impl_;
+    if (slot < 0 || slot >= I.slotCap) return false;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    int p = -1;
+    CFB_CUDA(cudaMemcpy(&p, I.V.pos + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    if (p < 0) return false;
+    double2 k;
+    int4 idv, nv;
+    CFB_CUDA(cudaMemcpy(&k, I.V.kin + p, sizeof(k), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(&idv, I.V.ids + p, sizeof(idv), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(&nv, I.V.nav + p, sizeof(nv), cudaMemcpyDeviceToHost));
+    if (idv.x != slot) return false;
+    out.pos = p;
+    out.drivable = (int) (std::upper_bound(I.offHost.begin(), I.offHost.end(), p) - I.offHost.begin()) - 1;
+    out.planIdx = nv.x;
+    out.nextDrv = idv.w;
+    out.dis = k.x;
+    out.speed = k.y;
+    return true;
+}
+
+void DeviceSim::setCustomSpeed(int slot, double speed) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    int p = -1;
+    CFB_CUDA(cudaMemcpy(&p, I.V.pos + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    double *dst = p >= 0 ? I.V.cust + p : I.V.slotCust + slot;
+    double old = 0;
+    CFB_CUDA(cudaMemcpy(&old, dst, sizeof(double), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(dst, &speed, sizeof(double), cudaMemcpyHostToDevice));
+    if (old != old) {  // was unset: one more outstanding request
+        readCtrlImpl(I.stream, I.hCtrl, I.V.ctrl);
+        int n = I.hCtrl->nCustom + 1;
+        CFB_CUDA(cudaMemcpy(&I.V.ctrl->nCustom, &n, sizeof(int), cudaMemcpyHostToDevice));
+    }
+}
+
+void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    int p = -1;
+    CFB_CUDA(cudaMemcpy(&p, I.V.pos + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    if (p >= 0) {
+        CFB_CUDA(cudaMemcpy(&I.V.nav[p].x, &planIdx, sizeof(int), cudaMemcpyHostToDevice));
+        CFB_CUDA(cudaMemcpy(&I.V.ids[p].w, &nextDrv, sizeof(int), cudaMemcpyHostToDevice));
+    } else {
+        CFB_CUDA(cudaMemcpy(&I.V.slotInfo[slot].z, &planId, sizeof(int), cudaMemcpyHostToDevice));
     }
 }
 

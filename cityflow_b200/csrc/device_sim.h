@@ -89,9 +89,21 @@ public:
     void laneVehicleSlots(std::vector<int32_t> &slots, std::vector<int32_t> &laneBeg);
     void debugDump(std::vector<DebugRec> &out);   // every running vehicle, drivable-major, list order
 
+    struct VehState { int pos, drivable, planIdx, nextDrv; double dis, speed; };
+    bool vehicleState(int slot, VehState &out);          // false: not running
+    void setCustomSpeed(int slot, double speed);         // Vehicle::setCustomSpeed (running or queued vehicle)
+    void setVehiclePlan(int slot, int planId, int planIdx, int nextDrv);
+
     // Control.
     void setPhase(int intersection, int phase);
     void reset();
+    // Whole dynamic state image (device resident); see Archive in host_engine.cpp.
+    struct Snapshot;
+    Snapshot *snapshot();
+    void restore(const Snapshot *s);
+    static void freeSnapshot(Snapshot *s);
+    static void snapshotToHost(const Snapshot *s, std::vector<unsigned char> &out);
+    static Snapshot *snapshotFromHost(const unsigned char *data, size_t n);
 
     // Measurement support for bench.py / profiles (CUDA-event timing of one kernel across launches).
     struct KernelTimes { double ingest = 0, notify = 0, control = 0, move = 0, leader = 0; long long launches = 0; };
@@ -107,8 +119,9 @@ public:
     int numPositions() const;
     int numDrivables() const;
 
-private:
     struct Impl;
+
+private:
     Impl *impl_;
     long long steps_ = 0;
     long long launches_ = 0;

@@ -15,6 +15,8 @@
 #include <memory>
 #include <random>
 #include <set>
+#include <sstream>
+#include <fstream>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -41,6 +43,8 @@ struct SlotInfo {
     int32_t flow = -1, index = -1;   // id: flow_<flow>_<index> / manually_pushed_<index> (flow == -2)
     int32_t priority = 0;
     double enterTime = 0;
+    int32_t routeId = -1;            // resolved route (Routing::route), for get_vehicle_info / set_vehicle_route
+    int32_t firstLane = -1;          // lane whose waiting queue the vehicle was put in
     bool live = false;
 };
 
@@ -274,6 +278,8 @@ public:
         s.index = index;
         s.priority = priority;
         s.enterTime = currentTime();
+        s.routeId = routeId;
+        s.firstLane = -1;
         s.live = true;
         pool.insert(priority, slot);
         idMapValid = false;
@@ -311,6 +317,7 @@ public:
                     r.tmpl = p.tmplId;
                     r.priority = slots[p.slot].priority;
                     r.plan = rt.planOfStartLane[pick];
+                    slots[p.slot].firstLane = r.lane;
                     batch.push_back(r);
                 } else {
                     if (p.flow >= 0) {
@@ -373,6 +380,39 @@ public:
         }
         auto it = idToSlot.find(key(flow, index));
         return it == idToSlot.end() ? -1 : it->second;
+    }
+
+    // ---- Archive (archive.cpp:9-151): host half of a snapshot ----
+    struct HostState {
+        std::mt19937 rnd;
+        size_t step = 0;
+        int manuallyPushCnt = 0, finishedCnt = 0;
+        double cumulativeTravelTime = 0;
+        std::vector<double> flowNow, flowCur;
+        std::vector<int> flowCnt;
+        std::vector<uint8_t> flowValid;
+        std::vector<SlotInfo> slots;
+        std::vector<int> freeSlots;
+        std::vector<Pending> pending;
+    };
+    void saveHost(HostState &s) {
+        drain();
+        s.rnd = rnd; s.step = step; s.manuallyPushCnt = manuallyPushCnt; s.finishedCnt = finishedCnt;
+        s.cumulativeTravelTime = cumulativeTravelTime;
+        s.flowNow.clear(); s.flowCur.clear(); s.flowCnt.clear(); s.flowValid.clear();
+        for (auto &f : flows) { s.flowNow.push_back(f.nowTime); s.flowCur.push_back(f.currentTime); s.flowCnt.push_back(f.cnt); s.flowValid.push_back(f.valid); }
+        s.slots = slots; s.freeSlots = freeSlots; s.pending = pending;
+    }
+    void loadHost(const HostState &s) {
+        if (s.flowNow.size() != flows.size()) throw std::runtime_error("archive does not match this engine (flows)");
+        rnd = s.rnd; step = s.step; manuallyPushCnt = s.manuallyPushCnt; finishedCnt = s.finishedCnt;
+        cumulativeTravelTime = s.cumulativeTravelTime;
+        for (size_t i = 0; i < flows.size(); ++i) { flows[i].nowTime = s.flowNow[i]; flows[i].currentTime = s.flowCur[i]; flows[i].cnt = s.flowCnt[i]; flows[i].valid = s.flowValid[i]; }
+        slots = s.slots; freeSlots = s.freeSlots; pending = s.pending;
+        pool.clear();
+        for (size_t k = 0; k < slots.size(); ++k) if (slots[k].live) pool.insert(slots[k].priority, (int) k);
+        idMapValid = false;
+        finishedDirty = false;
     }
 
     cfb_vehicle_ref refOf(int slot) const { return cfb_vehicle_ref{slots[slot].flow, slots[slot].index}; }
@@ -626,10 +666,16 @@ int cfb_timed_steps(cfb_engine *e, int n, int flush_l2, double *ms, int64_t *veh
         cfb::HostEngine &h = e->h;
         h.dev->synchronize();
         const unsigned long long v0 = h.dev->vehicleSteps();
-        for (int i = 0; i < n; ++i) {
-            if (flush_l2) h.dev->flushL2();
+        if (flush_l2) {
+            for (int i = 0; i < n; ++i) {  // one bracket per step, the flush sits between brackets
+                h.dev->flushL2();
+                h.dev->markTimed();
+                h.nextStep();
+                h.dev->markTimed();
+            }
+        } else {  // back to back: one bracket around all n steps (includes any host-paced gaps)
             h.dev->markTimed();
-            h.nextStep();
+            for (int i = 0; i < n; ++i) h.nextStep();
             h.dev->markTimed();
         }
         *ms = h.dev->collectTimedMs();
@@ -658,6 +704,105 @@ int64_t cfb_num_drivables(const cfb_engine *e) { return e->h.dev->numDrivables()
 
 }  // extern "C"
 
+// Engine::setVehicleSpeed engine.cpp:827-834
+extern "C" int cfb_set_vehicle_speed(cfb_engine *e, cfb_vehicle_ref v, double speed) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        h.drain();
+        const int s = h.slotOfId(v.flow, v.index);
+        if (s < 0) throw std::runtime_error("Vehicle not found");
+        h.dev->setCustomSpeed(s, speed);
+    )
+    return CFB_OK;
+}
+
+// Engine::setRoute engine.cpp:852-866 / Router::setRoute router.cpp:245-264.  *ok = 1 when the new
+// route was accepted.
+extern "C" int cfb_set_vehicle_route(cfb_engine *e, cfb_vehicle_ref v, const char *const *roads, int n_roads, int *ok) {
+    *ok = 0;
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        h.drain();
+        const int s = h.slotOfId(v.flow, v.index);
+        if (s < 0) return CFB_OK;                       // unknown vehicle: false
+        std::vector<int> anchors;
+        for (int k = 0; k < n_roads; ++k) {
+            auto it = h.net.roadIndex.find(roads[k]);
+            if (it == h.net.roadIndex.end()) return CFB_OK;  // unknown road: false
+            anchors.push_back(it->second);
+        }
+        cfb::DeviceSim::VehState st;
+        int curLane;
+        if (h.dev->vehicleState(s, st)) {
+            if (st.drivable >= h.net.nLanes()) return CFB_OK;  // on a laneLink: false (router.cpp:246)
+            curLane = st.drivable;
+        } else {
+            curLane = h.slots[s].firstLane;
+            if (curLane < 0) return CFB_OK;                    // still waiting for planRoute
+        }
+        std::vector<int> full;
+        full.push_back(h.net.laneRoad[curLane]);
+        full.insert(full.end(), anchors.begin(), anchors.end());
+        const int rid = h.routing->intern(full);
+        const cfb::Route &rt = h.routing->route(rid);
+        if (!rt.valid) return CFB_OK;
+        int plan = -1;
+        for (size_t k = 0; k < rt.startLanes.size(); ++k)
+            if (rt.startLanes[k] == curLane) plan = rt.planOfStartLane[k];
+        if (plan < 0) return CFB_OK;                           // !onValidLane(): restore the old route
+        if ((size_t) h.routing->numPlans() != h.uploadedPlans) { h.dev->uploadPlans(*h.routing); h.uploadedPlans = h.routing->numPlans(); }
+        const int planIdx = h.routing->planBeg()[plan];
+        h.dev->setVehiclePlan(s, plan, planIdx, h.routing->planData()[planIdx + 1]);
+        h.slots[s].routeId = rid;
+        *ok = 1;
+    )
+    return CFB_OK;
+}
+
+// Engine::getVehicleInfo engine.cpp:868-876 / Vehicle::getInfo vehicle.cpp:435-457.  Fills `out`
+// with "key\0value\0key\0value\0...\0"; returns the number of bytes needed.
+extern "C" int64_t cfb_get_vehicle_info(cfb_engine *e, cfb_vehicle_ref v, char *out, int64_t cap) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        h.drain();
+        const int s = h.slotOfId(v.flow, v.index);
+        if (s < 0) throw std::runtime_error("Vehicle not found");
+        std::string buf;
+        auto put = [&buf](const std::string &k, const std::string &val) { buf += k; buf.push_back('\0'); buf += val; buf.push_back('\0'); };
+        cfb::DeviceSim::VehState st;
+        const bool running = h.dev->vehicleState(s, st);
+        put("running", std::to_string(running));
+        if (running) {
+            const cfb::RoadNet &n = h.net;
+            put("distance", std::to_string(st.dis));
+            put("speed", std::to_string(st.speed));
+            const bool onLane = st.drivable < n.nLanes();
+            if (onLane) {
+                put("drivable", n.laneName(st.drivable));
+                const int road = n.laneRoad[st.drivable];
+                put("road", n.roadId[road]);
+                put("intersection", n.interId[n.roadEndInter[road]]);
+            } else {
+                const int ll = st.drivable - n.nLanes();
+                put("drivable", n.laneName(n.llStartLane[ll]) + "_TO_" + n.laneName(n.llEndLane[ll]));
+            }
+            // Router::getFollowingRoads: from the current road of the route to its end
+            std::string route;
+            const int rid = h.slots[s].routeId;
+            if (rid >= 0) {
+                const auto &pb = h.routing->planBeg();
+                int plan = (int) (std::upper_bound(pb.begin(), pb.end(), st.planIdx) - pb.begin()) - 1;
+                const int rpos = (st.planIdx - pb[plan]) / 2;
+                const auto &roads = h.routing->route(rid).roads;
+                for (size_t k = rpos; k < roads.size(); ++k) route += n.roadId[roads[k]] + " ";
+            }
+            put("route", route);
+        }
+        if (out && (int64_t) buf.size() <= cap) memcpy(out, buf.data(), buf.size());
+        return (int64_t) buf.size();
+    )
+}
+
 extern "C" int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2h) {
     if (h2d) *h2d = e->h.h2dBytes;
     if (d2h) *d2h = e->h.d2hBytes;
@@ -681,3 +826,112 @@ extern "C" int64_t cfb_debug_arrays(cfb_engine *e, uint32_t *cyc, uint32_t *path
     if (cap < e->h.dev->numPositions()) return e->h.dev->numPositions();
     return e->h.dev->debugArrays(cyc, path);
 }
+
+// ------------------------------------------------------------------------------------------
+// Archive: Engine::snapshot / load / loadFromFile, Archive::dump (engine.h:176-178, archive.cpp)
+struct cfb_archive {
+    cfb::HostEngine::HostState host;
+    cfb::DeviceSim::Snapshot *dev = nullptr;
+    ~cfb_archive() { if (dev) cfb::DeviceSim::freeSnapshot(dev); }
+};
+
+namespace {
+template <class T> void putVec(std::ostream &o, const std::vector<T> &v) {
+    uint64_t n = v.size();
+    o.write((const char *) &n, 8);
+    if (n) o.write((const char *) v.data(), n * sizeof(T));
+}
+template <class T> void getVec(std::istream &i, std::vector<T> &v) {
+    uint64_t n = 0;
+    i.read((char *) &n, 8);
+    v.resize(n);
+    if (n) i.read((char *) v.data(), n * sizeof(T));
+}
+}  // namespace
+
+extern "C" {
+
+cfb_archive *cfb_snapshot(cfb_engine *e) {
+    try {
+        cfb_archive *a = new cfb_archive();
+        e->h.saveHost(a->host);
+        a->dev = e->h.dev->snapshot();
+        return a;
+    } catch (const std::exception &ex) {
+        e->lastError = ex.what();
+        return nullptr;
+    }
+}
+
+void cfb_archive_destroy(cfb_archive *a) { delete a; }
+
+int cfb_load(cfb_engine *e, const cfb_archive *a) {
+    CFB_TRY(e,
+        e->h.dev->synchronize();
+        e->h.dev->restore(a->dev);
+        e->h.loadHost(a->host);
+    )
+    return CFB_OK;
+}
+
+int cfb_archive_dump(const cfb_archive *a, const char *path) {
+    try {
+        std::ofstream o(path, std::ios::binary);
+        if (!o) return CFB_ERR_ARGUMENT;
+        const auto &s = a->host;
+        const uint64_t magic = 0x3142464341ULL;  // "ACFB1"
+        o.write((const char *) &magic, 8);
+        std::ostringstream r;
+        r << s.rnd;
+        const std::string rs = r.str();
+        std::vector<char> rv(rs.begin(), rs.end());
+        putVec(o, rv);
+        uint64_t step = s.step;
+        o.write((const char *) &step, 8);
+        o.write((const char *) &s.manuallyPushCnt, 4);
+        o.write((const char *) &s.finishedCnt, 4);
+        o.write((const char *) &s.cumulativeTravelTime, 8);
+        putVec(o, s.flowNow); putVec(o, s.flowCur); putVec(o, s.flowCnt); putVec(o, s.flowValid);
+        putVec(o, s.slots); putVec(o, s.freeSlots); putVec(o, s.pending);
+        std::vector<unsigned char> blob;
+        cfb::DeviceSim::snapshotToHost(a->dev, blob);
+        putVec(o, blob);
+        return o ? CFB_OK : CFB_ERR_ARGUMENT;
+    } catch (const std::exception &) {
+        return CFB_ERR_DEVICE;
+    }
+}
+
+int cfb_load_from_file(cfb_engine *e, const char *path) {
+    CFB_TRY(e,
+        std::ifstream i(path, std::ios::binary);
+        if (!i) throw std::runtime_error(std::string("cannot open archive file ") + path);
+        uint64_t magic = 0;
+        i.read((char *) &magic, 8);
+        if (magic != 0x3142464341ULL) throw std::runtime_error("not an archive written by cityflow_b200 (the reference's JSON archive format is not supported)");
+        cfb_archive a;
+        auto &s = a.host;
+        std::vector<char> rv;
+        getVec(i, rv);
+        std::istringstream r(std::string(rv.begin(), rv.end()));
+        r >> s.rnd;
+        uint64_t step = 0;
+        i.read((char *) &step, 8);
+        s.step = step;
+        i.read((char *) &s.manuallyPushCnt, 4);
+        i.read((char *) &s.finishedCnt, 4);
+        i.read((char *) &s.cumulativeTravelTime, 8);
+        getVec(i, s.flowNow); getVec(i, s.flowCur); getVec(i, s.flowCnt); getVec(i, s.flowValid);
+        getVec(i, s.slots); getVec(i, s.freeSlots); getVec(i, s.pending);
+        std::vector<unsigned char> blob;
+        getVec(i, blob);
+        if (!i) throw std::runtime_error("truncated archive file");
+        a.dev = cfb::DeviceSim::snapshotFromHost(blob.data(), blob.size());
+        e->h.dev->synchronize();
+        e->h.dev->restore(a.dev);
+        e->h.loadHost(a.host);
+    )
+    return CFB_OK;
+}
+
+}  // extern "C"

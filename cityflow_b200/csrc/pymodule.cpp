@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <limits>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -44,6 +45,20 @@ bool parseVehicleName(const std::string &id, cfb_vehicle_ref &out) {
     }
     return false;
 }
+
+class Engine;
+
+class Archive {
+public:
+    explicit Archive(Engine &e);
+    explicit Archive(cfb_archive *a) : a_(a) {}
+    ~Archive() { if (a_) cfb_archive_destroy(a_); }
+    Archive(const Archive &) = delete;
+    void dump(const std::string &path) {
+        if (cfb_archive_dump(a_, path.c_str()) < 0) throw std::runtime_error("cannot write archive to " + path);
+    }
+    cfb_archive *a_ = nullptr;
+};
 
 class Engine {
 public:
@@ -181,6 +196,46 @@ public:
     void setSaveReplay(bool) {  // engine.cpp:736-742
         py::print("saveReplay is not set to true in config file!", "file"_a = py::module_::import("sys").attr("stderr"));
     }
+    void setVehicleSpeed(const std::string &id, double speed) {
+        cfb_vehicle_ref v;
+        if (!parseVehicleName(id, v) || cfb_set_vehicle_speed(e_, v, speed) < 0)
+            throw std::runtime_error("Vehicle '" + id + "' not found");  // engine.cpp:830
+    }
+    bool setVehicleRoute(const std::string &id, const std::vector<std::string> &route) {
+        cfb_vehicle_ref v;
+        if (!parseVehicleName(id, v)) return false;
+        std::vector<const char *> r;
+        for (auto &s : route) r.push_back(s.c_str());
+        int ok = 0;
+        check(cfb_set_vehicle_route(e_, v, r.data(), (int) r.size(), &ok));
+        return ok != 0;
+    }
+    std::map<std::string, std::string> getVehicleInfo(const std::string &id) {
+        cfb_vehicle_ref v;
+        int64_t n = -1;
+        if (parseVehicleName(id, v)) n = cfb_get_vehicle_info(e_, v, nullptr, 0);
+        if (n < 0) throw std::runtime_error("Vehicle '" + id + "' not found");  // engine.cpp:871
+        std::string buf((size_t) n, '\0');
+        cfb_get_vehicle_info(e_, v, &buf[0], n);
+        std::map<std::string, std::string> out;
+        size_t i = 0;
+        while (i < buf.size()) {
+            std::string k(buf.c_str() + i);
+            i += k.size() + 1;
+            std::string val(buf.c_str() + i);
+            i += val.size() + 1;
+            out[k] = val;
+        }
+        return out;
+    }
+    std::unique_ptr<Archive> snapshot() {
+        cfb_archive *a = cfb_snapshot(e_);
+        if (!a) throw std::runtime_error(cfb_last_error(e_));
+        return std::unique_ptr<Archive>(new Archive(a));
+    }
+    void load(const Archive &a) { check(cfb_load(e_, a.a_)); }
+    void loadFromFile(const std::string &path) { check(cfb_load_from_file(e_, path.c_str())); }
+    cfb_engine *raw() { return e_; }
     [[noreturn]] void unsupported(const char *what) const {
         throw std::runtime_error(std::string(what) + " is not implemented by the B200 engine yet");
     }
@@ -220,6 +275,10 @@ private:
     std::vector<int32_t> laneBuf_;
 };
 
+Archive::Archive(Engine &e) : a_(cfb_snapshot(e.raw())) {
+    if (!a_) throw std::runtime_error(cfb_last_error(e.raw()));
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_cityflow_b200, m) {
@@ -233,24 +292,22 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("get_lane_waiting_vehicle_count", &Engine::getLaneWaitingVehicleCount)
         .def("get_lane_vehicles", &Engine::getLaneVehicles)
         .def("get_vehicle_speed", &Engine::getVehicleSpeed)
-        .def("get_vehicle_info", [](Engine &e, const std::string &) { e.unsupported("get_vehicle_info"); }, "vehicle_id"_a)
+        .def("get_vehicle_info", &Engine::getVehicleInfo, "vehicle_id"_a)
         .def("get_vehicle_distance", &Engine::getVehicleDistance)
         .def("get_leader", &Engine::getLeader, "vehicle_id"_a)
         .def("get_current_time", &Engine::getCurrentTime)
         .def("get_average_travel_time", &Engine::getAverageTravelTime)
         .def("set_tl_phase", &Engine::setTrafficLightPhase, "intersection_id"_a, "phase_id"_a)
-        .def("set_vehicle_speed", [](Engine &e, const std::string &, double) { e.unsupported("set_vehicle_speed"); },
-             "vehicle_id"_a, "speed"_a)
+        .def("set_vehicle_speed", &Engine::setVehicleSpeed, "vehicle_id"_a, "speed"_a)
         .def("set_replay_file", &Engine::setReplayLogFile, "replay_file"_a)
         .def("set_random_seed", &Engine::setRandomSeed, "seed"_a)
         .def("set_save_replay", &Engine::setSaveReplay, "open"_a)
         .def("push_vehicle", &Engine::pushVehicle)
         .def("reset", &Engine::reset, "seed"_a = false)
-        .def("load", [](Engine &e, py::object) { e.unsupported("load"); }, "archive"_a)
-        .def("snapshot", [](Engine &e) { e.unsupported("snapshot"); })
-        .def("load_from_file", [](Engine &e, const std::string &) { e.unsupported("load_from_file"); }, "path"_a)
-        .def("set_vehicle_route", [](Engine &e, const std::string &, const std::vector<std::string> &) { e.unsupported("set_vehicle_route"); },
-             "vehicle_id"_a, "route"_a)
+        .def("load", &Engine::load, "archive"_a)
+        .def("snapshot", &Engine::snapshot)
+        .def("load_from_file", &Engine::loadFromFile, "path"_a)
+        .def("set_vehicle_route", &Engine::setVehicleRoute, "vehicle_id"_a, "route"_a)
         // extras
         .def("next_steps", &Engine::nextSteps, "n"_a)
         .def("gpu_launches", &Engine::gpuLaunches)
@@ -262,5 +319,8 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("num_drivables", [](Engine &e) { return e.numDrivables(); })
         .def("host_times", &Engine::hostTimes)
         .def("synchronize", &Engine::synchronize);
+    py::class_<Archive>(m, "Archive")
+        .def(py::init<Engine &>())
+        .def("dump", &Archive::dump, "path"_a);
     m.attr("__version__") = "b200-dev";
 }

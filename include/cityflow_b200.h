@@ -97,6 +97,25 @@ int cfb_reset(cfb_engine *e, int reset_rnd);
  * NaN = "not given" (struct default, vehicle.h:31-45). */
 int cfb_push_vehicle(cfb_engine *e, const double values[10], const char *const *roads, int n_roads);
 
+/* Engine::setVehicleSpeed  engine.cpp:827-834 (custom speed for the coming step) */
+int cfb_set_vehicle_speed(cfb_engine *e, cfb_vehicle_ref vehicle, double speed);
+/* Engine::setRoute  engine.cpp:852-866: *ok = 1 if the vehicle now follows cur_road + roads */
+int cfb_set_vehicle_route(cfb_engine *e, cfb_vehicle_ref vehicle, const char *const *roads, int n_roads, int *ok);
+/* Engine::getVehicleInfo  engine.cpp:868-876: "key\0value\0..." pairs; returns the bytes needed */
+int64_t cfb_get_vehicle_info(cfb_engine *e, cfb_vehicle_ref vehicle, char *out, int64_t cap);
+
+/* Archive.  Engine::snapshot() / Engine::load(archive) engine.h:176-177, Archive::dump
+ * archive.cpp:153-177, Engine::loadFromFile engine.cpp:822-825.  A snapshot is a device-resident
+ * image of the whole dynamic state plus the host bookkeeping (RNG, flows, id tables); it can be
+ * restored into the engine that made it or into another engine built from the same config.  The
+ * file written by cfb_archive_dump is this engine's own binary image, not the reference's JSON. */
+typedef struct cfb_archive cfb_archive;
+cfb_archive *cfb_snapshot(cfb_engine *e);
+void cfb_archive_destroy(cfb_archive *a);
+int cfb_load(cfb_engine *e, const cfb_archive *a);
+int cfb_archive_dump(const cfb_archive *a, const char *path);
+int cfb_load_from_file(cfb_engine *e, const char *path);
+
 /* Test support: full dynamic state of every running vehicle, drivable-major in list order.
  * Record = 8 x int32 {flow, index, priority, drivable, leader flow, leader index, blocker flow,
  * blocker index}, 3 x double {distance, speed, gap}, 1 x int64 {enterLaneLinkTime}; 64 bytes. */

@@ -148,3 +148,85 @@ def test_30x30_dense_lane_counts_vs_port(scenario_dir):
         bad = H.compare_states(_relax(ora.snapshot()), _gpu_state(eng, s))
         assert not bad, "step %d: %s" % (s, "; ".join(bad[:6]))
     assert ora.vehicle_count() > 50000
+
+
+def _archive_record(eng, n):
+    for _ in range(n):
+        eng.next_step()
+    return eng.get_lane_vehicle_count(), eng.get_average_travel_time(), eng.get_vehicle_speed()
+
+
+def test_archive_snapshot_load_like_reference_tests(cfg_3x3_dense, tmp_path):
+    """The reference's own result-pinning tests (tests/python/test_archive.py:16-23): run, snapshot,
+    run 100 -> record, load, run 100 -> the record must be equal; also via dump / load_from_file and
+    into a second engine built from the same config."""
+    import cityflow
+    eng = cityflow.Engine(cfg_3x3_dense, thread_num=1)
+    for _ in range(150):
+        eng.next_step()
+    arc = eng.snapshot()
+    rec1 = _archive_record(eng, 100)
+    eng.load(arc)
+    assert eng.get_current_time() == 150.0
+    rec2 = _archive_record(eng, 100)
+    assert rec1 == rec2
+    # multiple loads of the same archive, and Archive(engine) constructor
+    eng.load(arc)
+    arc2 = cityflow.Archive(eng)
+    assert _archive_record(eng, 100) == rec1
+    eng.load(arc2)
+    assert _archive_record(eng, 100) == rec1
+    # file round trip into a fresh engine
+    path = str(tmp_path / "save.bin")
+    arc.dump(path)
+    eng2 = cityflow.Engine(cfg_3x3_dense, thread_num=1)
+    eng2.load_from_file(path)
+    assert _archive_record(eng2, 100) == rec1
+
+
+def test_vehicle_api_info_speed_route(cfg_3x3_dense):
+    """get_vehicle_info / set_vehicle_speed / set_vehicle_route / get_leader."""
+    import cityflow
+    eng = cityflow.Engine(cfg_3x3_dense, thread_num=1)
+    for _ in range(120):
+        eng.next_step()
+    speeds = eng.get_vehicle_speed()
+    dist = eng.get_vehicle_distance()
+    vid = next(k for k, v in speeds.items() if v > 3.0)
+    info = eng.get_vehicle_info(vid)
+    assert info["running"] == "1"
+    assert float(info["speed"]) == pytest.approx(speeds[vid], abs=1e-6)
+    assert float(info["distance"]) == pytest.approx(dist[vid], abs=1e-6)
+    assert info["route"].endswith(" ") and "drivable" in info
+    with pytest.raises(RuntimeError, match="not found"):
+        eng.get_vehicle_info("flow_999999_0")
+    with pytest.raises(RuntimeError, match="not found"):
+        eng.set_vehicle_speed("nope", 1.0)
+    # custom speed caps the next step's speed (Vehicle::getCarFollowSpeed, vehicle.cpp:214-221) for one step
+    eng.set_vehicle_speed(vid, 0.5)
+    eng.next_step()
+    after = eng.get_vehicle_speed()
+    if vid in after:
+        assert after[vid] <= max(0.5, speeds[vid] - 4.5) + 1e-9
+    leader = eng.get_leader(vid) if vid in after else ""
+    assert isinstance(leader, str)
+    # waiting vehicles are known but not running
+    allv = eng.get_vehicles(include_waiting=True)
+    run = set(eng.get_vehicles())
+    assert run <= set(allv) and len(run) == eng.get_vehicle_count()
+    lanes = eng.get_lane_vehicles()
+    assert sum(len(v) for v in lanes.values()) == sum(eng.get_lane_vehicle_count().values())
+    # re-routing: an unknown road or a vehicle on a laneLink is refused, a vehicle on a lane may keep its road
+    assert eng.set_vehicle_route(vid, ["no_such_road"]) is False
+    assert eng.set_vehicle_route("flow_999999_0", []) is False
+    ok_any = False
+    for cand, inf in ((k, eng.get_vehicle_info(k)) for k in list(after)[:200]):
+        if "road" in inf:
+            roads = inf["route"].split()
+            if len(roads) >= 2:
+                ok_any = eng.set_vehicle_route(cand, roads[1:2]) or ok_any
+                break
+    assert ok_any
+    for _ in range(50):
+        eng.next_step()
+    assert eng.get_vehicle_count() > 0
