@@ -267,28 +267,29 @@ __device__ void headSearch(const View &V, int d, double dis, int nextDrv, int pl
 // Flow::nextStep / planRoute stay on the host (serial mt19937 order); their result arrives as
 // lane-sorted SpawnRec's whose lane keys are staged in shared memory for the per-lane lookup.
 // handleWaiting: engine.cpp:502-516, Lane::available roadnet.cpp:428-435.
-__global__ void __launch_bounds__(256) k_ingest(View V) {
+__device__ __forceinline__ void phase_ingest(const View &V, const int bid, const int nblk) {
     __shared__ int sLane[SPAWN_SMEM];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gtid0 = bid * blockDim.x + threadIdx.x;
+    int i = gtid0;
     const int nSpawn = V.spawn[-1].slot;
     const int cpar = V.par;
     const bool staged = nSpawn <= SPAWN_SMEM;
     if (staged)
         for (int k = threadIdx.x; k < nSpawn; k += blockDim.x) sLane[k] = V.spawn[k].lane;
     __syncthreads();
-    if (i < V.nRL) {
-        int in = V.rlInter[i];
+    for (int r = i; r < V.nRL; r += nblk * blockDim.x) {
+        int in = V.rlInter[r];
         int ph = V.interPhaseBeg[in] + V.curPhase[in];
-        V.rlAvail[i] = V.phaseAvail[V.phaseAvailBeg[ph] + (i - V.interRLBeg[in])];
+        V.rlAvail[r] = V.phaseAvail[V.phaseAvailBeg[ph] + (r - V.interRLBeg[in])];
     }
-    for (int k = i; k < V.nLinks * V.maskWords; k += gridDim.x * blockDim.x) V.foeMask[k] = 0u;
+    for (int k = i; k < V.nLinks * V.maskWords; k += nblk * blockDim.x) V.foeMask[k] = 0u;
     if (i == 0) {  // lists of the other parity are rebuilt by this step's k_move
         V.ctrl->moverCount = 0;
         V.ctrl->nVeh[cpar ^ 1] = 0;
         V.ctrl->nAct[cpar ^ 1] = 0;
         V.ctrl->nExtra = 0;
     }
-    if (i >= V.nLanes) return;
+    for (i = gtid0; i < V.nLanes; i += nblk * blockDim.x) {
     if (nSpawn > 0) {
         int lo = 0, hi = nSpawn;  // lower bound of lane i
         while (lo < hi) {
@@ -354,7 +355,9 @@ __global__ void __launch_bounds__(256) k_ingest(View V) {
         }
     }
     V.inserted[i] = ins;
+    }  // lanes
 }
+__global__ void __launch_bounds__(256) k_ingest(View V) { phase_ingest(V, blockIdx.x, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------
 // Cross::notify for one laneLink, executed by a whole warp: one lane per cross.
@@ -454,10 +457,10 @@ __device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
 // k_notify: warp per occupied drivable.  A link handles itself; a lane triggers the (empty)
 // links its tail vehicle came out of / its head vehicle heads for, so no empty link is swept.
 // Also runs the leader search of a vehicle admitted to an empty lane this step.
-__global__ void __launch_bounds__(256) k_notify(View V) {
+__device__ __forceinline__ void phase_notify(const View &V, const int bid, const int nblk) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (nblk * blockDim.x) >> 5;
     const int cpar = V.par;
     const int nAct = V.ctrl->nAct[cpar];
     const int epoch = V.ctrl->step + 1;
@@ -489,6 +492,7 @@ __global__ void __launch_bounds__(256) k_notify(View V) {
         if (nx >= V.nLanes && V.count[nx] == 0 && nx - V.nLanes != l1) notifyLink(V, nx - V.nLanes, lane, epoch);
     }
 }
+__global__ void __launch_bounds__(256) k_notify(View V) { phase_notify(V, blockIdx.x, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------
 // Cross::canPass roadnet.cpp:603-676.  `cs` = 2*cross + side of the asking vehicle's laneLink.
@@ -558,12 +562,12 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
 // k_control: one thread per running vehicle (grid-stride over the position list).
 // Vehicle::getNextSpeed vehicle.cpp:308-335, getCarFollowSpeed :212-238, getIntersectionRelatedSpeed
 // :337-376, Engine::vehicleControl engine.cpp:188-251, Vehicle::setDeltaDistance vehicle.cpp:49-68.
-__global__ void __launch_bounds__(512, 2) k_control(View V) {
+__device__ __forceinline__ void phase_control(const View &V, const int bid, const int nblk) {
     const int cpar = V.par;
     const int nVeh = min(V.ctrl->nVeh[cpar], V.vehCap);
     const double dt = V.dt;
     const int epoch = V.ctrl->step + 1;
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nVeh; it += gridDim.x * blockDim.x) {
+    for (int it = bid * blockDim.x + threadIdx.x; it < nVeh; it += nblk * blockDim.x) {
         const long long tStart = clock64();
         const int2 vd = V.vehList[cpar][it];
         const int p = vd.x, d = vd.y;
@@ -735,6 +739,7 @@ __global__ void __launch_bounds__(512, 2) k_control(View V) {
         }
     }
 }
+__global__ void __launch_bounds__(256, 4) k_control(View V) { phase_control(V, blockIdx.x, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------
 // k_move: warp per drivable that is occupied or receives entrants.  Survivors are compacted in
@@ -742,10 +747,10 @@ __global__ void __launch_bounds__(512, 2) k_control(View V) {
 // rank-sorted by (new distance desc, priority asc) -- the reference's global std::sort on distance
 // (engine.cpp:480) restricted to one target -- and appended.  Commits Buffer -> state
 // (Vehicle::update, vehicle.cpp:107-143) and emits the next step's work lists.
-__global__ void __launch_bounds__(256) k_move(View V) {
+__device__ __forceinline__ void phase_move(const View &V, const int bid, const int nblk) {
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = (bid * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (nblk * blockDim.x) >> 5;
     const int cpar = V.par, npar = cpar ^ 1;
     const int nAct = V.ctrl->nAct[cpar];
     const int nTot = nAct + V.ctrl->nExtra;
@@ -753,7 +758,7 @@ __global__ void __launch_bounds__(256) k_move(View V) {
     __shared__ int sBaseVeh, sBaseAct;
     const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     (void) warp; (void) nWarps;
-    for (int w0 = blockIdx.x * wpb; w0 < nTot; w0 += gridDim.x * wpb) {  // trip count uniform per block
+    for (int w0 = bid * wpb; w0 < nTot; w0 += nblk * wpb) {  // trip count uniform per block
         const int w = w0 + wib;
         int total = 0, d = -1, base = 0;
         if (w < nTot) {
@@ -861,6 +866,7 @@ __global__ void __launch_bounds__(256) k_move(View V) {
         __syncthreads();
     }
 }
+__global__ void __launch_bounds__(256) k_move(View V) { phase_move(V, blockIdx.x, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------
 // k_leader: warp per occupied drivable (the list k_move just wrote).  Non-heads: leader = list
@@ -868,11 +874,11 @@ __global__ void __launch_bounds__(256) k_move(View V) {
 // arrive by warp shuffle.  Heads: cross-drivable search.  Also drops blockers that left the
 // network this step (engine.cpp:419-421) and, in the leading threads, advances the traffic
 // lights (TrafficLight::passTime, trafficlight.cpp:29-37) and the step counter.
-__global__ void __launch_bounds__(256) k_leader(View V) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void phase_leader(const View &V, const int bid, const int nblk) {
+    const int gtid = bid * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int warp = gtid >> 5;
-    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const int nWarps = (nblk * blockDim.x) >> 5;
     const int npar = V.par ^ 1;
     const int nAct = V.ctrl->nAct[npar];
     if (gtid == 0) {  // nothing in this kernel reads these (list parity is the host-provided V.par)
@@ -880,7 +886,7 @@ __global__ void __launch_bounds__(256) k_leader(View V) {
         V.ctrl->vehicleSteps += (unsigned long long) V.ctrl->active;  // all finishes of this step are in
     }
     if (!V.rl) {
-        for (int in = gtid; in < V.nInter; in += gridDim.x * blockDim.x) {
+        for (int in = gtid; in < V.nInter; in += nblk * blockDim.x) {
             if (V.interVirtual[in]) continue;
             double rem = V.remain[in] - V.dt;
             int cur = V.curPhase[in];
@@ -933,6 +939,25 @@ __global__ void __launch_bounds__(256) k_leader(View V) {
             }
         }
     }
+}
+__global__ void __launch_bounds__(256) k_leader(View V) { phase_leader(V, blockIdx.x, gridDim.x); }
+
+// ------------------------------------------------------------------------------------------
+// k_step: the whole step as ONE cooperative kernel -- the five phases separated by grid-wide
+// barriers instead of kernel boundaries (each boundary costs a launch + drain + ramp of several
+// microseconds, comparable to the phases themselves at ~1e5 vehicles).  One resident wave of
+// 256-thread blocks; every phase is a grid-stride loop over its work list.
+__global__ void __launch_bounds__(256, 4) k_step(View V) {
+    cg::grid_group grid = cg::this_grid();
+    phase_ingest(V, blockIdx.x, gridDim.x);
+    grid.sync();
+    phase_notify(V, blockIdx.x, gridDim.x);
+    grid.sync();
+    phase_control(V, blockIdx.x, gridDim.x);
+    grid.sync();
+    phase_move(V, blockIdx.x, gridDim.x);
+    grid.sync();
+    phase_leader(V, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1042,6 +1067,9 @@ struct DeviceSim::Impl {
     cudaEvent_t spawnDone[RING] = {};
     int ringIdx = 0;
     int *hCounts = nullptr; // pinned, RING ints
+    std::vector<int> hPhase;            // authoritative phases in rlTrafficLight mode (set_tl_phase)
+    int *hPhaseRing[RING] = {};         // pinned staging, one per ring slot
+    bool phaseDirty = false;
     Ctrl *hCtrl = nullptr;  // pinned readback
     int *hInts = nullptr;   // pinned readback (lanes)
     size_t hIntsCap = 0;
@@ -1056,7 +1084,9 @@ struct DeviceSim::Impl {
     int slotCap = 0;
     int numSMs = 148;
     int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
-    bool useGraph = true, graphDirty = false;
+    bool useGraph = true, graphDirty = false, useCoop = false;   // cooperative k_step measured slower
+    cudaEvent_t graphDone[2] = {nullptr, nullptr};
+    int gridStep = 0;
     cudaGraphExec_t graphExec[2] = {nullptr, nullptr};
 
     void ensureHostInts(size_t n) {
@@ -1103,6 +1133,12 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     CFB_CUDA(cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking));
     CFB_CUDA(cudaDeviceGetAttribute(&I.numSMs, cudaDevAttrMultiProcessorCount, opt.device));
     if (const char *g = getenv("CITYFLOW_B200_NO_GRAPH")) I.useGraph = !(g[0] == '1');
+    if (const char *g = getenv("CITYFLOW_B200_COOP")) I.useCoop = (g[0] == '1');
+    {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, opt.device);
+        if (!coop) I.useCoop = false;
+    }
     View &V = I.V;
     const int nL = net.nLanes(), nK = net.nLinks(), nD = nL + nK;
     V.nLanes = nL; V.nLinks = nK; V.nDrv = nD; V.nInter = net.nInter(); V.nRL = net.nRoadLinks(); V.nCross = net.nCross();
@@ -1232,10 +1268,12 @@ DeviceSim::~DeviceSim() {
     for (int r = 0; r < Impl::RING; ++r) {
         if (I.hSpawn[r]) cudaFreeHost(I.hSpawn[r]);
         if (I.spawnDone[r]) cudaEventDestroy(I.spawnDone[r]);
+        if (I.hPhaseRing[r]) cudaFreeHost(I.hPhaseRing[r]);
     }
     for (auto &ev : I.ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : I.stepEv) cudaEventDestroy(ev);
     for (int k = 0; k < 2; ++k) if (I.graphExec[k]) cudaGraphExecDestroy(I.graphExec[k]);
+    for (int k = 0; k < 2; ++k) if (I.graphDone[k]) cudaEventDestroy(I.graphDone[k]);
     if (I.hCtrl) cudaFreeHost(I.hCtrl);
     if (I.hCounts) cudaFreeHost(I.hCounts);
     if (I.hInts) cudaFreeHost(I.hInts);
@@ -1303,6 +1341,8 @@ void DeviceSim::reset() {
     I.tail.fill(0xff);   // pos = -1: every drivable empty
     I.foeMask.fill(0);
     I.curPhase.fill(0);
+    I.hPhase.assign(I.V.nInter, 0);
+    I.phaseDirty = false;
     CFB_CUDA(cudaMemcpy(I.remain.p, I.phase0Time.data(), I.phase0Time.size() * sizeof(double), cudaMemcpyHostToDevice));
     I.rlAvail.fill(0);
     I.ctrl.fill(0);
@@ -1333,6 +1373,12 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
         I.hSpawnCap[r] = std::max(1024, (n + 1) * 2);
         CFB_CUDA(cudaMallocHost(&I.hSpawn[r], I.hSpawnCap[r] * sizeof(SpawnRec)));
     }
+    if (I.phaseDirty) {  // batched set_tl_phase: one H2D copy of all phases before the step
+        if (!I.hPhaseRing[r]) CFB_CUDA(cudaMallocHost(&I.hPhaseRing[r], std::max(V.nInter, 1) * sizeof(int)));
+        memcpy(I.hPhaseRing[r], I.hPhase.data(), V.nInter * sizeof(int));
+        CFB_CUDA(cudaMemcpyAsync(V.curPhase, I.hPhaseRing[r], V.nInter * sizeof(int), cudaMemcpyHostToDevice, s));
+        I.phaseDirty = false;
+    }
     I.hSpawn[r][0].slot = n;
     if (n > 0) memcpy(I.hSpawn[r] + 1, recs, n * sizeof(SpawnRec));
     CFB_CUDA(cudaMemcpyAsync(I.spawn.p, I.hSpawn[r], (size_t) (n + 1) * sizeof(SpawnRec), cudaMemcpyHostToDevice, s));
@@ -1348,7 +1394,7 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
         CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_notify, TPB, 0)); I.gridNotify = std::max(b, 1) * I.numSMs;
         CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move, TPB, 0)); I.gridMove = std::max(b, 1) * I.numSMs;
         CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_leader, TPB, 0)); I.gridLeader = std::max(b, 1) * I.numSMs;
-        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_control, 512, 0)); I.gridControl = std::max(b, 1) * I.numSMs;
+        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_control, 256, 0)); I.gridControl = std::max(b, 1) * I.numSMs;
     }
     const bool tm = I.timing;
     auto launchAll = [&](bool withEvents) {
@@ -1357,14 +1403,22 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
         if (withEvents) cudaEventRecord(I.ev[1], s);
         k_notify<<<I.gridNotify, TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[2], s);
-        k_control<<<I.gridControl, 512, 0, s>>>(V);
+        k_control<<<I.gridControl, 256, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[3], s);
         k_move<<<I.gridMove, TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[4], s);
         k_leader<<<I.gridLeader, TPB, 0, s>>>(V);
         if (withEvents) cudaEventRecord(I.ev[5], s);
     };
-    if (tm || !I.useGraph) {
+    if (!tm && I.useCoop) {
+        if (!I.gridStep) {
+            int b = 0;
+            CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_step, TPB, 0));
+            I.gridStep = std::max(b, 1) * I.numSMs;
+        }
+        void *args[] = {(void *) &V};
+        CFB_CUDA(cudaLaunchCooperativeKernel((void *) k_step, dim3(I.gridStep), dim3(TPB), args, 0, s));
+    } else if (tm || !I.useGraph) {
         launchAll(tm);
     } else {
         // The five kernels of one step are replayed as one CUDA graph per list parity: one launch
@@ -1383,10 +1437,17 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
             CFB_CUDA(cudaGraphInstantiate(&ge, g, 0));
             cudaGraphDestroy(g);
         }
+        // Re-launching an executable graph whose previous launch has not finished makes the driver
+        // wait on the host (observed: ~1 ms per step once the host runs more than two steps ahead).
+        // When that is the case fall back to the five plain launches, which only enqueue.
+        if (!I.graphDone[V.par]) CFB_CUDA(cudaEventCreateWithFlags(&I.graphDone[V.par], cudaEventDisableTiming));
+        else if (cudaEventQuery(I.graphDone[V.par]) != cudaSuccess) { launchAll(false); goto launched; }
         CFB_CUDA(cudaGraphLaunch(ge, s));
+        CFB_CUDA(cudaEventRecord(I.graphDone[V.par], s));
     }
+launched:
     CFB_CUDA(cudaGetLastError());
-    launches_ += 5;
+    launches_ += (!tm && I.useCoop) ? 1 : 5;
     steps_ += 1;
     if (tm) {
         CFB_CUDA(cudaEventSynchronize(I.ev[5]));
@@ -1521,6 +1582,7 @@ int DeviceSim::drainFinished(std::vector<FinRec> &slots) {
 
 void DeviceSim::phases(int32_t *out) {
     Impl &I = *impl_;
+    if (I.V.rl) { memcpy(out, I.hPhase.data(), I.V.nInter * sizeof(int)); return; }
     CFB_CUDA(cudaMemcpyAsync(out, I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
     CFB_CUDA(cudaStreamSynchronize(I.stream));
 }
@@ -1657,6 +1719,9 @@ void DeviceSim::restore(const Snapshot *s) {
         if (bytes) CFB_CUDA(cudaMemcpyAsync(regs[k].first, s->blob.p + off, bytes, cudaMemcpyDeviceToDevice, I.stream));
         off += (bytes + 255) & ~(size_t) 255;
     }
+    I.hPhase.resize(I.V.nInter);
+    if (I.V.nInter) CFB_CUDA(cudaMemcpy(I.hPhase.data(), I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost));
+    I.phaseDirty = false;
     I.notify.fill(0);      // epoch-stamped scratch: nothing of an older timeline may match
     I.foeMask.fill(0);
     CFB_CUDA(cudaStreamSynchronize(I.stream));
@@ -1744,9 +1809,11 @@ void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
 
 void DeviceSim::setPhase(int intersection, int phase) {
     Impl &I = *impl_;
-    // TrafficLight::setPhase only changes curPhaseIndex (trafficlight.cpp:39-41)
-    CFB_CUDA(cudaMemcpyAsync(I.V.curPhase + intersection, &phase, sizeof(int), cudaMemcpyHostToDevice, I.stream));
-    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    // TrafficLight::setPhase only changes curPhaseIndex (trafficlight.cpp:39-41).  Only reachable in
+    // rlTrafficLight mode, where the device never advances phases itself, so the host copy is
+    // authoritative; all changes made between two steps go up in one copy (see step()).
+    I.hPhase[intersection] = phase;
+    I.phaseDirty = true;
 }
 
 }  // namespace cfb

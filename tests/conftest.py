@@ -45,3 +45,26 @@ def cfg_6x6_dense(scenario_dir):
 @pytest.fixture(scope="session")
 def cfg_6x6_rl(scenario_dir):
     return _make(scenario_dir, 6, 6, "g6rl", dense=dict(frac=1.0, interval=5.0, seed=2), rl_traffic_light=True)
+
+
+@pytest.fixture(scope="session")
+def cfg_hetero_halfstep(scenario_dir):
+    """4x4 grid, interval = 0.5 s, every flow with its own (seeded) vehicle parameters: exercises the
+    dt-dependent formulas (vehicle.cpp:244, :257-266, :278-281) and the per-template gathers."""
+    import random
+    from cityflow_b200 import scenario
+    net = scenario.grid_roadnet(4, 4)
+    flows = scenario.random_walk_flows(net, frac=1.0, interval=4.0, seed=7)
+    rng = random.Random(11)
+    for f in flows:
+        f["vehicle"] = {
+            "length": rng.choice([4.0, 5.0, 6.5, 12.0]), "width": 2.0,
+            "maxPosAcc": rng.choice([1.5, 2.0, 3.0]), "maxNegAcc": rng.choice([3.5, 4.5, 6.0]),
+            "usualPosAcc": rng.choice([1.0, 2.0, 2.5]), "usualNegAcc": rng.choice([2.5, 3.5, 4.5]),
+            "minGap": rng.choice([1.5, 2.5, 3.0]), "maxSpeed": rng.choice([8.0, 11.11, 16.67, 20.0]),
+            "headwayTime": rng.choice([1.0, 1.5, 2.0]),
+        }
+        f["interval"] = float(rng.choice([3, 4, 5, 7]))
+        f["startTime"] = rng.choice([0, 0, 10, 50])
+        f["endTime"] = rng.choice([-1, -1, 400])
+    return scenario.write_scenario(scenario_dir, net, flows, interval=0.5, seed=3, name="hetero")
