@@ -90,6 +90,7 @@ struct Oracle {
     std::mt19937 rnd;
     size_t step = 0;
     size_t activeCount = 0;
+    int manuallyPushCnt = 0;
     int finishedCnt = 0;
     double cumulativeTravelTime = 0;
     std::map<int, Veh *> pool;                       // vehiclePool keyed by priority (engine.h:25)
@@ -741,6 +742,30 @@ void cfo_set_tl_phase(void *h, int inter, int phase) {  // engine.cpp:719-725
     Oracle *o = (Oracle *) h;
     if (!o->rlTrafficLight) return;
     o->curPhase[inter] = phase;
+}
+// Engine::pushVehicle(info, roads) engine.cpp:693-717 (values: NaN = keep the struct default)
+void cfo_push_vehicle(void *h, const double *v, const int32_t *roads, int n) {
+    Oracle *o = (Oracle *) h;
+    VehicleTemplate t;
+    double *f[10] = {&t.speed, &t.len, &t.width, &t.maxPosAcc, &t.maxNegAcc, &t.usualPosAcc, &t.usualNegAcc,
+                     &t.minGap, &t.maxSpeed, &t.headwayTime};
+    for (int k = 0; k < 10; ++k) if (v[k] == v[k]) *f[k] = v[k];
+    std::vector<int> anchors(roads, roads + n);
+    Veh *veh = o->newVehicle(t, anchors, -2, o->manuallyPushCnt++);
+    o->planRouteBuffer[anchors[0]].push_back(veh);
+}
+int cfo_road_index(void *h, const char *id) {
+    Oracle *o = (Oracle *) h;
+    auto it = o->net.roadIndex.find(id);
+    return it == o->net.roadIndex.end() ? -1 : it->second;
+}
+// Engine::getAverageTravelTime engine.cpp:682-691
+double cfo_average_travel_time(void *h) {
+    Oracle *o = (Oracle *) h;
+    double tt = o->cumulativeTravelTime;
+    int n = o->finishedCnt;
+    for (auto &kv : o->pool) { tt += o->currentTime() - kv.second->enterTime; n++; }
+    return n == 0 ? 0 : tt / n;
 }
 // running vehicles in vehiclePool (priority) order, like Engine::getRunningVehicles engine.cpp:780-790
 int cfo_vehicles(void *h, OracleVehRec *out, int cap) {

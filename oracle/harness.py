@@ -208,6 +208,22 @@ class PortOracle:
     def vehicle_count(self) -> int:
         return self.lib.cfo_vehicle_count(self.h)
 
+    def average_travel_time(self) -> float:
+        self.lib.cfo_average_travel_time.restype = ctypes.c_double
+        self.lib.cfo_average_travel_time.argtypes = [ctypes.c_void_p]
+        return float(self.lib.cfo_average_travel_time(self.h))
+
+    def push_vehicle(self, info: dict, roads: list):
+        names = ["speed", "length", "width", "maxPosAcc", "maxNegAcc", "usualPosAcc", "usualNegAcc", "minGap", "maxSpeed", "headwayTime"]
+        v = np.array([info.get(k, float("nan")) for k in names], np.float64)
+        self.lib.cfo_road_index.restype = ctypes.c_int
+        self.lib.cfo_road_index.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        r = np.array([self.lib.cfo_road_index(self.h, x.encode()) for x in roads], np.int32)
+        assert (r >= 0).all()
+        self.lib.cfo_push_vehicle.restype = None
+        self.lib.cfo_push_vehicle.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        self.lib.cfo_push_vehicle(self.h, v.ctypes.data, r.ctypes.data, len(r))
+
     def tie_count(self) -> int:
         return self.lib.cfo_tie_count(self.h)
 
