@@ -97,6 +97,7 @@ struct Ctrl {
 #define CFB_DBG_ADD(i, v)
 #endif
 
+constexpr int HEAD_BIT = 0x40000000;   // in vehList[].y: the vehicle is the first of its drivable's list
 constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
 constexpr int PLAN_LOOKAHEAD_END = -1;
 constexpr int SPAWN_SMEM = 2048;
@@ -347,7 +348,7 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
                 V.pos[h] = p;
                 atomicAdd(&V.ctrl->active, 1);
                 const int vi = atomicAdd(&V.ctrl->nVeh[cpar], 1);
-                if (vi < V.vehCap) V.vehList[cpar][vi] = make_int2(p, i);
+                if (vi < V.vehCap) V.vehList[cpar][vi] = make_int2(p, n == 0 ? (i | HEAD_BIT) : i);
                 int nx = V.waitNext[h];
                 V.waitHead[i] = nx;
                 if (nx < 0) V.waitTail[i] = -1;
@@ -570,7 +571,7 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
     for (int it = bid * blockDim.x + threadIdx.x; it < nVeh; it += nblk * blockDim.x) {
         const long long tStart = clock64();
         const int2 vd = V.vehList[cpar][it];
-        const int p = vd.x, d = vd.y;
+        const int p = vd.x, d = vd.y & ~HEAD_BIT;
         // ---- load phase: everything the branches below may need is requested up front with
         // clamped (always valid) indices, so the dependent-load depth is 3 levels, not one
         // round trip per branch ----
@@ -861,7 +862,7 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
             for (int k = 0; k < wib; ++k) { offV += sTot[k]; offA += sTot[k] > 0; }
             if (lane == 0) V.actList[npar][offA] = d;
             for (int k = lane; k < total; k += 32)
-                if (offV + k < V.vehCap) V.vehList[npar][offV + k] = make_int2(base + k, d);
+                if (offV + k < V.vehCap) V.vehList[npar][offV + k] = make_int2(base + k, k == 0 ? (d | HEAD_BIT) : d);
         }
         __syncthreads();
     }
@@ -899,45 +900,55 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
             V.curPhase[in] = cur;
         }
     }
-    for (int w = warp; w < nAct; w += nWarps) {
-        const int d = V.actList[npar][w];
-        const int n = V.count[d];
-        const int base = V.off[d];
-        double carryDis = 0, carryLen = 0;
-        for (int c0 = 0; c0 < n; c0 += 32) {
-            const int k = c0 + lane;
-            const bool valid = k < n;
-            const int p = base + k;
-            double dis = 0, len = 0;
-            int4 idv = make_int4(0, 0, 0, 0);
-            if (valid) {
-                dis = V.kin[p].x;
-                idv = V.ids[p];
-                len = V.tmpl[idv.y].len;
-            }
-            double pd = __shfl_up_sync(0xffffffffu, dis, 1);
-            double pl = __shfl_up_sync(0xffffffffu, len, 1);
-            if (lane == 0) {
-                pd = carryDis;
-                pl = carryLen;
-            }
-            carryDis = __shfl_sync(0xffffffffu, dis, 31);
-            carryLen = __shfl_sync(0xffffffffu, len, 31);
-            if (valid) {
-                if (k > 0) {
-                    V.leader[p] = p - 1;
-                    V.gap[p] = pd - pl - dis;
-                } else {
-                    int ld = -1;
-                    double g = 0;
-                    headSearch(V, d, dis, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
-                    V.leader[p] = ld;
-                    if (ld >= 0) V.gap[p] = g;
-                }
-                const int b = V.nav[p].z;
-                if (b >= 0 && V.pos[b] < 0) V.nav[p].z = -1;
-            }
+    // flat pass over the position list k_move just wrote (bucket order: a thread's list
+    // predecessor usually sits in the previous lane, its dis/len arrive by shuffle)
+    (void) warp; (void) nWarps;
+    const int nVeh = min(V.ctrl->nVeh[npar], V.vehCap);
+    const int stride = nblk * blockDim.x;
+    for (int it0 = gtid - lane; it0 < nVeh; it0 += stride) {
+        const int it = it0 + lane;
+        const bool valid = it < nVeh;
+        int p = -2, d = 0;
+        bool head = true;
+        double dis = 0, len = 0;
+        int4 idv = make_int4(0, 0, 0, 0);
+        if (valid) {
+            const int2 vd = V.vehList[npar][it];
+            p = vd.x;
+            d = vd.y & ~HEAD_BIT;
+            head = (vd.y & HEAD_BIT) != 0;
+            dis = V.kin[p].x;
+            idv = V.ids[p];
+            len = V.tmpl[idv.y].len;
         }
+        const int pp = __shfl_up_sync(0xffffffffu, p, 1);
+        double pd = __shfl_up_sync(0xffffffffu, dis, 1);
+        double pl = __shfl_up_sync(0xffffffffu, len, 1);
+        if (valid) {
+            if (!head) {
+                if (lane == 0 || pp != p - 1) {  // predecessor handled by another warp
+                    pd = V.kin[p - 1].x;
+                    pl = V.tmpl[V.ids[p - 1].y].len;
+                }
+                V.leader[p] = p - 1;
+                V.gap[p] = pd - pl - dis;
+            }
+            const int b = V.nav[p].z;
+            if (b >= 0 && V.pos[b] < 0) V.nav[p].z = -1;
+        }
+    }
+    // list heads: dense pass, one thread per occupied drivable (their cross-drivable search is a
+    // chain of dependent loads; keeping it out of the streaming pass above avoids one slow lane
+    // per warp)
+    for (int w = gtid; w < nAct; w += stride) {
+        const int d = V.actList[npar][w];
+        const int p = V.off[d];
+        const int4 idv = V.ids[p];
+        int ld = -1;
+        double g = 0;
+        headSearch(V, d, V.kin[p].x, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
+        V.leader[p] = ld;
+        if (ld >= 0) V.gap[p] = g;
     }
 }
 __global__ void __launch_bounds__(256) k_leader(View V) { phase_leader(V, blockIdx.x, gridDim.x); }
