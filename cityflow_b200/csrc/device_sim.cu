@@ -84,6 +84,7 @@ struct Ctrl {
     int nVeh[2];     // work lists, double-buffered on step parity
     int nAct[2];
     int nExtra;
+    int nBlkUpd;     // sharded mode: blocker changes of this step (see blkUpd)
     int nCustom;     // outstanding set_vehicle_speed requests (Vehicle::setCustomSpeed, vehicle.h:128)
     unsigned long long vehicleSteps;  // sum over steps of activeVehicleCount after the step (the bench metric)
     unsigned long long dbg[8];        // CFB_DEBUG_COUNTERS builds: in-kernel cycle / trip-count maxima
@@ -153,6 +154,15 @@ struct View {
     int *extraList;     // empty drivables that receive entrants this step
     double *cust;        // per position: custom speed for the coming step (NaN = none)
     double *slotCust;    // per slot: custom speed of a vehicle still in a waiting queue
+    int *blk;            // per slot: committed blocker slot (Vehicle::blocker), -1 none: chain walks need one load per hop
+    int *delStep;        // per slot: step at which the vehicle in that slot left the network
+    // ---- sharded mode (partition.h): null / 0 when the engine owns the whole network ----
+    const unsigned char *owned;   // per drivable: this rank owns it
+    const int *boundOut;          // lanes this rank feeds but does not own (all peers, concatenated)
+    const int *boundIn;           // lanes this rank owns but a peer feeds
+    int nBoundOut, nBoundIn;
+    int2 *blkUpd;                 // [0] = {count, 0}; then (slot, new blocker | -2 = left the network)
+    int blkUpdCap;
     unsigned *dbgCyc, *dbgPath;   // CFB_DEBUG_COUNTERS builds: per-position cycles / path bits of k_control
     Ctrl *ctrl;
     const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
@@ -207,6 +217,21 @@ __device__ __forceinline__ int reachSteps(double mySpeed, double distance, doubl
 // Vehicle::canYield vehicle.cpp:284-287
 __device__ __forceinline__ bool canYield(const DTmpl &T, double speed, double dist) {
     return (dist > 0 && 0.5 * speed * speed / T.maxNegAcc < dist - T.yieldDistance) || (dist < 0 && dist + T.len < 0);
+}
+
+// Commit a vehicle's blocker (slot-indexed copy used by chain walks); in sharded mode the change is
+// also queued for the other ranks.  val == -2: the vehicle left the network this step.
+__device__ __forceinline__ void blkSet(const View &V, int slot, int val) {
+    if (val == -2) {
+        V.blk[slot] = -1;
+        V.delStep[slot] = V.ctrl->step;
+    } else {
+        V.blk[slot] = val;
+    }
+    if (V.blkUpd) {
+        const int i = atomicAdd(&V.ctrl->nBlkUpd, 1);
+        if (i < V.blkUpdCap) V.blkUpd[1 + i] = make_int2(slot, val); else atomicOr(&V.ctrl->error, ERR_MOVER_OVERFLOW);
+    }
 }
 
 __device__ __forceinline__ int planAt(const View &V, int plan, int idx) { return V.planData[V.planBeg[plan] + idx]; }
@@ -291,6 +316,7 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
         V.ctrl->nExtra = 0;
     }
     for (i = gtid0; i < V.nLanes; i += nblk * blockDim.x) {
+    if (V.owned && !V.owned[i]) continue;   // another rank admits into this lane (its tail arrives by exchange)
     if (nSpawn > 0) {
         int lo = 0, hi = nSpawn;  // lower bound of lane i
         while (lo < hi) {
@@ -345,6 +371,7 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
                     if (cs == cs) { V.cust[p] = cs; V.slotCust[h] = __longlong_as_double(-1LL); }
                 }
                 V.count[i] = n + 1;
+                V.blk[h] = -1;
                 V.pos[h] = p;
                 atomicAdd(&V.ctrl->active, 1);
                 const int vi = atomicAdd(&V.ctrl->nVeh[cpar], 1);
@@ -484,13 +511,17 @@ __device__ __forceinline__ void phase_notify(const View &V, const int bid, const
         // the link the tail came out of, if it is empty now (otherwise it is on the list itself)
         const int prev = V.nav[base + c - 1].y;
         int l1 = -1;
-        if (prev >= V.nLanes && V.count[prev] == 0) {
+        if (prev >= V.nLanes && V.count[prev] == 0 && (!V.owned || V.owned[prev])) {
             l1 = prev - V.nLanes;
             notifyLink(V, l1, lane, epoch);
         }
         // the link the head is about to take, if empty
         const int nx = V.ids[base].w;
         if (nx >= V.nLanes && V.count[nx] == 0 && nx - V.nLanes != l1) notifyLink(V, nx - V.nLanes, lane, epoch);
+    }
+    for (int w = warp; w < V.nBoundOut; w += nWarps) {  // sharded: source 1 may sit on a lane another rank owns
+        const Tail t = V.tail[V.boundOut[w]];
+        if (t.pos >= 0 && t.prev >= V.nLanes && V.owned[t.prev] && V.count[t.prev] == 0) notifyLink(V, t.prev - V.nLanes, lane, epoch);
     }
 }
 __global__ void __launch_bounds__(256) k_notify(View V) { phase_notify(V, blockIdx.x, gridDim.x); }
@@ -539,11 +570,15 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
     }
     if (yield == 1) {
         // deadlock detection over the committed blocker chain (Floyd), roadnet.cpp:662-674
-        auto blockerOf = [&](int p) -> int {
-            int b = V.nav[p].z;
-            return b < 0 ? -1 : V.pos[b];
+        // A reference to a vehicle that left the network in the previous step counts as null
+        // (Engine::threadUpdateAction drops it, engine.cpp:419-421): evaluated lazily here.
+        const int prevStep = V.ctrl->step - 1;
+        auto blockerOf = [&](int s) -> int {
+            int b = V.blk[s];
+            if (b >= 0 && V.delStep[b] == prevStep) b = -1;
+            return b;
         };
-        int fast = fp, slow = fp;
+        int fast = fid.x, slow = fid.x;
         int trips = 0;
         while (fast >= 0) {
             ++trips;
@@ -735,7 +770,11 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
                 if (e >= ENT_CAP) atomicOr(&V.ctrl->error, ERR_ENTRANT_OVERFLOW);
                 else V.ent[newDrv * ENT_CAP + e] = m;
                 // an empty target is on no work list yet: queue it for k_move
-                if (e == 0 && V.count[newDrv] == 0) V.extraList[atomicAdd(&V.ctrl->nExtra, 1)] = newDrv;
+                if (V.owned && !V.owned[newDrv]) {
+                    V.pos[idv.x] = -1;   // the record travels to the owner of the lane (k_pack_movers)
+                } else if (e == 0 && V.count[newDrv] == 0) {
+                    V.extraList[atomicAdd(&V.ctrl->nExtra, 1)] = newDrv;
+                }
             }
         }
     }
@@ -789,6 +828,7 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
             if (keep) {
                 const int q = base + dst;
                 V.kin[q] = nk;                                     // dis, speed
+                if (nb.y != nv.z) blkSet(V, idv.x, nb.y);
                 nv.z = nb.y;                                       // blocker := buffer.blocker or null
                 V.nav[q] = nv;
                 if (dst != k) {
@@ -797,6 +837,7 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 }
             } else if (valid && nb.x == -2) {                      // finished (engine.cpp:296-310)
                 V.pos[idv.x] = -1;
+                blkSet(V, idv.x, -2);
                 const int f = atomicAdd(&V.ctrl->finCount, 1);
                 if (f < V.finCap) V.finSlots[f] = make_int2(idv.x, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
                 atomicSub(&V.ctrl->active, 1);
@@ -828,7 +869,9 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 const int4 idv = V.mids[mi];
                 V.kin[q] = V.mkin[mi];
                 V.ids[q] = idv;
-                V.nav[q] = V.mnav[mi];
+                const int4 mnv = V.mnav[mi];
+                V.nav[q] = mnv;
+                blkSet(V, idv.x, mnv.z);
                 V.pos[idv.x] = q;
             }
             if (lane == 0) V.entCnt[d] = 0;
@@ -933,8 +976,6 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
                 V.leader[p] = p - 1;
                 V.gap[p] = pd - pl - dis;
             }
-            const int b = V.nav[p].z;
-            if (b >= 0 && V.pos[b] < 0) V.nav[p].z = -1;
         }
     }
     // list heads: dense pass, one thread per occupied drivable (their cross-drivable search is a
@@ -969,6 +1010,125 @@ __global__ void __launch_bounds__(256, 4) k_step(View V) {
     phase_move(V, blockIdx.x, gridDim.x);
     grid.sync();
     phase_leader(V, blockIdx.x, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// Sharded mode: what crosses a seam (partition.h).  Fixed-size messages, one entry per boundary lane.
+struct __align__(16) TailMsg {     // owner -> feeder: Drivable::getLastVehicle of a boundary lane
+    Tail tail;
+    int count, inserted, pad0, pad1;
+    double2 kin;
+    int4 ids, nav;
+};
+struct __align__(16) MoverRec {
+    double2 kin;
+    int4 ids, nav;
+};
+struct __align__(16) MoverMsg {    // feeder -> owner: this step's entrants of a boundary lane
+    int n, pad0, pad1, pad2;
+    MoverRec rec[ENT_CAP];
+};
+
+__global__ void k_pack_tails(View V, TailMsg *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= V.nBoundIn) return;
+    const int L = V.boundIn[j];
+    TailMsg m;
+    m.tail = V.tail[L];
+    m.count = V.count[L];
+    m.inserted = V.inserted[L];
+    m.pad0 = m.pad1 = 0;
+    m.kin = make_double2(0, 0);
+    m.ids = m.nav = make_int4(0, 0, 0, 0);
+    if (m.tail.pos >= 0) {
+        m.kin = V.kin[m.tail.pos];
+        m.ids = V.ids[m.tail.pos];
+        m.nav = V.nav[m.tail.pos];
+    }
+    out[j] = m;
+}
+
+__global__ void k_unpack_tails(View V, const TailMsg *in) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= V.nBoundOut) return;
+    const int L = V.boundOut[j];
+    const TailMsg m = in[j];
+    V.tail[L] = m.tail;
+    V.count[L] = m.count;
+    V.inserted[L] = (unsigned char) m.inserted;
+    if (m.tail.pos >= 0) {  // ghost copy of the one vehicle this rank may look at
+        V.kin[m.tail.pos] = m.kin;
+        V.ids[m.tail.pos] = m.ids;
+        V.nav[m.tail.pos] = m.nav;
+    }
+}
+
+__global__ void k_pack_movers(View V, MoverMsg *out) {  // one warp per boundary lane this rank feeds
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= V.nBoundOut) return;
+    const int L = V.boundOut[j];
+    const int n = min(V.entCnt[L], ENT_CAP);
+    if (lane == 0) { out[j].n = n; out[j].pad0 = out[j].pad1 = out[j].pad2 = 0; }
+    if (lane < n) {
+        const int m = V.ent[L * ENT_CAP + lane];
+        MoverRec r;
+        r.kin = V.mkin[m];
+        r.ids = V.mids[m];
+        r.nav = V.mnav[m];
+        out[j].rec[lane] = r;
+    }
+    __syncwarp();
+    if (lane == 0) V.entCnt[L] = 0;
+}
+
+__global__ void k_unpack_movers(View V, const MoverMsg *in) {  // one warp per boundary lane this rank owns
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= V.nBoundIn) return;
+    const int L = V.boundIn[j];
+    const int n = in[j].n;
+    if (n == 0) return;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&V.ctrl->moverCount, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane < n) {
+        const int m = base + lane;
+        if (m < V.moverCap) {
+            const MoverRec r = in[j].rec[lane];
+            V.mkin[m] = r.kin;
+            V.mids[m] = r.ids;
+            V.mnav[m] = r.nav;
+            V.ent[L * ENT_CAP + lane] = m;
+        } else {
+            atomicOr(&V.ctrl->error, ERR_MOVER_OVERFLOW);
+        }
+    }
+    if (lane == 0) {
+        V.entCnt[L] = n;
+        if (V.count[L] == 0) V.extraList[atomicAdd(&V.ctrl->nExtra, 1)] = L;
+    }
+}
+
+// blocker changes: [0] = {count,0} header, filled right before the all-gather
+__global__ void k_seal_blk(View V) {
+    V.blkUpd[0] = make_int2(min(V.ctrl->nBlkUpd, V.blkUpdCap), 0);
+    V.ctrl->nBlkUpd = 0;
+}
+__global__ void k_apply_blk(View V, const int2 *all, int world, int me, int stridePerRank) {
+    const int r = blockIdx.y;
+    if (r == me) return;
+    const int2 *src = all + (size_t) r * stridePerRank;
+    const int n = src[0].x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int2 u = src[1 + i];
+        if (u.y == -2) {
+            V.blk[u.x] = -1;
+            V.delStep[u.x] = V.ctrl->step;
+        } else {
+            V.blk[u.x] = u.y;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1058,7 +1218,13 @@ struct DeviceSim::Impl {
     DevBuf<double> gap, remain, cust, slotCust;
     DevBuf<int> leader, count, pos, waitHead, waitTail, waitNext, curPhase, entCnt, ent, scratchI;
     DevBuf<int2> finSlots, vehList0, vehList1;
-    DevBuf<int> act0, act1, extra, lcPeer;
+    DevBuf<int> act0, act1, extra, lcPeer, blk, delStep, boundOut, boundIn;
+    DevBuf<unsigned char> owned;
+    DevBuf<TailMsg> tailSend, tailRecv;
+    DevBuf<MoverMsg> moverSend, moverRecv;
+    DevBuf<int2> blkUpd, blkAll;
+    std::vector<int> outBeg, inBeg;
+    int shardRank = 0, shardWorld = 1;
     DevBuf<Tail> tail;
     DevBuf<unsigned> dbgCyc, dbgPath;
     DevBuf<int4> linkInfo;
@@ -1325,20 +1491,26 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     DevBuf<int> npos, nnext;
     DevBuf<int4> ninfo;
     DevBuf<double> ncust;
+    DevBuf<int> nblk, ndel;
     npos.alloc(cap); nnext.alloc(cap); ninfo.alloc(cap); ncust.alloc(cap);
     npos.fill(0xff); nnext.fill(0xff); ninfo.fill(0); ncust.fill(0xff);
+    nblk.alloc(cap); ndel.alloc(cap); nblk.fill(0xff); ndel.fill(0x80);
     if (I.slotCap) {
         CFB_CUDA(cudaMemcpy(npos.p, I.pos.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
         CFB_CUDA(cudaMemcpy(nnext.p, I.waitNext.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
         CFB_CUDA(cudaMemcpy(ninfo.p, I.slotInfo.p, I.slotCap * sizeof(int4), cudaMemcpyDeviceToDevice));
         CFB_CUDA(cudaMemcpy(ncust.p, I.slotCust.p, I.slotCap * sizeof(double), cudaMemcpyDeviceToDevice));
+        CFB_CUDA(cudaMemcpy(nblk.p, I.blk.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
+        CFB_CUDA(cudaMemcpy(ndel.p, I.delStep.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
     }
     std::swap(I.pos.p, npos.p); std::swap(I.pos.n, npos.n);
     std::swap(I.waitNext.p, nnext.p); std::swap(I.waitNext.n, nnext.n);
     std::swap(I.slotInfo.p, ninfo.p); std::swap(I.slotInfo.n, ninfo.n);
     std::swap(I.slotCust.p, ncust.p); std::swap(I.slotCust.n, ncust.n);
+    std::swap(I.blk.p, nblk.p); std::swap(I.blk.n, nblk.n);
+    std::swap(I.delStep.p, ndel.p); std::swap(I.delStep.n, ndel.n);
     I.slotCap = cap;
-    I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p;
+    I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p; I.V.blk = I.blk.p; I.V.delStep = I.delStep.p;
     I.graphDirty = true;
 }
 
@@ -1348,6 +1520,7 @@ void DeviceSim::reset() {
     I.count.fill(0); I.entCnt.fill(0);
     I.waitHead.fill(0xff); I.waitTail.fill(0xff); I.inserted.fill(0);
     I.pos.fill(0xff); I.waitNext.fill(0xff); I.cust.fill(0xff); I.slotCust.fill(0xff);
+    I.blk.fill(0xff); I.delStep.fill(0x80);
     I.notify.fill(0);
     I.tail.fill(0xff);   // pos = -1: every drivable empty
     I.foeMask.fill(0);
@@ -1364,7 +1537,7 @@ void DeviceSim::reset() {
 int DeviceSim::numPositions() const { return impl_->P; }
 int DeviceSim::numDrivables() const { return impl_->V.nDrv; }
 
-void DeviceSim::step(const SpawnRec *recs, int n) {
+void DeviceSim::stageStep(const SpawnRec *recs, int n) {
     Impl &I = *impl_;
     View &V = I.V;
     cudaStream_t s = I.stream;
@@ -1395,18 +1568,17 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     CFB_CUDA(cudaMemcpyAsync(I.spawn.p, I.hSpawn[r], (size_t) (n + 1) * sizeof(SpawnRec), cudaMemcpyHostToDevice, s));
     CFB_CUDA(cudaEventRecord(I.spawnDone[r], s));
     V.par = (int) (steps_ & 1);
+}
+
+void DeviceSim::step(const SpawnRec *recs, int n) {
+    stageStep(recs, n);
+    Impl &I = *impl_;
+    View &V = I.V;
+    cudaStream_t s = I.stream;
     const int TPB = 256;
     const int gLaneRL = (std::max(V.nLanes, V.nRL) + TPB - 1) / TPB;
     // list-driven kernels: fixed grids sized to the machine (grid-stride loops inside)
-    // exactly one resident wave per kernel (occupancy x #SM blocks): a second, partial wave would
-    // double the latency of these dependent-load-bound kernels
-    if (!I.gridNotify) {
-        int b = 0;
-        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_notify, TPB, 0)); I.gridNotify = std::max(b, 1) * I.numSMs;
-        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move, TPB, 0)); I.gridMove = std::max(b, 1) * I.numSMs;
-        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_leader, TPB, 0)); I.gridLeader = std::max(b, 1) * I.numSMs;
-        CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_control, 256, 0)); I.gridControl = std::max(b, 1) * I.numSMs;
-    }
+    ensureGrids();   // one resident wave per kernel (occupancy x #SM blocks)
     const bool tm = I.timing;
     auto launchAll = [&](bool withEvents) {
         if (withEvents) cudaEventRecord(I.ev[0], s);
@@ -1472,6 +1644,135 @@ launched:
 
 static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src);
 void DeviceSim::synchronize() { CFB_CUDA(cudaStreamSynchronize(impl_->stream)); }
+
+// ------------------------------------------------------------------------------------------
+// Sharded mode (partition.h / shard.h): the step is run phase by phase, with the seam exchanges
+// (performed by a ShardTransport on this engine's stream) in between.
+void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned char> &owned,
+                               const std::vector<std::vector<int>> &feedPerPeer,
+                               const std::vector<std::vector<int>> &ownPerPeer) {
+    Impl &I = *impl_;
+    View &V = I.V;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    I.shardRank = rank;
+    I.shardWorld = world;
+    I.owned.upload(owned);
+    V.owned = I.owned.p;
+    std::vector<int> out, in;
+    I.outBeg.assign(1, 0);
+    I.inBeg.assign(1, 0);
+    for (int q = 0; q < world; ++q) {
+        out.insert(out.end(), feedPerPeer[q].begin(), feedPerPeer[q].end());
+        in.insert(in.end(), ownPerPeer[q].begin(), ownPerPeer[q].end());
+        I.outBeg.push_back((int) out.size());
+        I.inBeg.push_back((int) in.size());
+    }
+    V.nBoundOut = (int) out.size();
+    V.nBoundIn = (int) in.size();
+    if (out.empty()) out.push_back(0);
+    if (in.empty()) in.push_back(0);
+    I.boundOut.upload(out);
+    I.boundIn.upload(in);
+    V.boundOut = I.boundOut.p;
+    V.boundIn = I.boundIn.p;
+    I.tailSend.alloc(std::max(V.nBoundIn, 1));
+    I.tailRecv.alloc(std::max(V.nBoundOut, 1));
+    I.moverSend.alloc(std::max(V.nBoundOut, 1));
+    I.moverRecv.alloc(std::max(V.nBoundIn, 1));
+    I.tailSend.fill(0); I.tailRecv.fill(0); I.moverSend.fill(0); I.moverRecv.fill(0);
+    V.blkUpdCap = 1 << 14;
+    I.blkUpd.alloc(1 + V.blkUpdCap);
+    I.blkAll.alloc((size_t) world * (1 + V.blkUpdCap));
+    I.blkUpd.fill(0); I.blkAll.fill(0);
+    V.blkUpd = I.blkUpd.p;
+    I.useGraph = false;  // phases are launched one by one
+    I.useCoop = false;
+}
+
+ShardBuffers DeviceSim::shardBuffers() {
+    Impl &I = *impl_;
+    ShardBuffers b;
+    b.stream = (void *) I.stream;
+    b.rank = I.shardRank;
+    b.world = I.shardWorld;
+    b.tailSend = I.tailSend.p; b.tailRecv = I.tailRecv.p; b.moverSend = I.moverSend.p; b.moverRecv = I.moverRecv.p;
+    b.tailBytes = sizeof(TailMsg); b.moverBytes = sizeof(MoverMsg);
+    b.outBeg = I.outBeg; b.inBeg = I.inBeg;
+    b.blkSend = I.blkUpd.p; b.blkAll = I.blkAll.p;
+    b.blkBytesPerRank = (size_t) (1 + I.V.blkUpdCap) * sizeof(int2);
+    b.ctrlActive = &I.V.ctrl->active;
+    b.laneCount = I.V.count;
+    return b;
+}
+
+void DeviceSim::runIngest() {
+    Impl &I = *impl_;
+    const int TPB = 256;
+    const int g = (std::max(I.V.nLanes, I.V.nRL) + TPB - 1) / TPB;
+    k_ingest<<<std::max(g, 1), TPB, 0, I.stream>>>(I.V);
+    launches_ += 1;
+}
+void DeviceSim::runNotifyControl() {
+    Impl &I = *impl_;
+    ensureGrids();
+    k_notify<<<I.gridNotify, 256, 0, I.stream>>>(I.V);
+    k_control<<<I.gridControl, 256, 0, I.stream>>>(I.V);
+    launches_ += 2;
+}
+void DeviceSim::runMove() {
+    Impl &I = *impl_;
+    ensureGrids();
+    k_move<<<I.gridMove, 256, 0, I.stream>>>(I.V);
+    launches_ += 1;
+}
+void DeviceSim::runLeader() {
+    Impl &I = *impl_;
+    ensureGrids();
+    k_leader<<<I.gridLeader, 256, 0, I.stream>>>(I.V);
+    CFB_CUDA(cudaGetLastError());
+    launches_ += 1;
+    steps_ += 1;
+}
+void DeviceSim::packTails() {
+    Impl &I = *impl_;
+    if (I.V.nBoundIn) k_pack_tails<<<(I.V.nBoundIn + 127) / 128, 128, 0, I.stream>>>(I.V, I.tailSend.p);
+    launches_ += 1;
+}
+void DeviceSim::unpackTails() {
+    Impl &I = *impl_;
+    if (I.V.nBoundOut) k_unpack_tails<<<(I.V.nBoundOut + 127) / 128, 128, 0, I.stream>>>(I.V, I.tailRecv.p);
+    launches_ += 1;
+}
+void DeviceSim::packMovers() {
+    Impl &I = *impl_;
+    if (I.V.nBoundOut) k_pack_movers<<<(I.V.nBoundOut * 32 + 127) / 128, 128, 0, I.stream>>>(I.V, I.moverSend.p);
+    launches_ += 1;
+}
+void DeviceSim::unpackMovers() {
+    Impl &I = *impl_;
+    if (I.V.nBoundIn) k_unpack_movers<<<(I.V.nBoundIn * 32 + 127) / 128, 128, 0, I.stream>>>(I.V, I.moverRecv.p);
+    launches_ += 1;
+}
+void DeviceSim::sealBlk() {
+    Impl &I = *impl_;
+    k_seal_blk<<<1, 1, 0, I.stream>>>(I.V);
+    launches_ += 1;
+}
+void DeviceSim::applyBlk() {
+    Impl &I = *impl_;
+    dim3 grid(32, I.shardWorld);
+    k_apply_blk<<<grid, 256, 0, I.stream>>>(I.V, I.blkAll.p, I.shardWorld, I.shardRank, 1 + I.V.blkUpdCap);
+    launches_ += 1;
+}
+void DeviceSim::ensureGrids() {
+    Impl &I = *impl_;
+    if (I.gridNotify) return;
+    int b = 0;
+    CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_notify, 256, 0)); I.gridNotify = std::max(b, 1) * I.numSMs;
+    CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_move, 256, 0)); I.gridMove = std::max(b, 1) * I.numSMs;
+    CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_leader, 256, 0)); I.gridLeader = std::max(b, 1) * I.numSMs;
+    CFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_control, 256, 0)); I.gridControl = std::max(b, 1) * I.numSMs;
+}
 
 // ---- measurement support: CUDA-event brackets on the engine's own stream ----
 void DeviceSim::flushL2() {
@@ -1640,6 +1941,10 @@ void DeviceSim::debugDump(std::vector<DebugRec> &out) {
     std::vector<double2> kin(P);
     std::vector<double> gap(P);
     std::vector<int4> ids(P), nav(P);
+    std::vector<int> del(I.slotCap);
+    CFB_CUDA(cudaMemcpy(del.data(), I.V.delStep, del.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    readCtrlImpl(I.stream, I.hCtrl, I.V.ctrl);
+    const int lastStep = I.hCtrl->step - 1;
     CFB_CUDA(cudaMemcpy(count.data(), I.V.count, count.size() * sizeof(int), cudaMemcpyDeviceToHost));
     CFB_CUDA(cudaMemcpy(leader.data(), I.V.leader, P * sizeof(int), cudaMemcpyDeviceToHost));
     CFB_CUDA(cudaMemcpy(kin.data(), I.V.kin, P * sizeof(double2), cudaMemcpyDeviceToHost));
@@ -1655,6 +1960,7 @@ void DeviceSim::debugDump(std::vector<DebugRec> &out) {
             r.drivable = d;
             r.leaderSlot = leader[p] >= 0 ? ids[leader[p]].x : -1;
             r.blockerSlot = nav[p].z;
+            if (r.blockerSlot >= 0 && del[r.blockerSlot] == lastStep) r.blockerSlot = -1;  // dropped lazily on the device
             r.priority = ids[p].z;
             r.enterLaneLinkTime = nav[p].w;
             r.listIndex = k;
@@ -1693,6 +1999,7 @@ static std::vector<std::pair<void *, size_t>> snapshotRegions(DeviceSim::Impl &I
         {V.ctrl, sizeof(Ctrl)},
         // slot-indexed arrays last (their size may differ between snapshot and restore time)
         {V.pos, S * sizeof(int)}, {V.waitNext, S * sizeof(int)}, {V.slotInfo, S * sizeof(int4)}, {V.slotCust, S * sizeof(double)},
+        {V.blk, S * sizeof(int)}, {V.delStep, S * sizeof(int)},
     };
 }
 
@@ -1721,12 +2028,12 @@ void DeviceSim::restore(const Snapshot *s) {
     auto regs = snapshotRegions(I);
     if (regs.size() != s->regions.size()) throw std::runtime_error("cityflow_b200: archive does not match this engine");
     // slots beyond the archive's capacity: unused
-    I.pos.fill(0xff); I.waitNext.fill(0xff); I.slotCust.fill(0xff);
+    I.pos.fill(0xff); I.waitNext.fill(0xff); I.slotCust.fill(0xff); I.blk.fill(0xff); I.delStep.fill(0x80);
     size_t off = 0;
     for (size_t k = 0; k < regs.size(); ++k) {
         const size_t bytes = s->regions[k].bytes;
         if (bytes > regs[k].second) throw std::runtime_error("cityflow_b200: archive does not match this engine (region size)");
-        if (k + 4 < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
+        if (k + 6 < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
         if (bytes) CFB_CUDA(cudaMemcpyAsync(regs[k].first, s->blob.p + off, bytes, cudaMemcpyDeviceToDevice, I.stream));
         off += (bytes + 255) & ~(size_t) 255;
     }

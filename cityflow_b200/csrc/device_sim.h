@@ -58,6 +58,20 @@ struct DeviceSimOptions {
     int replicas = 1;           // bench only: K independent copies of the scenario in one engine
 };
 
+// Device buffers a ShardTransport moves between ranks (all on `stream`).  Per peer q the tail /
+// mover messages of the lanes shared with q are contiguous: entries [beg[q], beg[q+1]).
+struct ShardBuffers {
+    void *stream = nullptr;
+    int rank = 0, world = 1;
+    void *tailSend = nullptr, *tailRecv = nullptr, *moverSend = nullptr, *moverRecv = nullptr;
+    size_t tailBytes = 0, moverBytes = 0;       // bytes per boundary lane
+    std::vector<int> outBeg, inBeg;             // lanes this rank feeds / owns, per peer (prefix sums)
+    void *blkSend = nullptr, *blkAll = nullptr; // blocker changes: own list, all ranks' lists
+    size_t blkBytesPerRank = 0;
+    int *ctrlActive = nullptr;                  // device int: vehicles this rank accounts for
+    int *laneCount = nullptr;                   // device ints: list length per drivable
+};
+
 class DeviceSim {
 public:
     // Throws std::runtime_error when no CUDA device / extension is usable (no CPU fallback).
@@ -71,6 +85,22 @@ public:
     void uploadTemplates(const std::vector<VehicleTemplate> &templates);
     void uploadPlans(const Routing &routing);
     void ensureSlotCapacity(int slots);
+
+    // ---- sharded mode: the step phase by phase (see shard.h for the protocol) ----
+    void configureShard(int rank, int world, const std::vector<unsigned char> &owned,
+                        const std::vector<std::vector<int>> &feedPerPeer, const std::vector<std::vector<int>> &ownPerPeer);
+    ShardBuffers shardBuffers();
+    void stageStep(const SpawnRec *recs, int n);
+    void runIngest();
+    void runNotifyControl();
+    void runMove();
+    void runLeader();
+    void packTails();
+    void unpackTails();
+    void packMovers();
+    void unpackMovers();
+    void sealBlk();
+    void applyBlk();
 
     // Enqueue one simulation step (asynchronous). `recs` must stay valid until the call returns.
     void step(const SpawnRec *recs, int n);
@@ -122,6 +152,7 @@ public:
     struct Impl;
 
 private:
+    void ensureGrids();
     Impl *impl_;
     long long steps_ = 0;
     long long launches_ = 0;
