@@ -61,6 +61,13 @@ def load_library() -> ctypes.CDLL:
         "cfb_kernel_times": (i32, [vp, vp, vp]),
         "cfb_synchronize": (i32, [vp]),
         "cfb_num_drivables": (i64, [vp]),
+        "cfb_shard_group_create": (vp, [cp, i32, i32]),
+        "cfb_shard_group_destroy": (None, [vp]),
+        "cfb_shard_group_step": (i32, [vp, i32]),
+        "cfb_shard_group_last_error": (cp, [vp]),
+        "cfb_shard_group_vehicle_count": (i64, [vp]),
+        "cfb_shard_group_lane_counts": (i32, [vp, vp, i32, i32]),
+        "cfb_shard_group_debug_vehicles": (i64, [vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -138,3 +145,41 @@ class CEngine:
 
     def gpu_launches(self) -> int:
         return int(self.lib.cfb_gpu_launches(self.h))
+
+
+class CShardGroup:
+    """`world` ranks of one simulation on ONE GPU (loop-back exchanges): checks the seam protocol."""
+
+    def __init__(self, config: str, world: int, device: int = 0):
+        self.lib = load_library()
+        self.h = self.lib.cfb_shard_group_create(config.encode(), world, device)
+        if not self.h:
+            raise RuntimeError("cfb_shard_group_create failed: %s" % self.lib.cfb_last_error(None).decode())
+        self.world = world
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cfb_shard_group_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def next_step(self, n: int = 1):
+        if self.lib.cfb_shard_group_step(self.h, n) < 0:
+            raise RuntimeError(self.lib.cfb_shard_group_last_error(self.h).decode())
+
+    def vehicle_count(self) -> int:
+        return int(self.lib.cfb_shard_group_vehicle_count(self.h))
+
+    def lane_counts(self, n_lanes: int, waiting: bool = False):
+        a = np.zeros(n_lanes, np.int32)
+        rc = self.lib.cfb_shard_group_lane_counts(self.h, a.ctypes.data, n_lanes, int(waiting))
+        assert rc == 0
+        return a
+
+    def debug_vehicles(self):
+        n = int(self.lib.cfb_shard_group_debug_vehicles(self.h, None, 0))
+        a = np.zeros(n, VEH_DTYPE)
+        if n:
+            self.lib.cfb_shard_group_debug_vehicles(self.h, a.ctypes.data, n)
+        return a

@@ -44,6 +44,7 @@
 #include <vector>
 
 #include "device_sim.h"
+#include "shard.h"
 
 namespace cfb {
 namespace cg = cooperative_groups;
@@ -927,7 +928,7 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
     const int nAct = V.ctrl->nAct[npar];
     if (gtid == 0) {  // nothing in this kernel reads these (list parity is the host-provided V.par)
         V.ctrl->step += 1;                                             // Engine::step (engine.cpp:593)
-        V.ctrl->vehicleSteps += (unsigned long long) V.ctrl->active;  // all finishes of this step are in
+        V.ctrl->vehicleSteps += (unsigned long long) (long long) V.ctrl->active;   // may be negative on one rank of a sharded run  // all finishes of this step are in
     }
     if (!V.rl) {
         for (int in = gtid; in < V.nInter; in += nblk * blockDim.x) {
@@ -1110,6 +1111,16 @@ __global__ void k_unpack_movers(View V, const MoverMsg *in) {  // one warp per b
     }
 }
 
+__global__ void k_mask_counts(View V, int *out) {  // out[0] = vehicles this rank accounts for, out[1+l] = owned lane counts
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) out[0] = V.ctrl->active;
+    if (i < V.nLanes) out[1 + i] = (!V.owned || V.owned[i]) ? V.count[i] : 0;
+}
+__global__ void k_mask_waiting(View V, const int *waiting, int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V.nLanes) out[i] = (!V.owned || V.owned[i]) ? waiting[i] : 0;
+}
+
 // blocker changes: [0] = {count,0} header, filled right before the all-gather
 __global__ void k_seal_blk(View V) {
     V.blkUpd[0] = make_int2(min(V.ctrl->nBlkUpd, V.blkUpdCap), 0);
@@ -1224,7 +1235,10 @@ struct DeviceSim::Impl {
     DevBuf<MoverMsg> moverSend, moverRecv;
     DevBuf<int2> blkUpd, blkAll;
     std::vector<int> outBeg, inBeg;
+    std::vector<unsigned char> ownedHost;
     int shardRank = 0, shardWorld = 1;
+    DevBuf<int> shardScratch;
+    DevBuf<unsigned char> finGather;
     DevBuf<Tail> tail;
     DevBuf<unsigned> dbgCyc, dbgPath;
     DevBuf<int4> linkInfo;
@@ -1657,6 +1671,7 @@ void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned c
     I.shardRank = rank;
     I.shardWorld = world;
     I.owned.upload(owned);
+    I.ownedHost = owned;
     V.owned = I.owned.p;
     std::vector<int> out, in;
     I.outBeg.assign(1, 0);
@@ -1764,6 +1779,55 @@ void DeviceSim::applyBlk() {
     k_apply_blk<<<grid, 256, 0, I.stream>>>(I.V, I.blkAll.p, I.shardWorld, I.shardRank, 1 + I.V.blkUpdCap);
     launches_ += 1;
 }
+void DeviceSim::shardCounts(ShardTransport *t, int32_t *laneOut, int *activeOut) {
+    Impl &I = *impl_;
+    const int n = 1 + I.V.nLanes;
+    if (I.shardScratch.n < (size_t) n) I.shardScratch.alloc(n);
+    k_mask_counts<<<(n + 255) / 256, 256, 0, I.stream>>>(I.V, I.shardScratch.p);
+    t->allReduceSumInt((void *) I.stream, I.shardScratch.p, n);
+    std::vector<int> h(n);
+    CFB_CUDA(cudaMemcpyAsync(h.data(), I.shardScratch.p, n * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    if (activeOut) *activeOut = h[0];
+    if (laneOut) memcpy(laneOut, h.data() + 1, I.V.nLanes * sizeof(int));
+}
+
+void DeviceSim::shardWaitingCounts(ShardTransport *t, int32_t *laneOut) {
+    Impl &I = *impl_;
+    const int nL = I.V.nLanes;
+    if (I.scratchI.n < (size_t) nL) I.scratchI.alloc(nL);
+    if (I.shardScratch.n < (size_t) nL + 1) I.shardScratch.alloc(nL + 1);
+    k_lane_waiting<<<(nL * 32 + 255) / 256, 256, 0, I.stream>>>(I.V, I.scratchI.p);
+    k_mask_waiting<<<(nL + 255) / 256, 256, 0, I.stream>>>(I.V, I.scratchI.p, I.shardScratch.p);
+    t->allReduceSumInt((void *) I.stream, I.shardScratch.p, nL);
+    CFB_CUDA(cudaMemcpyAsync(laneOut, I.shardScratch.p, nL * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+}
+
+// Finished vehicles of ALL ranks since the last drain (every rank must call this at the same step).
+void DeviceSim::shardGatherFinished(ShardTransport *t, std::vector<FinRec> &inout) {
+    Impl &I = *impl_;
+    const int cap = 1 << 16, W = t->world();
+    const size_t per = (size_t) (1 + cap) * sizeof(FinRec);
+    if (I.finGather.n < per * (W + 1)) I.finGather.alloc(per * (W + 1));
+    if ((int) inout.size() > cap) throw std::runtime_error("cityflow_b200: too many finished vehicles between two drains (sharded capacity)");
+    std::vector<FinRec> send(1 + inout.size());
+    send[0].slot = (int) inout.size();
+    send[0].step = 0;
+    std::copy(inout.begin(), inout.end(), send.begin() + 1);
+    unsigned char *mine = I.finGather.p, *all = I.finGather.p + per;
+    CFB_CUDA(cudaMemcpyAsync(mine, send.data(), send.size() * sizeof(FinRec), cudaMemcpyHostToDevice, I.stream));
+    t->allGather((void *) I.stream, mine, all, per);
+    std::vector<FinRec> recv((size_t) W * (1 + cap));
+    CFB_CUDA(cudaMemcpyAsync(recv.data(), all, per * W, cudaMemcpyDeviceToHost, I.stream));
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    inout.clear();
+    for (int r = 0; r < W; ++r) {
+        const FinRec *p = recv.data() + (size_t) r * (1 + cap);
+        for (int k = 0; k < p[0].slot; ++k) inout.push_back(p[1 + k]);
+    }
+}
+
 void DeviceSim::ensureGrids() {
     Impl &I = *impl_;
     if (I.gridNotify) return;
@@ -1953,6 +2017,7 @@ void DeviceSim::debugDump(std::vector<DebugRec> &out) {
     CFB_CUDA(cudaMemcpy(nav.data(), I.V.nav, P * sizeof(int4), cudaMemcpyDeviceToHost));
     out.clear();
     for (int d = 0; d < I.V.nDrv; ++d) {
+        if (!I.ownedHost.empty() && !I.ownedHost[d]) continue;   // sharded: another rank's drivable (only ghost data here)
         for (int k = 0; k < count[d]; ++k) {
             const int p = I.offHost[d] + k;
             DebugRec r{};

@@ -60,6 +60,8 @@ struct DeviceSimOptions {
 
 // Device buffers a ShardTransport moves between ranks (all on `stream`).  Per peer q the tail /
 // mover messages of the lanes shared with q are contiguous: entries [beg[q], beg[q+1]).
+class ShardTransport;
+
 struct ShardBuffers {
     void *stream = nullptr;
     int rank = 0, world = 1;
@@ -101,6 +103,9 @@ public:
     void unpackMovers();
     void sealBlk();
     void applyBlk();
+    void shardCounts(ShardTransport *t, int32_t *laneOut, int *activeOut);   // global sums (collective)
+    void shardWaitingCounts(ShardTransport *t, int32_t *laneOut);
+    void shardGatherFinished(ShardTransport *t, std::vector<FinRec> &inout);
 
     // Enqueue one simulation step (asynchronous). `recs` must stay valid until the call returns.
     void step(const SpawnRec *recs, int n);

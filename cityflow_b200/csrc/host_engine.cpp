@@ -6,6 +6,8 @@
 // results depend on; vehicle id <-> slot tables; travel-time statistics.  Everything per
 // vehicle / lane / intersection per step runs in device_sim.cu.  There is no CPU path for the
 // simulation: without a CUDA device cfb_engine_create fails.
+#include <cuda_runtime.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -17,6 +19,7 @@
 #include <set>
 #include <sstream>
 #include <fstream>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -24,6 +27,8 @@
 
 #include "../../include/cityflow_b200.h"
 #include "device_sim.h"
+#include "partition.h"
+#include "shard.h"
 #include "flows.h"
 #include "json_min.h"
 #include "roadnet.h"
@@ -123,7 +128,10 @@ public:
     PriorityMap pool;                                        // priority -> slot (vehiclePool, engine.h:25)
     std::unordered_map<uint64_t, int> idToSlot;              // built lazily (get_leader)
     bool idMapValid = false;
-    long long hostGenNs = 0, hostEnqueueNs = 0;              // host time spent generating spawns / enqueuing
+    long long hostGenNs = 0, hostEnqueueNs = 0;
+    // sharded mode
+    ShardTransport *transport = nullptr;                      // not owned
+    std::function<void(std::vector<FinRec> &)> finishedHook;   // local list -> list of all ranks              // host time spent generating spawns / enqueuing
     std::vector<Pending> pending;
     std::vector<SpawnRec> batch;
     std::vector<std::string> laneIds;
@@ -233,6 +241,8 @@ public:
         if (!finishedDirty) return;
         std::vector<FinRec> fin;
         dev->drainFinished(fin);
+        if (transport) dev->shardGatherFinished(transport, fin);
+        else if (finishedHook) finishedHook(fin);
         // deterministic accumulation order for the travel-time sum (ring order is atomics order)
         std::sort(fin.begin(), fin.end(), [this](const FinRec &a, const FinRec &b) {
             return a.step != b.step ? a.step < b.step : slots[a.slot].priority < slots[b.slot].priority;
@@ -288,7 +298,8 @@ public:
     }
 
     // Engine::nextStep engine.cpp:566-594 (host part: P0 spawn, P1 planRoute; the rest is device work)
-    void nextStep() {
+    // P0/P1 on the host: flows, vehicle creation, first-lane draw -> `batch` (lane-sorted spawn records)
+    void prepareStep() {
         const auto t0 = std::chrono::steady_clock::now();
         for (size_t i = 0; i < flows.size(); ++i) {  // Flow::nextStep flow.cpp:6-22
             FlowRun &f = flows[i];
@@ -338,15 +349,58 @@ public:
         if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
         if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
         dev->ensureSlotCapacity((int) slots.size());
-        const auto t1 = std::chrono::steady_clock::now();
-        dev->step(batch.data(), (int) batch.size());
-        const auto t2 = std::chrono::steady_clock::now();
-        hostGenNs += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
-        hostEnqueueNs += std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
+        hostGenNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
+    void finishStep() {
         h2dBytes += (long long) batch.size() * sizeof(SpawnRec) + sizeof(int);
         finishedDirty = true;
         step += 1;
         if ((step & 255) == 0) drain();  // bound the finished ring / free slots in long unobserved runs
+    }
+    // device phases up to (not including) the exchange points; see shard.h
+    void shardPhase(int k) {
+        switch (k) {
+            case 0: dev->stageStep(batch.data(), (int) batch.size()); dev->runIngest(); dev->packTails(); break;
+            case 1: dev->unpackTails(); dev->runNotifyControl(); dev->packMovers(); break;
+            case 2: dev->unpackMovers(); dev->runMove(); dev->packTails(); dev->sealBlk(); break;
+            case 3: dev->unpackTails(); dev->applyBlk(); dev->runLeader(); break;
+        }
+    }
+    void nextStep() {
+        prepareStep();
+        const auto t1 = std::chrono::steady_clock::now();
+        if (!transport) {
+            dev->step(batch.data(), (int) batch.size());
+        } else {  // one rank of a sharded run: phases with the seam exchanges in between
+            ShardBuffers b = dev->shardBuffers();
+            shardPhase(0);
+            transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X3
+            shardPhase(1);
+            transport->exchange(b.stream, b.moverSend, b.outBeg, b.moverRecv, b.inBeg, b.moverBytes);  // X1
+            shardPhase(2);
+            transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X2
+            transport->allGather(b.stream, b.blkSend, b.blkAll, b.blkBytesPerRank);
+            shardPhase(3);
+        }
+        hostEnqueueNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
+        finishStep();
+    }
+    // Cut the network and tell the device which part is ours (before the first step).
+    std::string configureShard(int rank, int world) {
+        Partition part = Partition::columnStrips(net, world);
+        double look = 0;
+        for (const auto &t : templates) look = std::max(look, t.maxSpeed * t.maxSpeed / t.usualNegAcc / 2 + t.maxSpeed * interval * 2);
+        std::string bad = part.validate(net, look);
+        if (!bad.empty()) return bad;
+        std::vector<unsigned char> owned(part.drvOwner.size());
+        for (size_t d = 0; d < owned.size(); ++d) owned[d] = part.drvOwner[d] == rank;
+        std::vector<std::vector<int>> feed(world), own(world);
+        for (int q = 0; q < world; ++q) {
+            feed[q] = part.boundary[rank][q];   // lanes I feed, q owns
+            own[q] = part.boundary[q][rank];    // lanes q feeds, I own
+        }
+        dev->configureShard(rank, world, owned, feed, own);
+        return "";
     }
 
     // Engine::reset engine.cpp:744-760
@@ -932,6 +986,199 @@ int cfb_load_from_file(cfb_engine *e, const char *path) {
         e->h.loadHost(a.host);
     )
     return CFB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Sharded execution: one rank of a multi-GPU run over NCCL, and an in-process
+// loop-back group (several ranks on one GPU, exchanges by device copies) that the parity tests use
+// to check the seam protocol against the unsharded engine.
+struct cfb_engine_shard_state {
+    std::unique_ptr<cfb::ShardTransport> transport;
+};
+static std::map<cfb_engine *, std::unique_ptr<cfb_engine_shard_state>> g_shards;
+
+extern "C" {
+
+int cfb_nccl_unique_id(unsigned char out[128]) {
+    std::string err;
+    if (!cfb::ncclUniqueIdBytes(out, err)) { g_createError = err; return CFB_ERR_DEVICE; }
+    return CFB_OK;
+}
+
+cfb_engine *cfb_engine_create_sharded(const char *config_file, int thread_num, int device, int rank, int world,
+                                      const unsigned char nccl_id[128]) {
+    cfb_engine *e = cfb_engine_create(config_file, thread_num, device);
+    if (!e || world <= 1) return e;
+    std::string err = e->h.configureShard(rank, world);
+    std::unique_ptr<cfb_engine_shard_state> st(new cfb_engine_shard_state());
+    if (err.empty()) st->transport.reset(cfb::createNcclTransport(rank, world, nccl_id, device < 0 ? 0 : device, err));
+    if (!err.empty() || !st->transport) {
+        g_createError = "sharded engine: " + err;
+        cfb_engine_destroy(e);
+        return nullptr;
+    }
+    e->h.transport = st->transport.get();
+    g_shards[e] = std::move(st);
+    return e;
+}
+
+// global observations in sharded mode (collective: every rank must call them at the same step)
+int64_t cfb_shard_vehicle_count(cfb_engine *e) {
+    CFB_TRY(e,
+        if (!e->h.transport) return (int64_t) e->h.dev->vehicleCount();
+        int a = 0;
+        e->h.dev->shardCounts(e->h.transport, nullptr, &a);
+        e->h.checkDevice();
+        return (int64_t) a;
+    )
+}
+int cfb_shard_lane_vehicle_count(cfb_engine *e, int32_t *out, int n, int waiting) {
+    if (n < e->h.net.nLanes()) { e->lastError = "output buffer too small"; return CFB_ERR_ARGUMENT; }
+    CFB_TRY(e,
+        if (!e->h.transport) { if (waiting) e->h.dev->laneWaitingVehicleCount(out); else e->h.dev->laneVehicleCount(out); }
+        else if (waiting) e->h.dev->shardWaitingCounts(e->h.transport, out);
+        else e->h.dev->shardCounts(e->h.transport, out, nullptr);
+    )
+    return CFB_OK;
+}
+
+}  // extern "C"
+
+// ---- loop-back group ----
+struct cfb_shard_group {
+    std::vector<cfb_engine *> ranks;
+    std::string lastError;
+};
+
+namespace {
+// copies between the ranks' exchange buffers (same device): a[send range for b] -> b[recv range for a]
+void loopExchange(std::vector<cfb::ShardBuffers> &B, bool tails) {
+    const int W = (int) B.size();
+    for (int a = 0; a < W; ++a) cudaStreamSynchronize((cudaStream_t) B[a].stream);
+    for (int a = 0; a < W; ++a)
+        for (int b = 0; b < W; ++b) {
+            if (a == b) continue;
+            if (tails) {  // owner a -> feeder b: a.tailSend over a's "own" list for peer b; b.tailRecv over b's "feed" list for peer a
+                const size_t n = (size_t) (B[a].inBeg[b + 1] - B[a].inBeg[b]) * B[a].tailBytes;
+                if (n) cudaMemcpy((char *) B[b].tailRecv + (size_t) B[b].outBeg[a] * B[b].tailBytes,
+                                  (char *) B[a].tailSend + (size_t) B[a].inBeg[b] * B[a].tailBytes, n, cudaMemcpyDeviceToDevice);
+            } else {      // feeder a -> owner b
+                const size_t n = (size_t) (B[a].outBeg[b + 1] - B[a].outBeg[b]) * B[a].moverBytes;
+                if (n) cudaMemcpy((char *) B[b].moverRecv + (size_t) B[b].inBeg[a] * B[b].moverBytes,
+                                  (char *) B[a].moverSend + (size_t) B[a].outBeg[b] * B[a].moverBytes, n, cudaMemcpyDeviceToDevice);
+            }
+        }    cudaDeviceSynchronize();   // D2D cudaMemcpy may return early; the ranks' streams are non-blocking
+}
+void loopAllGatherBlk(std::vector<cfb::ShardBuffers> &B) {
+    const int W = (int) B.size();
+    for (int a = 0; a < W; ++a) cudaStreamSynchronize((cudaStream_t) B[a].stream);
+    for (int a = 0; a < W; ++a)
+        for (int b = 0; b < W; ++b)
+            cudaMemcpy((char *) B[b].blkAll + (size_t) a * B[a].blkBytesPerRank, B[a].blkSend, B[a].blkBytesPerRank, cudaMemcpyDeviceToDevice);    cudaDeviceSynchronize();
+}
+}  // namespace
+
+extern "C" {
+
+cfb_shard_group *cfb_shard_group_create(const char *config_file, int world, int device) {
+    std::unique_ptr<cfb_shard_group> g(new cfb_shard_group());
+    for (int r = 0; r < world; ++r) {
+        cfb_engine *e = cfb_engine_create(config_file, 1, device);
+        if (!e) { for (auto *x : g->ranks) cfb_engine_destroy(x); return nullptr; }
+        g->ranks.push_back(e);
+        std::string err = e->h.configureShard(r, world);
+        if (!err.empty()) { g_createError = "sharded engine: " + err; for (auto *x : g->ranks) cfb_engine_destroy(x); return nullptr; }
+    }
+    // finished vehicles: union over the ranks (the hook sees each rank's local list in turn)
+    cfb_shard_group *gp = g.get();
+    for (int r = 0; r < world; ++r) {
+        gp->ranks[r]->h.finishedHook = [gp, r](std::vector<cfb::FinRec> &fin) {
+            // every rank drains at the same step; collect all local lists once, hand the union to each
+            static thread_local std::vector<cfb::FinRec> all;
+            if (r == 0) {
+                all = fin;
+                for (size_t q = 1; q < gp->ranks.size(); ++q) {
+                    std::vector<cfb::FinRec> f;
+                    gp->ranks[q]->h.dev->drainFinished(f);
+                    all.insert(all.end(), f.begin(), f.end());
+                }
+            }
+            fin = all;
+        };
+    }
+    return g.release();
+}
+
+void cfb_shard_group_destroy(cfb_shard_group *g) {
+    if (!g) return;
+    for (auto *e : g->ranks) cfb_engine_destroy(e);
+    delete g;
+}
+
+int cfb_shard_group_step(cfb_shard_group *g, int n) {
+    try {
+        const int W = (int) g->ranks.size();
+        for (int it = 0; it < n; ++it) {
+            std::vector<cfb::ShardBuffers> B;
+            for (auto *e : g->ranks) { e->h.prepareStep(); B.push_back(e->h.dev->shardBuffers()); }
+            for (auto *e : g->ranks) e->h.shardPhase(0);
+            loopExchange(B, true);
+            for (auto *e : g->ranks) e->h.shardPhase(1);
+            loopExchange(B, false);
+            for (auto *e : g->ranks) e->h.shardPhase(2);
+            loopExchange(B, true);
+            loopAllGatherBlk(B);
+            for (auto *e : g->ranks) e->h.shardPhase(3);
+            for (int r = 0; r < W; ++r) g->ranks[r]->h.finishStep();   // rank 0 first: its drain collects all lists
+        }
+        for (auto *e : g->ranks) e->h.checkDevice();
+        return CFB_OK;
+    } catch (const std::exception &ex) {
+        g->lastError = ex.what();
+        return CFB_ERR_DEVICE;
+    }
+}
+
+const char *cfb_shard_group_last_error(const cfb_shard_group *g) { return g ? g->lastError.c_str() : g_createError.c_str(); }
+
+int64_t cfb_shard_group_vehicle_count(cfb_shard_group *g) {
+    int64_t s = 0;
+    for (auto *e : g->ranks) s += e->h.dev->vehicleCount();
+    return s;
+}
+
+// lane counts assembled from the owning ranks; `waiting` selects speed < 0.1 counts
+int cfb_shard_group_lane_counts(cfb_shard_group *g, int32_t *out, int n, int waiting) {
+    const int nL = g->ranks[0]->h.net.nLanes();
+    if (n < nL) return CFB_ERR_ARGUMENT;
+    cfb::Partition part = cfb::Partition::columnStrips(g->ranks[0]->h.net, (int) g->ranks.size());
+    std::vector<int32_t> tmp(nL);
+    for (size_t r = 0; r < g->ranks.size(); ++r) {
+        if (waiting) g->ranks[r]->h.dev->laneWaitingVehicleCount(tmp.data()); else g->ranks[r]->h.dev->laneVehicleCount(tmp.data());
+        for (int l = 0; l < nL; ++l) if (part.drvOwner[l] == (int) r) out[l] = tmp[l];
+    }
+    return CFB_OK;
+}
+
+// every running vehicle of the owning ranks (same record as cfb_debug_vehicles)
+int64_t cfb_shard_group_debug_vehicles(cfb_shard_group *g, void *out, int64_t cap) {
+    cfb::Partition part = cfb::Partition::columnStrips(g->ranks[0]->h.net, (int) g->ranks.size());
+    struct Rec { int32_t w[8]; double d[3]; int64_t e; };
+    int64_t total = 0;
+    std::vector<Rec> tmp;
+    for (size_t r = 0; r < g->ranks.size(); ++r) {
+        int64_t n = cfb_debug_vehicles(g->ranks[r], nullptr, 0);
+        tmp.resize(n);
+        cfb_debug_vehicles(g->ranks[r], tmp.data(), n);
+        for (auto &x : tmp) {
+            if (part.drvOwner[x.w[3]] != (int) r) continue;  // ghost copies
+            if (total < cap && out) ((Rec *) out)[total] = x;
+            ++total;
+        }
+    }
+    return total;
 }
 
 }  // extern "C"

@@ -1,0 +1,42 @@
+// Multi-GPU execution of one simulation: one process per GPU, the road graph cut by intersection
+// (partition.h), the seam records exchanged on the engine's CUDA stream.
+//
+// Per step and rank (DeviceSim phase API):
+//   stage + k_ingest                       admission into owned lanes
+//   X3  tails      owner -> feeder         (an admission may have changed a seam lane's tail)
+//   k_notify, k_control
+//   X1  movers     feeder -> owner         vehicles that left a laneLink into a seam lane
+//   k_move
+//   X2  tails      owner -> feeder         + all-gather of the step's blocker changes
+//   k_leader
+// Host bookkeeping (RNG, flows, ids) is replicated: every rank runs the same spawner and ingests
+// only the records of lanes it owns; finished vehicles are all-gathered when the host drains.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "device_sim.h"
+
+namespace cfb {
+
+class ShardTransport {
+public:
+    virtual ~ShardTransport() {}
+    virtual int rank() const = 0;
+    virtual int world() const = 0;
+    // send[beg_s[q]..beg_s[q+1]) -> peer q; recv[beg_r[q]..beg_r[q+1]) <- peer q; entries of `bytes`
+    virtual void exchange(void *stream, const void *send, const std::vector<int> &sendBeg, void *recv,
+                          const std::vector<int> &recvBeg, size_t bytes) = 0;
+    virtual void allGather(void *stream, const void *send, void *recvAll, size_t bytesPerRank) = 0;
+    virtual void allReduceSumInt(void *stream, int *devBuf, int n) = 0;   // in place, device ints
+};
+
+// NCCL transport (libnccl is loaded at run time with dlopen, so the single-GPU engine has no
+// dependency on it).  `uniqueId` = the 128-byte ncclUniqueId created by rank 0.
+ShardTransport *createNcclTransport(int rank, int world, const void *uniqueId, int device, std::string &err);
+// 128-byte id for createNcclTransport (call on one rank, broadcast by any means)
+bool ncclUniqueIdBytes(unsigned char out[128], std::string &err);
+
+}  // namespace cfb

@@ -116,6 +116,28 @@ int cfb_load(cfb_engine *e, const cfb_archive *a);
 int cfb_archive_dump(const cfb_archive *a, const char *path);
 int cfb_load_from_file(cfb_engine *e, const char *path);
 
+/* Multi-GPU (no reference counterpart -- the reference's threads share memory).
+ * One process per GPU: the road graph is cut into column strips by intersection, every rank runs
+ * cfb_next_step in lock step, seam records travel over NCCL on the engine's stream (shard.h).
+ * `nccl_id`: the 128 bytes produced by cfb_nccl_unique_id on one rank and broadcast by the caller.
+ * The two cfb_shard_* observations are collective; other getters of a sharded engine see only the
+ * calling rank's part. */
+int cfb_nccl_unique_id(unsigned char out[128]);
+cfb_engine *cfb_engine_create_sharded(const char *config_file, int thread_num, int device, int rank, int world,
+                                      const unsigned char nccl_id[128]);
+int64_t cfb_shard_vehicle_count(cfb_engine *e);
+int cfb_shard_lane_vehicle_count(cfb_engine *e, int32_t *out, int n, int waiting);
+/* In-process loop-back group: `world` ranks on ONE GPU exchanging by device copies.  Exists so the
+ * seam protocol can be checked against the unsharded engine without several GPUs. */
+typedef struct cfb_shard_group cfb_shard_group;
+cfb_shard_group *cfb_shard_group_create(const char *config_file, int world, int device);
+void cfb_shard_group_destroy(cfb_shard_group *g);
+int cfb_shard_group_step(cfb_shard_group *g, int n);
+const char *cfb_shard_group_last_error(const cfb_shard_group *g);
+int64_t cfb_shard_group_vehicle_count(cfb_shard_group *g);
+int cfb_shard_group_lane_counts(cfb_shard_group *g, int32_t *out, int n, int waiting);
+int64_t cfb_shard_group_debug_vehicles(cfb_shard_group *g, void *out, int64_t cap);
+
 /* Test support: full dynamic state of every running vehicle, drivable-major in list order.
  * Record = 8 x int32 {flow, index, priority, drivable, leader flow, leader index, blocker flow,
  * blocker index}, 3 x double {distance, speed, gap}, 1 x int64 {enterLaneLinkTime}; 64 bytes. */

@@ -259,3 +259,28 @@ def test_push_vehicle_rng_interleaving_vs_port(cfg_3x3_dense):
             assert all(sp[n] == v for n, v in zip(names, ov["speed"]))
             assert eng.get_average_travel_time() == ora.average_travel_time()
     assert any(k.startswith("manually_pushed_") for k in sp)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_loopback_equals_unsharded(cfg_6x6_dense, world):
+    """SURVEY.md §8e exactness requirement: the network cut into `world` column strips (ranks on one
+    GPU, seam exchanges by device copies) evolves bit-identically to the unsharded engine."""
+    from cityflow_b200.capi import CEngine, CShardGroup
+    ref = CEngine(cfg_6x6_dense)
+    grp = CShardGroup(cfg_6x6_dense, world)
+    for s in range(1, 801):
+        ref.next_step()
+        grp.next_step()
+        if s % 20 == 0 or s < 40:
+            assert grp.vehicle_count() == ref.vehicle_count(), "step %d" % s
+            assert np.array_equal(grp.lane_counts(ref.n_lanes), ref.lane_vehicle_count()), "lane counts differ at step %d" % s
+        if s % 100 == 0:
+            assert np.array_equal(grp.lane_counts(ref.n_lanes, True), ref.lane_waiting_count())
+            a = np.sort(ref.debug_vehicles(), order=["flow", "cnt"])
+            b = np.sort(grp.debug_vehicles(), order=["flow", "cnt"])
+            assert len(a) == len(b)
+            for f in ("flow", "cnt", "drivable", "blocker_flow", "blocker_cnt", "enter_ll_time"):
+                assert np.array_equal(a[f], b[f]), (s, f)
+            for f in ("dis", "speed"):
+                assert np.array_equal(a[f], b[f]), (s, f)
+    assert ref.vehicle_count() > 3000
