@@ -11,7 +11,7 @@ _HERE = _os.path.dirname(_os.path.abspath(__file__))
 LIB_PATH = _os.path.join(_HERE, "libcityflow_b200.so")
 
 try:
-    from ._cityflow_b200 import Archive, Engine, __version__  # noqa: F401
+    from ._cityflow_b200 import Archive, Engine, __version__, nccl_unique_id  # noqa: F401
 except ImportError as _e:  # extension not built: fail loudly at use, not silently
     _IMPORT_ERROR = _e
 

@@ -62,14 +62,19 @@ public:
 
 class Engine {
 public:
-    Engine(const std::string &configFile, int threadNum, int device) {
+    Engine(const std::string &configFile, int threadNum, int device, int shardRank, int shardWorld, const py::bytes &ncclId) {
         if (device < 0) {
             const char *env = std::getenv("CITYFLOW_B200_DEVICE");
             device = env ? std::atoi(env) : 0;
         }
+        const std::string id = ncclId;
+        sharded_ = shardWorld > 1;
+        if (sharded_ && id.size() != 128) throw std::runtime_error("nccl_id must be the 128 bytes of cityflow_b200.nccl_unique_id()");
         {
             py::gil_scoped_release rel;
-            e_ = cfb_engine_create(configFile.c_str(), threadNum, device);
+            e_ = sharded_ ? cfb_engine_create_sharded(configFile.c_str(), threadNum, device, shardRank, shardWorld,
+                                                      (const unsigned char *) id.data())
+                          : cfb_engine_create(configFile.c_str(), threadNum, device);
         }
         if (!e_) throw std::runtime_error(std::string("load config failed! ") + cfb_last_error(nullptr));
         const int n = cfb_num_lanes(e_);
@@ -107,13 +112,14 @@ public:
         check(rc);
     }
     size_t getVehicleCount() {
-        int64_t c = cfb_get_vehicle_count(e_);
+        int64_t c = sharded_ ? cfb_shard_vehicle_count(e_) : cfb_get_vehicle_count(e_);
         if (c < 0) check((int) c);
         return (size_t) c;
     }
     py::dict laneDict(bool waiting) {
-        int rc = waiting ? cfb_get_lane_waiting_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size())
-                         : cfb_get_lane_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size());
+        int rc = sharded_ ? cfb_shard_lane_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size(), waiting)
+                 : waiting ? cfb_get_lane_waiting_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size())
+                           : cfb_get_lane_vehicle_count(e_, laneBuf_.data(), (int) laneBuf_.size());
         check(rc);
         py::dict d;
         for (size_t i = 0; i < laneOrder_.size(); ++i) d[laneKeys_[i]] = py::int_(laneBuf_[laneOrder_[i]]);
@@ -270,6 +276,7 @@ public:
 
 private:
     cfb_engine *e_ = nullptr;
+    bool sharded_ = false;
     std::vector<int> laneOrder_;
     std::vector<py::str> laneKeys_;
     std::vector<int32_t> laneBuf_;
@@ -284,7 +291,8 @@ Archive::Archive(Engine &e) : a_(cfb_snapshot(e.raw())) {
 PYBIND11_MODULE(_cityflow_b200, m) {
     m.doc() = "B200-native CityFlow step engine (drop-in for cityflow.Engine)";
     py::class_<Engine>(m, "Engine")
-        .def(py::init<const std::string &, int, int>(), "config_file"_a, "thread_num"_a = 1, "device"_a = -1)
+        .def(py::init<const std::string &, int, int, int, int, const py::bytes &>(), "config_file"_a, "thread_num"_a = 1,
+             "device"_a = -1, "shard_rank"_a = 0, "shard_world"_a = 1, "nccl_id"_a = py::bytes())
         .def("next_step", &Engine::nextStep)
         .def("get_vehicle_count", &Engine::getVehicleCount)
         .def("get_vehicles", &Engine::getVehicles, "include_waiting"_a = false)
@@ -322,5 +330,10 @@ PYBIND11_MODULE(_cityflow_b200, m) {
     py::class_<Archive>(m, "Archive")
         .def(py::init<Engine &>())
         .def("dump", &Archive::dump, "path"_a);
+    m.def("nccl_unique_id", []() {
+        unsigned char id[128];
+        if (cfb_nccl_unique_id(id) < 0) throw std::runtime_error(cfb_last_error(nullptr));
+        return py::bytes((const char *) id, 128);
+    }, "128-byte id for Engine(..., shard_world=N, nccl_id=...): create on one rank, broadcast to all");
     m.attr("__version__") = "b200-dev";
 }
