@@ -44,6 +44,9 @@ def parse_args():
     p.add_argument("--threads", type=int, default=0, help="reference arm: thread_num (default nproc)")
     p.add_argument("--cpu-steps", type=int, default=100, help="cpu_baseline sample: timed steps after the prefill")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                   help="N>1: 'sharded' = ONE simulation of a rows x (cols*N) grid cut into N column strips with NCCL seam "
+                        "exchange (weak scaling); 'replicas' = N independent copies of the N=1 workload")
     p.add_argument("--clock-ms", type=int, default=200, help="nvidia-smi sampling period (0 = off)")
     p.add_argument("--profile-steps", type=int, default=0,
                    help="ncu mode: after prefill+warmup run this many steps between cudaProfilerStart/Stop and exit "
@@ -51,16 +54,22 @@ def parse_args():
     return p.parse_args()
 
 
+def grid_cols(args):
+    """Weak scaling of the sharded engine: one strip of `cols` columns per GPU."""
+    n = max(args.gpus, 1)
+    return args.cols * n if (n > 1 and args.multi == "sharded") else args.cols
+
+
 def make_scenario(args, directory):
     from cityflow_b200 import scenario
     return scenario.make_grid_scenario(
-        directory, args.rows, args.cols, name="bench",
+        directory, args.rows, grid_cols(args), name="bench",
         dense=dict(frac=args.frac, interval=args.flow_interval, seed=1))
 
 
 def workload_name(args):
     return "%dx%d grid (tools/generator layout), random-walk flows frac=%g interval=%gs seed=1, interval=1.0s, seed=0" % (
-        args.rows, args.cols, args.frac, args.flow_interval)
+        args.rows, grid_cols(args), args.frac, args.flow_interval)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -179,10 +188,17 @@ def run_ours(args):
     world, rank, dist = ranks.world, ranks.rank, ranks.dist
 
     import cityflow  # our drop-in module (repo root)
+    import cityflow_b200
+    sharded = world > 1 and args.multi == "sharded"
     tmp = tempfile.TemporaryDirectory()
     cfg = make_scenario(args, tmp.name)
     t0 = time.perf_counter()
-    eng = cityflow.Engine(cfg, thread_num=1, device=local)
+    if sharded:
+        ids = [cityflow_b200.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng = cityflow.Engine(cfg, thread_num=1, device=local, shard_rank=rank, shard_world=world, nccl_id=ids[0])
+    else:
+        eng = cityflow.Engine(cfg, thread_num=1, device=local)
     load_s = time.perf_counter() - t0
 
     def barrier():
@@ -238,17 +254,21 @@ def run_ours(args):
     barrier()
     h2d1, d2h1 = eng.transfer_bytes()
     host_gen_ms, host_enq_ms = eng.host_times()
-    e2e_value = reduce_sum(acc) / reduce_max(e2e_s)
+    # sharded: get_vehicle_count() already is the network-wide count on every rank
+    e2e_value = (acc if sharded else reduce_sum(acc)) / reduce_max(e2e_s)
     clocks = sampler.stop() if rank == 0 else {}
 
     eng_steps_total = args.prefill + max(args.warmup, 3) + 3 * args.steps
     # ---- per-kernel device time (CUDA events around every kernel; separate pass, serialised) ----
-    eng.enable_kernel_timing(True)
-    ksteps = min(args.steps, 50)
-    for _ in range(ksteps):
-        eng.next_step()
-    (k_ing, k_not, k_ctl, k_mov, k_led), kn = eng.kernel_times()
-    eng.enable_kernel_timing(False)
+    if sharded:   # per-kernel events are only wired for the single-engine launch path
+        (k_ing, k_not, k_ctl, k_mov, k_led), kn = (0.0, 0.0, 0.0, 0.0, 0.0), 1
+    else:
+        eng.enable_kernel_timing(True)
+        ksteps = min(args.steps, 50)
+        for _ in range(ksteps):
+            eng.next_step()
+        (k_ing, k_not, k_ctl, k_mov, k_led), kn = eng.kernel_times()
+        eng.enable_kernel_timing(False)
     n_now = eng.get_vehicle_count()
     n_drv = eng.num_drivables() if hasattr(eng, "num_drivables") else 0
     kms = {"k_ingest": k_ing / kn, "k_notify": k_not / kn, "k_control": k_ctl / kn, "k_move": k_mov / kn, "k_leader": k_led / kn}
@@ -277,7 +297,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": workload_name(args), "prefill_steps": args.prefill, "mean_vehicles_per_gpu": mean_n,
-                "vehicles_at_start": n_start, "parallelism": "replicas x%d (one engine per GPU, no exchange)" % world,
+                "vehicles_at_start": n_start, "parallelism": ("sharded: %d column strips of ONE simulation, seam records over NCCL (3 neighbour exchanges + 1 all-gather per step)" % world)
+                if sharded else "replicas x%d (one engine per GPU, no exchange)" % world,
                 "l2": "value: 256 MiB memset between timed steps (state ~30 MB would otherwise stay L2-resident); "
                       "value_l2_warm and e2e: steps back to back as in real stepping",
                 "load_seconds": load_s,
@@ -292,8 +313,8 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "kernel_ms": kms,
             "host_ms_per_step": {"spawn_generation": host_gen_ms / max(eng_steps_total, 1), "enqueue": host_enq_ms / max(eng_steps_total, 1)},
-            "roofline": roof(dominant),
-            "roofline_leader_scan": roof("k_leader"),
+            "roofline": roof(dominant) if not sharded else None,
+            "roofline_leader_scan": roof("k_leader") if not sharded else None,
             "clocks": clocks,
         }
     if dist is not None:
