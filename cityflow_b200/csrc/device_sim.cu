@@ -1237,6 +1237,9 @@ struct DeviceSim::Impl {
     std::vector<int> outBeg, inBeg;
     std::vector<unsigned char> ownedHost;
     int shardRank = 0, shardWorld = 1;
+    cudaGraphExec_t shardGraph[2] = {nullptr, nullptr};
+    cudaEvent_t shardGraphDone[2] = {nullptr, nullptr};
+    bool shardGraphOk = false;   // whole-step graph incl. NCCL: works, measured no faster (host is not the limiter); opt-in
     DevBuf<int> shardScratch;
     DevBuf<unsigned char> finGather;
     DevBuf<Tail> tail;
@@ -1280,6 +1283,10 @@ struct DeviceSim::Impl {
     int gridStep = 0;
     cudaGraphExec_t graphExec[2] = {nullptr, nullptr};
 
+    void dropShardGraphs() {
+        for (int k = 0; k < 2; ++k)
+            if (shardGraph[k]) { cudaStreamSynchronize(stream); cudaGraphExecDestroy(shardGraph[k]); shardGraph[k] = nullptr; }
+    }
     void ensureHostInts(size_t n) {
         if (n <= hIntsCap) return;
         if (hInts) cudaFreeHost(hInts);
@@ -1481,6 +1488,7 @@ void DeviceSim::uploadTemplates(const std::vector<VehicleTemplate> &templates) {
     I.tmpl.upload(t);
     I.V.tmpl = I.tmpl.p;
     I.graphDirty = true;
+    I.dropShardGraphs();
 }
 
 void DeviceSim::uploadPlans(const Routing &routing) {
@@ -1494,6 +1502,7 @@ void DeviceSim::uploadPlans(const Routing &routing) {
     I.V.planBeg = I.planBeg.p;
     I.V.planData = I.planData.p;
     I.graphDirty = true;
+    I.dropShardGraphs();
 }
 
 void DeviceSim::ensureSlotCapacity(int slots) {
@@ -1526,6 +1535,7 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     I.slotCap = cap;
     I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p; I.V.blk = I.blk.p; I.V.delStep = I.delStep.p;
     I.graphDirty = true;
+    I.dropShardGraphs();
 }
 
 void DeviceSim::reset() {
@@ -1561,6 +1571,7 @@ void DeviceSim::stageStep(const SpawnRec *recs, int n) {
         I.spawnCap = std::max(1024, (n + 1) * 2);
         I.spawn.alloc(I.spawnCap);
         I.graphDirty = true;
+        I.dropShardGraphs();
     }
     V.spawn = I.spawn.p + 1;
     const int r = I.ringIdx;
@@ -1700,8 +1711,9 @@ void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned c
     I.blkAll.alloc((size_t) world * (1 + V.blkUpdCap));
     I.blkUpd.fill(0); I.blkAll.fill(0);
     V.blkUpd = I.blkUpd.p;
-    I.useGraph = false;  // phases are launched one by one
+    I.useGraph = false;  // phases are launched one by one (or replayed as one sharded-step graph)
     I.useCoop = false;
+    if (const char *g = getenv("CITYFLOW_B200_SHARD_GRAPH")) I.shardGraphOk = (g[0] == '1');
 }
 
 ShardBuffers DeviceSim::shardBuffers() {
@@ -1744,9 +1756,7 @@ void DeviceSim::runLeader() {
     Impl &I = *impl_;
     ensureGrids();
     k_leader<<<I.gridLeader, 256, 0, I.stream>>>(I.V);
-    CFB_CUDA(cudaGetLastError());
     launches_ += 1;
-    steps_ += 1;
 }
 void DeviceSim::packTails() {
     Impl &I = *impl_;
@@ -1826,6 +1836,55 @@ void DeviceSim::shardGatherFinished(ShardTransport *t, std::vector<FinRec> &inou
         const FinRec *p = recv.data() + (size_t) r * (1 + cap);
         for (int k = 0; k < p[0].slot; ++k) inout.push_back(p[1 + k]);
     }
+}
+
+// One sharded step (kernels + NCCL operations enqueued by the caller between begin and end) is
+// captured into a CUDA graph per list parity and replayed: one launch call per step instead of ~17.
+// The first steps run uncaptured so that NCCL can set up its connections; any capture failure
+// switches the engine back to plain launches for good.
+int DeviceSim::shardStepBegin() {
+    Impl &I = *impl_;
+    const int par = I.V.par;
+    if (!I.shardGraphOk || steps_ < 8) return 0;                       // plain
+    if (I.shardGraph[par]) {
+        if (cudaEventQuery(I.shardGraphDone[par]) != cudaSuccess) return 0;  // previous replay still running: just enqueue
+        CFB_CUDA(cudaGraphLaunch(I.shardGraph[par], I.stream));
+        CFB_CUDA(cudaEventRecord(I.shardGraphDone[par], I.stream));
+        return 1;                                                     // replayed: the caller skips the phases
+    }
+    if (cudaStreamBeginCapture(I.stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        I.shardGraphOk = false;
+        return 0;
+    }
+    return 2;                                                         // capturing: the caller enqueues the phases
+}
+
+bool DeviceSim::shardStepEnd(int state) {
+    Impl &I = *impl_;
+    bool ok = true;
+    if (state == 2) {
+        const int par = I.V.par;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(I.stream, &g);
+        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&I.shardGraph[par], g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || !I.shardGraph[par]) {
+            cudaGetLastError();
+            I.shardGraph[par] = nullptr;
+            I.shardGraphOk = false;
+            ok = false;                                                // nothing ran: the caller repeats the step plainly
+        } else {
+            if (!I.shardGraphDone[par]) CFB_CUDA(cudaEventCreateWithFlags(&I.shardGraphDone[par], cudaEventDisableTiming));
+            CFB_CUDA(cudaGraphLaunch(I.shardGraph[par], I.stream));
+            CFB_CUDA(cudaEventRecord(I.shardGraphDone[par], I.stream));
+        }
+    }
+    if (ok) {
+        CFB_CUDA(cudaGetLastError());
+        steps_ += 1;
+    }
+    return ok;
 }
 
 void DeviceSim::ensureGrids() {

@@ -93,6 +93,8 @@ public:
                         const std::vector<std::vector<int>> &feedPerPeer, const std::vector<std::vector<int>> &ownPerPeer);
     ShardBuffers shardBuffers();
     void stageStep(const SpawnRec *recs, int n);
+    int shardStepBegin();            // 0 plain, 1 replayed (skip the phases), 2 capturing
+    bool shardStepEnd(int state);    // false: capture failed, nothing ran -> repeat the phases plainly
     void runIngest();
     void runNotifyControl();
     void runMove();

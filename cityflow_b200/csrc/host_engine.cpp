@@ -35,6 +35,13 @@
 
 namespace cfb {
 
+struct FlowHot {            // the per-step fields of a Flow (flow.h:21-30), packed for the spawn loop
+    double nowTime, currentTime, interval;
+    int startTime, endTime;
+    int cnt;
+    int valid;
+};
+
 struct FlowRun {            // Flow, flow.h:17-53
     FlowDef def;
     double nowTime = 0, currentTime = 0;
@@ -111,6 +118,10 @@ public:
     std::string error;
     RoadNet net;
     std::vector<FlowRun> flows;
+    std::vector<FlowHot> hot;                                // hot[i] mirrors flows[i]'s runtime state (authoritative)
+    std::vector<uint64_t> sortKeys;
+    std::vector<Pending> pendingSorted;
+    std::vector<SpawnRec> batchTmp;
     std::unique_ptr<Routing> routing;
     std::vector<VehicleTemplate> templates;
     std::map<VehicleTemplate, int> templateIndex;
@@ -204,6 +215,7 @@ public:
             f.nowTime = d.interval;  // flow.h:35
             f.routeId = routing->intern(d.anchors);
             f.tmplId = internTemplate(d.tmpl);
+            hot.push_back(FlowHot{d.interval, 0.0, d.interval, d.startTime, d.endTime, 0, 1});  // nowTime = interval (flow.h:35)
             flows.push_back(std::move(f));
         }
         if (saveReplay)
@@ -301,14 +313,17 @@ public:
     // P0/P1 on the host: flows, vehicle creation, first-lane draw -> `batch` (lane-sorted spawn records)
     void prepareStep() {
         const auto t0 = std::chrono::steady_clock::now();
-        for (size_t i = 0; i < flows.size(); ++i) {  // Flow::nextStep flow.cpp:6-22
-            FlowRun &f = flows[i];
+        const size_t nFlows = hot.size();
+        FlowHot *H = hot.data();
+        for (size_t i = 0; i < nFlows; ++i) {  // Flow::nextStep flow.cpp:6-22
+            FlowHot &f = H[i];
             if (!f.valid) continue;
-            if (f.def.endTime != -1 && f.currentTime > f.def.endTime) continue;
-            if (f.currentTime >= f.def.startTime) {
-                while (f.nowTime >= f.def.interval) {
-                    createVehicle((int) i, f.cnt++, f.routeId, f.tmplId, f.def.anchors[0]);
-                    f.nowTime -= f.def.interval;
+            if (f.endTime != -1 && f.currentTime > f.endTime) continue;
+            if (f.currentTime >= f.startTime) {
+                while (f.nowTime >= f.interval) {
+                    const FlowRun &fr = flows[i];
+                    createVehicle((int) i, f.cnt++, fr.routeId, fr.tmplId, fr.def.anchors[0]);
+                    f.nowTime -= f.interval;
                 }
                 f.nowTime += interval;
             }
@@ -317,8 +332,13 @@ public:
         batch.clear();
         if (!pending.empty()) {
             // Engine::planRoute walks roads in file order, each road's buffer in spawn order
-            std::stable_sort(pending.begin(), pending.end(), [](const Pending &a, const Pending &b) { return a.road < b.road; });
-            for (const Pending &p : pending) {
+            // (road, arrival index) keys: same order as a stable sort by road, cheaper than moving structs
+            sortKeys.resize(pending.size());
+            for (size_t k = 0; k < pending.size(); ++k) sortKeys[k] = ((uint64_t) (uint32_t) pending[k].road << 32) | (uint32_t) k;
+            std::sort(sortKeys.begin(), sortKeys.end());
+            pendingSorted.resize(pending.size());
+            for (size_t k = 0; k < pending.size(); ++k) pendingSorted[k] = pending[(uint32_t) sortKeys[k]];
+            for (const Pending &p : pendingSorted) {
                 const Route &rt = routing->route(p.routeId);
                 if (rt.valid) {
                     const size_t pick = rnd() % rt.startLanes.size();  // Router::selectLaneIndex router.cpp:99
@@ -332,9 +352,9 @@ public:
                     batch.push_back(r);
                 } else {
                     if (p.flow >= 0) {
-                        if (flows[p.flow].valid)
+                        if (hot[p.flow].valid)
                             std::cerr << "[warning] Invalid route '" << flows[p.flow].def.id << "'. Omitted by default." << std::endl;
-                        flows[p.flow].valid = false;
+                        hot[p.flow].valid = 0;
                     }
                     SlotInfo &s = slots[p.slot];
                     pool.erase(s.priority);
@@ -344,7 +364,12 @@ public:
                 }
             }
             pending.clear();
-            std::stable_sort(batch.begin(), batch.end(), [](const SpawnRec &a, const SpawnRec &b) { return a.lane < b.lane; });
+            sortKeys.resize(batch.size());
+            for (size_t k = 0; k < batch.size(); ++k) sortKeys[k] = ((uint64_t) (uint32_t) batch[k].lane << 32) | (uint32_t) k;
+            std::sort(sortKeys.begin(), sortKeys.end());
+            batchTmp.resize(batch.size());
+            for (size_t k = 0; k < batch.size(); ++k) batchTmp[k] = batch[(uint32_t) sortKeys[k]];
+            batch.swap(batchTmp);
         }
         if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
         if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
@@ -360,7 +385,7 @@ public:
     // device phases up to (not including) the exchange points; see shard.h
     void shardPhase(int k) {
         switch (k) {
-            case 0: dev->stageStep(batch.data(), (int) batch.size()); dev->runIngest(); dev->packTails(); break;
+            case 0: dev->stageStep(batch.data(), (int) batch.size()); dev->runIngest(); dev->packTails(); break;   // loop-back group only
             case 1: dev->unpackTails(); dev->runNotifyControl(); dev->packMovers(); break;
             case 2: dev->unpackMovers(); dev->runMove(); dev->packTails(); dev->sealBlk(); break;
             case 3: dev->unpackTails(); dev->applyBlk(); dev->runLeader(); break;
@@ -372,15 +397,25 @@ public:
         if (!transport) {
             dev->step(batch.data(), (int) batch.size());
         } else {  // one rank of a sharded run: phases with the seam exchanges in between
-            ShardBuffers b = dev->shardBuffers();
-            shardPhase(0);
-            transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X3
-            shardPhase(1);
-            transport->exchange(b.stream, b.moverSend, b.outBeg, b.moverRecv, b.inBeg, b.moverBytes);  // X1
-            shardPhase(2);
-            transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X2
-            transport->allGather(b.stream, b.blkSend, b.blkAll, b.blkBytesPerRank);
-            shardPhase(3);
+            dev->stageStep(batch.data(), (int) batch.size());
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                const int st = dev->shardStepBegin();
+                if (st != 1) try {
+                    ShardBuffers b = dev->shardBuffers();
+                    dev->runIngest(); dev->packTails();
+                    transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X3
+                    shardPhase(1);
+                    transport->exchange(b.stream, b.moverSend, b.outBeg, b.moverRecv, b.inBeg, b.moverBytes);  // X1
+                    shardPhase(2);
+                    transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X2
+                    transport->allGather(b.stream, b.blkSend, b.blkAll, b.blkBytesPerRank);
+                    shardPhase(3);
+                } catch (const std::exception &) {
+                    if (st != 2) throw;
+                    // an operation refused to be captured: abandon the graph, run this step plainly
+                }
+                if (dev->shardStepEnd(st)) break;
+            }
         }
         hostEnqueueNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
         finishStep();
@@ -415,8 +450,8 @@ public:
         pending.clear();
         finishedCnt = 0;
         cumulativeTravelTime = 0;
-        for (auto &f : flows) {  // Flow::reset flow.cpp:28-32 (valid / manuallyPushCnt are not reset)
-            f.nowTime = f.def.interval;
+        for (auto &f : hot) {  // Flow::reset flow.cpp:28-32 (valid / manuallyPushCnt are not reset)
+            f.nowTime = f.interval;
             f.currentTime = 0;
             f.cnt = 0;
         }
@@ -454,14 +489,14 @@ public:
         s.rnd = rnd; s.step = step; s.manuallyPushCnt = manuallyPushCnt; s.finishedCnt = finishedCnt;
         s.cumulativeTravelTime = cumulativeTravelTime;
         s.flowNow.clear(); s.flowCur.clear(); s.flowCnt.clear(); s.flowValid.clear();
-        for (auto &f : flows) { s.flowNow.push_back(f.nowTime); s.flowCur.push_back(f.currentTime); s.flowCnt.push_back(f.cnt); s.flowValid.push_back(f.valid); }
+        for (auto &f : hot) { s.flowNow.push_back(f.nowTime); s.flowCur.push_back(f.currentTime); s.flowCnt.push_back(f.cnt); s.flowValid.push_back((uint8_t) f.valid); }
         s.slots = slots; s.freeSlots = freeSlots; s.pending = pending;
     }
     void loadHost(const HostState &s) {
         if (s.flowNow.size() != flows.size()) throw std::runtime_error("archive does not match this engine (flows)");
         rnd = s.rnd; step = s.step; manuallyPushCnt = s.manuallyPushCnt; finishedCnt = s.finishedCnt;
         cumulativeTravelTime = s.cumulativeTravelTime;
-        for (size_t i = 0; i < flows.size(); ++i) { flows[i].nowTime = s.flowNow[i]; flows[i].currentTime = s.flowCur[i]; flows[i].cnt = s.flowCnt[i]; flows[i].valid = s.flowValid[i]; }
+        for (size_t i = 0; i < hot.size(); ++i) { hot[i].nowTime = s.flowNow[i]; hot[i].currentTime = s.flowCur[i]; hot[i].cnt = s.flowCnt[i]; hot[i].valid = s.flowValid[i]; }
         slots = s.slots; freeSlots = s.freeSlots; pending = s.pending;
         pool.clear();
         for (size_t k = 0; k < slots.size(); ++k) if (slots[k].live) pool.insert(slots[k].priority, (int) k);
@@ -1130,7 +1165,7 @@ int cfb_shard_group_step(cfb_shard_group *g, int n) {
             for (auto *e : g->ranks) e->h.shardPhase(2);
             loopExchange(B, true);
             loopAllGatherBlk(B);
-            for (auto *e : g->ranks) e->h.shardPhase(3);
+            for (auto *e : g->ranks) { e->h.shardPhase(3); e->h.dev->shardStepEnd(0); }
             for (int r = 0; r < W; ++r) g->ranks[r]->h.finishStep();   // rank 0 first: its drain collects all lists
         }
         for (auto *e : g->ranks) e->h.checkDevice();
