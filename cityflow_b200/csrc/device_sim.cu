@@ -158,7 +158,7 @@ struct View {
     int *blk;            // per slot: committed blocker slot (Vehicle::blocker), -1 none: chain walks need one load per hop
     int *delStep;        // per slot: step at which the vehicle in that slot left the network
     // ---- sharded mode (partition.h): null / 0 when the engine owns the whole network ----
-    const unsigned char *owned;   // per drivable: this rank owns it
+    const unsigned char *owned;   // per drivable: 1 = this rank owns it, 2 = a lane it feeds (ghost copy kept in step), 0 = foreign
     const int *boundOut;          // lanes this rank feeds but does not own (all peers, concatenated)
     const int *boundIn;           // lanes this rank owns but a peer feeds
     int nBoundOut, nBoundIn;
@@ -317,7 +317,11 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
         V.ctrl->nExtra = 0;
     }
     for (i = gtid0; i < V.nLanes; i += nblk * blockDim.x) {
-    if (V.owned && !V.owned[i]) continue;   // another rank admits into this lane (its tail arrives by exchange)
+    // Sharded: a lane this rank FEEDS is admitted into here as well, on the ghost copy, with the same
+    // inputs as on its owner (spawn records and queue are replicated, the ghost tail is exact after
+    // the previous step's exchange) -- so the owner need not report the admission.
+    const int own = V.owned ? V.owned[i] : 1;
+    if (own == 0) continue;
     if (nSpawn > 0) {
         int lo = 0, hi = nSpawn;  // lower bound of lane i
         while (lo < hi) {
@@ -365,7 +369,7 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
                 } else {
                     V.leader[p] = -1;
                     ins = 3;  // admitted to an empty lane: leader search runs in k_notify
-                    V.actList[cpar][atomicAdd(&V.ctrl->nAct[cpar], 1)] = i;
+                    if (own == 1) V.actList[cpar][atomicAdd(&V.ctrl->nAct[cpar], 1)] = i;
                 }
                 if (V.ctrl->nCustom > 0) {
                     const double cs = V.slotCust[h];
@@ -373,10 +377,12 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
                 }
                 V.count[i] = n + 1;
                 V.blk[h] = -1;
-                V.pos[h] = p;
-                atomicAdd(&V.ctrl->active, 1);
-                const int vi = atomicAdd(&V.ctrl->nVeh[cpar], 1);
-                if (vi < V.vehCap) V.vehList[cpar][vi] = make_int2(p, n == 0 ? (i | HEAD_BIT) : i);
+                if (own == 1) {
+                    V.pos[h] = p;
+                    atomicAdd(&V.ctrl->active, 1);
+                    const int vi = atomicAdd(&V.ctrl->nVeh[cpar], 1);
+                    if (vi < V.vehCap) V.vehList[cpar][vi] = make_int2(p, n == 0 ? (i | HEAD_BIT) : i);
+                }
                 int nx = V.waitNext[h];
                 V.waitHead[i] = nx;
                 if (nx < 0) V.waitTail[i] = -1;
@@ -512,7 +518,7 @@ __device__ __forceinline__ void phase_notify(const View &V, const int bid, const
         // the link the tail came out of, if it is empty now (otherwise it is on the list itself)
         const int prev = V.nav[base + c - 1].y;
         int l1 = -1;
-        if (prev >= V.nLanes && V.count[prev] == 0 && (!V.owned || V.owned[prev])) {
+        if (prev >= V.nLanes && V.count[prev] == 0 && (!V.owned || V.owned[prev] == 1)) {
             l1 = prev - V.nLanes;
             notifyLink(V, l1, lane, epoch);
         }
@@ -522,7 +528,7 @@ __device__ __forceinline__ void phase_notify(const View &V, const int bid, const
     }
     for (int w = warp; w < V.nBoundOut; w += nWarps) {  // sharded: source 1 may sit on a lane another rank owns
         const Tail t = V.tail[V.boundOut[w]];
-        if (t.pos >= 0 && t.prev >= V.nLanes && V.owned[t.prev] && V.count[t.prev] == 0) notifyLink(V, t.prev - V.nLanes, lane, epoch);
+        if (t.pos >= 0 && t.prev >= V.nLanes && V.owned[t.prev] == 1 && V.count[t.prev] == 0) notifyLink(V, t.prev - V.nLanes, lane, epoch);
     }
 }
 __global__ void __launch_bounds__(256) k_notify(View V) { phase_notify(V, blockIdx.x, gridDim.x); }
@@ -771,7 +777,7 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
                 if (e >= ENT_CAP) atomicOr(&V.ctrl->error, ERR_ENTRANT_OVERFLOW);
                 else V.ent[newDrv * ENT_CAP + e] = m;
                 // an empty target is on no work list yet: queue it for k_move
-                if (V.owned && !V.owned[newDrv]) {
+                if (V.owned && V.owned[newDrv] != 1) {
                     V.pos[idv.x] = -1;   // the record travels to the owner of the lane (k_pack_movers)
                 } else if (e == 0 && V.count[newDrv] == 0) {
                     V.extraList[atomicAdd(&V.ctrl->nExtra, 1)] = newDrv;
@@ -1114,11 +1120,11 @@ __global__ void k_unpack_movers(View V, const MoverMsg *in) {  // one warp per b
 __global__ void k_mask_counts(View V, int *out) {  // out[0] = vehicles this rank accounts for, out[1+l] = owned lane counts
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) out[0] = V.ctrl->active;
-    if (i < V.nLanes) out[1 + i] = (!V.owned || V.owned[i]) ? V.count[i] : 0;
+    if (i < V.nLanes) out[1 + i] = (!V.owned || V.owned[i] == 1) ? V.count[i] : 0;
 }
 __global__ void k_mask_waiting(View V, const int *waiting, int *out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V.nLanes) out[i] = (!V.owned || V.owned[i]) ? waiting[i] : 0;
+    if (i < V.nLanes) out[i] = (!V.owned || V.owned[i] == 1) ? waiting[i] : 0;
 }
 
 // blocker changes: [0] = {count,0} header, filled right before the all-gather
@@ -1681,7 +1687,10 @@ void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned c
     CFB_CUDA(cudaStreamSynchronize(I.stream));
     I.shardRank = rank;
     I.shardWorld = world;
-    I.owned.upload(owned);
+    std::vector<unsigned char> own3 = owned;
+    for (int q = 0; q < world; ++q)
+        for (int l : feedPerPeer[q]) own3[l] = 2;   // ghost lanes: admitted into locally, never listed as work
+    I.owned.upload(own3);
     I.ownedHost = owned;
     V.owned = I.owned.p;
     std::vector<int> out, in;

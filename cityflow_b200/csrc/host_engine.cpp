@@ -385,8 +385,6 @@ public:
     // device phases up to (not including) the exchange points; see shard.h
     void shardPhase(int k) {
         switch (k) {
-            case 0: dev->stageStep(batch.data(), (int) batch.size()); dev->runIngest(); dev->packTails(); break;   // loop-back group only
-            case 1: dev->unpackTails(); dev->runNotifyControl(); dev->packMovers(); break;
             case 2: dev->unpackMovers(); dev->runMove(); dev->packTails(); dev->sealBlk(); break;
             case 3: dev->unpackTails(); dev->applyBlk(); dev->runLeader(); break;
         }
@@ -402,13 +400,13 @@ public:
                 const int st = dev->shardStepBegin();
                 if (st != 1) try {
                     ShardBuffers b = dev->shardBuffers();
-                    dev->runIngest(); dev->packTails();
-                    transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X3
-                    shardPhase(1);
+                    dev->runIngest();
+                    dev->runNotifyControl();
+                    dev->packMovers();
                     transport->exchange(b.stream, b.moverSend, b.outBeg, b.moverRecv, b.inBeg, b.moverBytes);  // X1
                     shardPhase(2);
-                    transport->exchange(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes);     // X2
-                    transport->allGather(b.stream, b.blkSend, b.blkAll, b.blkBytesPerRank);
+                    transport->exchangeAndGather(b.stream, b.tailSend, b.inBeg, b.tailRecv, b.outBeg, b.tailBytes,
+                                                 b.blkSend, b.blkAll, b.blkBytesPerRank);                      // X2
                     shardPhase(3);
                 } catch (const std::exception &) {
                     if (st != 2) throw;
@@ -1158,9 +1156,8 @@ int cfb_shard_group_step(cfb_shard_group *g, int n) {
         for (int it = 0; it < n; ++it) {
             std::vector<cfb::ShardBuffers> B;
             for (auto *e : g->ranks) { e->h.prepareStep(); B.push_back(e->h.dev->shardBuffers()); }
-            for (auto *e : g->ranks) e->h.shardPhase(0);
-            loopExchange(B, true);
-            for (auto *e : g->ranks) e->h.shardPhase(1);
+            for (auto *e : g->ranks) { e->h.dev->stageStep(e->h.batch.data(), (int) e->h.batch.size()); e->h.dev->runIngest(); }
+            for (auto *e : g->ranks) { e->h.dev->runNotifyControl(); e->h.dev->packMovers(); }
             loopExchange(B, false);
             for (auto *e : g->ranks) e->h.shardPhase(2);
             loopExchange(B, true);

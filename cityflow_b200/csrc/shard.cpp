@@ -87,6 +87,20 @@ public:
     void allGather(void *stream, const void *send, void *recvAll, size_t bytesPerRank) override {
         CFB_NCCL(api().AllGather(send, recvAll, bytesPerRank, ncclChar, comm_, (cudaStream_t) stream));
     }
+    void exchangeAndGather(void *stream, const void *send, const std::vector<int> &sb, void *recv, const std::vector<int> &rb,
+                           size_t bytes, const void *gSend, void *gRecvAll, size_t gBytes) override {
+        cudaStream_t s = (cudaStream_t) stream;
+        CFB_NCCL(api().GroupStart());
+        for (int q = 0; q < world_; ++q) {
+            if (q == rank_) continue;
+            const size_t ns = (size_t) (sb[q + 1] - sb[q]) * bytes, nr = (size_t) (rb[q + 1] - rb[q]) * bytes;
+            if (ns) CFB_NCCL(api().Send((const char *) send + (size_t) sb[q] * bytes, ns, ncclChar, q, comm_, s));
+            if (nr) CFB_NCCL(api().Recv((char *) recv + (size_t) rb[q] * bytes, nr, ncclChar, q, comm_, s));
+            CFB_NCCL(api().Send(gSend, gBytes, ncclChar, q, comm_, s));
+            CFB_NCCL(api().Recv((char *) gRecvAll + (size_t) q * gBytes, gBytes, ncclChar, q, comm_, s));
+        }
+        CFB_NCCL(api().GroupEnd());
+    }
     void allReduceSumInt(void *stream, int *devBuf, int n) override {
         CFB_NCCL(api().AllReduce(devBuf, devBuf, (size_t) n, ncclInt, ncclSum, comm_, (cudaStream_t) stream));
     }

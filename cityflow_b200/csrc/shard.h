@@ -2,12 +2,12 @@
 // (partition.h), the seam records exchanged on the engine's CUDA stream.
 //
 // Per step and rank (DeviceSim phase API):
-//   stage + k_ingest                       admission into owned lanes
-//   X3  tails      owner -> feeder         (an admission may have changed a seam lane's tail)
+//   stage + k_ingest                       admission into owned lanes -- and, identically, into the ghost
+//                                          copies of the lanes this rank feeds (so no exchange is needed here)
 //   k_notify, k_control
 //   X1  movers     feeder -> owner         vehicles that left a laneLink into a seam lane
 //   k_move
-//   X2  tails      owner -> feeder         + all-gather of the step's blocker changes
+//   X2  tails      owner -> feeder         + every rank's blocker changes to every rank, one NCCL group
 //   k_leader
 // Host bookkeeping (RNG, flows, ids) is replicated: every rank runs the same spawner and ingests
 // only the records of lanes it owns; finished vehicles are all-gathered when the host drains.
@@ -30,6 +30,10 @@ public:
     virtual void exchange(void *stream, const void *send, const std::vector<int> &sendBeg, void *recv,
                           const std::vector<int> &recvBeg, size_t bytes) = 0;
     virtual void allGather(void *stream, const void *send, void *recvAll, size_t bytesPerRank) = 0;
+    // exchange() and allGather() issued as ONE group (one launch on the stream)
+    virtual void exchangeAndGather(void *stream, const void *send, const std::vector<int> &sendBeg, void *recv,
+                                   const std::vector<int> &recvBeg, size_t bytes, const void *gSend, void *gRecvAll,
+                                   size_t gBytesPerRank) = 0;
     virtual void allReduceSumInt(void *stream, int *devBuf, int n) = 0;   // in place, device ints
 };
 
