@@ -1245,7 +1245,7 @@ struct DeviceSim::Impl {
     int shardRank = 0, shardWorld = 1;
     cudaGraphExec_t shardGraph[2] = {nullptr, nullptr};
     cudaEvent_t shardGraphDone[2] = {nullptr, nullptr};
-    bool shardGraphOk = false;   // whole-step graph incl. NCCL: works, measured no faster (host is not the limiter); opt-in
+    bool shardGraphOk = true;    // whole sharded step (kernels + NCCL groups) replayed as one graph per parity
     DevBuf<int> shardScratch;
     DevBuf<unsigned char> finGather;
     DevBuf<Tail> tail;
@@ -1722,7 +1722,7 @@ void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned c
     V.blkUpd = I.blkUpd.p;
     I.useGraph = false;  // phases are launched one by one (or replayed as one sharded-step graph)
     I.useCoop = false;
-    if (const char *g = getenv("CITYFLOW_B200_SHARD_GRAPH")) I.shardGraphOk = (g[0] == '1');
+    if (const char *g = getenv("CITYFLOW_B200_SHARD_GRAPH")) I.shardGraphOk = (g[0] != '0');
 }
 
 ShardBuffers DeviceSim::shardBuffers() {

@@ -1,0 +1,34 @@
+// Test helper: prints the column-strip partition of a scenario as JSON.
+#include <cstdio>
+#include <cstdlib>
+#include "../cityflow_b200/csrc/json_min.h"
+#include "../cityflow_b200/csrc/partition.h"
+int main(int argc, char **argv) {
+    if (argc < 3) return 2;
+    bool ok = false;
+    cfb::Json cfg = cfb::Json::parseFile(argv[1], &ok);
+    cfb::RoadNet n;
+    if (!ok || !n.load(cfg.find("dir")->s + cfg.find("roadnetFile")->s)) return 1;
+    const int world = atoi(argv[2]);
+    cfb::Partition p = cfb::Partition::columnStrips(n, world);
+    printf("{\"world\": %d, \"n_lanes\": %d, \"inter_owner\": [", world, n.nLanes());
+    for (int i = 0; i < n.nInter(); ++i) printf("%s%d", i ? "," : "", p.interOwner[i]);
+    printf("], \"inter_virtual\": [");
+    for (int i = 0; i < n.nInter(); ++i) printf("%s%d", i ? "," : "", (int) n.interVirtual[i]);
+    printf("], \"lane_owner\": [");
+    for (int l = 0; l < n.nLanes(); ++l) printf("%s%d", l ? "," : "", p.drvOwner[l]);
+    printf("], \"lane_feeder\": [");
+    for (int l = 0; l < n.nLanes(); ++l) printf("%s%d", l ? "," : "", p.interOwner[n.roadStartInter[n.laneRoad[l]]]);
+    printf("], \"boundary\": [");
+    for (int a = 0; a < world; ++a) {
+        printf("%s[", a ? "," : "");
+        for (int b = 0; b < world; ++b) {
+            printf("%s[", b ? "," : "");
+            for (size_t k = 0; k < p.boundary[a][b].size(); ++k) printf("%s%d", k ? "," : "", p.boundary[a][b][k]);
+            printf("]");
+        }
+        printf("]");
+    }
+    printf("], \"validate\": \"%s\"}\n", p.validate(n, 64.2).c_str());
+    return 0;
+}
