@@ -283,10 +283,17 @@ def run_ours(args):
         "k_ingest": 12 * n_drv,
     }
 
+    try:  # DRAM bytes per launch from the committed ncu --set full capture (same workload)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01f_dram_traffic_bytes_per_launch.json")))
+    except Exception:
+        traffic = {}
+    same_workload = (args.rows, args.cols, args.frac, args.flow_interval) == (30, 30, 0.5, 10.0)
+
     def roof(k):
         gbs = alg[k] / (kms[k] * 1e-3) / 1e9 if kms[k] > 0 else 0.0
         return {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": alg[k], "avg_launch_ms": kms[k], "peak_source": peak_src}
+                "traffic": traffic.get(k) if same_workload else None,
+                "note": "latency-bound at this size (dependent loads + FP64 div/sqrt chains), see profiles/r01c_control_cycles.md", "algorithmic_bytes_per_launch": alg[k], "avg_launch_ms": kms[k], "peak_source": peak_src}
 
     line = None
     if rank == 0:
