@@ -304,7 +304,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": workload_name(args), "prefill_steps": args.prefill, "mean_vehicles_per_gpu": mean_n,
-                "vehicles_at_start": n_start, "parallelism": ("sharded: %d column strips of ONE simulation, seam records over NCCL (3 neighbour exchanges + 1 all-gather per step)" % world)
+                "vehicles_at_start": n_start, "parallelism": ("sharded: %d column strips of ONE simulation, seam records over NCCL (2 send/recv groups per step: movers, tails + blocker lists)" % world)
                 if sharded else "replicas x%d (one engine per GPU, no exchange)" % world,
                 "l2": "value: 256 MiB memset between timed steps (state ~30 MB would otherwise stay L2-resident); "
                       "value_l2_warm and e2e: steps back to back as in real stepping",

@@ -1800,8 +1800,8 @@ void DeviceSim::applyBlk() {
 }
 void DeviceSim::shardCounts(ShardTransport *t, int32_t *laneOut, int *activeOut) {
     Impl &I = *impl_;
-    const int n = 1 + I.V.nLanes;
-    if (I.shardScratch.n < (size_t) n) I.shardScratch.alloc(n);
+    const int n = laneOut ? 1 + I.V.nLanes : 1;   // the vehicle count alone is a 4-byte all-reduce
+    if (I.shardScratch.n < (size_t) (1 + I.V.nLanes)) I.shardScratch.alloc(1 + I.V.nLanes);
     k_mask_counts<<<(n + 255) / 256, 256, 0, I.stream>>>(I.V, I.shardScratch.p);
     t->allReduceSumInt((void *) I.stream, I.shardScratch.p, n);
     std::vector<int> h(n);
