@@ -2207,6 +2207,14 @@ DeviceSim::Snapshot *DeviceSim::snapshotFromHost(const unsigned char *data, size
     return s;
 }
 
+int DeviceSim::slotDelStep(int slot) {
+    Impl &I = *impl_;
+    if (slot < 0 || slot >= I.slotCap) return INT_MIN;
+    int d = INT_MIN;
+    CFB_CUDA(cudaMemcpy(&d, I.V.delStep + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    return d;
+}
+
 bool DeviceSim::vehicleState(int slot, VehState &out) {
     Impl &I = *impl_;
     if (slot < 0 || slot >= I.slotCap) return false;

@@ -128,6 +128,7 @@ public:
 
     struct VehState { int pos, drivable, planIdx, nextDrv; double dis, speed; };
     bool vehicleState(int slot, VehState &out);          // false: not running
+    int slotDelStep(int slot);                           // step at which the slot's vehicle left (very negative: never)
     void setCustomSpeed(int slot, double speed);         // Vehicle::setCustomSpeed (running or queued vehicle)
     void setVehiclePlan(int slot, int planId, int planIdx, int nextDrv);
 

@@ -55,6 +55,7 @@ struct SlotInfo {
     int32_t flow = -1, index = -1;   // id: flow_<flow>_<index> / manually_pushed_<index> (flow == -2)
     int32_t priority = 0;
     double enterTime = 0;
+    int32_t spawnStep = 0;           // Engine::step when the vehicle was created
     int32_t routeId = -1;            // resolved route (Routing::route), for get_vehicle_info / set_vehicle_route
     int32_t firstLane = -1;          // lane whose waiting queue the vehicle was put in
     bool live = false;
@@ -71,6 +72,7 @@ class PriorityMap {
 public:
     PriorityMap() { rehash(1 << 12); }
     bool contains(int k) const { return find(k) >= 0; }
+    int get(int k) const { long i = find(k); return i >= 0 ? val_[i] : -1; }
     void insert(int k, int v) {
         if ((used_ + 1) * 2 > cap_) rehash(cap_ * 2);
         size_t i = hash(k);
@@ -264,7 +266,7 @@ public:
             if (!s.live) continue;
             finishedCnt += 1;
             cumulativeTravelTime += f.step * interval - s.enterTime;
-            pool.erase(s.priority);
+            if (pool.get(s.priority) == f.slot) pool.erase(s.priority);   // (the priority may already be re-issued)
             s.live = false;
             freeSlots.push_back(f.slot);
         }
@@ -288,10 +290,17 @@ public:
         int priority;
         for (;;) {
             priority = (int) rnd();
-            if (!pool.contains(priority)) break;
-            // the candidate may belong to a vehicle that already left the network on the device
-            drain();
-            if (!pool.contains(priority)) break;
+            const int other = pool.get(priority);
+            if (other < 0) break;
+            // The holder of this priority may have left the network on the device already (the host
+            // learns about finishes lazily).  Ask the device about that one slot -- its delStep array
+            // is complete on every rank of a sharded run, so no collective drain is needed -- and let
+            // the regular drain do the bookkeeping later.
+            dev->synchronize();
+            if (dev->slotDelStep(other) >= slots[other].spawnStep) {
+                pool.erase(priority);
+                break;
+            }
         }
         (void) rnd();  // threadIndex = rnd() % threadNum (engine.cpp:606): drawn, not needed here
         const int slot = allocSlot();
@@ -300,6 +309,7 @@ public:
         s.index = index;
         s.priority = priority;
         s.enterTime = currentTime();
+        s.spawnStep = (int32_t) step;
         s.routeId = routeId;
         s.firstLane = -1;
         s.live = true;

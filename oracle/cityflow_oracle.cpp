@@ -754,6 +754,7 @@ void cfo_push_vehicle(void *h, const double *v, const int32_t *roads, int n) {
     Veh *veh = o->newVehicle(t, anchors, -2, o->manuallyPushCnt++);
     o->planRouteBuffer[anchors[0]].push_back(veh);
 }
+void cfo_set_random_seed(void *h, int seed) { ((Oracle *) h)->rnd.seed(seed); }  // Engine::setRandomSeed engine.h:170
 int cfo_road_index(void *h, const char *id) {
     Oracle *o = (Oracle *) h;
     auto it = o->net.roadIndex.find(id);

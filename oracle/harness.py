@@ -208,6 +208,11 @@ class PortOracle:
     def vehicle_count(self) -> int:
         return self.lib.cfo_vehicle_count(self.h)
 
+    def set_random_seed(self, seed: int):
+        self.lib.cfo_set_random_seed.restype = None
+        self.lib.cfo_set_random_seed.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.lib.cfo_set_random_seed(self.h, seed)
+
     def average_travel_time(self) -> float:
         self.lib.cfo_average_travel_time.restype = ctypes.c_double
         self.lib.cfo_average_travel_time.argtypes = [ctypes.c_void_p]

@@ -284,3 +284,27 @@ def test_sharded_loopback_equals_unsharded(cfg_6x6_dense, world):
             for f in ("dis", "speed"):
                 assert np.array_equal(a[f], b[f]), (s, f)
     assert ref.vehicle_count() > 3000
+
+
+def test_priority_collisions_after_reseed_vs_port(cfg_3x3_dense):
+    """Re-seeding the engine RNG mid-run makes it re-issue the priorities it drew at the start:
+    draws collide with vehicles that are still alive (redraw, vehicle.cpp:45) and re-use the
+    priorities of vehicles that already left (legal).  Exercises Engine::checkPriority
+    (engine.cpp:601) against the host's lazily drained bookkeeping."""
+    import cityflow
+    eng = cityflow.Engine(cfg_3x3_dense, thread_num=1)
+    ora = H.PortOracle(cfg_3x3_dense)
+    for s in range(1, 701):
+        if s in (250, 400, 401, 550):
+            eng.set_random_seed(0)
+            ora.set_random_seed(0)
+        eng.next_step()
+        ora.next_step()
+        if s % 50 == 0 or s in (251, 252, 402):
+            assert eng.get_vehicle_count() == ora.vehicle_count(), s
+            ov = ora.vehicles()
+            sp = eng.get_vehicle_speed()
+            names = ["flow_%d_%d" % (f, c) for f, c in zip(ov["flow"], ov["cnt"])]
+            assert set(names) == set(sp.keys()), s
+            assert all(sp[n] == v for n, v in zip(names, ov["speed"])), s
+    assert eng.get_average_travel_time() == ora.average_travel_time()
