@@ -81,7 +81,7 @@ struct Ctrl {
     int moverCount;
     int finCount;
     int error;
-    int spawnCount;
+    int reserved0;   // (layout: keeps the counters below 8-byte aligned)
     int nVeh[2];     // work lists, double-buffered on step parity
     int nAct[2];
     int nExtra;
@@ -92,11 +92,7 @@ struct Ctrl {
 };
 
 #ifdef CFB_DEBUG_COUNTERS
-#define CFB_DBG_MAX(i, v) atomicMax(&V.ctrl->dbg[i], (unsigned long long) (v))
-#define CFB_DBG_ADD(i, v) atomicAdd(&V.ctrl->dbg[i], (unsigned long long) (v))
-#else
-#define CFB_DBG_MAX(i, v)
-#define CFB_DBG_ADD(i, v)
+// (per-vehicle cycle / path samples of k_control are recorded in this build: tools/dbg_control_cycles.py)
 #endif
 
 constexpr int HEAD_BIT = 0x40000000;   // in vehList[].y: the vehicle is the first of its drivable's list
@@ -1266,7 +1262,6 @@ struct DeviceSim::Impl {
     int hSpawnCap[RING] = {};
     cudaEvent_t spawnDone[RING] = {};
     int ringIdx = 0;
-    int *hCounts = nullptr; // pinned, RING ints
     std::vector<int> hPhase;            // authoritative phases in rlTrafficLight mode (set_tl_phase)
     int *hPhaseRing[RING] = {};         // pinned staging, one per ring slot
     bool phaseDirty = false;
@@ -1443,8 +1438,10 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.cust.alloc(P); I.cust.fill(0xff); V.cust = I.cust.p;
     I.tail.alloc(nD); I.foeMask.alloc((size_t) std::max(nK, 1) * V.maskWords);
     V.tail = I.tail.p; V.foeMask = I.foeMask.p;
+#ifdef CFB_DEBUG_COUNTERS
     I.dbgCyc.alloc(P); I.dbgPath.alloc(P); I.dbgCyc.fill(0); I.dbgPath.fill(0);
     V.dbgCyc = I.dbgCyc.p; V.dbgPath = I.dbgPath.p;
+#endif
     V.vehCap = I.P;
     I.vehList0.alloc(P); I.vehList1.alloc(P); I.act0.alloc(nD); I.act1.alloc(nD); I.extra.alloc(nD);
     V.vehList[0] = I.vehList0.p; V.vehList[1] = I.vehList1.p; V.actList[0] = I.act0.p; V.actList[1] = I.act1.p;
@@ -1453,7 +1450,6 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.finSlots.alloc(V.finCap);
     I.ctrl.alloc(1);
     CFB_CUDA(cudaMallocHost(&I.hCtrl, sizeof(Ctrl)));
-    CFB_CUDA(cudaMallocHost(&I.hCounts, Impl::RING * sizeof(int)));
     V.kin = I.kin.p; V.nkin = I.nkin.p; V.gap = I.gap.p; V.leader = I.leader.p; V.ids = I.ids.p; V.nav = I.nav.p;
     V.nbuf = I.nbuf.p; V.count = I.count.p; V.entCnt = I.entCnt.p; V.ent = I.ent.p;
     V.waitHead = I.waitHead.p; V.waitTail = I.waitTail.p; V.inserted = I.inserted.p; V.notify = I.notify.p;
@@ -1479,7 +1475,6 @@ DeviceSim::~DeviceSim() {
     for (int k = 0; k < 2; ++k) if (I.graphExec[k]) cudaGraphExecDestroy(I.graphExec[k]);
     for (int k = 0; k < 2; ++k) if (I.graphDone[k]) cudaEventDestroy(I.graphDone[k]);
     if (I.hCtrl) cudaFreeHost(I.hCtrl);
-    if (I.hCounts) cudaFreeHost(I.hCounts);
     if (I.hInts) cudaFreeHost(I.hInts);
     if (I.stream) cudaStreamDestroy(I.stream);
     delete impl_;
@@ -1937,6 +1932,11 @@ double DeviceSim::collectTimedMs() {
 int DeviceSim::debugArrays(unsigned *cyc, unsigned *path) {
     Impl &I = *impl_;
     CFB_CUDA(cudaStreamSynchronize(I.stream));
+    if (!I.dbgCyc.p) {  // not a CFB_DEBUG_COUNTERS build
+        memset(cyc, 0, (size_t) I.P * 4);
+        memset(path, 0, (size_t) I.P * 4);
+        return I.P;
+    }
     CFB_CUDA(cudaMemcpy(cyc, I.dbgCyc.p, (size_t) I.P * 4, cudaMemcpyDeviceToHost));
     CFB_CUDA(cudaMemcpy(path, I.dbgPath.p, (size_t) I.P * 4, cudaMemcpyDeviceToHost));
     I.dbgCyc.fill(0); I.dbgPath.fill(0);
