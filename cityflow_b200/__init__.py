@@ -26,3 +26,32 @@ except ImportError as _e:  # extension not built: fail loudly at use, not silent
     class Archive:  # type: ignore
         def __init__(self, *a, **k):
             raise RuntimeError("cityflow_b200: the CUDA extension is not built")
+
+
+class _DeviceArray:
+    """A device array of the engine exposed through ``__cuda_array_interface__`` (keeps the engine alive)."""
+
+    def __init__(self, owner, ptr, n, typestr):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def lane_observation_tensors(engine, stream=None):
+    """Zero-copy per-lane observations as torch CUDA tensors.
+
+    Returns ``(lane_ids, vehicle_count[int32], waiting_count[int32], speed_sum[float64])``: the
+    arrays ``get_lane_vehicle_count`` / ``get_lane_waiting_vehicle_count`` report (engine.cpp:628-648)
+    plus the per-lane sum of speeds, in ``engine.lane_ids()`` order, living on the engine's GPU.
+    Nothing is copied to the host and the host does not wait: the refresh is ordered against
+    ``stream`` (default: torch's current stream on the engine's device).  The tensors alias the
+    engine's buffers: they are overwritten by the next call, so ``clone()`` what must survive it.
+    """
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream(engine.device()).cuda_stream
+    o = engine.observe_device(int(stream))
+    n = o["n_lanes"]
+    dev = torch.device("cuda", o["device"])
+    mk = lambda key, ts: torch.as_tensor(_DeviceArray(engine, o[key], n, ts), device=dev)
+    return (engine.lane_ids(), mk("lane_vehicle_count", "<i4"), mk("lane_waiting_count", "<i4"), mk("lane_speed_sum", "<f8"))

@@ -1157,6 +1157,31 @@ __global__ void __launch_bounds__(256) k_lane_waiting(View V, int *out) {  // en
     if (lane == 0) out[d] = c;
 }
 
+// Per-lane observation vector for consumers on the same GPU (RL policies): list length
+// (engine.cpp:628-634), vehicles slower than 0.1 m/s (:636-648) and the sum of speeds, one warp per lane.
+__global__ void __launch_bounds__(256) k_lane_obs(View V, int *cnt, int *wait, double *speedSum) {
+    const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (d >= V.nLanes) return;
+    const int n = V.count[d], base = V.off[d];
+    int c = 0;
+    double s = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        const double v = V.kin[base + k].y;
+        c += v < 0.1;
+        s += v;
+    }
+    for (int o = 16; o; o >>= 1) {
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) {
+        cnt[d] = n;
+        wait[d] = c;
+        speedSum[d] = s;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_gather_running(View V, SpeedRec *out, int *cursor, int cap) {
     const int d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -1271,6 +1296,9 @@ struct DeviceSim::Impl {
     // timing
     bool timing = false;
     cudaEvent_t ev[6] = {};
+    DevBuf<int> obsI;                  // observeOnDevice(): [count | waiting] per lane
+    DevBuf<double> obsD;               //                    speed sum per lane
+    cudaEvent_t obsReady = nullptr, obsConsumed = nullptr;
     std::vector<cudaEvent_t> stepEv;   // timed-step brackets (bench)
     size_t stepEvUsed = 0;
     DevBuf<unsigned char> flushBuf;
@@ -1561,6 +1589,7 @@ void DeviceSim::reset() {
 
 int DeviceSim::numPositions() const { return impl_->P; }
 int DeviceSim::numDrivables() const { return impl_->V.nDrv; }
+int DeviceSim::device() const { return impl_->opt.device; }
 
 void DeviceSim::stageStep(const SpawnRec *recs, int n) {
     Impl &I = *impl_;
@@ -1992,6 +2021,36 @@ void DeviceSim::laneWaitingVehicleCount(int32_t *out) {
     CFB_CUDA(cudaStreamSynchronize(I.stream));
     memcpy(out, I.hInts, I.V.nLanes * sizeof(int));
     launches_ += 1;
+}
+
+DeviceObs DeviceSim::observeOnDevice(void *consumerStream) {
+    Impl &I = *impl_;
+    if (I.V.owned) throw std::runtime_error("observeOnDevice: not available on one rank of a sharded run");
+    const int nL = I.V.nLanes;
+    if (I.obsI.n < (size_t) 2 * nL) {
+        I.obsI.alloc((size_t) 2 * std::max(nL, 1));
+        I.obsD.alloc((size_t) std::max(nL, 1));
+        CFB_CUDA(cudaEventCreateWithFlags(&I.obsReady, cudaEventDisableTiming));
+        CFB_CUDA(cudaEventCreateWithFlags(&I.obsConsumed, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = (cudaStream_t) consumerStream;
+    // the consumer's earlier reads of the buffers finish before this refresh overwrites them ...
+    CFB_CUDA(cudaEventRecord(I.obsConsumed, cs));
+    CFB_CUDA(cudaStreamWaitEvent(I.stream, I.obsConsumed, 0));
+    const int TPB = 256;
+    if (nL > 0) k_lane_obs<<<(int) (((size_t) nL * 32 + TPB - 1) / TPB), TPB, 0, I.stream>>>(I.V, I.obsI.p, I.obsI.p + nL, I.obsD.p);
+    CFB_CUDA(cudaGetLastError());
+    // ... and its later reads see this refresh, without the host waiting for either stream
+    CFB_CUDA(cudaEventRecord(I.obsReady, I.stream));
+    CFB_CUDA(cudaStreamWaitEvent(cs, I.obsReady, 0));
+    launches_ += 1;
+    DeviceObs o;
+    o.laneCount = I.obsI.p;
+    o.laneWaiting = I.obsI.p + nL;
+    o.laneSpeedSum = I.obsD.p;
+    o.nLanes = nL;
+    o.device = I.opt.device;
+    return o;
 }
 
 int DeviceSim::runningVehicles(std::vector<SpeedRec> &out) {

@@ -74,6 +74,14 @@ struct ShardBuffers {
     int *laneCount = nullptr;                   // device ints: list length per drivable
 };
 
+struct DeviceObs {
+    const int32_t *laneCount = nullptr;     // nLanes ints, roadnet lane order
+    const int32_t *laneWaiting = nullptr;   // nLanes ints, speed < 0.1
+    const double *laneSpeedSum = nullptr;   // nLanes doubles
+    int nLanes = 0;
+    int device = 0;
+};
+
 class DeviceSim {
 public:
     // Throws std::runtime_error when no CUDA device / extension is usable (no CPU fallback).
@@ -113,6 +121,10 @@ public:
     void step(const SpawnRec *recs, int n);
     void synchronize();
 
+    // Observations left on the device for a consumer on the same GPU: refreshed on the engine's
+    // stream, ordered against `consumerStream` (a cudaStream_t; null = legacy default stream) with
+    // events in both directions, no host synchronisation.  Valid until the next call.
+    DeviceObs observeOnDevice(void *consumerStream);
     // Observations (synchronise the stream).
     int vehicleCount();
     int errorFlags();
@@ -156,6 +168,7 @@ public:
     long long launchesDone() const { return launches_; }
     int numPositions() const;
     int numDrivables() const;
+    int device() const;   // CUDA device ordinal the engine lives on
 
     struct Impl;
 

@@ -619,6 +619,19 @@ int cfb_get_lane_waiting_vehicle_count(cfb_engine *e, int32_t *out, int n) {
     return CFB_OK;
 }
 
+int cfb_observe_device(cfb_engine *e, void *consumer_stream, cfb_device_obs *out) {
+    if (!out) { e->lastError = "null output"; return CFB_ERR_ARGUMENT; }
+    CFB_TRY(e,
+        const cfb::DeviceObs o = e->h.dev->observeOnDevice(consumer_stream);
+        out->lane_vehicle_count = o.laneCount;
+        out->lane_waiting_count = o.laneWaiting;
+        out->lane_speed_sum = o.laneSpeedSum;
+        out->n_lanes = o.nLanes;
+        out->device = o.device;
+    )
+    return CFB_OK;
+}
+
 int64_t cfb_get_vehicle_speed(cfb_engine *e, cfb_vehicle_ref *ids, double *speed, double *distance, int64_t cap) {
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
@@ -798,6 +811,7 @@ int cfb_synchronize(cfb_engine *e) {
     return CFB_OK;
 }
 int64_t cfb_num_drivables(const cfb_engine *e) { return e->h.dev->numDrivables(); }
+int cfb_device(const cfb_engine *e) { return e->h.dev->device(); }
 
 }  // extern "C"
 
@@ -1113,14 +1127,16 @@ void loopExchange(std::vector<cfb::ShardBuffers> &B, bool tails) {
                 if (n) cudaMemcpy((char *) B[b].moverRecv + (size_t) B[b].inBeg[a] * B[b].moverBytes,
                                   (char *) B[a].moverSend + (size_t) B[a].outBeg[b] * B[a].moverBytes, n, cudaMemcpyDeviceToDevice);
             }
-        }    cudaDeviceSynchronize();   // D2D cudaMemcpy may return early; the ranks' streams are non-blocking
+        }
+    cudaDeviceSynchronize();   // D2D cudaMemcpy may return early; the ranks' streams are non-blocking
 }
 void loopAllGatherBlk(std::vector<cfb::ShardBuffers> &B) {
     const int W = (int) B.size();
     for (int a = 0; a < W; ++a) cudaStreamSynchronize((cudaStream_t) B[a].stream);
     for (int a = 0; a < W; ++a)
         for (int b = 0; b < W; ++b)
-            cudaMemcpy((char *) B[b].blkAll + (size_t) a * B[a].blkBytesPerRank, B[a].blkSend, B[a].blkBytesPerRank, cudaMemcpyDeviceToDevice);    cudaDeviceSynchronize();
+            cudaMemcpy((char *) B[b].blkAll + (size_t) a * B[a].blkBytesPerRank, B[a].blkSend, B[a].blkBytesPerRank, cudaMemcpyDeviceToDevice);
+    cudaDeviceSynchronize();
 }
 }  // namespace
 

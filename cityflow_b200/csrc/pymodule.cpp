@@ -125,6 +125,23 @@ public:
         for (size_t i = 0; i < laneOrder_.size(); ++i) d[laneKeys_[i]] = py::int_(laneBuf_[laneOrder_[i]]);
         return d;
     }
+    std::vector<std::string> laneIds() {
+        std::vector<std::string> ids(cfb_num_lanes(e_));
+        for (size_t i = 0; i < ids.size(); ++i) ids[i] = cfb_lane_id(e_, (int) i);
+        return ids;
+    }
+    // device pointers of the per-lane observation arrays, ordered against CUDA stream `stream`
+    py::dict observeDevice(uintptr_t stream) {
+        cfb_device_obs o{};
+        check(cfb_observe_device(e_, (void *) stream, &o));
+        py::dict d;
+        d["lane_vehicle_count"] = py::int_((uintptr_t) o.lane_vehicle_count);
+        d["lane_waiting_count"] = py::int_((uintptr_t) o.lane_waiting_count);
+        d["lane_speed_sum"] = py::int_((uintptr_t) o.lane_speed_sum);
+        d["n_lanes"] = py::int_(o.n_lanes);
+        d["device"] = py::int_(o.device);
+        return d;
+    }
     py::dict getLaneVehicleCount() { return laneDict(false); }
     py::dict getLaneWaitingVehicleCount() { return laneDict(true); }
 
@@ -326,6 +343,9 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("transfer_bytes", &Engine::transferBytes)
         .def("num_drivables", [](Engine &e) { return e.numDrivables(); })
         .def("host_times", &Engine::hostTimes)
+        .def("lane_ids", &Engine::laneIds)
+        .def("device", [](Engine &e) { return cfb_device(e.raw()); })
+        .def("observe_device", &Engine::observeDevice, "stream"_a = 0)
         .def("synchronize", &Engine::synchronize);
     py::class_<Archive>(m, "Archive")
         .def(py::init<Engine &>())

@@ -74,6 +74,23 @@ const char *cfb_intersection_id(const cfb_engine *e, int intersection);
 int cfb_get_lane_vehicle_count(cfb_engine *e, int32_t *out, int n);
 /* Engine::getLaneWaitingVehicleCount  engine.cpp:636-648 (speed < 0.1) */
 int cfb_get_lane_waiting_vehicle_count(cfb_engine *e, int32_t *out, int n);
+/* The same per-lane observations left ON THE DEVICE for a consumer on the same GPU (the policy
+ * network of an RL loop): no device->host copy, no host synchronisation.  The three arrays
+ * (cfb_num_lanes() entries each, roadnet lane order) are refreshed on the engine's stream and
+ * ordered against `consumer_stream` (a cudaStream_t; NULL = the legacy default stream) in both
+ * directions, so kernels enqueued on that stream after this call read this step's values and the
+ * next refresh waits for the reads enqueued before it.  The pointers stay valid for the engine's
+ * lifetime; their content is valid until the next cfb_observe_device call.
+ * lane_speed_sum / lane_vehicle_count = the mean speed the reference's users derive from
+ * getVehicleSpeed + getLaneVehicles (engine.cpp:650-668).  Single-GPU engines only. */
+typedef struct {
+    const int32_t *lane_vehicle_count;   /* engine.cpp:628-634 */
+    const int32_t *lane_waiting_count;   /* engine.cpp:636-648 (speed < 0.1) */
+    const double *lane_speed_sum;
+    int32_t n_lanes;
+    int32_t device;                      /* CUDA device ordinal the pointers live on */
+} cfb_device_obs;
+int cfb_observe_device(cfb_engine *e, void *consumer_stream, cfb_device_obs *out);
 /* Engine::getVehicleSpeed  engine.cpp:662-668 / getVehicleDistance :670-676: running vehicles in
  * vehiclePool (priority) order.  Returns the number of running vehicles (may exceed cap; only
  * cap entries are written); any of the three output pointers may be NULL. */
@@ -163,6 +180,8 @@ int cfb_enable_kernel_timing(cfb_engine *e, int on);
 int cfb_kernel_times(cfb_engine *e, double ms_out[5], int64_t *steps_timed);
 int cfb_synchronize(cfb_engine *e);
 int64_t cfb_num_drivables(const cfb_engine *e);
+/* CUDA device ordinal the engine was created on */
+int cfb_device(const cfb_engine *e);
 
 #ifdef __cplusplus
 }

@@ -68,3 +68,36 @@ def cfg_hetero_halfstep(scenario_dir):
         f["startTime"] = rng.choice([0, 0, 10, 50])
         f["endTime"] = rng.choice([-1, -1, 400])
     return scenario.write_scenario(scenario_dir, net, flows, interval=0.5, seed=3, name="hetero")
+
+
+@pytest.fixture(scope="session")
+def cfg_irregular(scenario_dir):
+    """A 3x3 grid bent out of shape: road polylines with interior points, unequal lane widths and
+    speed limits, laneLinks WITHOUT explicit points (the loader's default curve, roadnet.cpp:212-247),
+    odd intersection widths and phase times.  Exercises the geometry code the generator's tidy
+    output never reaches."""
+    import random
+    from cityflow_b200 import scenario
+    rng = random.Random(5)
+    net = scenario.grid_roadnet(3, 3)
+    for road in net["roads"]:
+        a, b = road["points"]
+        mx, my = (a["x"] + b["x"]) / 2, (a["y"] + b["y"]) / 2
+        dx, dy = b["x"] - a["x"], b["y"] - a["y"]
+        k = rng.uniform(-0.08, 0.08)
+        road["points"] = [a, {"x": mx - dy * k, "y": my + dx * k}, b]          # a bend
+        road["lanes"] = [{"width": rng.choice([3, 3.5, 4]), "maxSpeed": rng.choice([11.11, 13.89, 16.67])} for _ in road["lanes"]]
+    for inter in net["intersections"]:
+        if inter["virtual"]:
+            continue
+        inter["width"] = rng.choice([20, 25, 30, 12.5])
+        for i, rl in enumerate(inter["roadLinks"]):
+            for j, ll in enumerate(rl["laneLinks"]):
+                if (i + j) % 2 == 0:
+                    ll.pop("points")                                             # default curve
+                elif (i + j) % 5 == 0:
+                    ll["points"] = []                                            # empty list = default curve too
+        for ph in inter["trafficLight"]["lightphases"]:
+            ph["time"] = rng.choice([5, 17, 30, 12.5])
+    flows = scenario.random_walk_flows(net, frac=1.0, interval=4.0, seed=9)
+    return scenario.write_scenario(scenario_dir, net, flows, seed=7, name="irregular")

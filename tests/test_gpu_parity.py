@@ -308,3 +308,43 @@ def test_priority_collisions_after_reseed_vs_port(cfg_3x3_dense):
             assert set(names) == set(sp.keys()), s
             assert all(sp[n] == v for n, v in zip(names, ov["speed"])), s
     assert eng.get_average_travel_time() == ora.average_travel_time()
+
+
+def test_irregular_roadnet_vs_port(cfg_irregular):
+    _run_against_port(cfg_irregular, 600, every=10)
+
+
+def test_device_resident_lane_observations(cfg_6x6_dense):
+    """SURVEY.md §8f-3 zero-copy observations: the torch CUDA tensors alias the engine's buffers and
+    carry exactly what the host getters report, refreshed without a host synchronisation."""
+    import torch
+    import cityflow
+    import cityflow_b200
+    eng = cityflow.Engine(cfg_6x6_dense, thread_num=1)
+    side = torch.cuda.Stream()
+    for rounds in range(3):
+        for _ in range(100):
+            eng.next_step()
+        with torch.cuda.stream(side if rounds == 1 else torch.cuda.current_stream()):
+            ids, cnt, wait, ssum = cityflow_b200.lane_observation_tensors(eng)
+            total = cnt.sum()                               # consumer work on the ordered stream
+            cnt_h, wait_h, ssum_h = cnt.cpu(), wait.cpu(), ssum.cpu()
+        assert cnt.is_cuda and cnt.dtype == torch.int32 and ssum.dtype == torch.float64
+        counts = eng.get_lane_vehicle_count()
+        waiting = eng.get_lane_waiting_vehicle_count()
+        assert ids == eng.lane_ids() and set(ids) == set(counts)
+        assert cnt_h.tolist() == [counts[i] for i in ids]
+        assert wait_h.tolist() == [waiting[i] for i in ids]
+        assert int(total) == sum(counts.values())
+        speeds = eng.get_vehicle_speed()
+        per_lane = {i: 0.0 for i in ids}
+        for lane, vs in eng.get_lane_vehicles().items():
+            per_lane[lane] = sum(speeds[v] for v in vs)
+        np.testing.assert_allclose(ssum_h.numpy(), np.array([per_lane[i] for i in ids]), rtol=0, atol=1e-9)
+    assert sum(counts.values()) > 500
+    # same storage every call (zero-copy): the next refresh shows through the old tensor
+    old_ptr = cnt.data_ptr()
+    eng.next_steps(50)
+    ids2, cnt2, _, _ = cityflow_b200.lane_observation_tensors(eng)
+    assert cnt2.data_ptr() == old_ptr
+    assert cnt.tolist() == [eng.get_lane_vehicle_count()[i] for i in ids]
