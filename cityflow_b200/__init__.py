@@ -55,3 +55,19 @@ def lane_observation_tensors(engine, stream=None):
     dev = torch.device("cuda", o["device"])
     mk = lambda key, ts: torch.as_tensor(_DeviceArray(engine, o[key], n, ts), device=dev)
     return (engine.lane_ids(), mk("lane_vehicle_count", "<i4"), mk("lane_waiting_count", "<i4"), mk("lane_speed_sum", "<f8"))
+
+
+def set_tl_phases_tensor(engine, phases, stream=None):
+    """``set_tl_phase`` for every traffic light at once from a torch CUDA tensor (no host copy).
+
+    ``phases``: int32, contiguous, one entry per intersection in ``engine.intersection_ids()`` order
+    (virtual intersections included, their entries ignored), on the engine's GPU, produced on
+    ``stream`` (default: torch's current stream there).  Needs ``"rlTrafficLight": true``.
+    """
+    import torch
+    if not (phases.is_cuda and phases.dtype == torch.int32 and phases.is_contiguous()
+            and phases.device.index == engine.device() and phases.numel() == engine.num_intersections()):
+        raise ValueError("phases must be a contiguous int32 CUDA tensor on the engine's device, one entry per intersection")
+    if stream is None:
+        stream = torch.cuda.current_stream(engine.device()).cuda_stream
+    engine.set_tl_phases_device(phases.data_ptr(), int(stream))

@@ -1157,6 +1157,14 @@ __global__ void __launch_bounds__(256) k_lane_waiting(View V, int *out) {  // en
     if (lane == 0) out[d] = c;
 }
 
+__global__ void k_set_phases(View V, const int *src) {  // TrafficLight::setPhase trafficlight.cpp:39-41, all lights at once
+    const int in = blockIdx.x * blockDim.x + threadIdx.x;
+    if (in >= V.nInter || V.interVirtual[in]) return;
+    const int p = src[in], nph = V.interPhaseBeg[in + 1] - V.interPhaseBeg[in];
+    if (p >= 0 && p < nph) V.curPhase[in] = p;
+    else atomicOr(&V.ctrl->error, ERR_PHASE_RANGE);
+}
+
 // Per-lane observation vector for consumers on the same GPU (RL policies): list length
 // (engine.cpp:628-634), vehicles slower than 0.1 m/s (:636-648) and the sum of speeds, one warp per lane.
 __global__ void __launch_bounds__(256) k_lane_obs(View V, int *cnt, int *wait, double *speedSum) {
@@ -1238,6 +1246,12 @@ struct DevBuf {
     ~DevBuf() { release(); }
 };
 
+// The engine's stream is non-blocking, so it is NOT ordered against the legacy default stream that
+// plain cudaMemcpy / cudaMemset run on (and those may return before the device side is done:
+// memsets, device-to-device copies, staged pageable uploads).  Every function that writes device
+// state that way ends with this barrier, before anything can be enqueued on the engine's stream.
+static void legacySync() { CFB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); }
+
 struct DeviceSim::Impl {
     DeviceSimOptions opt;
     View V{};
@@ -1299,6 +1313,8 @@ struct DeviceSim::Impl {
     DevBuf<int> obsI;                  // observeOnDevice(): [count | waiting] per lane
     DevBuf<double> obsD;               //                    speed sum per lane
     cudaEvent_t obsReady = nullptr, obsConsumed = nullptr;
+    cudaEvent_t actReady = nullptr, actTaken = nullptr;   // setPhasesFromDevice()
+    bool hPhaseStale = false;          // the device copy is newer than hPhase (phases were set on the device)
     std::vector<cudaEvent_t> stepEv;   // timed-step brackets (bench)
     size_t stepEvUsed = 0;
     DevBuf<unsigned char> flushBuf;
@@ -1518,6 +1534,7 @@ void DeviceSim::uploadTemplates(const std::vector<VehicleTemplate> &templates) {
     I.V.tmpl = I.tmpl.p;
     I.graphDirty = true;
     I.dropShardGraphs();
+    legacySync();
 }
 
 void DeviceSim::uploadPlans(const Routing &routing) {
@@ -1532,6 +1549,7 @@ void DeviceSim::uploadPlans(const Routing &routing) {
     I.V.planData = I.planData.p;
     I.graphDirty = true;
     I.dropShardGraphs();
+    legacySync();
 }
 
 void DeviceSim::ensureSlotCapacity(int slots) {
@@ -1547,6 +1565,7 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     npos.alloc(cap); nnext.alloc(cap); ninfo.alloc(cap); ncust.alloc(cap);
     npos.fill(0xff); nnext.fill(0xff); ninfo.fill(0); ncust.fill(0xff);
     nblk.alloc(cap); ndel.alloc(cap); nblk.fill(0xff); ndel.fill(0x80);
+    legacySync();   // fills before the copies (same stream, but keep the order explicit)
     if (I.slotCap) {
         CFB_CUDA(cudaMemcpy(npos.p, I.pos.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
         CFB_CUDA(cudaMemcpy(nnext.p, I.waitNext.p, I.slotCap * sizeof(int), cudaMemcpyDeviceToDevice));
@@ -1561,6 +1580,7 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     std::swap(I.slotCust.p, ncust.p); std::swap(I.slotCust.n, ncust.n);
     std::swap(I.blk.p, nblk.p); std::swap(I.blk.n, nblk.n);
     std::swap(I.delStep.p, ndel.p); std::swap(I.delStep.n, ndel.n);
+    legacySync();   // ... and the copies before the old buffers are freed / the new ones are used
     I.slotCap = cap;
     I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p; I.V.blk = I.blk.p; I.V.delStep = I.delStep.p;
     I.graphDirty = true;
@@ -1580,11 +1600,13 @@ void DeviceSim::reset() {
     I.curPhase.fill(0);
     I.hPhase.assign(I.V.nInter, 0);
     I.phaseDirty = false;
+    I.hPhaseStale = false;
     CFB_CUDA(cudaMemcpy(I.remain.p, I.phase0Time.data(), I.phase0Time.size() * sizeof(double), cudaMemcpyHostToDevice));
     I.rlAvail.fill(0);
     I.ctrl.fill(0);
     // leader = -1 everywhere is not required (only occupied positions are read)
     steps_ = 0;
+    legacySync();
 }
 
 int DeviceSim::numPositions() const { return impl_->P; }
@@ -1747,6 +1769,7 @@ void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned c
     I.useGraph = false;  // phases are launched one by one (or replayed as one sharded-step graph)
     I.useCoop = false;
     if (const char *g = getenv("CITYFLOW_B200_SHARD_GRAPH")) I.shardGraphOk = (g[0] != '0');
+    legacySync();
 }
 
 ShardBuffers DeviceSim::shardBuffers() {
@@ -2023,6 +2046,25 @@ void DeviceSim::laneWaitingVehicleCount(int32_t *out) {
     launches_ += 1;
 }
 
+void DeviceSim::setPhasesFromDevice(const int32_t *phases, void *producerStream) {
+    Impl &I = *impl_;
+    if (I.V.owned) throw std::runtime_error("setPhasesFromDevice: not available on one rank of a sharded run");
+    if (!I.actReady) {
+        CFB_CUDA(cudaEventCreateWithFlags(&I.actReady, cudaEventDisableTiming));
+        CFB_CUDA(cudaEventCreateWithFlags(&I.actTaken, cudaEventDisableTiming));
+    }
+    cudaStream_t ps = (cudaStream_t) producerStream;
+    CFB_CUDA(cudaEventRecord(I.actReady, ps));
+    CFB_CUDA(cudaStreamWaitEvent(I.stream, I.actReady, 0));
+    if (I.V.nInter > 0) k_set_phases<<<(I.V.nInter + 127) / 128, 128, 0, I.stream>>>(I.V, phases);
+    CFB_CUDA(cudaGetLastError());
+    CFB_CUDA(cudaEventRecord(I.actTaken, I.stream));      // the producer may reuse its buffer after this
+    CFB_CUDA(cudaStreamWaitEvent(ps, I.actTaken, 0));
+    I.phaseDirty = false;    // every light was just overwritten: pending host-side changes are superseded
+    I.hPhaseStale = true;
+    launches_ += 1;
+}
+
 DeviceObs DeviceSim::observeOnDevice(void *consumerStream) {
     Impl &I = *impl_;
     if (I.V.owned) throw std::runtime_error("observeOnDevice: not available on one rank of a sharded run");
@@ -2085,9 +2127,13 @@ int DeviceSim::drainFinished(std::vector<FinRec> &slots) {
 
 void DeviceSim::phases(int32_t *out) {
     Impl &I = *impl_;
-    if (I.V.rl) { memcpy(out, I.hPhase.data(), I.V.nInter * sizeof(int)); return; }
+    if (I.V.rl && !I.hPhaseStale) { memcpy(out, I.hPhase.data(), I.V.nInter * sizeof(int)); return; }
     CFB_CUDA(cudaMemcpyAsync(out, I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
     CFB_CUDA(cudaStreamSynchronize(I.stream));
+    if (I.V.rl) {
+        I.hPhase.assign(out, out + I.V.nInter);
+        I.hPhaseStale = false;
+    }
 }
 
 int DeviceSim::leaderSlotOf(int slot) {
@@ -2221,6 +2267,7 @@ void DeviceSim::restore(const Snapshot *s) {
     if (regs.size() != s->regions.size()) throw std::runtime_error("cityflow_b200: archive does not match this engine");
     // slots beyond the archive's capacity: unused
     I.pos.fill(0xff); I.waitNext.fill(0xff); I.slotCust.fill(0xff); I.blk.fill(0xff); I.delStep.fill(0x80);
+    legacySync();   // the fills land before the image is copied over them on the engine's stream
     size_t off = 0;
     for (size_t k = 0; k < regs.size(); ++k) {
         const size_t bytes = s->regions[k].bytes;
@@ -2230,11 +2277,16 @@ void DeviceSim::restore(const Snapshot *s) {
         off += (bytes + 255) & ~(size_t) 255;
     }
     I.hPhase.resize(I.V.nInter);
-    if (I.V.nInter) CFB_CUDA(cudaMemcpy(I.hPhase.data(), I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost));
+    if (I.V.nInter) {  // on the engine's stream: it is non-blocking, a plain cudaMemcpy would not wait for the copies above
+        CFB_CUDA(cudaMemcpyAsync(I.hPhase.data(), I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+        CFB_CUDA(cudaStreamSynchronize(I.stream));
+    }
     I.phaseDirty = false;
+    I.hPhaseStale = false;
     I.notify.fill(0);      // epoch-stamped scratch: nothing of an older timeline may match
     I.foeMask.fill(0);
     CFB_CUDA(cudaStreamSynchronize(I.stream));
+    legacySync();
     steps_ = s->steps;
 }
 
@@ -2263,6 +2315,7 @@ DeviceSim::Snapshot *DeviceSim::snapshotFromHost(const unsigned char *data, size
     if (n < hb + s->total) { delete s; throw std::runtime_error("cityflow_b200: truncated archive"); }
     s->blob.alloc(s->total);
     if (s->total) CFB_CUDA(cudaMemcpy(s->blob.p, data + hb, s->total, cudaMemcpyHostToDevice));
+    legacySync();
     return s;
 }
 
@@ -2310,6 +2363,7 @@ void DeviceSim::setCustomSpeed(int slot, double speed) {
         int n = I.hCtrl->nCustom + 1;
         CFB_CUDA(cudaMemcpy(&I.V.ctrl->nCustom, &n, sizeof(int), cudaMemcpyHostToDevice));
     }
+    legacySync();
 }
 
 void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
@@ -2323,6 +2377,7 @@ void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
     } else {
         CFB_CUDA(cudaMemcpy(&I.V.slotInfo[slot].z, &planId, sizeof(int), cudaMemcpyHostToDevice));
     }
+    legacySync();
 }
 
 void DeviceSim::setPhase(int intersection, int phase) {
@@ -2330,6 +2385,11 @@ void DeviceSim::setPhase(int intersection, int phase) {
     // TrafficLight::setPhase only changes curPhaseIndex (trafficlight.cpp:39-41).  Only reachable in
     // rlTrafficLight mode, where the device never advances phases itself, so the host copy is
     // authoritative; all changes made between two steps go up in one copy (see step()).
+    if (I.hPhaseStale) {  // phases were last set on the device: start from what is there
+        CFB_CUDA(cudaMemcpyAsync(I.hPhase.data(), I.V.curPhase, I.V.nInter * sizeof(int), cudaMemcpyDeviceToHost, I.stream));
+        CFB_CUDA(cudaStreamSynchronize(I.stream));
+        I.hPhaseStale = false;
+    }
     I.hPhase[intersection] = phase;
     I.phaseDirty = true;
 }

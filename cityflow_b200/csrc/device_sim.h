@@ -48,6 +48,7 @@ enum DeviceError : int {
     ERR_MOVER_OVERFLOW = 4,
     ERR_ROUTE_DEAD_END = 8,     // lane cannot reach the next road of the route (reference asserts)
     ERR_FINISHED_OVERFLOW = 16,
+    ERR_PHASE_RANGE = 32,       // a phase index handed over on the device is outside the intersection's phase list
 };
 
 struct DeviceSimOptions {
@@ -125,6 +126,12 @@ public:
     // stream, ordered against `consumerStream` (a cudaStream_t; null = legacy default stream) with
     // events in both directions, no host synchronisation.  Valid until the next call.
     DeviceObs observeOnDevice(void *consumerStream);
+    // rlTrafficLight actions handed over on the device: `phases` = one int per intersection
+    // (roadnet order, entries of virtual intersections ignored) in device memory, produced on
+    // `producerStream`.  Same effect as setPhase() on every signalised intersection
+    // (trafficlight.cpp:39-41); an out-of-range index leaves that light unchanged and raises
+    // ERR_PHASE_RANGE.  No host synchronisation.
+    void setPhasesFromDevice(const int32_t *phases, void *producerStream);
     // Observations (synchronise the stream).
     int vehicleCount();
     int errorFlags();

@@ -245,6 +245,7 @@ public:
             if (err & ERR_MOVER_OVERFLOW) m += " mover staging overflow;";
             if (err & ERR_ROUTE_DEAD_END) m += " a vehicle reached a lane that cannot continue its route (the reference asserts here, vehicle.cpp:60);";
             if (err & ERR_FINISHED_OVERFLOW) m += " finished ring overflow;";
+            if (err & ERR_PHASE_RANGE) m += " a phase index set from the device is out of range (the reference throws from phases.at(), trafficlight.cpp:17);";
             throw std::runtime_error(m);
         }
     }
@@ -701,6 +702,16 @@ int cfb_set_tl_phase_index(cfb_engine *e, int intersection, int phase) {
         return CFB_ERR_ARGUMENT;
     }
     CFB_TRY(e, h.dev->setPhase(intersection, phase);)
+    return CFB_OK;
+}
+
+int cfb_set_tl_phases_device(cfb_engine *e, const int32_t *phases, void *producer_stream) {
+    if (!e->h.rlTrafficLight) {  // engine.cpp:720-723
+        std::cerr << "please set rlTrafficLight to true to enable traffic light control" << std::endl;
+        return CFB_OK;
+    }
+    if (!phases) { e->lastError = "null phase array"; return CFB_ERR_ARGUMENT; }
+    CFB_TRY(e, e->h.dev->setPhasesFromDevice(phases, producer_stream);)
     return CFB_OK;
 }
 

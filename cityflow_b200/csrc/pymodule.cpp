@@ -344,6 +344,16 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("num_drivables", [](Engine &e) { return e.numDrivables(); })
         .def("host_times", &Engine::hostTimes)
         .def("lane_ids", &Engine::laneIds)
+        .def("intersection_ids", [](Engine &e) {
+            std::vector<std::string> ids(cfb_num_intersections(e.raw()));
+            for (size_t i = 0; i < ids.size(); ++i) ids[i] = cfb_intersection_id(e.raw(), (int) i);
+            return ids;
+        })
+        .def("num_intersections", [](Engine &e) { return cfb_num_intersections(e.raw()); })
+        .def("set_tl_phases_device", [](Engine &e, uintptr_t phases, uintptr_t stream) {
+            if (cfb_set_tl_phases_device(e.raw(), (const int32_t *) phases, (void *) stream) < 0)
+                throw std::runtime_error(cfb_last_error(e.raw()));
+        }, "phases_ptr"_a, "stream"_a = 0)
         .def("device", [](Engine &e) { return cfb_device(e.raw()); })
         .def("observe_device", &Engine::observeDevice, "stream"_a = 0)
         .def("synchronize", &Engine::synchronize);

@@ -105,6 +105,14 @@ int cfb_get_leader(cfb_engine *e, cfb_vehicle_ref vehicle, cfb_vehicle_ref *lead
 /* Engine::setTrafficLightPhase  engine.cpp:719-725 (no-op with a message unless rlTrafficLight) */
 int cfb_set_tl_phase(cfb_engine *e, const char *intersection_id, int phase);
 int cfb_set_tl_phase_index(cfb_engine *e, int intersection, int phase);
+/* The same for every traffic light at once, with the actions already ON THE DEVICE (the output of
+ * a policy network on this GPU): `phases` = cfb_num_intersections() int32 in device memory,
+ * intersection order of cfb_intersection_id(); entries of virtual intersections are ignored.
+ * Consumed on the engine's stream after the work enqueued on `producer_stream` (a cudaStream_t,
+ * NULL = legacy default stream) so far; that stream may reuse the buffer afterwards.  No host
+ * synchronisation.  An out-of-range index leaves that light unchanged and is reported as a
+ * device error by the next synchronising call.  Single-GPU engines only. */
+int cfb_set_tl_phases_device(cfb_engine *e, const int32_t *phases, void *producer_stream);
 /* Engine::setRandomSeed  engine.h:170 */
 int cfb_set_random_seed(cfb_engine *e, int seed);
 /* Engine::reset(resetRnd)  engine.cpp:744-760 */

@@ -348,3 +348,51 @@ def test_device_resident_lane_observations(cfg_6x6_dense):
     ids2, cnt2, _, _ = cityflow_b200.lane_observation_tensors(eng)
     assert cnt2.data_ptr() == old_ptr
     assert cnt.tolist() == [eng.get_lane_vehicle_count()[i] for i in ids]
+
+
+def test_rl_actions_and_observations_on_device_vs_port(cfg_6x6_rl):
+    """The RL loop with nothing crossing to the host: actions come from a torch tensor
+    (cfb_set_tl_phases_device), observations are torch tensors; the oracle gets the same actions
+    through its host API and must see the same lane counts every step."""
+    import torch
+    import cityflow
+    import cityflow_b200
+    eng = cityflow.Engine(cfg_6x6_rl, thread_num=1)
+    ora = H.PortOracle(cfg_6x6_rl)
+    ph0 = np.zeros(ora.n_inter, np.int32)
+    ora.lib.cfo_phases(ora.h, ph0.ctypes.data)
+    real = np.nonzero(ph0 >= 0)[0]
+    assert eng.num_intersections() == ora.n_inter
+    idx = torch.arange(ora.n_inter, device="cuda", dtype=torch.int32)
+    for s in range(1, 301):
+        if s % 10 == 1:
+            act = ((s // 10 + idx) % 8).to(torch.int32)       # computed on the GPU, never copied down
+            cityflow_b200.set_tl_phases_tensor(eng, act)
+            del act
+            for i in real:
+                ora.set_tl_phase(int(i), int((s // 10 + i) % 8))
+        eng.next_step()
+        ora.next_step()
+        if s % 5 == 0:
+            ids, cnt, wait, _ = cityflow_b200.lane_observation_tensors(eng)
+            snap = ora.snapshot()
+            assert cnt.cpu().numpy().tolist() == list(snap.lane_count)
+            assert wait.cpu().numpy().tolist() == list(snap.lane_waiting)
+    assert int(cnt.sum()) > 300
+    # host-side set_tl_phase after a device-side one starts from the device's phases
+    some = eng.intersection_ids()[int(real[0])]
+    eng.set_tl_phase(some, 3)
+    ora.set_tl_phase(int(real[0]), 3)
+    for _ in range(40):
+        eng.next_step()
+        ora.next_step()
+    counts = eng.get_lane_vehicle_count()
+    assert [counts[i] for i in ids] == list(ora.snapshot().lane_count)
+    # an out-of-range action is reported (the reference would throw from phases.at())
+    bad = torch.full((ora.n_inter,), 99, device="cuda", dtype=torch.int32)
+    cityflow_b200.set_tl_phases_tensor(eng, bad)
+    eng.next_step()
+    with pytest.raises(RuntimeError, match="out of range"):
+        for _ in range(300):          # surfaced by the next bookkeeping drain at the latest
+            eng.next_step()
+        eng.get_average_travel_time()
