@@ -37,24 +37,49 @@ class _DeviceArray:
                                          "version": 2, "strides": None}
 
 
-def lane_observation_tensors(engine, stream=None):
+class LaneObservations:
     """Zero-copy per-lane observations as torch CUDA tensors.
 
-    Returns ``(lane_ids, vehicle_count[int32], waiting_count[int32], speed_sum[float64])``: the
-    arrays ``get_lane_vehicle_count`` / ``get_lane_waiting_vehicle_count`` report (engine.cpp:628-648)
-    plus the per-lane sum of speeds, in ``engine.lane_ids()`` order, living on the engine's GPU.
-    Nothing is copied to the host and the host does not wait: the refresh is ordered against
-    ``stream`` (default: torch's current stream on the engine's device).  The tensors alias the
-    engine's buffers: they are overwritten by the next call, so ``clone()`` what must survive it.
+    ``vehicle_count`` (int32) and ``waiting_count`` (int32) are the arrays
+    ``get_lane_vehicle_count`` / ``get_lane_waiting_vehicle_count`` report (engine.cpp:628-648),
+    ``speed_sum`` (float64) the per-lane sum of speeds, all in ``lane_ids`` (= ``engine.lane_ids()``)
+    order and living on the engine's GPU.  The tensors alias the engine's buffers and are created
+    once; ``refresh()`` re-computes their content on the engine's stream, ordered against ``stream``
+    (default: torch's current stream on that device) in both directions -- nothing is copied to the
+    host and the host does not wait.  ``clone()`` what must survive the next refresh.
     """
-    import torch
-    if stream is None:
-        stream = torch.cuda.current_stream(engine.device()).cuda_stream
-    o = engine.observe_device(int(stream))
-    n = o["n_lanes"]
-    dev = torch.device("cuda", o["device"])
-    mk = lambda key, ts: torch.as_tensor(_DeviceArray(engine, o[key], n, ts), device=dev)
-    return (engine.lane_ids(), mk("lane_vehicle_count", "<i4"), mk("lane_waiting_count", "<i4"), mk("lane_speed_sum", "<f8"))
+
+    def __init__(self, engine, stream=None):
+        import torch
+        self.engine = engine
+        self.lane_ids = engine.lane_ids()
+        self._device = engine.device()
+        o = engine.observe_device(self._stream(stream))
+        n = o["n_lanes"]
+        dev = torch.device("cuda", o["device"])
+        self._ptrs = (o["lane_vehicle_count"], o["lane_waiting_count"], o["lane_speed_sum"])
+        mk = lambda ptr, ts: torch.as_tensor(_DeviceArray(engine, ptr, n, ts), device=dev)  # noqa: E731
+        self.vehicle_count = mk(self._ptrs[0], "<i4")
+        self.waiting_count = mk(self._ptrs[1], "<i4")
+        self.speed_sum = mk(self._ptrs[2], "<f8")
+
+    def _stream(self, stream):
+        if stream is None:
+            import torch
+            return torch.cuda.current_stream(self._device).cuda_stream
+        return int(getattr(stream, "cuda_stream", stream))
+
+    def refresh(self, stream=None):
+        o = self.engine.observe_device(self._stream(stream))
+        assert (o["lane_vehicle_count"], o["lane_waiting_count"], o["lane_speed_sum"]) == self._ptrs
+        return self
+
+
+def lane_observation_tensors(engine, stream=None):
+    """One-shot form of :class:`LaneObservations`:
+    ``(lane_ids, vehicle_count, waiting_count, speed_sum)``, freshly computed."""
+    o = LaneObservations(engine, stream)
+    return o.lane_ids, o.vehicle_count, o.waiting_count, o.speed_sum
 
 
 def set_tl_phases_tensor(engine, phases, stream=None):

@@ -348,6 +348,14 @@ def test_device_resident_lane_observations(cfg_6x6_dense):
     ids2, cnt2, _, _ = cityflow_b200.lane_observation_tensors(eng)
     assert cnt2.data_ptr() == old_ptr
     assert cnt.tolist() == [eng.get_lane_vehicle_count()[i] for i in ids]
+    # the persistent form: tensors made once, refresh() only re-computes their content
+    obs = cityflow_b200.LaneObservations(eng)
+    eng.next_steps(25)
+    before = obs.vehicle_count.clone()
+    assert obs.refresh() is obs and obs.vehicle_count.data_ptr() == old_ptr
+    now = eng.get_lane_vehicle_count()
+    assert obs.vehicle_count.tolist() == [now[i] for i in obs.lane_ids]
+    assert not torch.equal(before, obs.vehicle_count)
 
 
 def test_rl_actions_and_observations_on_device_vs_port(cfg_6x6_rl):

@@ -57,8 +57,9 @@ def run_device(cfg, steps):
     for _ in range(100):
         eng.next_step()
     n_int = eng.num_intersections()
-    ids, cnt, wait, ssum = cityflow_b200.lane_observation_tensors(eng)
-    n_lanes = len(ids)
+    obs = cityflow_b200.LaneObservations(eng)
+    cnt, wait = obs.vehicle_count, obs.waiting_count
+    n_lanes = len(obs.lane_ids)
     bucket = (torch.arange(n_lanes, device=cnt.device) % 8).to(torch.int64)          # lane -> phase it "votes" for
     owner = (torch.arange(n_lanes, device=cnt.device) * n_int // n_lanes).to(torch.int64)
     votes = torch.zeros(n_int * 8, device=cnt.device, dtype=torch.int32)
@@ -67,7 +68,7 @@ def run_device(cfg, steps):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for t in range(steps):
-        _, cnt, wait, ssum = cityflow_b200.lane_observation_tensors(eng)
+        obs.refresh()
         votes.zero_()
         votes.index_add_(0, key, wait)
         act = votes.view(n_int, 8).argmax(1).to(torch.int32)
