@@ -50,6 +50,8 @@ def main():
     rl = cityflow.Engine(cfg_rl, thread_num=1)
     inters = rl.intersection_ids()
     try:
+        if os.environ.get("SAN_NO_TORCH") == "1":
+            raise RuntimeError("SAN_NO_TORCH=1")
         import torch
         obs = cityflow_b200.LaneObservations(rl)
         idx = torch.arange(rl.num_intersections(), device="cuda", dtype=torch.int32)
