@@ -58,6 +58,7 @@ public:
     // Interns the route; builds plans for every candidate start lane. Returns route id.
     int intern(const std::vector<int> &anchors);
     const Route &route(int id) const { return routes_[id]; }
+    int numRoutes() const { return (int) routes_.size(); }
     // plan storage (flat, PLAN_END terminated)
     const std::vector<int> &planData() const { return planData_; }
     const std::vector<int> &planBeg() const { return planBeg_; }

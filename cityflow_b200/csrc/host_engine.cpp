@@ -27,6 +27,7 @@
 
 #include "../../include/cityflow_b200.h"
 #include "device_sim.h"
+#include "priority_map.h"
 #include "partition.h"
 #include "shard.h"
 #include "flows.h"
@@ -61,58 +62,17 @@ struct SlotInfo {
     bool live = false;
 };
 
-struct Pending {            // a vehicle created this step, waiting for planRoute (engine.cpp:450-470)
-    int slot, road, routeId, tmplId, flow;
+struct FlowStatic {         // what a spawn needs from its Flow, 12 bytes instead of a walk through FlowRun/FlowDef
+    int routeId, tmplId, firstRoad;
 };
 
-// Open-addressing hash map priority -> slot: Engine::checkPriority (engine.cpp:601) is on the
-// per-spawn path; the reference's ordered std::map is only materialised (sorted) when an API call
-// needs vehiclePool order.
-class PriorityMap {
-public:
-    PriorityMap() { rehash(1 << 12); }
-    bool contains(int k) const { return find(k) >= 0; }
-    int get(int k) const { long i = find(k); return i >= 0 ? val_[i] : -1; }
-    void insert(int k, int v) {
-        if ((used_ + 1) * 2 > cap_) rehash(cap_ * 2);
-        size_t i = hash(k);
-        while (state_[i] == 1) i = (i + 1) & (cap_ - 1);
-        if (state_[i] == 0) ++used_;
-        state_[i] = 1; key_[i] = k; val_[i] = v; ++size_;
-    }
-    void erase(int k) {
-        long i = find(k);
-        if (i >= 0) { state_[i] = 2; --size_; }
-    }
-    void clear() { std::fill(state_.begin(), state_.end(), 0); used_ = size_ = 0; }
-    size_t size() const { return size_; }
-    // (priority, slot) pairs in ascending priority = vehiclePool iteration order
-    std::vector<std::pair<int, int>> sorted() const {
-        std::vector<std::pair<int, int>> out;
-        out.reserve(size_);
-        for (size_t i = 0; i < cap_; ++i) if (state_[i] == 1) out.emplace_back(key_[i], val_[i]);
-        std::sort(out.begin(), out.end());
-        return out;
-    }
-private:
-    size_t hash(int k) const { return ((uint32_t) k * 2654435761u) & (cap_ - 1); }
-    long find(int k) const {
-        size_t i = hash(k);
-        while (state_[i] != 0) {
-            if (state_[i] == 1 && key_[i] == k) return (long) i;
-            i = (i + 1) & (cap_ - 1);
-        }
-        return -1;
-    }
-    void rehash(size_t n) {
-        std::vector<int> ok = std::move(key_), ov = std::move(val_);
-        std::vector<uint8_t> os = std::move(state_);
-        cap_ = n; key_.assign(n, 0); val_.assign(n, 0); state_.assign(n, 0); used_ = size_ = 0;
-        for (size_t i = 0; i < os.size(); ++i) if (os[i] == 1) insert(ok[i], ov[i]);
-    }
-    std::vector<int> key_, val_;
-    std::vector<uint8_t> state_;
-    size_t cap_ = 0, used_ = 0, size_ = 0;
+struct RouteHot {           // Route's candidate first lanes (<= 4 in practice) in one cache line
+    int valid, n;
+    int lane[4], plan[4];
+};
+
+struct Pending {            // a vehicle created this step, waiting for planRoute (engine.cpp:450-470)
+    int slot, road, routeId, tmplId, flow;
 };
 
 class HostEngine {
@@ -120,6 +80,9 @@ public:
     std::string error;
     RoadNet net;
     std::vector<FlowRun> flows;
+    std::vector<FlowStatic> flowStatic;
+    std::vector<RouteHot> routeHot;                          // filled on demand from routing (n = -1: not cached / too many lanes)
+    std::vector<int> due;                                    // flows spawning this step, one entry per vehicle
     std::vector<FlowHot> hot;                                // hot[i] mirrors flows[i]'s runtime state (authoritative)
     std::vector<uint64_t> sortKeys;
     std::vector<Pending> pendingSorted;
@@ -218,6 +181,7 @@ public:
             f.routeId = routing->intern(d.anchors);
             f.tmplId = internTemplate(d.tmpl);
             hot.push_back(FlowHot{d.interval, 0.0, d.interval, d.startTime, d.endTime, 0, 1});  // nowTime = interval (flow.h:35)
+            flowStatic.push_back(FlowStatic{f.routeId, f.tmplId, d.anchors[0]});
             flows.push_back(std::move(f));
         }
         if (saveReplay)
@@ -320,6 +284,21 @@ public:
         return slot;
     }
 
+    const RouteHot &hotRoute(int id) {
+        if ((size_t) id >= routeHot.size()) {
+            const size_t from = routeHot.size();
+            routeHot.resize(routing->numRoutes());
+            for (size_t r = from; r < routeHot.size(); ++r) {
+                const Route &rt = routing->route((int) r);
+                RouteHot &hr = routeHot[r];
+                hr.valid = rt.valid;
+                hr.n = rt.valid && rt.startLanes.size() <= 4 ? (int) rt.startLanes.size() : -1;
+                for (int k = 0; k < hr.n; ++k) { hr.lane[k] = rt.startLanes[k]; hr.plan[k] = rt.planOfStartLane[k]; }
+            }
+        }
+        return routeHot[id];
+    }
+
     // Engine::nextStep engine.cpp:566-594 (host part: P0 spawn, P1 planRoute; the rest is device work)
     // P0/P1 on the host: flows, vehicle creation, first-lane draw -> `batch` (lane-sorted spawn records)
     void prepareStep() {
@@ -332,14 +311,31 @@ public:
             if (f.endTime != -1 && f.currentTime > f.endTime) continue;
             if (f.currentTime >= f.startTime) {
                 while (f.nowTime >= f.interval) {
-                    const FlowRun &fr = flows[i];
-                    createVehicle((int) i, f.cnt++, fr.routeId, fr.tmplId, fr.def.anchors[0]);
+                    due.push_back((int) i);   // created below, in this order (nothing a Vehicle ctor does feeds back into a Flow)
                     f.nowTime -= f.interval;
                 }
                 f.nowTime += interval;
             }
             f.currentTime += interval;
         }
+        if (due.size() >= 8) {
+            // Each creation costs a few cache misses (priority table, slot record) and nothing else; the
+            // keys are known in advance because the RNG can be run ahead on a copy: priority, thread
+            // index, priority, ... (engine.cpp:601-606).  A priority collision makes the real sequence
+            // leave the predicted one -- then the remaining prefetches are merely useless.
+            std::mt19937 ahead = rnd;
+            const size_t nFree = freeSlots.size();
+            for (size_t k = 0; k < due.size(); ++k) {
+                pool.prefetch((int) ahead());
+                (void) ahead();
+                if (k < nFree) __builtin_prefetch(&slots[freeSlots[nFree - 1 - k]], 1);
+            }
+        }
+        for (const int i : due) {
+            const FlowStatic &fs = flowStatic[i];
+            createVehicle(i, H[i].cnt++, fs.routeId, fs.tmplId, fs.firstRoad);
+        }
+        due.clear();
         batch.clear();
         if (!pending.empty()) {
             // Engine::planRoute walks roads in file order, each road's buffer in spawn order
@@ -350,15 +346,22 @@ public:
             pendingSorted.resize(pending.size());
             for (size_t k = 0; k < pending.size(); ++k) pendingSorted[k] = pending[(uint32_t) sortKeys[k]];
             for (const Pending &p : pendingSorted) {
-                const Route &rt = routing->route(p.routeId);
+                const RouteHot &rt = hotRoute(p.routeId);
                 if (rt.valid) {
-                    const size_t pick = rnd() % rt.startLanes.size();  // Router::selectLaneIndex router.cpp:99
                     SpawnRec r{};
                     r.slot = p.slot;
-                    r.lane = rt.startLanes[pick];
+                    if (rt.n > 0) {
+                        const size_t pick = rnd() % (size_t) rt.n;  // Router::selectLaneIndex router.cpp:99
+                        r.lane = rt.lane[pick];
+                        r.plan = rt.plan[pick];
+                    } else {
+                        const Route &full = routing->route(p.routeId);
+                        const size_t pick = rnd() % full.startLanes.size();
+                        r.lane = full.startLanes[pick];
+                        r.plan = full.planOfStartLane[pick];
+                    }
                     r.tmpl = p.tmplId;
                     r.priority = slots[p.slot].priority;
-                    r.plan = rt.planOfStartLane[pick];
                     slots[p.slot].firstLane = r.lane;
                     batch.push_back(r);
                 } else {

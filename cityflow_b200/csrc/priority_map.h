@@ -1,0 +1,72 @@
+// priority_map.h -- the host engine's vehiclePool index (Engine::vehiclePool, engine.h:25).
+#pragma once
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace cfb {
+
+// Open-addressing hash map priority -> slot: Engine::checkPriority (engine.cpp:601) is on the
+// per-spawn path; the reference's ordered std::map is only materialised (sorted) when an API call
+// needs vehiclePool order.
+class PriorityMap {
+public:
+    PriorityMap() { rehash(1 << 12); }
+    bool contains(int k) const { return find(k) >= 0; }
+    int get(int k) const { long i = find(k); return i >= 0 ? cell_[i].val : -1; }
+    void insert(int k, int v) {
+        if ((used_ + 1) * 2 > cap_) rehash(roomFor(size_ + 1));
+        size_t i = hash(k);
+        while (cell_[i].val >= 0) i = (i + 1) & (cap_ - 1);
+        if (cell_[i].val == EMPTY) ++used_;
+        cell_[i].key = k; cell_[i].val = v; ++size_;
+    }
+    void erase(int k) {
+        long i = find(k);
+        if (i >= 0) { cell_[i].val = DELETED; --size_; }
+    }
+    void clear() { rehash(1 << 12, false); }
+    size_t size() const { return size_; }
+    size_t capacity() const { return cap_; }
+    // the spawn loop knows the keys it is about to look up (the RNG can be run ahead): start the
+    // one cache miss a lookup costs early
+    void prefetch(int k) const { __builtin_prefetch(&cell_[hash(k)]); }
+    // (priority, slot) pairs in ascending priority = vehiclePool iteration order
+    std::vector<std::pair<int, int>> sorted() const {
+        std::vector<std::pair<int, int>> out;
+        out.reserve(size_);
+        for (size_t i = 0; i < cap_; ++i) if (cell_[i].val >= 0) out.emplace_back(cell_[i].key, cell_[i].val);
+        std::sort(out.begin(), out.end());
+        return out;
+    }
+private:
+    enum { EMPTY = -1, DELETED = -2 };
+    struct Cell { int key, val; };   // val >= 0: slot; one 8-byte cell = one cache line touched per probe
+    size_t hash(int k) const { return ((uint32_t) k * 2654435761u) & (cap_ - 1); }
+    long find(int k) const {
+        size_t i = hash(k);
+        while (cell_[i].val != EMPTY) {
+            if (cell_[i].val >= 0 && cell_[i].key == k) return (long) i;
+            i = (i + 1) & (cap_ - 1);
+        }
+        return -1;
+    }
+    // table size for n live entries: load <= 1/4 after a rehash.  Sized from the LIVE count -- cells
+    // of vehicles that left are dropped by the rehash, so a long run does not grow the table.
+    static size_t roomFor(size_t n) {
+        size_t c = 1 << 12;
+        while (c < n * 4) c *= 2;
+        return c;
+    }
+    void rehash(size_t n, bool keep = true) {
+        std::vector<Cell> old = std::move(cell_);
+        cap_ = n; cell_.assign(n, Cell{0, EMPTY}); used_ = size_ = 0;
+        if (keep) for (const Cell &c : old) if (c.val >= 0) insert(c.key, c.val);
+    }
+    std::vector<Cell> cell_;
+    size_t cap_ = 0, used_ = 0, size_ = 0;
+};
+
+}  // namespace cfb
