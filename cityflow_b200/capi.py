@@ -18,6 +18,8 @@ VEH_DTYPE = np.dtype([
     ("dis", "<f8"), ("speed", "<f8"), ("gap", "<f8"), ("enter_ll_time", "<i8"),
 ])
 REF_DTYPE = np.dtype([("flow", "<i4"), ("index", "<i4")])
+REPLAY_DTYPE = np.dtype([("drivable", "<i4"), ("distance", "<f8"), ("flow", "<i4"), ("index", "<i4"),
+                         ("length", "<f8"), ("width", "<f8")], align=True)   # cfb_replay_vehicle
 
 
 def declared_symbols() -> list:
@@ -68,6 +70,12 @@ def load_library() -> ctypes.CDLL:
         "cfb_shard_group_vehicle_count": (i64, [vp]),
         "cfb_shard_group_lane_counts": (i32, [vp, vp, i32, i32]),
         "cfb_shard_group_debug_vehicles": (i64, [vp, vp, i64]),
+        "cfb_replay_create": (vp, [cp]),
+        "cfb_replay_destroy": (None, [vp]),
+        "cfb_replay_roadnet_json": (i64, [vp, vp, i64]),
+        "cfb_replay_format_step": (i64, [vp, vp, i64, vp, vp, i64]),
+        "cfb_set_replay_file": (i32, [vp, cp]),
+        "cfb_set_save_replay": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -183,3 +191,34 @@ class CShardGroup:
         if n:
             self.lib.cfb_shard_group_debug_vehicles(self.h, a.ctypes.data, n)
         return a
+
+
+class CReplay:
+    """The replay formatter on its own (cfb_replay_*): needs the roadnet file only, no GPU."""
+
+    def __init__(self, roadnet_file: str):
+        self.lib = load_library()
+        self.h = self.lib.cfb_replay_create(roadnet_file.encode())
+        if not self.h:
+            raise RuntimeError("cfb_replay_create failed: %s" % self.lib.cfb_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cfb_replay_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def roadnet_json(self) -> str:
+        n = int(self.lib.cfb_replay_roadnet_json(self.h, None, 0))
+        buf = ctypes.create_string_buffer(n)
+        self.lib.cfb_replay_roadnet_json(self.h, buf, n)
+        return buf.value.decode()
+
+    def format_step(self, vehicles: np.ndarray, phases: np.ndarray) -> str:
+        v = np.ascontiguousarray(vehicles, REPLAY_DTYPE)
+        ph = np.ascontiguousarray(phases, np.int32)
+        n = int(self.lib.cfb_replay_format_step(self.h, v.ctypes.data, len(v), ph.ctypes.data, None, 0))
+        buf = ctypes.create_string_buffer(n)
+        self.lib.cfb_replay_format_step(self.h, v.ctypes.data, len(v), ph.ctypes.data, buf, n)
+        return buf.value.decode()

@@ -28,6 +28,7 @@
 #include "../../include/cityflow_b200.h"
 #include "device_sim.h"
 #include "priority_map.h"
+#include "replay.h"
 #include "partition.h"
 #include "shard.h"
 #include "flows.h"
@@ -59,6 +60,7 @@ struct SlotInfo {
     int32_t spawnStep = 0;           // Engine::step when the vehicle was created
     int32_t routeId = -1;            // resolved route (Routing::route), for get_vehicle_info / set_vehicle_route
     int32_t firstLane = -1;          // lane whose waiting queue the vehicle was put in
+    int32_t tmplId = -1;             // vehicle template (length / width for the replay log)
     bool live = false;
 };
 
@@ -94,6 +96,14 @@ public:
     double interval = 1.0;
     int seed = 0;
     bool rlTrafficLight = false, laneChange = false, saveReplay = false;
+    bool saveReplayInConfig = false;                         // engine.h:48
+    std::string dir, roadnetLogFile, replayLogFile;       // "dir" of the config: prefix of every file name
+    std::unique_ptr<ReplayWriter> replay;
+    std::ofstream logOut;                                    // Engine::logOut engine.h:40
+    std::vector<SpeedRec> replayRecs;
+    std::vector<ReplayVehicle> replayVeh;
+    std::vector<int32_t> replayPhase;
+    std::string replayLine;
     std::mt19937 rnd;
     size_t step = 0;
     int manuallyPushCnt = 0;
@@ -137,7 +147,7 @@ public:
             if (!v) throw JsonError(std::string(k) + " is required but missing in json file");
             return *v;
         };
-        std::string dir, roadnetFile, flowFile;
+        std::string roadnetFile, flowFile;
         try {
             const Json &iv = need("interval");
             if (!iv.isNumber()) throw JsonError("interval: expected type d");
@@ -161,7 +171,11 @@ public:
             flowFile = str("flowFile");
             const Json &sr = need("saveReplay");
             if (!sr.isBool()) throw JsonError("saveReplay: expected type b");
-            saveReplay = sr.asBool();
+            saveReplayInConfig = saveReplay = sr.asBool();
+            if (saveReplay) {  // engine.cpp:73-77
+                roadnetLogFile = str("roadnetLogFile");
+                replayLogFile = str("replayLogFile");
+            }
         } catch (const JsonError &e) {
             error = e.what();
             return false;
@@ -184,8 +198,13 @@ public:
             flowStatic.push_back(FlowStatic{f.routeId, f.tmplId, d.anchors[0]});
             flows.push_back(std::move(f));
         }
-        if (saveReplay)
-            std::cerr << "[cityflow_b200] saveReplay is not implemented by the GPU engine; no replay is written" << std::endl;
+        if (saveReplay) {  // Engine::setLogFile engine.cpp:773-778
+            replay.reset(new ReplayWriter(net));
+            std::ofstream js(dir + roadnetLogFile);
+            if (js) js << replay->roadnetJson();
+            if (!js) std::cerr << "write roadnet log file error" << std::endl;
+            logOut.open(dir + replayLogFile);
+        }
         laneIds.resize(net.nLanes());
         for (int l = 0; l < net.nLanes(); ++l) laneIds[l] = net.laneName(l);
         DeviceSimOptions opt;
@@ -277,6 +296,7 @@ public:
         s.spawnStep = (int32_t) step;
         s.routeId = routeId;
         s.firstLane = -1;
+        s.tmplId = tmplId;
         s.live = true;
         pool.insert(priority, slot);
         idMapValid = false;
@@ -390,9 +410,29 @@ public:
         dev->ensureSlotCapacity((int) slots.size());
         hostGenNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     }
+    // Engine::updateLog engine.cpp:518-554: positions of the running vehicles and the light states
+    // after this step, one line.  Gathers from the device (synchronises), so stepping with
+    // saveReplay on is as slow as it is in the reference.
+    void writeReplayLine() {
+        const int n = dev->runningVehicles(replayRecs);
+        std::sort(replayRecs.begin(), replayRecs.end(), [this](const SpeedRec &a, const SpeedRec &b) {
+            return slots[a.slot].priority < slots[b.slot].priority;   // vehiclePool order (engine.cpp:780-790)
+        });
+        replayVeh.resize(n);
+        for (int k = 0; k < n; ++k) {
+            const SlotInfo &s = slots[replayRecs[k].slot];
+            const VehicleTemplate &t = templates[s.tmplId];
+            replayVeh[k] = ReplayVehicle{replayRecs[k].drivable, replayRecs[k].dis, s.flow, s.index, t.len, t.width};
+        }
+        replayPhase.resize(net.nInter());
+        dev->phases(replayPhase.data());
+        replay->formatStep(replayVeh.data(), (size_t) n, replayPhase.data(), replayLine);
+        logOut << replayLine << std::endl;
+    }
     void finishStep() {
         h2dBytes += (long long) batch.size() * sizeof(SpawnRec) + sizeof(int);
         finishedDirty = true;
+        if (saveReplay && replay && !transport) writeReplayLine();   // before step += 1, like engine.cpp:589-593
         step += 1;
         if ((step & 255) == 0) drain();  // bound the finished ring / free slots in long unobserved runs
     }
@@ -434,6 +474,10 @@ public:
     }
     // Cut the network and tell the device which part is ours (before the first step).
     std::string configureShard(int rank, int world) {
+        if (saveReplay) {
+            std::cerr << "[cityflow_b200] saveReplay is not available on one rank of a sharded run; no replay is written" << std::endl;
+            saveReplay = false;
+        }
         Partition part = Partition::columnStrips(net, world);
         double look = 0;
         for (const auto &t : templates) look = std::max(look, t.maxSpeed * t.maxSpeed / t.usualNegAcc / 2 + t.maxSpeed * interval * 2);
@@ -726,6 +770,56 @@ int cfb_set_tl_phase(cfb_engine *e, const char *id, int phase) {
         return CFB_ERR_ARGUMENT;
     }
     return cfb_set_tl_phase_index(e, it->second, phase);
+}
+
+int cfb_set_replay_file(cfb_engine *e, const char *log_file) {  // Engine::setReplayLogFile engine.cpp:727-734
+    cfb::HostEngine &h = e->h;
+    if (!h.saveReplayInConfig) {
+        std::cerr << "saveReplay is not set to true in config file!" << std::endl;
+        return CFB_OK;
+    }
+    if (h.logOut.is_open()) h.logOut.close();
+    h.logOut.clear();
+    h.logOut.open(h.dir + (log_file ? log_file : ""));
+    return CFB_OK;
+}
+
+int cfb_set_save_replay(cfb_engine *e, int open) {  // Engine::setSaveReplay engine.cpp:736-742
+    cfb::HostEngine &h = e->h;
+    if (!h.saveReplayInConfig) {
+        std::cerr << "saveReplay is not set to true in config file!" << std::endl;
+        return CFB_OK;
+    }
+    h.saveReplay = open != 0 && !h.transport && h.replay;
+    return CFB_OK;
+}
+
+struct cfb_replay {
+    cfb::RoadNet net;
+    std::unique_ptr<cfb::ReplayWriter> w;
+    std::string buf;
+};
+
+cfb_replay *cfb_replay_create(const char *roadnet_file) {
+    std::unique_ptr<cfb_replay> r(new cfb_replay());
+    if (!roadnet_file || !r->net.load(roadnet_file)) { g_createError = "loading roadnet file error!"; return nullptr; }
+    r->w.reset(new cfb::ReplayWriter(r->net));
+    return r.release();
+}
+void cfb_replay_destroy(cfb_replay *r) { delete r; }
+static int64_t copyOut(const std::string &s, char *out, int64_t cap) {
+    if (out && cap > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t) cap - 1);
+        memcpy(out, s.data(), n);
+        out[n] = 0;
+    }
+    return (int64_t) s.size() + 1;
+}
+int64_t cfb_replay_roadnet_json(cfb_replay *r, char *out, int64_t cap) { return copyOut(r->w->roadnetJson(), out, cap); }
+int64_t cfb_replay_format_step(cfb_replay *r, const cfb_replay_vehicle *v, int64_t n, const int32_t *phase, char *out, int64_t cap) {
+    static_assert(sizeof(cfb_replay_vehicle) == sizeof(cfb::ReplayVehicle), "cfb_replay_vehicle layout");
+    r->w->formatStep(reinterpret_cast<const cfb::ReplayVehicle *>(v), (size_t) n, phase, r->buf);
+    return copyOut(r->buf, out, cap);
 }
 
 int cfb_set_random_seed(cfb_engine *e, int seed) {

@@ -213,12 +213,8 @@ public:
         for (auto &s : roads) r.push_back(s.c_str());
         check(cfb_push_vehicle(e_, v, r.data(), (int) r.size()));
     }
-    void setReplayLogFile(const std::string &) {  // engine.cpp:727-734
-        py::print("saveReplay is not set to true in config file!", "file"_a = py::module_::import("sys").attr("stderr"));
-    }
-    void setSaveReplay(bool) {  // engine.cpp:736-742
-        py::print("saveReplay is not set to true in config file!", "file"_a = py::module_::import("sys").attr("stderr"));
-    }
+    void setReplayLogFile(const std::string &f) { check(cfb_set_replay_file(e_, f.c_str())); }  // engine.cpp:727-734
+    void setSaveReplay(bool open) { check(cfb_set_save_replay(e_, open)); }                    // engine.cpp:736-742
     void setVehicleSpeed(const std::string &id, double speed) {
         cfb_vehicle_ref v;
         if (!parseVehicleName(id, v) || cfb_set_vehicle_speed(e_, v, speed) < 0)

@@ -268,7 +268,7 @@ def random_walk_flows(roadnet: dict, frac=0.5, interval=10.0, max_len=12, seed=1
 
 
 def write_scenario(directory: str, roadnet: dict, flows: list, *, interval=1.0, seed=0,
-                   rl_traffic_light=False, lane_change=False, name="") -> str:
+                   rl_traffic_light=False, lane_change=False, save_replay=False, name="") -> str:
     """Write roadnet / flow / config JSON into ``directory``; returns the config path."""
     os.makedirs(directory, exist_ok=True)
     sfx = ("_" + name) if name else ""
@@ -281,7 +281,7 @@ def write_scenario(directory: str, roadnet: dict, flows: list, *, interval=1.0, 
     if not d.endswith("/"):
         d += "/"  # the engine concatenates dir + file (engine.cpp:60,65)
     cfg = {"interval": interval, "seed": seed, "dir": d, "roadnetFile": rn, "flowFile": fl,
-           "rlTrafficLight": rl_traffic_light, "laneChange": lane_change, "saveReplay": False,
+           "rlTrafficLight": rl_traffic_light, "laneChange": lane_change, "saveReplay": save_replay,
            "roadnetLogFile": "replay_roadnet%s.json" % sfx, "replayLogFile": "replay%s.txt" % sfx}
     path = os.path.join(directory, cf)
     with open(path, "w") as f:

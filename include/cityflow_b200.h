@@ -113,6 +113,12 @@ int cfb_set_tl_phase_index(cfb_engine *e, int intersection, int phase);
  * synchronisation.  An out-of-range index leaves that light unchanged and is reported as a
  * device error by the next synchronising call.  Single-GPU engines only. */
 int cfb_set_tl_phases_device(cfb_engine *e, const int32_t *phases, void *producer_stream);
+/* Replay log ("saveReplay": true in the config; roadnetLogFile / replayLogFile relative to "dir").
+ * Engine::setReplayLogFile engine.cpp:727-734, Engine::setSaveReplay :736-742; both only print the
+ * reference's message when saveReplay is not set in the config.  File content: see the
+ * cfb_replay_* functions below. */
+int cfb_set_replay_file(cfb_engine *e, const char *log_file);
+int cfb_set_save_replay(cfb_engine *e, int open);
 /* Engine::setRandomSeed  engine.h:170 */
 int cfb_set_random_seed(cfb_engine *e, int seed);
 /* Engine::reset(resetRnd)  engine.cpp:744-760 */
@@ -190,6 +196,27 @@ int cfb_synchronize(cfb_engine *e);
 int64_t cfb_num_drivables(const cfb_engine *e);
 /* CUDA device ordinal the engine was created on */
 int cfb_device(const cfb_engine *e);
+
+/* The replay formatter on its own (no engine, no GPU): what the engine writes with saveReplay, for
+ * callers that hold vehicle states themselves.  RoadNet::convertToJson roadnet.cpp:327-394 and
+ * Engine::updateLog engine.cpp:518-554.  Doubles are printed in shortest round-trip form, so every
+ * token parses to the double the reference computed (the reference's own printer, dtoa_milo, does
+ * not define the last digit: byte-identical files are not definable).  "Count then fill": both
+ * return the bytes needed including the terminating NUL. */
+typedef struct cfb_replay cfb_replay;
+typedef struct {
+    int32_t drivable;          /* lane index, or cfb_num_lanes() + laneLink index */
+    double distance;           /* along the drivable */
+    int32_t flow, index;       /* cfb_vehicle_ref */
+    double length, width;      /* VehicleInfo len / width */
+} cfb_replay_vehicle;
+cfb_replay *cfb_replay_create(const char *roadnet_file);
+void cfb_replay_destroy(cfb_replay *r);
+int64_t cfb_replay_roadnet_json(cfb_replay *r, char *out, int64_t cap);
+/* vehicles: running vehicles in vehiclePool (ascending priority) order; phase: current phase index
+ * per intersection (cfb_num_intersections() entries) */
+int64_t cfb_replay_format_step(cfb_replay *r, const cfb_replay_vehicle *vehicles, int64_t n, const int32_t *phase,
+                               char *out, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -70,15 +70,14 @@ def cfg_hetero_halfstep(scenario_dir):
     return scenario.write_scenario(scenario_dir, net, flows, interval=0.5, seed=3, name="hetero")
 
 
-@pytest.fixture(scope="session")
-def cfg_irregular(scenario_dir):
+def _irregular_net(seed=5):
     """A 3x3 grid bent out of shape: road polylines with interior points, unequal lane widths and
     speed limits, laneLinks WITHOUT explicit points (the loader's default curve, roadnet.cpp:212-247),
     odd intersection widths and phase times.  Exercises the geometry code the generator's tidy
     output never reaches."""
     import random
     from cityflow_b200 import scenario
-    rng = random.Random(5)
+    rng = random.Random(seed)
     net = scenario.grid_roadnet(3, 3)
     for road in net["roads"]:
         a, b = road["points"]
@@ -99,5 +98,27 @@ def cfg_irregular(scenario_dir):
                     ll["points"] = []                                            # empty list = default curve too
         for ph in inter["trafficLight"]["lightphases"]:
             ph["time"] = rng.choice([5, 17, 30, 12.5])
+    return net
+
+
+@pytest.fixture(scope="session")
+def cfg_irregular(scenario_dir):
+    from cityflow_b200 import scenario
+    net = _irregular_net()
     flows = scenario.random_walk_flows(net, frac=1.0, interval=4.0, seed=9)
     return scenario.write_scenario(scenario_dir, net, flows, seed=7, name="irregular")
+
+
+@pytest.fixture(scope="session")
+def cfg_replay(scenario_dir):
+    """saveReplay on, on the irregular network, with vehicles of assorted lengths and widths
+    (the replay line carries both).  Returns the config path; the log files land next to it."""
+    import random
+    from cityflow_b200 import scenario
+    net = _irregular_net(seed=11)
+    flows = scenario.random_walk_flows(net, frac=1.0, interval=5.0, seed=3)
+    rng = random.Random(2)
+    for f in flows:
+        f["vehicle"]["length"] = rng.choice([4.0, 5.0, 7.5, 12.25])
+        f["vehicle"]["width"] = rng.choice([1.8, 2.0, 2.55])
+    return scenario.write_scenario(scenario_dir, net, flows, seed=4, save_replay=True, name="replay")

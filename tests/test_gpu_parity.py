@@ -404,3 +404,47 @@ def test_rl_actions_and_observations_on_device_vs_port(cfg_6x6_rl):
         for _ in range(300):          # surfaced by the next bookkeeping drain at the latest
             eng.next_step()
         eng.get_average_travel_time()
+
+
+def test_replay_files_written_by_the_engine(cfg_replay):
+    """with saveReplay the engine writes the reference's two log files.  The step
+    lines must be exactly what the stand-alone formatter makes of the ORACLE's states (so: device
+    positions, priority order and light states all agree); tests/test_cpu.py pins that formatter
+    against the files the compiled reference writes."""
+    import json
+    import os
+    import cityflow
+    from cityflow_b200.capi import CReplay, REPLAY_DTYPE
+    c = json.load(open(cfg_replay))
+    log, netlog, log2 = c["dir"] + c["replayLogFile"], c["dir"] + c["roadnetLogFile"], c["dir"] + "replay_second.txt"
+    for f in (log, netlog, log2):
+        if os.path.exists(f):
+            os.remove(f)
+    flows = json.load(open(c["dir"] + c["flowFile"]))
+    eng = cityflow.Engine(cfg_replay, thread_num=1)
+    ora = H.PortOracle(cfg_replay)
+    rp = CReplay(c["dir"] + c["roadnetFile"])
+    assert open(netlog).read() == rp.roadnet_json()
+    expect = []
+    for s in range(1, 201):
+        if s == 151:
+            eng.set_save_replay(False)          # engine.cpp:736-742: steps 151..160 leave no line
+        if s == 161:
+            eng.set_save_replay(True)
+            eng.set_replay_file("replay_second.txt")   # engine.cpp:727-734: relative to "dir"
+        eng.next_step()
+        ora.next_step()
+        st = ora.snapshot()
+        v = np.zeros(len(st.vehicles), REPLAY_DTYPE)
+        v["drivable"], v["distance"] = st.vehicles["drivable"], st.vehicles["dis"]
+        v["flow"], v["index"] = st.vehicles["flow"], st.vehicles["cnt"]
+        v["length"] = [flows[f]["vehicle"]["length"] for f in st.vehicles["flow"]]
+        v["width"] = [flows[f]["vehicle"]["width"] for f in st.vehicles["flow"]]
+        expect.append(rp.format_step(v, np.where(st.phases < 0, 0, st.phases)))
+    del eng                                      # closes the log like ~Engine (engine.cpp:763)
+    first = open(log).read().split("\n")
+    second = open(log2).read().split("\n")
+    assert first[-1] == "" and second[-1] == ""
+    assert first[:-1] == expect[:150]
+    assert second[:-1] == expect[160:]
+    assert len(expect[-1].split(",")) > 100
