@@ -10,7 +10,14 @@
 //   Router lookahead          router.cpp:23-129
 //   Cross::canPass/notify     roadnet.cpp:595-676   Lane::available/canEnter roadnet.cpp:428-445
 //   TrafficLight::passTime    trafficlight.cpp:29-37
-// Every function cites the reference lines it follows.  laneChange=true is not restated.
+// Every function cites the reference lines it follows.
+//
+// laneChange=true (lanechange.cpp, engine.cpp:195-244, 374-400, 792-820, roadnet.cpp:837-898) IS
+// restated, but the unmodified reference cannot pin it: there the order in which lane-change
+// candidates are scheduled is the heap-address order of a std::set<Vehicle*> and one input of the
+// decision (ControllerInfo::gap of a vehicle that never had a leader) is read uninitialised.  The
+// pin is the reference built with those two things defined (oracle/lc_order_patch.sh: set ordered
+// by priority, gap = 0) -- oracle/_ref/refdump_lcorder, single worker thread.
 //
 // PARITY PINNING: tests/test_oracle_vs_ref.py runs this oracle and the compiled, unmodified
 // reference (oracle/_ref, built by oracle/Makefile) side by side and requires bit-equal
@@ -30,6 +37,7 @@
 #include <deque>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <random>
 #include <set>
 #include <string>
@@ -72,6 +80,25 @@ struct Veh {
     bool bEnd = false;
     Veh *bBlocker = nullptr;
     int64_t bEnter = 0;
+    // LaneChangeInfo (vehicle.h:74-79)
+    int partnerType = 0;             // 0 none, 1 = has a shadow, 2 = is a shadow
+    Veh *partner = nullptr;
+    double offset = 0;
+    size_t segIndex = 0;
+    // LaneChange / SimpleLaneChange state (lanechange.h:15-44)
+    struct Signal {                  // lanechange.h:17-24 (value-initialised by make_shared: all zero)
+        int urgency = 0, direction = 0;
+        int target = -1;             // lane id
+        Veh *source = nullptr;
+    };
+    std::shared_ptr<Signal> sigRecv, sigSend;
+    int lastDir = 0;
+    Veh *targetLeader = nullptr, *targetFollower = nullptr;
+    double leaderGap = 0, followerGap = 0, waitingTime = 0;
+    bool changing = false, lcFinished = false;
+    double lastChangeTime = 0;
+    bool isReal() const { return partnerType != 2; }                                   // vehicle.h:278
+    bool planChange() const { return (sigSend && sigSend->target >= 0 && sigSend->target != drivable) || changing; }  // lanechange.cpp:23-25
 };
 
 struct FlowState {
@@ -103,6 +130,11 @@ struct Oracle {
     std::vector<double> remain;
     std::vector<std::pair<Veh *, double>> pushBuffer;
     std::set<Veh *> removeBuffer;
+    // laneChange=true (restated against the reference built with the priority-ordered worker set,
+    // oracle/lc_order_patch.sh): segment index per lane (roadnet.cpp:687-691, :852-875)
+    bool laneChange = false;
+    std::vector<std::vector<double>> segStart;            // [lane][segment] startPos
+    std::vector<std::vector<std::vector<Veh *>>> segVeh;  // [lane][segment] vehicles, list order
     int ties = 0;  // pushBuffer ties (same target drivable, equal dis): order unspecified in the reference
     cfb::Routing *routing = nullptr;
 
@@ -318,8 +350,249 @@ struct Oracle {
         s = min2(s, drvMaxSpeed(v.drivable));
         s = min2(s, carFollowSpeed(v));
         if (isIntersectionRelated(v)) s = min2(s, intersectionRelatedSpeed(v));
+        if (laneChange) {  // vehicle.cpp:323-329 (the yield term is a no-op without signals)
+            s = min2(s, yieldSpeed(v));
+            if (!onValidLane(v)) {
+                double vn = noCollisionSpeed(0, 1, v.t.speed, v.t.maxNegAcc, drvLength(v.drivable) - v.dis, interval, v.t.minGap);
+                s = min2(s, vn);
+            }
+        }
         s = max2(s, v.t.speed - v.t.maxNegAcc * interval);
         return s;
+    }
+
+    // ---------------- lane change (lanechange.cpp, engine.cpp:195-244, 374-400, 792-820) ----------------
+    bool isLastRoad(const Veh &v, int d) const { return !isLink(d) && net.laneRoad[d] == v.route.back(); }   // router.cpp:131-134
+    bool onLastRoad(const Veh &v) const { return isLastRoad(v, v.drivable); }                                  // router.cpp:136-138
+    bool onValidLane(Veh &v) const { return !(nextDrivable(v) < 0 && !onLastRoad(v)); }                        // router.h:66-68
+    int innerLane(int l) const { return net.laneIdx[l] > 0 ? l - 1 : -1; }                                     // roadnet.h:335-337
+    int outerLane(int l) const { return net.laneIdx[l] < net.roadNumLanes(net.laneRoad[l]) - 1 ? l + 1 : -1; } // roadnet.h:339-342
+    // Lane::initSegments roadnet.cpp:863-875
+    void initSegments() {
+        for (int l = 0; l < nLanes(); ++l) {
+            auto it = lists[l].begin(), end = lists[l].end();
+            for (int i = (int) segStart[l].size() - 1; i >= 0; --i) {
+                auto &sv = segVeh[l][i];
+                sv.clear();
+                while (it != end && (*it)->dis >= segStart[l][i]) {
+                    sv.push_back(*it);
+                    (*it)->segIndex = (size_t) i;
+                    ++it;
+                }
+            }
+        }
+    }
+    // Lane::getVehicleBeforeDistance roadnet.cpp:877-887
+    Veh *vehicleBefore(int lane, double dis, size_t segIndex) const {
+        for (int i = (int) segIndex; i >= 0; --i)
+            for (Veh *v : segVeh[lane][i])
+                if (v->dis < dis) return v;
+        return nullptr;
+    }
+    // Lane::getVehicleAfterDistance roadnet.cpp:889-898
+    Veh *vehicleAfter(int lane, double dis, size_t segIndex) const {
+        for (size_t i = segIndex; i < segVeh[lane].size(); ++i)
+            for (auto it = segVeh[lane][i].rbegin(); it != segVeh[lane][i].rend(); ++it)
+                if ((*it)->dis >= dis) return *it;
+        return nullptr;
+    }
+    // SimpleLaneChange::estimateGap lanechange.cpp:220-225
+    double estimateGap(const Veh &v, int lane) const {
+        Veh *leader = vehicleAfter(lane, v.dis, v.segIndex);
+        if (!leader) return net.laneLength[lane] - v.dis;
+        return leader->dis - v.dis - leader->t.len;
+    }
+    // LaneChange::getDirection lanechange.cpp:104-113
+    int lcDirection(const Veh &v) const {
+        if (isLink(v.drivable)) return 0;
+        if (!v.sigSend) return 0;
+        if (v.sigSend->target < 0) return 0;
+        if (v.sigSend->target == outerLane(v.drivable)) return 1;
+        if (v.sigSend->target == innerLane(v.drivable)) return -1;
+        return 0;
+    }
+    // SimpleLaneChange::makeSignal lanechange.cpp:152-187 (+ LaneChange::makeSignal lanechange.h:73)
+    void makeSignal(Veh &v) {
+        if (v.changing) return;
+        if (currentTime() - v.lastChangeTime < 3) return;   // coolingTime, lanechange.h:46
+        v.sigSend = std::make_shared<Veh::Signal>();
+        v.sigSend->source = &v;
+        if (!isLink(v.drivable)) {
+            const int cur = v.drivable;
+            if (net.laneLength[cur] - v.dis < 30) return;
+            double curEst = v.gap;
+            double outerEst = 0;
+            double expectedGap = 2 * v.t.len + 4 * interval * v.t.maxSpeed;
+            if (v.gap > expectedGap || v.gap < 1.5 * v.t.len) return;
+            if (net.laneIdx[cur] < net.roadNumLanes(net.laneRoad[cur]) - 1) {
+                if (onLastRoad(v) || routerNextOf(v, outerLane(cur)) >= 0) {
+                    outerEst = estimateGap(v, outerLane(cur));
+                    if (outerEst > curEst + v.t.len) v.sigSend->target = outerLane(cur);
+                }
+            }
+            if (net.laneIdx[cur] > 0) {
+                if (onLastRoad(v) || routerNextOf(v, innerLane(cur)) >= 0) {
+                    double innerEst = estimateGap(v, innerLane(cur));
+                    if (innerEst > curEst + v.t.len && innerEst > outerEst) v.sigSend->target = innerLane(cur);
+                }
+            }
+            v.sigSend->urgency = 1;
+        }
+        if (v.sigSend) v.sigSend->direction = lcDirection(v);
+    }
+    // LaneChange::updateLeaderAndFollower lanechange.cpp:27-62
+    void updateLeaderAndFollower(Veh &v) {
+        v.targetLeader = v.targetFollower = nullptr;
+        const int target = v.sigSend->target;
+        v.targetLeader = vehicleAfter(target, v.dis, v.segIndex);
+        const int cur = v.drivable;
+        v.leaderGap = v.followerGap = std::numeric_limits<double>::max();
+        if (!v.targetLeader) {
+            double rest = net.laneLength[cur] - v.dis;
+            v.leaderGap = rest;
+            double gap = std::numeric_limits<double>::max();
+            for (int ll : net.laneOutLinks[target]) {
+                Veh *leader = lastVeh(nLanes() + ll);
+                if (leader && leader->dis + rest < gap) {
+                    gap = leader->dis + rest;
+                    if (gap < leader->t.len) {
+                        v.targetLeader = leader;
+                        v.leaderGap = rest - (leader->t.len - gap);
+                    }
+                }
+            }
+        } else {
+            v.leaderGap = v.targetLeader->dis - v.dis - v.targetLeader->t.len;
+        }
+        v.targetFollower = vehicleBefore(target, v.dis, v.segIndex);
+        if (v.targetFollower) v.followerGap = v.dis - v.targetFollower->dis - v.t.len;
+        else v.followerGap = std::numeric_limits<double>::max();
+    }
+    // Vehicle::receiveSignal vehicle.cpp:391-402
+    static void receiveSignal(Veh &me, Veh &sender) {
+        if (me.changing) return;
+        int curPriority = me.sigRecv ? me.sigRecv->source->priority : -1;
+        int newPriority = sender.priority;
+        if ((!me.sigRecv || curPriority < newPriority) && (!me.sigSend || me.priority < newPriority))
+            me.sigRecv = sender.sigSend;
+    }
+    // LaneChange::clearSignal lanechange.cpp:129-139
+    static void clearSignal(Veh &v) {
+        v.targetLeader = nullptr;
+        v.targetFollower = nullptr;
+        v.lastDir = v.sigSend ? v.sigSend->direction : 0;
+        if (v.changing) return;
+        v.sigSend = nullptr;
+        v.sigRecv = nullptr;
+    }
+    double safeGapBefore(const Veh &v) const { return v.targetFollower ? minBrakeDistance(*v.targetFollower) : 0; }  // lanechange.cpp:212-214
+    // SimpleLaneChange::yieldSpeed lanechange.cpp:189-210
+    double yieldSpeed(Veh &v) {
+        if (v.planChange()) v.waitingTime += interval;
+        if (v.sigRecv) {
+            Veh *source = v.sigRecv->source;
+            if (&v == source->targetLeader) return 100;
+            double srcSpeed = source->t.speed;
+            double gap = source->followerGap - safeGapBefore(*source);
+            double s = noCollisionSpeed(srcSpeed, source->t.maxNegAcc, v.t.speed, v.t.maxNegAcc, gap, interval, 0);
+            if (s < 0) s = 100;
+            return s;
+        }
+        return 100;
+    }
+    // Engine::insertShadow engine.cpp:811-819, Vehicle copy ctor vehicle.cpp:27-36,
+    // LaneChange::insertShadow lanechange.cpp:73-102
+    void insertShadow(Veh &v) {
+        Veh *sh = new Veh();
+        sh->t = v.t;
+        // ControllerInfo copy (vehicle.cpp:15-17); Router copy restarts its road cursor and forgets the
+        // planned drivables (router.cpp:11-14)
+        sh->dis = v.dis; sh->drivable = v.drivable; sh->prevDrivable = v.prevDrivable;
+        sh->approachDist = v.approachDist; sh->gap = v.gap; sh->enterLaneLinkTime = v.enterLaneLinkTime;
+        sh->leader = v.leader; sh->blocker = v.blocker; sh->running = v.running;
+        sh->route = v.route; sh->iCur = 0; sh->routeValid = false;
+        // LaneChangeInfo and Buffer are copied member-wise
+        sh->partnerType = v.partnerType; sh->partner = v.partner; sh->offset = v.offset; sh->segIndex = v.segIndex;
+        sh->bDisSet = v.bDisSet; sh->bSpeedSet = v.bSpeedSet; sh->bDrvSet = v.bDrvSet; sh->bEndSet = v.bEndSet;
+        sh->bBlockerSet = v.bBlockerSet; sh->bEnterSet = v.bEnterSet; sh->bCustomSet = v.bCustomSet;
+        sh->bDis = v.bDis; sh->bDelta = v.bDelta; sh->bSpeed = v.bSpeed; sh->bCustom = v.bCustom;
+        sh->bDrv = v.bDrv; sh->bEnd = v.bEnd; sh->bBlocker = v.bBlocker; sh->bEnter = v.bEnter;
+        sh->flow = v.flow; sh->cnt = v.cnt;   // id + "_shadow": same (flow, cnt), told apart by priority
+        do { sh->priority = (int) rnd(); } while (pool.count(sh->priority));
+        sh->enterTime = v.enterTime;
+        pool.emplace(sh->priority, sh);
+        // LaneChange::insertShadow
+        v.changing = true;
+        v.waitingTime = 0;
+        const int target = v.sigSend->target;
+        sh->partnerType = 2; sh->partner = &v;     // setParent
+        v.partnerType = 1; v.partner = sh;         // setShadow
+        sh->blocker = nullptr;
+        sh->drivable = target;
+        routerUpdate(*sh);
+        auto &L = lists[target];
+        auto pos = L.end();
+        if (v.targetFollower) {  // targetFollower->getListIterator(): looked up through ITS segment (vehicle.cpp:404-411)
+            auto &sv = segVeh[target][v.targetFollower->segIndex];
+            if (std::find(sv.begin(), sv.end(), v.targetFollower) != sv.end())
+                pos = std::find(L.begin(), L.end(), v.targetFollower);
+        }
+        L.insert(pos, sh);
+        {   // Segment::insertVehicle roadnet.cpp:944-948 (into the segment with the PARENT's index)
+            auto &sv = segVeh[target][v.segIndex];
+            auto it = sv.begin();
+            for (; it != sv.end() && (*it)->dis > sh->dis; ++it) {}
+            sv.insert(it, sh);
+        }
+        updateLeaderAndGap(*sh, v.targetLeader);
+        if (v.targetFollower) updateLeaderAndGap(*v.targetFollower, sh);
+        activeCount++;
+    }
+    // Engine::threadPlanLaneChange engine.cpp:374-389 + Engine::scheduleLaneChange :792-809
+    void planLaneChange() {
+        std::vector<Veh *> buffer;
+        for (auto &kv : pool) {
+            Veh *v = kv.second;
+            if (v->running && v->isReal()) {
+                makeSignal(*v);
+                if (v->planChange()) buffer.push_back(v);
+            }
+        }
+        // same library sort and comparator as the reference: with every urgency equal to 1 the
+        // (unstable) result is a function of the input order alone
+        std::sort(buffer.begin(), buffer.end(), [](Veh *a, Veh *b) { return a->sigSend->urgency > b->sigSend->urgency; });
+        for (Veh *v : buffer) {
+            updateLeaderAndFollower(*v);
+            if (v->targetLeader) receiveSignal(*v->targetLeader, *v);      // SimpleLaneChange::sendSignal lanechange.cpp:207-210
+            if (v->targetFollower) receiveSignal(*v->targetFollower, *v);
+            if (v->planChange() && (v->sigSend && !v->sigRecv) && !v->changing) {
+                const bool gapValid = v->leaderGap >= minBrakeDistance(*v) && v->followerGap >= safeGapBefore(*v);  // lanechange.h:79
+                if (gapValid && !isLink(v->drivable)) insertShadow(*v);
+            }
+        }
+    }
+    // LaneChange::finishChanging lanechange.cpp:115-127 + Vehicle::finishChanging vehicle.cpp:378-381
+    void finishChanging(Veh &v) {
+        v.changing = false;
+        v.lcFinished = true;
+        v.lastChangeTime = currentTime();
+        Veh *partner = v.partner;
+        partner->partnerType = 0;     // (and takes over the name: same (flow, cnt) here)
+        partner->offset = 0;
+        partner->partner = nullptr;
+        v.partner = nullptr;
+        clearSignal(v);
+        v.bEnd = true; v.bEndSet = true;
+    }
+    // Vehicle::abortLaneChange vehicle.cpp:413-417 + LaneChange::abortChanging lanechange.cpp:141-148
+    void abortLaneChange(Veh &v) {
+        v.bEnd = true; v.bEndSet = true;
+        Veh *partner = v.partner;
+        partner->changing = false;
+        partner->partnerType = 0;
+        partner->offset = 0;
+        partner->partner = nullptr;
+        clearSignal(v);
     }
     // vehicle.cpp:49-68
     void setDeltaDistance(Veh &v, double dis) {
@@ -344,6 +617,16 @@ struct Oracle {
     // engine.cpp:188-251 (laneChange off)
     void vehicleControl(Veh &v) {
         double ns = v.bSpeedSet ? v.bSpeed : nextSpeed(v);
+        if (laneChange) {  // engine.cpp:195-205: a vehicle and its shadow move as one
+            Veh *partner = v.partner;
+            if (partner != nullptr && !partner->bSpeedSet) {
+                double partnerSpeed = nextSpeed(*partner);
+                ns = min2(ns, partnerSpeed);
+                partner->bSpeed = ns;
+                partner->bSpeedSet = true;
+                if (partner->bEndSet) { v.bEnd = true; v.bEndSet = true; }
+            }
+        }
         double deltaDis, speed = v.t.speed;
         if (ns < 0) {
             deltaDis = 0.5 * speed * speed / v.t.maxNegAcc;
@@ -354,6 +637,18 @@ struct Oracle {
         v.bSpeed = ns;
         v.bSpeedSet = true;
         setDeltaDistance(v, deltaDis);
+        if (laneChange) {  // engine.cpp:224-244
+            if (!v.isReal() && v.bDrvSet && v.bDrv >= 0) abortLaneChange(v);   // getChangedDrivable() != nullptr
+            if (v.changing) {
+                int dir = v.sigSend ? v.sigSend->direction : 0;
+                const double curWidth = isLink(v.drivable) ? 0.0 : net.laneWidth[v.drivable];   // (getCurLane() on a laneLink is undefined in the reference)
+                const double maxOffset = (net.laneWidth[v.sigSend->target] + curWidth) / 2;   // vehicle.h:347-350
+                double newOffset = std::fabs(v.offset + max2(0.2 * ns, 1) * interval * dir);
+                newOffset = min2(newOffset, maxOffset);
+                v.offset = newOffset * dir;
+                if (newOffset >= maxOffset) finishChanging(v);
+            }
+        }
         if (!v.bEndSet && v.bDrvSet) pushBuffer.emplace_back(&v, v.bDis);
     }
     // vehicle.cpp:107-143
@@ -542,8 +837,10 @@ struct Oracle {
                 if (!(changed && v->bDrv >= 0) && !v->bEndSet) L[w++] = v;
                 if (v->bEndSet) {
                     removeBuffer.insert(v);
-                    finishedCnt += 1;
-                    cumulativeTravelTime += currentTime() - v->enterTime;
+                    if (!v->lcFinished) {  // engine.cpp:297-301: a vehicle replaced by its shadow is not "finished"
+                        finishedCnt += 1;
+                        cumulativeTravelTime += currentTime() - v->enterTime;
+                    }
                     pool.erase(v->priority);
                     activeCount--;
                 }
@@ -576,6 +873,7 @@ struct Oracle {
                 v->bBlockerSet = true;
             }
             commit(*v);
+            clearSignal(*v);   // engine.cpp:424 (no-op without lane change: nothing is ever set)
         }
         for (Veh *v : removeBuffer) delete v;
         removeBuffer.clear();
@@ -608,6 +906,11 @@ struct Oracle {
         for (size_t i = 0; i < flows.size(); ++i) flowStep(flows[i], (int) i);
         planRoute();
         handleWaiting();
+        if (laneChange) {  // engine.cpp:570-574
+            initSegments();
+            planLaneChange();
+            updateLeaderAndGapAll();
+        }
         notifyCross();
         // threadGetAction: running vehicles; order only matters for pushBuffer ties
         for (auto &kv : pool)
@@ -654,6 +957,7 @@ struct Oracle {
         };
         interval = get("interval").asDouble();
         rlTrafficLight = get("rlTrafficLight").asBool();
+        if (const cfb::Json *lc = doc.find("laneChange")) laneChange = lc->isBool() && lc->asBool();   // engine.cpp:52 (optional, default false)
         seed = get("seed").asInt();
         rnd.seed(seed);
         std::string dir = get("dir").s;
@@ -675,6 +979,25 @@ struct Oracle {
             notifyDist[s].assign(net.nCross(), 0.0);
         }
         initLights();
+        // Road::buildSegmentationByInterval roadnet.cpp:687-691 with (len + minGap) * MAX_NUM_CARS_ON_SEGMENT
+        // of a default VehicleInfo = (5 + 2) * 10 (roadnet.cpp:305-312, config.h:5); Lane::buildSegmentation :852-861
+        segStart.resize(net.nLanes());
+        segVeh.resize(net.nLanes());
+        for (int r = 0; r < net.nRoads(); ++r) {
+            double len = 0.0;
+            const auto &pts = net.roadPoints[r];
+            for (size_t i = 0; i + 1 < pts.size(); ++i) {
+                const double dx = pts[i + 1].x - pts[i].x, dy = pts[i + 1].y - pts[i].y;
+                len += sqrt(dx * dx + dy * dy);
+            }
+            const double segInterval = (5.0 + 2.0) * 10;
+            const size_t numSegs = std::max((size_t) ceil(len / segInterval), (size_t) 1);
+            for (int l = net.roadLaneBeg[r]; l < net.roadLaneBeg[r + 1]; ++l) {
+                segStart[l].resize(numSegs);
+                segVeh[l].assign(numSegs, {});
+                for (size_t i = 0; i < numSegs; ++i) segStart[l][i] = i * net.laneLength[l] / numSegs;
+            }
+        }
         return true;
     }
     ~Oracle() {
@@ -789,6 +1112,45 @@ int cfo_vehicles(void *h, OracleVehRec *out, int cap) {
     }
     return n;
 }
+// laneChange runs: every running vehicle including shadows, vehiclePool order; mirrors `refdump runlc`
+struct OracleLcRec {
+    int32_t flow, cnt, priority, partnerType, partnerPriority, drivable, leaderPriority, blockerPriority, flags, lastDir;
+    double dis, speed, gap, offset, waitingTime, lastChangeTime;
+};
+int cfo_lc_vehicles(void *h, OracleLcRec *out, int cap) {
+    Oracle *o = (Oracle *) h;
+    int n = 0;
+    for (auto &kv : o->pool) {
+        Veh *v = kv.second;
+        if (!v->running) continue;
+        if (n < cap) {
+            OracleLcRec &r = out[n];
+            r.flow = v->flow; r.cnt = v->cnt; r.priority = v->priority;
+            r.partnerType = v->partnerType;
+            r.partnerPriority = v->partner ? v->partner->priority : -1;
+            r.drivable = v->drivable;
+            r.leaderPriority = v->leader ? v->leader->priority : -1;
+            r.blockerPriority = v->blocker ? v->blocker->priority : -1;
+            r.flags = (int32_t) v->changing | ((int32_t) v->lcFinished << 1);
+            r.lastDir = v->lastDir;
+            r.dis = v->dis; r.speed = v->t.speed; r.gap = v->leader ? v->gap : 0.0;
+            r.offset = v->offset; r.waitingTime = v->waitingTime; r.lastChangeTime = v->lastChangeTime;
+        }
+        ++n;
+    }
+    return n;
+}
+// list order of one drivable as priorities; returns the count
+int cfo_drivable_priorities(void *h, int drivable, int32_t *out, int cap) {
+    Oracle *o = (Oracle *) h;
+    int n = 0;
+    for (Veh *v : o->lists[drivable]) {
+        if (n < cap) out[n] = v->priority;
+        ++n;
+    }
+    return n;
+}
+int cfo_lane_change(void *h) { return ((Oracle *) h)->laneChange ? 1 : 0; }
 // list order of one drivable as (flow,cnt) pairs; returns the count
 int cfo_drivable_vehicles(void *h, int drivable, int32_t *out, int cap) {
     Oracle *o = (Oracle *) h;

@@ -30,6 +30,19 @@ VEH_DTYPE = np.dtype([
 ])
 
 
+LC_DTYPE = np.dtype([   # `refdump runlc` / cfo_lc_vehicles: every running vehicle incl. shadows, keyed by priority
+    ("flow", "<i4"), ("cnt", "<i4"), ("priority", "<i4"), ("partner_type", "<i4"), ("partner", "<i4"),
+    ("drivable", "<i4"), ("leader", "<i4"), ("blocker", "<i4"), ("flags", "<i4"), ("last_dir", "<i4"),
+    ("dis", "<f8"), ("speed", "<f8"), ("gap", "<f8"), ("offset", "<f8"), ("waiting_time", "<f8"),
+    ("last_change_time", "<f8"),
+])
+REFDUMP_LC = os.path.join(os.path.dirname(REFDUMP), "refdump_lcorder")
+
+
+def have_lc_ref() -> bool:
+    return os.path.exists(REFDUMP_LC)
+
+
 def have_ref() -> bool:
     return os.path.exists(REFDUMP)
 
@@ -132,6 +145,33 @@ def parse_run(path: str, n_inter: int, n_drivables: int):
     return out
 
 
+def parse_runlc(path: str, n_inter: int, n_drivables: int):
+    buf = open(path, "rb").read()
+    off = 0
+    magic, n_lanes = np.frombuffer(buf, "<i4", 2, off)
+    off += 8
+    assert magic == 0x43464C31
+    out = []
+    while off < len(buf):
+        st = StepState()
+        hdr = np.frombuffer(buf, "<i4", 5, off)
+        off += 20
+        st.step, st.vehicle_count, n_run, st.pool_size, st.finished = (int(x) for x in hdr)
+        st.cum_travel_time = float(np.frombuffer(buf, "<f8", 1, off)[0])
+        off += 8
+        st.lane_count = np.frombuffer(buf, "<i4", n_lanes, off); off += 4 * n_lanes
+        st.lane_waiting = st.lane_queue = None
+        st.phases = np.frombuffer(buf, "<i4", n_inter, off); off += 4 * n_inter
+        st.vehicles = np.frombuffer(buf, LC_DTYPE, n_run, off); off += LC_DTYPE.itemsize * n_run
+        order = []
+        for _ in range(n_drivables):
+            m = int(np.frombuffer(buf, "<i4", 1, off)[0]); off += 4
+            order.append(np.frombuffer(buf, "<i4", m, off)); off += 4 * m
+        st.order = order
+        out.append(st)
+    return out
+
+
 class RefDump:
     """The compiled reference (oracle/_ref/refdump)."""
 
@@ -146,6 +186,14 @@ class RefDump:
         with tempfile.NamedTemporaryFile(suffix=".bin") as f:
             subprocess.check_call([REFDUMP, "run", config, str(steps), str(threads), f.name, str(every)])
             return parse_run(f.name, n_inter, n_drivables)
+
+    @staticmethod
+    def runlc(config: str, steps: int, every: int = 1, *, n_inter: int, n_drivables: int, patched: bool = True, threads: int = 1):
+        """laneChange=true run of the reference with the priority-ordered worker set (`patched`,
+        oracle/lc_order_patch.sh) or of the unmodified build; states incl. shadows."""
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            subprocess.check_call([REFDUMP_LC if patched else REFDUMP, "runlc", config, str(steps), str(threads), f.name, str(every)])
+            return parse_runlc(f.name, n_inter, n_drivables)
 
     @staticmethod
     def bench(config: str, steps: int, threads: int, warmup: int = 0) -> dict:
@@ -249,6 +297,33 @@ class PortOracle:
         self.lib.cfo_vehicles(self.h, a.ctypes.data, n)
         return a
 
+    def lc_snapshot(self) -> StepState:
+        """State in the shape of parse_runlc (laneChange runs)."""
+        lib = self.lib
+        lib.cfo_lc_vehicles.restype = ctypes.c_int
+        lib.cfo_lc_vehicles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.cfo_drivable_priorities.restype = ctypes.c_int
+        lib.cfo_drivable_priorities.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        st = StepState()
+        st.step = self.steps
+        st.vehicle_count = self.vehicle_count()
+        st.pool_size = lib.cfo_pool_size(self.h)
+        st.finished = lib.cfo_finished_count(self.h)
+        st.cum_travel_time = lib.cfo_cumulative_travel_time(self.h)
+        st.lane_count = self.lane_vehicle_count()
+        st.lane_waiting = st.lane_queue = None
+        st.phases = self._lane_array("cfo_phases", self.n_inter)
+        n = lib.cfo_lc_vehicles(self.h, None, 0)
+        a = np.zeros(n, LC_DTYPE)
+        lib.cfo_lc_vehicles(self.h, a.ctypes.data, n)
+        st.vehicles = a
+        st.order = []
+        tmp = np.zeros(4096, np.int32)
+        for d in range(self.n_drivables):
+            m = lib.cfo_drivable_priorities(self.h, d, tmp.ctypes.data, len(tmp))
+            st.order.append(tmp[:m].copy())
+        return st
+
     def snapshot(self, with_order: bool = False) -> StepState:
         st = StepState()
         st.step = self.steps
@@ -312,4 +387,33 @@ def compare_states(a: StepState, b: StepState, *, speed_tol: float = 0.0, check_
             if not np.array_equal(x, y):
                 bad.append("list order differs in drivable %d" % d)
                 break
+    return bad
+
+
+def compare_lc_states(ref: StepState, got: StepState) -> list:
+    """Lane-change runs: bit-equal or a list of differences (vehicles keyed by priority)."""
+    bad = []
+    for f in ("step", "vehicle_count", "pool_size", "finished"):
+        if getattr(ref, f) != getattr(got, f):
+            bad.append("%s: ref %s got %s" % (f, getattr(ref, f), getattr(got, f)))
+    if ref.cum_travel_time != got.cum_travel_time:
+        bad.append("cum_travel_time: ref %r got %r" % (ref.cum_travel_time, got.cum_travel_time))
+    if not np.array_equal(ref.lane_count, got.lane_count):
+        bad.append("lane counts differ on %d lanes" % int((np.asarray(ref.lane_count) != np.asarray(got.lane_count)).sum()))
+    if not np.array_equal(ref.phases, got.phases):
+        bad.append("phases differ")
+    a, b = ref.vehicles, got.vehicles
+    if len(a) != len(b):
+        bad.append("running vehicles: ref %d got %d" % (len(a), len(b)))
+    else:
+        for f in LC_DTYPE.names:
+            ne = np.nonzero(a[f] != b[f])[0]
+            if len(ne):
+                k = ne[0]
+                bad.append("%s differs for %d vehicles, first flow_%d_%d prio %d: ref %r got %r" %
+                           (f, len(ne), a["flow"][k], a["cnt"][k], a["priority"][k], a[f][k], b[f][k]))
+    for d, (x, y) in enumerate(zip(ref.order, got.order)):
+        if not np.array_equal(x, y):
+            bad.append("list order differs on drivable %d" % d)
+            break
     return bad

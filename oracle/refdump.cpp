@@ -10,6 +10,9 @@
 //   refdump run <config.json> <steps> <threads> <out.bin> [every]
 //       per-step dynamic state of every running vehicle (raw IEEE-754 bits) ->
 //       the parity oracle for tests/ and for generating tests/golden/.
+//   refdump runlc <config.json> <steps> <threads> <out.bin> [every]
+//       the same for laneChange=true runs: every running vehicle including shadows, keyed by
+//       priority, with the lane-change state (partner, offset, changing, waiting time).
 //   refdump bench <config.json> <steps> <threads> [warmup]
 //       timing loop in the shape of tools/debug/simple_run.cpp:42-57, prints one
 //       JSON line -> the `--impl reference` arm of bench.py.
@@ -201,6 +204,60 @@ int dumpRun(const char *cfg, int steps, int threads, const char *outPath, int ev
     return 0;
 }
 
+// Lane-change runs (laneChange=true): every running vehicle INCLUDING shadows, identified by
+// priority (a shadow shares its parent's name until the change completes).  Meant for the build with
+// the priority-ordered worker set (oracle/lc_order_patch.sh -> refdump_lcorder); the unmodified
+// build produces the same record layout for the statistical comparison.
+int dumpRunLC(const char *cfg, int steps, int threads, const char *outPath, int every) {
+    Engine e(cfg, threads);
+    Index ix(e);
+    Out o(outPath);
+    const auto &lanes = e.roadnet.getLanes();
+    o.i32(0x43464C31);  // 'CFL1'
+    o.i32((int32_t) lanes.size());
+    for (int s = 0; s < steps; ++s) {
+        e.nextStep();
+        if ((s + 1) % every != 0 && s + 1 != steps) continue;
+        std::vector<const Vehicle *> run;
+        for (const auto &vp : e.vehiclePool)
+            if (vp.second.first->isRunning()) run.push_back(vp.second.first);
+        o.i32(s + 1);
+        o.i32((int32_t) e.getVehicleCount());
+        o.i32((int32_t) run.size());
+        o.i32((int32_t) e.vehiclePool.size());
+        o.i32(e.finishedVehicleCnt);
+        o.f64(e.cumulativeTravelTime);
+        for (Lane *l : lanes) o.i32((int32_t) l->getVehicleCount());
+        for (Intersection &in : e.roadnet.getIntersections())
+            o.i32(in.isVirtualIntersection() ? -1 : in.getTrafficLight().getCurrentPhaseIndex());
+        for (const Vehicle *v : run) {
+            int32_t f, c;
+            parseId(v->getId(), f, c);
+            const LaneChange &lc = *v->laneChange;
+            o.i32(f); o.i32(c);
+            o.i32(v->getPriority());
+            o.i32(v->laneChangeInfo.partnerType);
+            o.i32(v->getPartner() ? v->getPartner()->getPriority() : -1);
+            o.i32(ix.drivable[v->getCurDrivable()]);
+            o.i32(v->getLeader() ? v->getLeader()->getPriority() : -1);
+            o.i32(v->getBlocker() ? v->getBlocker()->getPriority() : -1);
+            o.i32((int32_t) lc.changing | ((int32_t) lc.finished << 1));
+            o.i32(lc.lastDir);
+            o.f64(v->getDistance());
+            o.f64(v->getSpeed());
+            o.f64(v->getLeader() ? v->getGap() : 0.0);
+            o.f64(v->laneChangeInfo.offset);
+            o.f64(lc.waitingTime);
+            o.f64(lc.lastChangeTime);
+        }
+        for (Drivable *d : e.roadnet.getDrivables()) {  // list order (front -> back) as priorities
+            o.i32((int32_t) d->getVehicles().size());
+            for (Vehicle *v : d->getVehicles()) o.i32(v->getPriority());
+        }
+    }
+    return 0;
+}
+
 int bench(const char *cfg, int steps, int threads, int warmup) {
     auto t0 = std::chrono::steady_clock::now();
     Engine e(cfg, threads);
@@ -231,8 +288,10 @@ int main(int argc, char **argv) {
     if (argc >= 4 && !strcmp(argv[1], "static")) return dumpStatic(argv[2], argv[3]);
     if (argc >= 6 && !strcmp(argv[1], "run"))
         return dumpRun(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
+    if (argc >= 6 && !strcmp(argv[1], "runlc"))
+        return dumpRunLC(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
     if (argc >= 5 && !strcmp(argv[1], "bench"))
         return bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0);
-    fprintf(stderr, "usage: refdump static|run|bench ...\n");
+    fprintf(stderr, "usage: refdump static|run|runlc|bench ...\n");
     return 64;
 }
