@@ -97,6 +97,7 @@ struct Veh {
     double leaderGap = 0, followerGap = 0, waitingTime = 0;
     bool changing = false, lcFinished = false;
     double lastChangeTime = 0;
+    double ctlHead = 0;              // device form: order-independent part of the next speed
     bool isReal() const { return partnerType != 2; }                                   // vehicle.h:278
     bool planChange() const { return (sigSend && sigSend->target >= 0 && sigSend->target != drivable) || changing; }  // lanechange.cpp:23-25
 };
@@ -133,6 +134,11 @@ struct Oracle {
     // laneChange=true (restated against the reference built with the priority-ordered worker set,
     // oracle/lc_order_patch.sh): segment index per lane (roadnet.cpp:687-691, :852-875)
     bool laneChange = false;
+    // "Device form" (DESIGN.md section 10): the same step computed in the decomposition planned for the
+    // GPU -- order-independent work in arbitrary order, per-road scheduling, only the few vehicles
+    // involved in a lane change processed in priority order.  Must give identical states; exists to
+    // check that decomposition on the CPU (tests/test_cpu.py).
+    bool deviceForm = false;
     std::vector<std::vector<double>> segStart;            // [lane][segment] startPos
     std::vector<std::vector<std::vector<Veh *>>> segVeh;  // [lane][segment] vehicles, list order
     int ties = 0;  // pushBuffer ties (same target drivable, equal dis): order unspecified in the reference
@@ -344,12 +350,20 @@ struct Oracle {
         return s;
     }
     // vehicle.cpp:308-335 (laneChange off)
-    double nextSpeed(Veh &v) {
+    // The part of getNextSpeed that reads only state committed before the phase (and buffers only
+    // the vehicle's own blocker): independent of the order vehicles are processed in.
+    double nextSpeedHead(Veh &v) {
         double s = v.t.maxSpeed;
         s = min2(s, v.t.speed + v.t.maxPosAcc * interval);
         s = min2(s, drvMaxSpeed(v.drivable));
         s = min2(s, carFollowSpeed(v));
         if (isIntersectionRelated(v)) s = min2(s, intersectionRelatedSpeed(v));
+        return s;
+    }
+    double nextSpeed(Veh &v) {
+        double s;
+        if (deviceForm) { s = v.ctlHead; }   // computed by controlDeviceForm()'s first pass
+        else s = nextSpeedHead(v);
         if (laneChange) {  // vehicle.cpp:323-329 (the yield term is a no-op without signals)
             s = min2(s, yieldSpeed(v));
             if (!onValidLane(v)) {
@@ -518,9 +532,12 @@ struct Oracle {
         sh->bDis = v.bDis; sh->bDelta = v.bDelta; sh->bSpeed = v.bSpeed; sh->bCustom = v.bCustom;
         sh->bDrv = v.bDrv; sh->bEnd = v.bEnd; sh->bBlocker = v.bBlocker; sh->bEnter = v.bEnter;
         sh->flow = v.flow; sh->cnt = v.cnt;   // id + "_shadow": same (flow, cnt), told apart by priority
-        do { sh->priority = (int) rnd(); } while (pool.count(sh->priority));
         sh->enterTime = v.enterTime;
-        pool.emplace(sh->priority, sh);
+        if (deferShadowPriority) sh->priority = INT_MIN;   // device form: drawn after all roads are done
+        else {
+            do { sh->priority = (int) rnd(); } while (pool.count(sh->priority));
+            pool.emplace(sh->priority, sh);
+        }
         // LaneChange::insertShadow
         v.changing = true;
         v.waitingTime = 0;
@@ -561,6 +578,7 @@ struct Oracle {
         // same library sort and comparator as the reference: with every urgency equal to 1 the
         // (unstable) result is a function of the input order alone
         std::sort(buffer.begin(), buffer.end(), [](Veh *a, Veh *b) { return a->sigSend->urgency > b->sigSend->urgency; });
+        if (deviceForm) { scheduleByRoad(buffer); return; }
         for (Veh *v : buffer) {
             updateLeaderAndFollower(*v);
             if (v->targetLeader) receiveSignal(*v->targetLeader, *v);      // SimpleLaneChange::sendSignal lanechange.cpp:207-210
@@ -570,6 +588,59 @@ struct Oracle {
                 if (gapValid && !isLink(v->drivable)) insertShadow(*v);
             }
         }
+    }
+    // Device form of scheduleLaneChange: candidates of different roads never interact (a candidate
+    // reads its road's lanes and the laneLinks leaving them, writes signals of vehicles on those), so
+    // every road walks ITS candidates in the global order, roads in any order (here: descending);
+    // the shadows' priorities -- the only global coupling, through the RNG -- are drawn afterwards
+    // in the global order.
+    void scheduleByRoad(const std::vector<Veh *> &buffer) {
+        std::vector<std::vector<Veh *>> byRoad(net.nRoads());
+        for (Veh *v : buffer) byRoad[net.laneRoad[v->drivable]].push_back(v);   // candidates are on lanes (planChange)
+        statCandidates += (long long) buffer.size();
+        statMaxCandidates = std::max(statMaxCandidates, (int) buffer.size());
+        for (auto &b : byRoad) statMaxCandidatesPerRoad = std::max(statMaxCandidatesPerRoad, (int) b.size());
+        deferShadowPriority = true;
+        for (int r = net.nRoads() - 1; r >= 0; --r)
+            for (Veh *v : byRoad[r]) {
+                updateLeaderAndFollower(*v);
+                if (v->targetLeader) receiveSignal(*v->targetLeader, *v);
+                if (v->targetFollower) receiveSignal(*v->targetFollower, *v);
+                if (v->planChange() && (v->sigSend && !v->sigRecv) && !v->changing) {
+                    const bool gapValid = v->leaderGap >= minBrakeDistance(*v) && v->followerGap >= safeGapBefore(*v);
+                    if (gapValid && !isLink(v->drivable)) insertShadow(*v);
+                }
+            }
+        deferShadowPriority = false;
+        for (Veh *v : buffer)
+            if (v->partnerType == 1 && v->partner->priority == INT_MIN) {   // got its shadow in this step
+                Veh *sh = v->partner;
+                do { sh->priority = (int) rnd(); } while (pool.count(sh->priority));
+                pool.emplace(sh->priority, sh);
+            }
+    }
+    bool deferShadowPriority = false;
+    // sizes of the sequential parts of the device form, summed / maximised over the steps so far
+    long long statCandidates = 0, statInvolved = 0, statRunning = 0;
+    int statMaxCandidatesPerRoad = 0, statMaxInvolved = 0, statMaxCandidates = 0;
+    // Device form of threadGetAction: pass 1 in arbitrary (here: descending priority) order computes
+    // what does not depend on the order; pass 2 finishes the plain vehicles in arbitrary order and
+    // only the vehicles involved in a lane change (a partner, or a received signal) in ascending
+    // priority, as the reference's single worker does.
+    void controlDeviceForm() {
+        for (auto it = pool.rbegin(); it != pool.rend(); ++it)
+            if (it->second->running) it->second->ctlHead = nextSpeedHead(*it->second);
+        std::vector<Veh *> involved;
+        for (auto it = pool.rbegin(); it != pool.rend(); ++it) {
+            Veh *v = it->second;
+            if (!v->running) continue;
+            if (v->partner || v->sigRecv || v->partnerType != 0 || v->changing) involved.push_back(v);
+            else vehicleControl(*v);
+        }
+        statInvolved += (long long) involved.size();
+        statMaxInvolved = std::max(statMaxInvolved, (int) involved.size());
+        statRunning += (long long) activeCount;
+        for (auto it = involved.rbegin(); it != involved.rend(); ++it) vehicleControl(**it);   // ascending priority
     }
     // LaneChange::finishChanging lanechange.cpp:115-127 + Vehicle::finishChanging vehicle.cpp:378-381
     void finishChanging(Veh &v) {
@@ -913,8 +984,10 @@ struct Oracle {
         }
         notifyCross();
         // threadGetAction: running vehicles; order only matters for pushBuffer ties
-        for (auto &kv : pool)
-            if (kv.second->running) vehicleControl(*kv.second);
+        if (deviceForm) controlDeviceForm();
+        else
+            for (auto &kv : pool)
+                if (kv.second->running) vehicleControl(*kv.second);
         updateLocation();
         updateAction();
         updateLeaderAndGapAll();
@@ -1151,6 +1224,13 @@ int cfo_drivable_priorities(void *h, int drivable, int32_t *out, int cap) {
     return n;
 }
 int cfo_lane_change(void *h) { return ((Oracle *) h)->laneChange ? 1 : 0; }
+// switch to the decomposition planned for the GPU (must not change any result)
+void cfo_device_form_stats(void *h, double out[6]) {
+    Oracle *o = (Oracle *) h;
+    out[0] = (double) o->statCandidates; out[1] = o->statMaxCandidates; out[2] = o->statMaxCandidatesPerRoad;
+    out[3] = (double) o->statInvolved; out[4] = o->statMaxInvolved; out[5] = (double) o->statRunning;
+}
+void cfo_set_device_form(void *h, int on) { ((Oracle *) h)->deviceForm = on != 0; }
 // list order of one drivable as (flow,cnt) pairs; returns the count
 int cfo_drivable_vehicles(void *h, int drivable, int32_t *out, int cap) {
     Oracle *o = (Oracle *) h;
