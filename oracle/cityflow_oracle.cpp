@@ -383,6 +383,19 @@ struct Oracle {
     int outerLane(int l) const { return net.laneIdx[l] < net.roadNumLanes(net.laneRoad[l]) - 1 ? l + 1 : -1; } // roadnet.h:339-342
     // Lane::initSegments roadnet.cpp:863-875
     void initSegments() {
+        if (deviceForm) {  // no segment lists: segmentIndex(p) = min(natural segment of p, segmentIndex(p-1)), a prefix-min
+            for (int l = 0; l < nLanes(); ++l) {
+                int run = (int) segStart[l].size() - 1;
+                for (Veh *v : lists[l]) {
+                    int nat = (int) segStart[l].size() - 1;
+                    while (nat > 0 && !(v->dis >= segStart[l][nat])) --nat;   // highest i with dis >= startPos(i); segment 0 starts at 0
+                    if (!(v->dis >= segStart[l][nat])) nat = -1;              // (dis < 0 cannot happen; the reference would skip the vehicle)
+                    run = std::min(run, nat);
+                    if (run >= 0) v->segIndex = (size_t) run;
+                }
+            }
+            return;
+        }
         for (int l = 0; l < nLanes(); ++l) {
             auto it = lists[l].begin(), end = lists[l].end();
             for (int i = (int) segStart[l].size() - 1; i >= 0; --i) {
@@ -398,6 +411,12 @@ struct Oracle {
     }
     // Lane::getVehicleBeforeDistance roadnet.cpp:877-887
     Veh *vehicleBefore(int lane, double dis, size_t segIndex) const {
+        if (deviceForm) {  // the segment lists are the list filtered by segmentIndex
+            for (int i = (int) segIndex; i >= 0; --i)
+                for (Veh *v : lists[lane])
+                    if ((int) v->segIndex == i && v->dis < dis) return v;
+            return nullptr;
+        }
         for (int i = (int) segIndex; i >= 0; --i)
             for (Veh *v : segVeh[lane][i])
                 if (v->dis < dis) return v;
@@ -405,6 +424,12 @@ struct Oracle {
     }
     // Lane::getVehicleAfterDistance roadnet.cpp:889-898
     Veh *vehicleAfter(int lane, double dis, size_t segIndex) const {
+        if (deviceForm) {
+            for (size_t i = segIndex; i < segStart[lane].size(); ++i)
+                for (auto it = lists[lane].rbegin(); it != lists[lane].rend(); ++it)
+                    if ((*it)->segIndex == i && (*it)->dis >= dis) return *it;
+            return nullptr;
+        }
         for (size_t i = segIndex; i < segVeh[lane].size(); ++i)
             for (auto it = segVeh[lane][i].rbegin(); it != segVeh[lane][i].rend(); ++it)
                 if ((*it)->dis >= dis) return *it;
@@ -550,16 +575,24 @@ struct Oracle {
         auto &L = lists[target];
         auto pos = L.end();
         if (v.targetFollower) {  // targetFollower->getListIterator(): looked up through ITS segment (vehicle.cpp:404-411)
-            auto &sv = segVeh[target][v.targetFollower->segIndex];
-            if (std::find(sv.begin(), sv.end(), v.targetFollower) != sv.end())
-                pos = std::find(L.begin(), L.end(), v.targetFollower);
+            if (deviceForm) pos = std::find(L.begin(), L.end(), v.targetFollower);
+            else {
+                auto &sv = segVeh[target][v.targetFollower->segIndex];
+                if (std::find(sv.begin(), sv.end(), v.targetFollower) != sv.end())
+                    pos = std::find(L.begin(), L.end(), v.targetFollower);
+            }
         }
         L.insert(pos, sh);
-        {   // Segment::insertVehicle roadnet.cpp:944-948 (into the segment with the PARENT's index)
+        if (!deviceForm) {   // Segment::insertVehicle roadnet.cpp:944-948 (into the segment with the PARENT's index)
             auto &sv = segVeh[target][v.segIndex];
             auto it = sv.begin();
             for (; it != sv.end() && (*it)->dis > sh->dis; ++it) {}
             sv.insert(it, sh);
+            // the planned device form reads a segment as "the list filtered by segmentIndex": count
+            // the cases where the segment list is NOT that subsequence (needs two equal distances)
+            std::vector<Veh *> sub;
+            for (Veh *x : L) if (x->segIndex == v.segIndex) sub.push_back(x);
+            if (sub != sv) ++segOrderMismatch;
         }
         updateLeaderAndGap(*sh, v.targetLeader);
         if (v.targetFollower) updateLeaderAndGap(*v.targetFollower, sh);
@@ -620,6 +653,7 @@ struct Oracle {
             }
     }
     bool deferShadowPriority = false;
+    long long segOrderMismatch = 0;
     // sizes of the sequential parts of the device form, summed / maximised over the steps so far
     long long statCandidates = 0, statInvolved = 0, statRunning = 0;
     int statMaxCandidatesPerRoad = 0, statMaxInvolved = 0, statMaxCandidates = 0;
@@ -1230,6 +1264,8 @@ void cfo_device_form_stats(void *h, double out[6]) {
     out[0] = (double) o->statCandidates; out[1] = o->statMaxCandidates; out[2] = o->statMaxCandidatesPerRoad;
     out[3] = (double) o->statInvolved; out[4] = o->statMaxInvolved; out[5] = (double) o->statRunning;
 }
+// reference-ordered mode: shadow insertions after which a segment list was not the lane list filtered by segment index
+long long cfo_segment_order_mismatches(void *h) { return ((Oracle *) h)->segOrderMismatch; }
 void cfo_set_device_form(void *h, int on) { ((Oracle *) h)->deviceForm = on != 0; }
 // list order of one drivable as (flow,cnt) pairs; returns the count
 int cfo_drivable_vehicles(void *h, int drivable, int32_t *out, int cap) {
