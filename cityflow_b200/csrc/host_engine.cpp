@@ -971,6 +971,9 @@ extern "C" int cfb_set_vehicle_route(cfb_engine *e, cfb_vehicle_ref v, const cha
         if (plan < 0) return CFB_OK;                           // !onValidLane(): restore the old route
         if ((size_t) h.routing->numPlans() != h.uploadedPlans) { h.dev->uploadPlans(*h.routing); h.uploadedPlans = h.routing->numPlans(); }
         const int planIdx = h.routing->planBeg()[plan];
+        // onValidLane() (router.h:66-68) also fails when the lane links to the next road but none of
+        // those links ends in a lane that can continue to the road after it (router.cpp:65-73)
+        if (h.routing->planData()[planIdx + 1] == cfb::PLAN_DEAD) return CFB_OK;
         h.dev->setVehiclePlan(s, plan, planIdx, h.routing->planData()[planIdx + 1]);
         h.slots[s].routeId = rid;
         *ok = 1;

@@ -1184,6 +1184,56 @@ void cfo_push_vehicle(void *h, const double *v, const int32_t *roads, int n) {
     Veh *veh = o->newVehicle(t, anchors, -2, o->manuallyPushCnt++);
     o->planRouteBuffer[anchors[0]].push_back(veh);
 }
+// Engine::setVehicleSpeed engine.cpp:827-834 -> Vehicle::setCustomSpeed vehicle.h:128-131; -1 = no such vehicle
+int cfo_set_vehicle_speed(void *h, int flow, int cnt, double speed) {
+    Oracle *o = (Oracle *) h;
+    for (auto &kv : o->pool) {
+        Veh *v = kv.second;
+        if (v->flow == flow && v->cnt == cnt && v->isReal()) {
+            v->bCustom = speed;
+            v->bCustomSet = true;
+            return 0;
+        }
+    }
+    return -1;
+}
+// Engine::setRoute engine.cpp:852-866 -> Router::setRoute router.cpp:245-264: 1 = the vehicle now follows
+// [current road] + roads, 0 = refused (on a laneLink, unreachable, or the current lane cannot continue), -1 = no such vehicle
+int cfo_set_vehicle_route(void *h, int flow, int cnt, const int32_t *roads, int n) {
+    Oracle *o = (Oracle *) h;
+    for (auto &kv : o->pool) {
+        Veh *v = kv.second;
+        if (!(v->flow == flow && v->cnt == cnt && v->isReal())) continue;
+        if (v->drivable < 0 || o->isLink(v->drivable)) return 0;
+        const int curRoad = v->route[v->iCur];
+        std::vector<int> anchors{curRoad};
+        anchors.insert(anchors.end(), roads, roads + n);
+        std::vector<int> backup = v->route, fresh;
+        const int backupCur = v->iCur;
+        bool ok = o->routing->resolve(anchors, fresh);   // Router::updateShortestPath router.cpp:228-243
+        v->planned.clear();
+        if (ok) { v->route = fresh; v->iCur = 0; }
+        if (ok && o->onValidLane(*v)) return 1;
+        v->route = backup;
+        v->planned.clear();
+        v->iCur = backupCur;   // the road cursor goes back to cur_road (router.cpp:258-260)
+        return 0;
+    }
+    return -1;
+}
+// Engine::getLeader engine.cpp:836-850: 1 + (flow, cnt) of the leader, 0 = none, -1 = no such vehicle
+int cfo_get_leader(void *h, int flow, int cnt, int32_t *leaderFlow, int32_t *leaderCnt) {
+    Oracle *o = (Oracle *) h;
+    for (auto &kv : o->pool) {
+        Veh *v = kv.second;
+        if (v->flow == flow && v->cnt == cnt && v->isReal()) {
+            if (!v->leader) return 0;
+            *leaderFlow = v->leader->flow; *leaderCnt = v->leader->cnt;
+            return 1;
+        }
+    }
+    return -1;
+}
 void cfo_set_random_seed(void *h, int seed) { ((Oracle *) h)->rnd.seed(seed); }  // Engine::setRandomSeed engine.h:170
 int cfo_road_index(void *h, const char *id) {
     Oracle *o = (Oracle *) h;

@@ -43,6 +43,22 @@ def have_lc_ref() -> bool:
     return os.path.exists(REFDUMP_LC)
 
 
+def load_reference_module():
+    """The reference's own pybind11 module (oracle/_ref/cityflow*.so), loaded without touching
+    sys.modules['cityflow'] (that name is this repository's drop-in package)."""
+    import glob
+    import importlib.machinery
+    import importlib.util
+    so = glob.glob(os.path.join(os.path.dirname(REFDUMP), "cityflow*.so"))
+    if not so:
+        return None
+    loader = importlib.machinery.ExtensionFileLoader("cityflow", so[0])
+    spec = importlib.util.spec_from_loader("cityflow", loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
+
+
 def have_ref() -> bool:
     return os.path.exists(REFDUMP)
 
@@ -260,6 +276,31 @@ class PortOracle:
         self.lib.cfo_set_random_seed.restype = None
         self.lib.cfo_set_random_seed.argtypes = [ctypes.c_void_p, ctypes.c_int]
         self.lib.cfo_set_random_seed(self.h, seed)
+
+    def set_vehicle_speed(self, flow: int, cnt: int, speed: float) -> bool:
+        self.lib.cfo_set_vehicle_speed.restype = ctypes.c_int
+        self.lib.cfo_set_vehicle_speed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+        return self.lib.cfo_set_vehicle_speed(self.h, flow, cnt, speed) == 0
+
+    def set_vehicle_route(self, flow: int, cnt: int, roads: list) -> bool:
+        self.lib.cfo_road_index.restype = ctypes.c_int
+        self.lib.cfo_road_index.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        r = np.array([self.lib.cfo_road_index(self.h, x.encode()) for x in roads], np.int32)
+        if (r < 0).any():
+            return False            # unknown road id (engine.cpp:859-861)
+        self.lib.cfo_set_vehicle_route.restype = ctypes.c_int
+        self.lib.cfo_set_vehicle_route.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        return self.lib.cfo_set_vehicle_route(self.h, flow, cnt, r.ctypes.data, len(r)) == 1
+
+    def get_leader(self, flow: int, cnt: int):
+        """(flow, cnt) of the leader, None if there is none; KeyError for an unknown vehicle."""
+        self.lib.cfo_get_leader.restype = ctypes.c_int
+        self.lib.cfo_get_leader.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        rc = self.lib.cfo_get_leader(self.h, flow, cnt, ctypes.byref(a), ctypes.byref(b))
+        if rc < 0:
+            raise KeyError((flow, cnt))
+        return (a.value, b.value) if rc else None
 
     def average_travel_time(self) -> float:
         self.lib.cfo_average_travel_time.restype = ctypes.c_double
