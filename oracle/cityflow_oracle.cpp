@@ -364,7 +364,12 @@ struct Oracle {
         double s;
         if (deviceForm) { s = v.ctlHead; }   // computed by controlDeviceForm()'s first pass
         else s = nextSpeedHead(v);
-        if (laneChange) {  // vehicle.cpp:323-329 (the yield term is a no-op without signals)
+        {   // vehicle.cpp:323-329.  `if (laneChange)` there tests the vehicle's LaneChange OBJECT (always
+            // present), not the engine's laneChange option: the block also runs with laneChange=false.
+            // Without signals the yield term is 100 (no effect below 100 m/s); the second term makes a
+            // vehicle whose lane cannot continue its route stop at the end of the lane -- reachable on
+            // networks where a first lane links to the next road only through lanes that cannot reach
+            // the road after it (router.cpp:23-37 vs :65-73).
             s = min2(s, yieldSpeed(v));
             if (!onValidLane(v)) {
                 double vn = noCollisionSpeed(0, 1, v.t.speed, v.t.maxNegAcc, drvLength(v.drivable) - v.dis, interval, v.t.minGap);
