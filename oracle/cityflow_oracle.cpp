@@ -1312,6 +1312,15 @@ int cfo_drivable_priorities(void *h, int drivable, int32_t *out, int cap) {
     }
     return n;
 }
+// running vehicles whose lane cannot continue their route (Router::onValidLane false): the case the GPU
+// engine does not handle like the reference yet ("Fuzzing")
+int cfo_invalid_lane_vehicles(void *h) {
+    Oracle *o = (Oracle *) h;
+    int n = 0;
+    for (auto &kv : o->pool)
+        if (kv.second->running && !o->onValidLane(*kv.second)) ++n;
+    return n;
+}
 int cfo_lane_change(void *h) { return ((Oracle *) h)->laneChange ? 1 : 0; }
 // switch to the decomposition planned for the GPU (must not change any result)
 void cfo_device_form_stats(void *h, double out[6]) {

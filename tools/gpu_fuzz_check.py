@@ -64,9 +64,10 @@ def fuzz(first, last, steps=500):
                 print("seed %d step %d: engine error: %s" % (seed, s, str(e)[:120]))
                 break
             if bad:
-                # a parked vehicle on a dead-end lane changes everything behind it: classify by whether the
-                # restatement holds a vehicle whose lane cannot continue (next drivable < 0, not on its last road)
-                verdict = "UNEXPECTED"
+                # a vehicle braking for the end of a dead-end lane changes everything behind it: a mismatch is
+                # the known divergence iff the restatement holds such a vehicle at this point
+                ora.lib.cfo_invalid_lane_vehicles.restype = __import__('ctypes').c_int; ora.lib.cfo_invalid_lane_vehicles.argtypes = [__import__('ctypes').c_void_p]
+                verdict = "dead_end_divergence" if ora.lib.cfo_invalid_lane_vehicles(ora.h) > 0 else "UNEXPECTED"
                 print("seed %d step %d: %s" % (seed, s, "; ".join(bad[:3])))
                 break
         summary[verdict] += 1
