@@ -719,6 +719,15 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
             }
             v = min2(v, s);
         }
+#ifdef CFB_DEAD_END_STOP
+        // vehicle.cpp:323-329 runs with laneChange=false too (the `if` there tests the LaneChange OBJECT):
+        // yieldSpeed() is 100 without signals, and a vehicle whose lane cannot continue its route stops
+        // at the end of the lane.  Found by the fuzz tests; NOT compiled in by
+        // default until it has been validated on a GPU (tools/gpu_fuzz_check.py).
+        v = min2(v, 100.0);
+        if (!onLink && nd0 == PLAN_DEAD)
+            v = min2(v, noCollisionSpeed(0, 1, speed, T.maxNegAcc, dLen - dis, dt, T.minGap));
+#endif
         v = max2(v, speed - T.maxNegAcc * dt);
         // ---- Engine::vehicleControl ----
         double deltaDis;
