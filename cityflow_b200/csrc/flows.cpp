@@ -98,11 +98,13 @@ int Routing::chooseLink(int lane, const std::vector<int> &roads, int r) const {
     return best < 0 ? PLAN_DEAD : best;
 }
 
-int Routing::buildPlan(const std::vector<int> &roads, int startLane) {
+int Routing::buildPlan(const std::vector<int> &roads, int startLane, int roadPos, int routeId) {
     const int id = (int) planBeg_.size();
     planBeg_.push_back((int) planData_.size());
+    planRoute_.push_back(routeId);
+    planRoadPos_.push_back(roadPos);
     int lane = startLane;
-    for (int r = 0;; ++r) {
+    for (int r = roadPos;; ++r) {
         planData_.push_back(lane);
         int ll = chooseLink(lane, roads, r);
         if (ll < 0) {
@@ -129,9 +131,25 @@ int Routing::intern(const std::vector<int> &anchors) {
                 if (net_.laneRoad[net_.llEndLane[ll]] == rt.roads[1]) { ok = true; break; }
             if (ok) rt.startLanes.push_back(l);
         }
-        for (int l : rt.startLanes) rt.planOfStartLane.push_back(buildPlan(rt.roads, l));
     }
     const int id = (int) routes_.size();
+    if (rt.valid)
+        for (int l : rt.startLanes) rt.planOfStartLane.push_back(buildPlan(rt.roads, l, 0, id));
+    lanePlanRoad_.push_back((int) lanePlanBeg_.size());
+    if (rt.valid && lanePlans_) {
+        for (int r = 0; r < (int) rt.roads.size(); ++r) {
+            lanePlanBeg_.push_back((int) lanePlanId_.size());
+            const int road = rt.roads[r];
+            for (int l = net_.roadLaneBeg[road]; l < net_.roadLaneBeg[road + 1]; ++l) {
+                int plan = -1;
+                if (r == 0)
+                    for (size_t k = 0; k < rt.startLanes.size(); ++k)
+                        if (rt.startLanes[k] == l) plan = rt.planOfStartLane[k];
+                if (plan < 0) plan = buildPlan(rt.roads, l, r, id);
+                lanePlanId_.push_back(plan);
+            }
+        }
+    }
     routes_.push_back(std::move(rt));
     byAnchors_[anchors] = id;
     return id;

@@ -65,14 +65,34 @@ public:
     int numPlans() const { return (int) planBeg_.size(); }
     // next laneLink for a vehicle on `lane` whose route continues with roads[r+1] (, roads[r+2])
     int chooseLink(int lane, const std::vector<int> &roads, int r) const;
+    // Lane change (not enabled by the engine yet): a shadow vehicle continues its
+    // parent's route from the lane it was inserted into, so every lane of every road of a route gets
+    // a plan.  Must be switched on before the first intern().
+    void enableLanePlans() { lanePlans_ = true; }
+    bool lanePlansEnabled() const { return lanePlans_; }
+    // plan that starts on lane `laneIdx` of the route's road number `roadPos`
+    int lanePlan(int routeId, int roadPos, int laneIdx) const {
+        return lanePlanId_[lanePlanBeg_[lanePlanRoad_[routeId] + roadPos] + laneIdx];
+    }
+    int planRoute(int plan) const { return planRoute_[plan]; }      // route a plan belongs to
+    int planRoadPos(int plan) const { return planRoadPos_[plan]; }  // position in that route of the plan's first road
+    const std::vector<int> &lanePlanRoadTable() const { return lanePlanRoad_; }
+    const std::vector<int> &lanePlanBegTable() const { return lanePlanBeg_; }
+    const std::vector<int> &lanePlanIdTable() const { return lanePlanId_; }
+    const std::vector<int> &planRouteTable() const { return planRoute_; }
+    const std::vector<int> &planRoadPosTable() const { return planRoadPos_; }
 
 private:
     bool dijkstra(int start, int end, std::vector<int> &buffer) const;
-    int buildPlan(const std::vector<int> &roads, int startLane);
+    int buildPlan(const std::vector<int> &roads, int startLane, int roadPos = 0, int routeId = -1);
     const RoadNet &net_;
     std::vector<Route> routes_;
     std::map<std::vector<int>, int> byAnchors_;
     std::vector<int> planData_, planBeg_;
+    bool lanePlans_ = false;
+    std::vector<int> planRoute_, planRoadPos_;            // per plan
+    std::vector<int> lanePlanRoad_;                       // per route: first entry of its roads in lanePlanBeg_
+    std::vector<int> lanePlanBeg_, lanePlanId_;           // per (route, road position): first entry of its lanes in lanePlanId_
 };
 
 // Parses the flow file; returns false with a message on stderr on format errors.
