@@ -95,6 +95,12 @@ struct Ctrl {
 // (per-vehicle cycle / path samples of k_control are recorded in this build: tools/dbg_control_cycles.py)
 #endif
 
+#ifdef CFB_LANE_CHANGE
+}  // namespace cfb
+#include "device_lc_types.cuh"
+namespace cfb {
+#endif
+
 constexpr int HEAD_BIT = 0x40000000;   // in vehList[].y: the vehicle is the first of its drivable's list
 constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
 constexpr int PLAN_LOOKAHEAD_END = -1;
@@ -163,6 +169,10 @@ struct View {
     unsigned *dbgCyc, *dbgPath;   // CFB_DEBUG_COUNTERS builds: per-position cycles / path bits of k_control
     Ctrl *ctrl;
     const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
+#ifdef CFB_LANE_CHANGE
+    int lcOn;                   // "laneChange": true
+    LcView lc;
+#endif
 };
 
 // ------------------------------------------------------------------------------------------
@@ -358,9 +368,15 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
                 Tail nt;
                 nt.dis = 0.0; nt.len = T.len; nt.speed = T.speed0; nt.pos = p; nt.prev = -1;
                 V.tail[i] = nt;
+#ifdef CFB_LANE_CHANGE
+                if (V.lcOn) lcResetSlot(V.lc.slot[h], info.z);
+#endif
                 if (n > 0) {
                     V.leader[p] = p - 1;
                     V.gap[p] = tl.dis - tl.len - 0.0;
+#ifdef CFB_LANE_CHANGE
+                    if (V.lcOn) V.lc.slot[h].gap = tl.dis - tl.len - 0.0;
+#endif
                     ins = 1;
                 } else {
                     V.leader[p] = -1;
@@ -510,6 +526,9 @@ __device__ __forceinline__ void phase_notify(const View &V, const int bid, const
             headSearch(V, d, 0.0, idv.w, V.nav[base].x, V.tmpl[idv.y], d, ld, g);
             V.leader[base] = ld;
             if (ld >= 0) V.gap[base] = g;
+#ifdef CFB_LANE_CHANGE
+            if (V.lcOn && ld >= 0) V.lc.slot[idv.x].gap = g;
+#endif
         }
         // the link the tail came out of, if it is empty now (otherwise it is on the list itself)
         const int prev = V.nav[base + c - 1].y;
@@ -597,6 +616,12 @@ __device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, 
     }
     return yield == -1;
 }
+
+#ifdef CFB_LANE_CHANGE
+}  // namespace cfb
+#include "device_lc.cuh"
+namespace cfb {
+#endif
 
 // k_control: one thread per running vehicle (grid-stride over the position list).
 // Vehicle::getNextSpeed vehicle.cpp:308-335, getCarFollowSpeed :212-238, getIntersectionRelatedSpeed
@@ -719,6 +744,24 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
             }
             v = min2(v, s);
         }
+#ifdef CFB_LANE_CHANGE
+        if (V.lcOn) {   // vehicle.cpp:323-329 / engine.cpp:195-244, see device_lc.cuh
+            LcSlot &L = V.lc.slot[idv.x];
+            if (L.partner >= 0 || lcRecvValid(L, epoch) || L.type != 0 || L.changing) {
+                // involved in a lane change: the rest depends on the order vehicles are processed in
+                L.head = v;
+                L.headBlocker = newBlocker;
+                const int k = atomicAdd(&V.lc.ctrl->nInvolved, 1);
+                if (k < LC_MAX_CAND) V.lc.involved[k] = idv.x; else atomicOr(&V.lc.ctrl->error, 1);
+                continue;
+            }
+            if (lcPlanChange(L, d, epoch)) L.waiting += dt;                 // yieldSpeed's side effect (lanechange.cpp:190)
+            v = min2(v, 100.0);                                             // no signal received: yieldSpeed() == 100
+            if (!onLink && nd0 == PLAN_DEAD)
+                v = min2(v, noCollisionSpeed(0, 1, speed, T.maxNegAcc, dLen - dis, dt, T.minGap));
+            lcClearSignal(L, epoch);                                        // Engine::threadUpdateAction (engine.cpp:424)
+        }
+#endif
 #ifdef CFB_DEAD_END_STOP
         // vehicle.cpp:323-329 runs with laneChange=false too (the `if` there tests the LaneChange OBJECT):
         // yieldSpeed() is 100 without signals, and a vehicle whose lane cannot continue its route stops
@@ -851,7 +894,13 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 V.pos[idv.x] = -1;
                 blkSet(V, idv.x, -2);
                 const int f = atomicAdd(&V.ctrl->finCount, 1);
+#ifdef CFB_LANE_CHANGE
+                // a vehicle replaced by its shadow is not a "finished vehicle" (engine.cpp:297-301): flagged for the host
+                const int finTag = (V.lcOn && V.lc.slot[idv.x].finished) ? (idv.x | 0x40000000) : idv.x;
+                if (f < V.finCap) V.finSlots[f] = make_int2(finTag, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
+#else
                 if (f < V.finCap) V.finSlots[f] = make_int2(idv.x, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
+#endif
                 atomicSub(&V.ctrl->active, 1);
             }
             nsurv += __popc(mask);
@@ -987,6 +1036,9 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
                 }
                 V.leader[p] = p - 1;
                 V.gap[p] = pd - pl - dis;
+#ifdef CFB_LANE_CHANGE
+                if (V.lcOn) V.lc.slot[idv.x].gap = pd - pl - dis;
+#endif
             }
         }
     }
@@ -1002,6 +1054,9 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
         headSearch(V, d, V.kin[p].x, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
         V.leader[p] = ld;
         if (ld >= 0) V.gap[p] = g;
+#ifdef CFB_LANE_CHANGE
+        if (V.lcOn && ld >= 0) V.lc.slot[idv.x].gap = g;
+#endif
     }
 }
 __global__ void __launch_bounds__(256) k_leader(View V) { phase_leader(V, blockIdx.x, gridDim.x); }
