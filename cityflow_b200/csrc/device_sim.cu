@@ -759,7 +759,10 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
             v = min2(v, 100.0);                                             // no signal received: yieldSpeed() == 100
             if (!onLink && nd0 == PLAN_DEAD)
                 v = min2(v, noCollisionSpeed(0, 1, speed, T.maxNegAcc, dLen - dis, dt, T.minGap));
-            lcClearSignal(L, epoch);                                        // Engine::threadUpdateAction (engine.cpp:424)
+            // Engine::threadUpdateAction -> clearSignal (engine.cpp:424) happens after EVERY vehicle's control:
+            // a receiver finished later (k_lc_control_tail) still reads this vehicle's target leader /
+            // follower, so only lastDir is taken here; the epoch-stamped signals expire by themselves
+            L.lastDir = lcSendValid(L, epoch) ? L.sendDir : 0;
         }
 #endif
 #ifdef CFB_DEAD_END_STOP
@@ -1384,6 +1387,16 @@ struct DeviceSim::Impl {
     DevBuf<unsigned char> flushBuf;
     KernelTimes times;
 
+#ifdef CFB_LANE_CHANGE
+    DevBuf<LcSlot> lcSlot;
+    DevBuf<int> lcSegIdx, lcPosDrv, lcSegBeg, lcLaneIdx, lcLaneRoadN, lcPlanRoute, lcPlanRoadPos, lcLanePlanRoad,
+        lcLanePlanBeg, lcLanePlanId, lcCand, lcInvolved, lcSpare, lcPrio;
+    DevBuf<double> lcSegStart, lcLaneWidth;
+    DevBuf<int2> lcShadowLog;
+    DevBuf<LcCtrl> lcCtrl;
+    LcCtrl *hLcCtrl = nullptr;        // pinned readback
+    int lcSpareCap = 0;
+#endif
     int slotCap = 0;
     int numSMs = 148;
     int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
@@ -1644,6 +1657,16 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     std::swap(I.slotCust.p, ncust.p); std::swap(I.slotCust.n, ncust.n);
     std::swap(I.blk.p, nblk.p); std::swap(I.blk.n, nblk.n);
     std::swap(I.delStep.p, ndel.p); std::swap(I.delStep.n, ndel.n);
+#ifdef CFB_LANE_CHANGE
+    if (I.V.lcOn) {
+        DevBuf<LcSlot> nlc;
+        nlc.alloc(cap);
+        nlc.fill(0);
+        if (I.slotCap) CFB_CUDA(cudaMemcpy(nlc.p, I.lcSlot.p, I.slotCap * sizeof(LcSlot), cudaMemcpyDeviceToDevice));
+        std::swap(I.lcSlot.p, nlc.p); std::swap(I.lcSlot.n, nlc.n);
+        I.V.lc.slot = I.lcSlot.p;
+    }
+#endif
     legacySync();   // ... and the copies before the old buffers are freed / the new ones are used
     I.slotCap = cap;
     I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p; I.V.blk = I.blk.p; I.V.delStep = I.delStep.p;
@@ -2457,5 +2480,158 @@ void DeviceSim::setPhase(int intersection, int phase) {
     I.hPhase[intersection] = phase;
     I.phaseDirty = true;
 }
+
+#ifdef CFB_LANE_CHANGE
+// ------------------------------------------------------------------------------------------
+// Lane change, DRAFT (device_lc.cuh).  Not validated on a GPU yet; not compiled by default.
+void DeviceSim::uploadLanePlans(const Routing &routing) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    auto up = [](DevBuf<int> &b, std::vector<int> v) { if (v.empty()) v.push_back(0); b.upload(v); };
+    up(I.lcPlanRoute, routing.planRouteTable());
+    up(I.lcPlanRoadPos, routing.planRoadPosTable());
+    up(I.lcLanePlanRoad, routing.lanePlanRoadTable());
+    up(I.lcLanePlanBeg, routing.lanePlanBegTable());
+    up(I.lcLanePlanId, routing.lanePlanIdTable());
+    LcView &C = I.V.lc;
+    C.planRoute = I.lcPlanRoute.p; C.planRoadPos = I.lcPlanRoadPos.p;
+    C.lanePlanRoad = I.lcLanePlanRoad.p; C.lanePlanBeg = I.lcLanePlanBeg.p; C.lanePlanId = I.lcLanePlanId.p;
+    legacySync();
+}
+
+void DeviceSim::enableLaneChange(const RoadNet &net, const Routing &routing) {
+    Impl &I = *impl_;
+    View &V = I.V;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    const int nL = net.nLanes();
+    // Road::buildSegmentationByInterval roadnet.cpp:687-691 with (len + minGap) * MAX_NUM_CARS_ON_SEGMENT of a
+    // default VehicleInfo = (5 + 2) * 10 (roadnet.cpp:305-312, config.h:5); Lane::buildSegmentation :852-861
+    std::vector<int> segBeg(nL + 1, 0), laneIdx(nL), laneRoadN(nL);
+    std::vector<double> segStart, laneWidth(nL);
+    for (int r = 0; r < net.nRoads(); ++r) {
+        double len = 0.0;
+        const auto &pts = net.roadPoints[r];
+        for (size_t i = 0; i + 1 < pts.size(); ++i) {
+            const double dx = pts[i + 1].x - pts[i].x, dy = pts[i + 1].y - pts[i].y;
+            len += sqrt(dx * dx + dy * dy);
+        }
+        const size_t numSegs = std::max((size_t) ceil(len / ((5.0 + 2.0) * 10)), (size_t) 1);
+        for (int l = net.roadLaneBeg[r]; l < net.roadLaneBeg[r + 1]; ++l) {
+            segBeg[l] = (int) segStart.size();
+            for (size_t i = 0; i < numSegs; ++i) segStart.push_back(i * net.laneLength[l] / numSegs);
+            laneIdx[l] = net.laneIdx[l];
+            laneRoadN[l] = net.roadNumLanes(r);
+            laneWidth[l] = net.laneWidth[l];
+        }
+    }
+    segBeg[nL] = (int) segStart.size();
+    std::vector<int> posDrv(I.P);
+    for (int d = 0; d < V.nDrv; ++d)
+        for (int p = I.offHost[d]; p < I.offHost[d + 1]; ++p) posDrv[p] = d;
+    I.lcSegBeg.upload(segBeg); I.lcSegStart.upload(segStart); I.lcLaneIdx.upload(laneIdx); I.lcLaneRoadN.upload(laneRoadN);
+    I.lcLaneWidth.upload(laneWidth); I.lcPosDrv.upload(posDrv);
+    I.lcSegIdx.alloc(I.P); I.lcSegIdx.fill(0);
+    I.lcCand.alloc(LC_MAX_CAND); I.lcInvolved.alloc(LC_MAX_CAND); I.lcShadowLog.alloc(LC_MAX_CAND); I.lcPrio.alloc(LC_MAX_CAND);
+    I.lcCtrl.alloc(1); I.lcCtrl.fill(0);
+    I.lcSlot.alloc(std::max(I.slotCap, 1)); I.lcSlot.fill(0);
+    CFB_CUDA(cudaMallocHost(&I.hLcCtrl, sizeof(LcCtrl)));
+    LcView &C = V.lc;
+    C.slot = I.lcSlot.p; C.segIdx = I.lcSegIdx.p; C.posDrv = I.lcPosDrv.p; C.segBeg = I.lcSegBeg.p; C.segStart = I.lcSegStart.p;
+    C.laneIdx = I.lcLaneIdx.p; C.laneRoadN = I.lcLaneRoadN.p; C.laneWidth = I.lcLaneWidth.p;
+    C.cand = I.lcCand.p; C.involved = I.lcInvolved.p; C.shadowLog = I.lcShadowLog.p; C.ctrl = I.lcCtrl.p;
+    C.spare = nullptr; C.nSpare = 0;
+    V.lcOn = 1;
+    I.useGraph = false;   // the step has a host round trip in the middle (shadow priorities come from the engine RNG)
+    I.useCoop = false;
+    legacySync();
+    uploadLanePlans(routing);
+}
+
+void DeviceSim::stepLcBegin(const SpawnRec *recs, int n, const int32_t *spare, int nSpare, std::vector<LcShadow> &created) {
+    stageStep(recs, n);
+    Impl &I = *impl_;
+    View &V = I.V;
+    cudaStream_t s = I.stream;
+    const int TPB = 256;
+    ensureGrids();
+    if (nSpare > I.lcSpareCap) {
+        CFB_CUDA(cudaStreamSynchronize(s));
+        I.lcSpareCap = std::max(1024, nSpare * 2);
+        I.lcSpare.alloc(I.lcSpareCap);
+    }
+    if (nSpare > 0) CFB_CUDA(cudaMemcpyAsync(I.lcSpare.p, spare, nSpare * sizeof(int), cudaMemcpyHostToDevice, s));
+    V.lc.spare = I.lcSpare.p;
+    V.lc.nSpare = nSpare;
+    const int gLaneRL = (std::max(V.nLanes, V.nRL) + TPB - 1) / TPB;
+    k_lc_begin<<<1, 1, 0, s>>>(V.lc);
+    k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
+    k_lc_segments<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
+    k_lc_signal<<<I.gridControl, TPB, 0, s>>>(V, V.lc);
+    k_lc_schedule<<<1, 32, 0, s>>>(V, V.lc);
+    CFB_CUDA(cudaMemcpyAsync(I.hLcCtrl, I.lcCtrl.p, sizeof(LcCtrl), cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaStreamSynchronize(s));
+    CFB_CUDA(cudaGetLastError());
+    if (I.hLcCtrl->error) throw std::runtime_error("cityflow_b200: lane-change capacity exceeded (candidates per step or spare slots)");
+    const int ns = I.hLcCtrl->nShadows;
+    created.resize(ns);
+    if (ns > 0) {
+        static_assert(sizeof(LcShadow) == sizeof(int2), "LcShadow layout");
+        CFB_CUDA(cudaMemcpyAsync(created.data(), I.lcShadowLog.p, ns * sizeof(int2), cudaMemcpyDeviceToHost, s));
+        CFB_CUDA(cudaStreamSynchronize(s));
+    }
+    launches_ += 5;
+}
+
+void DeviceSim::stepLcEnd(const int32_t *priorities, int n) {
+    Impl &I = *impl_;
+    View &V = I.V;
+    cudaStream_t s = I.stream;
+    const int TPB = 256;
+    if (n > 0) {
+        CFB_CUDA(cudaMemcpyAsync(I.lcPrio.p, priorities, n * sizeof(int), cudaMemcpyHostToDevice, s));
+        k_lc_priorities<<<(n + 127) / 128, 128, 0, s>>>(V, V.lc, I.lcPrio.p, n);
+    }
+    k_lc_leader<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
+    k_notify<<<I.gridNotify, TPB, 0, s>>>(V);
+    k_control<<<I.gridControl, 256, 0, s>>>(V);
+    k_lc_control_tail<<<1, 32, 0, s>>>(V, V.lc);
+    k_move<<<I.gridMove, TPB, 0, s>>>(V);
+    k_leader<<<I.gridLeader, TPB, 0, s>>>(V);
+    CFB_CUDA(cudaGetLastError());
+    launches_ += 6 + (n > 0);
+    steps_ += 1;
+}
+
+void DeviceSim::debugDumpLc(std::vector<LcDebugRec> &out) {
+    Impl &I = *impl_;
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    const size_t P = (size_t) I.P;
+    std::vector<int> count(I.V.nDrv), leader(P);
+    std::vector<double2> kin(P);
+    std::vector<int4> ids(P), nav(P);
+    std::vector<LcSlot> lc(I.slotCap);
+    CFB_CUDA(cudaMemcpy(count.data(), I.V.count, count.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(leader.data(), I.V.leader, P * sizeof(int), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(kin.data(), I.V.kin, P * sizeof(double2), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(ids.data(), I.V.ids, P * sizeof(int4), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(nav.data(), I.V.nav, P * sizeof(int4), cudaMemcpyDeviceToHost));
+    CFB_CUDA(cudaMemcpy(lc.data(), I.lcSlot.p, lc.size() * sizeof(LcSlot), cudaMemcpyDeviceToHost));
+    out.clear();
+    for (int d = 0; d < I.V.nDrv; ++d)
+        for (int k = 0; k < count[d]; ++k) {
+            const int p = I.offHost[d] + k;
+            const LcSlot &L = lc[ids[p].x];
+            LcDebugRec r{};
+            r.slot = ids[p].x; r.priority = ids[p].z; r.partnerType = L.type; r.partnerSlot = L.partner; r.drivable = d;
+            r.leaderSlot = leader[p] >= 0 ? ids[leader[p]].x : -1;
+            r.blockerSlot = nav[p].z;
+            r.flags = L.changing | (L.finished << 1);
+            r.lastDir = L.lastDir;
+            r.dis = kin[p].x; r.speed = kin[p].y; r.gap = leader[p] >= 0 ? L.gap : 0.0;
+            r.offset = L.offset; r.waiting = L.waiting; r.lastChange = L.lastChange;
+            out.push_back(r);
+        }
+}
+#endif  // CFB_LANE_CHANGE
 
 }  // namespace cfb

@@ -177,6 +177,25 @@ public:
     int numDrivables() const;
     int device() const;   // CUDA device ordinal the engine lives on
 
+#ifdef CFB_LANE_CHANGE
+    // ---- lane change, DRAFT (device_lc.cuh): not validated on a GPU yet ----
+    struct LcShadow { int32_t parentSlot, shadowSlot; };
+    struct LcDebugRec {   // every running vehicle incl. shadows; mirrors oracle/harness.py LC_DTYPE with slots for identities
+        int32_t slot, priority, partnerType, partnerSlot, drivable, leaderSlot, blockerSlot, flags, lastDir, pad;
+        double dis, speed, gap, offset, waiting, lastChange;
+    };
+    // allocate the lane-change state and upload its static tables (segments, lane geometry, lane plans)
+    void enableLaneChange(const RoadNet &net, const Routing &routing);
+    void uploadLanePlans(const Routing &routing);
+    // First half of a step: ingest, segment index, signals, scheduling.  `spare` = free slots lent for this
+    // step's shadows.  Synchronises and returns the shadows created, in schedule order (= the order their
+    // priorities are drawn from the engine RNG, vehicle.cpp:33).
+    void stepLcBegin(const SpawnRec *recs, int n, const int32_t *spare, int nSpare, std::vector<LcShadow> &created);
+    // Second half: the drawn priorities, then leader pass, notify, control (+ sequential tail), move, leader.
+    void stepLcEnd(const int32_t *priorities, int n);
+    void debugDumpLc(std::vector<LcDebugRec> &out);
+#endif
+
     struct Impl;
 
 private:

@@ -61,6 +61,7 @@ struct SlotInfo {
     int32_t routeId = -1;            // resolved route (Routing::route), for get_vehicle_info / set_vehicle_route
     int32_t firstLane = -1;          // lane whose waiting queue the vehicle was put in
     int32_t tmplId = -1;             // vehicle template (length / width for the replay log)
+    bool shadow = false;             // lane-change draft: a shadow vehicle (Vehicle::isReal() == false)
     bool live = false;
 };
 
@@ -180,14 +181,19 @@ public:
             error = e.what();
             return false;
         }
+#ifndef CFB_LANE_CHANGE
         if (laneChange) {
             error = "laneChange=true is not supported by the B200 engine yet";
             return false;
         }
+#endif
         if (!net.load(dir + roadnetFile)) { error = "loading roadnet file error!"; return false; }
         std::vector<FlowDef> defs;
         if (!loadFlows(dir + flowFile, net, defs)) { error = "loading flow file error!"; return false; }
         routing.reset(new Routing(net));
+#ifdef CFB_LANE_CHANGE
+        if (laneChange) routing->enableLanePlans();   // a shadow continues the route from the lane it was inserted into
+#endif
         for (auto &d : defs) {
             FlowRun f;
             f.def = d;
@@ -212,6 +218,9 @@ public:
         opt.interval = interval;
         opt.rlTrafficLight = rlTrafficLight;
         dev.reset(new DeviceSim(net, templates, *routing, opt));
+#ifdef CFB_LANE_CHANGE
+        if (laneChange) dev->enableLaneChange(net, *routing);   // DRAFT, see device_lc.cuh
+#endif
         uploadedPlans = routing->numPlans();
         uploadedTemplates = templates.size();
         return true;
@@ -242,6 +251,24 @@ public:
         if (transport) dev->shardGatherFinished(transport, fin);
         else if (finishedHook) finishedHook(fin);
         // deterministic accumulation order for the travel-time sum (ring order is atomics order)
+#ifdef CFB_LANE_CHANGE
+        // a vehicle replaced by its shadow is tagged by the device (engine.cpp:297-301): it is not a
+        // finished vehicle, its shadow (same name) carries on as the real one
+        std::vector<char> replaced(fin.size(), 0);
+        for (size_t k = 0; k < fin.size(); ++k)
+            if (fin[k].slot & 0x40000000) { fin[k].slot &= ~0x40000000; replaced[k] = 1; }
+        for (size_t k = 0; k < fin.size(); ++k)
+            if (replaced[k]) {
+                SlotInfo &s = slots[fin[k].slot];
+                if (!s.live) continue;
+                for (SlotInfo &o : slots)   // its shadow: same name, live, flagged (rare event: linear search is fine in the draft)
+                    if (o.live && o.shadow && o.flow == s.flow && o.index == s.index) { o.shadow = false; break; }
+                if (pool.get(s.priority) == fin[k].slot) pool.erase(s.priority);
+                s.live = false;
+                freeSlots.push_back(fin[k].slot);
+                idMapValid = false;
+            }
+#endif
         std::sort(fin.begin(), fin.end(), [this](const FinRec &a, const FinRec &b) {
             return a.step != b.step ? a.step < b.step : slots[a.slot].priority < slots[b.slot].priority;
         });
@@ -443,7 +470,44 @@ public:
             case 3: dev->unpackTails(); dev->applyBlk(); dev->runLeader(); break;
         }
     }
+#ifdef CFB_LANE_CHANGE
+    // One step with lane change (DRAFT): the shadows' priorities come from the engine RNG right after
+    // this step's spawn draws (vehicle.cpp:33), so the step has a host round trip in the middle.
+    void nextStepLaneChange() {
+        std::vector<int32_t> spare(256);
+        for (auto &x : spare) { x = allocSlot(); slots[x].live = false; }
+        prepareStep();                                   // (ensures device capacity for every slot handed out so far)
+        std::vector<DeviceSim::LcShadow> created;
+        dev->stepLcBegin(batch.data(), (int) batch.size(), spare.data(), (int) spare.size(), created);
+        std::vector<int32_t> prio(created.size());
+        for (size_t k = 0; k < created.size(); ++k) {    // Vehicle copy constructor vehicle.cpp:27-36
+            const SlotInfo parent = slots[created[k].parentSlot];
+            int priority;
+            for (;;) {
+                priority = (int) rnd();
+                const int other = pool.get(priority);
+                if (other < 0) break;
+                if (dev->slotDelStep(other) >= slots[other].spawnStep) { pool.erase(priority); break; }
+            }
+            SlotInfo &s = slots[created[k].shadowSlot];
+            s = parent;
+            s.priority = priority;
+            s.spawnStep = (int32_t) step;
+            s.shadow = true;
+            s.live = true;
+            pool.insert(priority, created[k].shadowSlot);
+            prio[k] = priority;
+        }
+        for (size_t k = created.size(); k < spare.size(); ++k) freeSlots.push_back(spare[k]);   // the device takes spares in order
+        idMapValid = false;
+        dev->stepLcEnd(prio.data(), (int) prio.size());
+        finishStep();
+    }
+#endif
     void nextStep() {
+#ifdef CFB_LANE_CHANGE
+        if (laneChange) { nextStepLaneChange(); return; }
+#endif
         prepareStep();
         const auto t1 = std::chrono::steady_clock::now();
         if (!transport) {
@@ -821,6 +885,34 @@ int64_t cfb_replay_format_step(cfb_replay *r, const cfb_replay_vehicle *v, int64
     r->w->formatStep(reinterpret_cast<const cfb::ReplayVehicle *>(v), (size_t) n, phase, r->buf);
     return copyOut(r->buf, out, cap);
 }
+
+#ifdef CFB_LANE_CHANGE
+// DRAFT (include/cityflow_b200_lc_draft.h): every running vehicle including shadows in vehiclePool
+// (priority) order, in the layout of oracle/harness.py LC_DTYPE, for the parity tests of the lane-change path.
+struct cfb_lc_vehicle {
+    int32_t flow, cnt, priority, partner_type, partner, drivable, leader, blocker, flags, last_dir;
+    double dis, speed, gap, offset, waiting_time, last_change_time;
+};
+int64_t cfb_debug_lc_vehicles(cfb_engine *e, cfb_lc_vehicle *out, int64_t cap) {
+    CFB_TRY(e,
+        cfb::HostEngine &h = e->h;
+        std::vector<cfb::DeviceSim::LcDebugRec> recs;
+        h.dev->debugDumpLc(recs);
+        std::sort(recs.begin(), recs.end(), [](const cfb::DeviceSim::LcDebugRec &a, const cfb::DeviceSim::LcDebugRec &b) { return a.priority < b.priority; });
+        auto prio = [&h](int slot) { return slot >= 0 ? h.slots[slot].priority : -1; };
+        for (int64_t i = 0; i < (int64_t) recs.size() && i < cap; ++i) {
+            const auto &r = recs[i];
+            cfb_lc_vehicle &o = out[i];
+            o.flow = h.slots[r.slot].flow; o.cnt = h.slots[r.slot].index; o.priority = r.priority;
+            o.partner_type = r.partnerType; o.partner = prio(r.partnerSlot); o.drivable = r.drivable;
+            o.leader = prio(r.leaderSlot); o.blocker = prio(r.blockerSlot); o.flags = r.flags; o.last_dir = r.lastDir;
+            o.dis = r.dis; o.speed = r.speed; o.gap = r.gap; o.offset = r.offset; o.waiting_time = r.waiting;
+            o.last_change_time = r.lastChange;
+        }
+        return (int64_t) recs.size();
+    )
+}
+#endif
 
 int cfb_set_random_seed(cfb_engine *e, int seed) {
     e->h.rnd.seed(seed);
