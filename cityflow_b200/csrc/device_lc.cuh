@@ -472,6 +472,23 @@ __global__ void __launch_bounds__(256) k_lc_segments(View V, LcView C) {
         if (d < V.nLanes) lcInitSegments(V, C, d);
     }
 }
+// Engine::handleWaiting gives a vehicle admitted to an EMPTY lane its leader at once (engine.cpp:512); the
+// default pipeline defers that search to k_notify, but makeSignal reads the gap before.
+__global__ void __launch_bounds__(256) k_lc_admitted(View V, LcView C) {
+    const int cpar = V.par;
+    const int nAct = V.ctrl->nAct[cpar];
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nAct; w += gridDim.x * blockDim.x) {
+        const int d = V.actList[cpar][w];
+        if (d >= V.nLanes || !(V.inserted[d] & 2) || V.count[d] == 0) continue;
+        const int base = V.off[d];
+        const int4 idv = V.ids[base];
+        int ld = -1;
+        double g = 0;
+        headSearch(V, d, 0.0, idv.w, V.nav[base].x, V.tmpl[idv.y], d, ld, g);
+        V.leader[base] = ld;
+        if (ld >= 0) { V.gap[base] = g; C.slot[idv.x].gap = g; }
+    }
+}
 __global__ void __launch_bounds__(256) k_lc_signal(View V, LcView C) {
     const int cpar = V.par;
     const int nVeh = min(V.ctrl->nVeh[cpar], V.vehCap);

@@ -519,7 +519,13 @@ __device__ __forceinline__ void phase_notify(const View &V, const int bid, const
         }
         const int c = V.count[d], base = V.off[d];
         if (c == 0) continue;
+#ifdef CFB_LANE_CHANGE
+        // with lane change the search already ran before the signals (k_lc_admitted) and the full leader
+        // pass after scheduling (k_lc_leader) has the final word
+        if ((V.inserted[d] & 2) && lane == 0 && !V.lcOn) {
+#else
         if ((V.inserted[d] & 2) && lane == 0) {  // vehicle admitted to an empty lane this step
+#endif
             const int4 idv = V.ids[base];
             int ld = -1;
             double g = 0;
@@ -2565,6 +2571,7 @@ void DeviceSim::stepLcBegin(const SpawnRec *recs, int n, const int32_t *spare, i
     const int gLaneRL = (std::max(V.nLanes, V.nRL) + TPB - 1) / TPB;
     k_lc_begin<<<1, 1, 0, s>>>(V.lc);
     k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
+    k_lc_admitted<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
     k_lc_segments<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
     k_lc_signal<<<I.gridControl, TPB, 0, s>>>(V, V.lc);
     k_lc_schedule<<<1, 32, 0, s>>>(V, V.lc);
@@ -2579,7 +2586,7 @@ void DeviceSim::stepLcBegin(const SpawnRec *recs, int n, const int32_t *spare, i
         CFB_CUDA(cudaMemcpyAsync(created.data(), I.lcShadowLog.p, ns * sizeof(int2), cudaMemcpyDeviceToHost, s));
         CFB_CUDA(cudaStreamSynchronize(s));
     }
-    launches_ += 5;
+    launches_ += 6;
 }
 
 void DeviceSim::stepLcEnd(const int32_t *priorities, int n) {
