@@ -462,6 +462,7 @@ __device__ void lcControlTail(const View &V, const LcView &C, int epoch) {
     for (int i = 0; i < n; ++i) lcClearSignal(C.slot[C.involved[i]], epoch);
 }
 
+#ifndef CFB_LC_HOST_PROBE   // (tests/lc_device_probe.cpp compiles the functions above for the host)
 // ---- kernels ----------------------------------------------------------------------------------
 // segment index of every vehicle on an occupied lane (warp per list entry would be overkill: <= ~40 per lane)
 __global__ void __launch_bounds__(256) k_lc_segments(View V, LcView C) {
@@ -538,5 +539,7 @@ __global__ void k_lc_control_tail(View V, LcView C) {
 __global__ void k_lc_begin(LcView C) {
     C.ctrl->nCand = 0; C.ctrl->nInvolved = 0; C.ctrl->nShadows = 0; C.ctrl->spareUsed = 0;
 }
+
+#endif  // CFB_LC_HOST_PROBE
 
 }  // namespace cfb

@@ -658,6 +658,7 @@ struct Oracle {
             }
     }
     bool deferShadowPriority = false;
+    void (*lcProbe)(Oracle &, int) = nullptr;
     long long segOrderMismatch = 0;
     // sizes of the sequential parts of the device form, summed / maximised over the steps so far
     long long statCandidates = 0, statInvolved = 0, statRunning = 0;
@@ -1017,8 +1018,10 @@ struct Oracle {
         planRoute();
         handleWaiting();
         if (laneChange) {  // engine.cpp:570-574
+            if (lcProbe) lcProbe(*this, 0);    // tests/lc_device_probe.cpp: state right before the lane-change phases
             initSegments();
             planLaneChange();
+            if (lcProbe) lcProbe(*this, 1);    // ... and right after scheduling
             updateLeaderAndGapAll();
         }
         notifyCross();

@@ -1,0 +1,289 @@
+// CPU probe for the lane-change DRAFT's device functions (cityflow_b200/csrc/device_lc.cuh):
+// compiles lcInitSegments / lcMakeSignal / lcSchedule (shadow insertion included) for the HOST, runs them
+// on structure-of-arrays built from the restatement's state right before its own lane-change phases, and
+// compares what they decide with what the restatement decides in the reference's order -- every step:
+// who signals where, who receives whose signal, target leader / follower and gaps, who starts changing,
+// and the exact list position of every new shadow.  (The restatement itself is pinned against
+// oracle/_ref/refdump_lcorder.)  This checks the LOGIC of the draft on the lane-bucket layout; it says
+// nothing about the kernels' launch plumbing, which needs a GPU.
+//
+//   g++ -std=c++17 -O1 -I/usr/local/cuda/include -Icityflow_b200/csrc tests/lc_device_probe.cpp \
+//       cityflow_b200/csrc/roadnet.cpp cityflow_b200/csrc/flows.cpp -o probe && ./probe config.json steps
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include <vector_types.h>
+#include <vector_functions.h>
+#undef __device__
+#undef __global__
+#undef __forceinline__
+#undef __launch_bounds__
+#undef __align__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define CFB_LANE_CHANGE 1
+#define CFB_LC_HOST_PROBE 1
+static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+static inline int atomicSub(int *p, int v) { int o = *p; *p -= v; return o; }
+static inline int atomicOr(int *p, int v) { int o = *p; *p |= v; return o; }
+using std::max;
+using std::min;
+
+#include "device_sim.h"
+#include "device_view.cuh"
+#include "device_lc.cuh"
+
+#include "../oracle/cityflow_oracle.cpp"   // Oracle / Veh (anonymous namespace: visible in this translation unit)
+
+namespace {
+
+using namespace cfb;
+
+struct Soa {   // the arrays the draft's functions touch, sized for this step
+    std::vector<int> off, count, pos, leader, laneOutBeg, laneOutLinks, planBeg, planData, segIdx, posDrv, segBeg,
+        laneIdx, laneRoadN, planRoute, planRoadPos, lpRoad, lpBeg, lpId, cand, involved, spare, act[2], blk, extra, entCnt, ent;
+    std::vector<double> drvLength, gap, cust, segStart, laneWidth;
+    std::vector<double2> kin, mkin;
+    std::vector<int4> ids, nav, mids, mnav;
+    std::vector<int2> veh[2], shadowLog;
+    std::vector<Tail> tail;
+    std::vector<DTmpl> tmpl;
+    std::vector<LcSlot> slot;
+    std::vector<Veh *> vehOfSlot;
+    std::map<Veh *, int> slotOf;
+    Ctrl ctrl{};
+    LcCtrl lcCtrl{};
+    View V{};
+    int epoch = 0;
+};
+
+Soa *g = nullptr;
+long long g_checked = 0, g_candidates = 0, g_shadows = 0, g_steps = 0;
+int g_fail = 0;
+
+#define CHECK(cond, ...)                                  \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            if (g_fail < 10) { printf("FAIL step %zu: ", o.step + 1); printf(__VA_ARGS__); printf("\n"); } \
+            ++g_fail;                                     \
+        }                                                 \
+    } while (0)
+
+void build(Oracle &o) {
+    delete g;
+    g = new Soa();
+    Soa &S = *g;
+    const RoadNet &net = o.net;
+    const int nL = net.nLanes(), nD = net.nDrivables();
+    S.epoch = (int) o.step + 1;
+    // buckets: list size + headroom
+    S.off.assign(nD + 1, 0);
+    for (int d = 0; d < nD; ++d) S.off[d + 1] = S.off[d] + (int) o.lists[d].size() + 6;
+    const int P = S.off[nD];
+    S.count.assign(nD, 0);
+    S.kin.assign(P, make_double2(0, 0)); S.ids.assign(P, make_int4(0, 0, 0, 0)); S.nav.assign(P, make_int4(0, 0, 0, 0));
+    S.gap.assign(P, 0); S.cust.assign(P, 0); S.segIdx.assign(P, 0); S.leader.assign(P, -1); S.posDrv.assign(P, 0);
+    for (int d = 0; d < nD; ++d) for (int p = S.off[d]; p < S.off[d + 1]; ++p) S.posDrv[p] = d;
+    S.drvLength.resize(nD);
+    for (int d = 0; d < nD; ++d) S.drvLength[d] = o.drvLength(d);
+    S.laneOutBeg.assign(nL + 1, 0);
+    for (int l = 0; l < nL; ++l) {
+        S.laneOutBeg[l + 1] = S.laneOutBeg[l] + (int) net.laneOutLinks[l].size();
+        for (int ll : net.laneOutLinks[l]) S.laneOutLinks.push_back(ll);
+    }
+    // static lane tables + segments exactly like DeviceSim::enableLaneChange
+    S.segBeg.assign(nL + 1, 0); S.laneIdx.resize(nL); S.laneRoadN.resize(nL); S.laneWidth.resize(nL);
+    for (int l = 0; l < nL; ++l) {
+        S.segBeg[l] = (int) S.segStart.size();
+        for (double x : o.segStart[l]) S.segStart.push_back(x);
+        S.laneIdx[l] = net.laneIdx[l]; S.laneRoadN[l] = net.roadNumLanes(net.laneRoad[l]); S.laneWidth[l] = net.laneWidth[l];
+    }
+    S.segBeg[nL] = (int) S.segStart.size();
+    // slots and per-vehicle records
+    int nSlots = 0;
+    for (auto &kv : o.pool) if (kv.second->running) { S.slotOf[kv.second] = nSlots++; S.vehOfSlot.push_back(kv.second); }
+    const int nSpare = 64;
+    S.slot.assign(nSlots + nSpare, LcSlot{});
+    S.pos.assign(nSlots + nSpare, -1);
+    S.blk.assign(nSlots + nSpare, -1);
+    S.tmpl.resize(nSlots + nSpare);
+    for (int k = 0; k < nSpare; ++k) S.spare.push_back(nSlots + k);
+    // plans: every vehicle gets "the plan from its current lane" of its route (Routing::lanePlan)
+    Routing &R = *o.routing;
+    for (int d = 0; d < nD; ++d) {
+        int k = 0;
+        for (Veh *v : o.lists[d]) {
+            const int p = S.off[d] + k++;
+            const int s = S.slotOf.at(v);
+            int plan = 0, planIdx = 0, next = -1;
+            if (!o.isLink(d)) {
+                const int route = R.intern(v->route);
+                plan = R.lanePlan(route, v->iCur, net.laneIdx[d]);
+                planIdx = R.planBeg()[plan];
+                next = R.planData()[planIdx + 1];
+                const int want = o.nextDrivable(*v);
+                if (!(next == want || (next < 0 && want < 0))) { printf("PROBE: plan disagrees with the router (%d vs %d)\n", next, want); ++g_fail; }
+            } else {
+                next = o.nextDrivable(*v);
+            }
+            S.kin[p] = make_double2(v->dis, v->t.speed);
+            S.ids[p] = make_int4(s, s, v->priority, next);
+            S.nav[p] = make_int4(planIdx, v->prevDrivable, v->blocker ? S.slotOf.at(v->blocker) : -1, (int) v->enterLaneLinkTime);
+            S.gap[p] = v->gap;
+            S.cust[p] = v->bCustomSet ? v->bCustom : NAN;
+            S.pos[s] = p;
+            DTmpl t{};
+            t.len = v->t.len; t.maxNegAcc = v->t.maxNegAcc; t.maxSpeed = v->t.maxSpeed; t.minGap = v->t.minGap;
+            S.tmpl[s] = t;
+            LcSlot &L = S.slot[s];
+            lcResetSlot(L, plan);
+            L.partner = v->partner ? S.slotOf.at(v->partner) : -1;
+            L.type = v->partnerType; L.changing = v->changing; L.finished = v->lcFinished;
+            if (v->sigSend) { L.sendTarget = v->sigSend->target; L.sendDir = v->sigSend->direction; }   // only changing vehicles still hold one here
+            L.offset = v->offset; L.waiting = v->waitingTime; L.lastChange = v->lastChangeTime; L.gap = v->gap; L.lastDir = v->lastDir;
+        }
+        S.count[d] = k;
+    }
+    S.planBeg = R.planBeg(); S.planData = R.planData();
+    S.planRoute = R.planRouteTable(); S.planRoadPos = R.planRoadPosTable();
+    S.lpRoad = R.lanePlanRoadTable(); S.lpBeg = R.lanePlanBegTable(); S.lpId = R.lanePlanIdTable();
+    S.tail.resize(nD);
+    for (int d = 0; d < nD; ++d) {
+        Tail t{}; t.pos = -1; t.prev = -1;
+        if (S.count[d] > 0) {
+            const int q = S.off[d] + S.count[d] - 1;
+            t.dis = S.kin[q].x; t.speed = S.kin[q].y; t.len = S.tmpl[S.ids[q].y].len; t.pos = q; t.prev = S.nav[q].y;
+        }
+        S.tail[d] = t;
+    }
+    for (int par = 0; par < 2; ++par) { S.veh[par].assign(P + 64, make_int2(0, 0)); S.act[par].assign(nD + 8, 0); }
+    S.cand.assign(LC_MAX_CAND, 0); S.involved.assign(LC_MAX_CAND, 0); S.shadowLog.assign(LC_MAX_CAND, make_int2(0, 0));
+    View &V = S.V;
+    V.nLanes = nL; V.nLinks = net.nLinks(); V.nDrv = nD; V.dt = o.interval; V.par = 0; V.vehCap = P + 64;
+    V.drvLength = S.drvLength.data(); V.off = S.off.data(); V.laneOutBeg = S.laneOutBeg.data(); V.laneOutLinks = S.laneOutLinks.data();
+    V.tmpl = S.tmpl.data(); V.planBeg = S.planBeg.data(); V.planData = S.planData.data();
+    V.kin = S.kin.data(); V.gap = S.gap.data(); V.leader = S.leader.data(); V.ids = S.ids.data(); V.nav = S.nav.data();
+    V.count = S.count.data(); V.pos = S.pos.data(); V.tail = S.tail.data(); V.cust = S.cust.data(); V.blk = S.blk.data();
+    V.vehList[0] = S.veh[0].data(); V.vehList[1] = S.veh[1].data(); V.actList[0] = S.act[0].data(); V.actList[1] = S.act[1].data();
+    S.ctrl.step = (int) o.step;
+    V.ctrl = &S.ctrl;
+    V.lcOn = 1;
+    LcView &C = V.lc;
+    C.slot = S.slot.data(); C.segIdx = S.segIdx.data(); C.posDrv = S.posDrv.data(); C.segBeg = S.segBeg.data(); C.segStart = S.segStart.data();
+    C.laneIdx = S.laneIdx.data(); C.laneRoadN = S.laneRoadN.data(); C.laneWidth = S.laneWidth.data();
+    C.planRoute = S.planRoute.data(); C.planRoadPos = S.planRoadPos.data();
+    C.lanePlanRoad = S.lpRoad.data(); C.lanePlanBeg = S.lpBeg.data(); C.lanePlanId = S.lpId.data();
+    C.cand = S.cand.data(); C.involved = S.involved.data(); C.spare = S.spare.data(); C.nSpare = nSpare;
+    C.shadowLog = S.shadowLog.data(); C.ctrl = &S.lcCtrl;
+}
+
+void before(Oracle &o) {
+    build(o);
+    Soa &S = *g;
+    View &V = S.V;
+    for (int l = 0; l < V.nLanes; ++l) lcInitSegments(V, V.lc, l);
+    for (int d = 0; d < V.nDrv; ++d)
+        for (int k = 0; k < S.count[d]; ++k) lcMakeSignal(V, V.lc, S.off[d] + k, d, S.epoch);
+    lcSchedule(V, V.lc, S.epoch);
+}
+
+void after(Oracle &o) {
+    Soa &S = *g;
+    View &V = S.V;
+    const int epoch = S.epoch;
+    ++g_steps;
+    CHECK(S.lcCtrl.error == 0, "capacity error %d", S.lcCtrl.error);
+    // shadows: the restatement's new shadows <-> the draft's, by parent
+    int newShadows = 0;
+    for (auto &kv : o.pool) {
+        Veh *v = kv.second;
+        if (!v->running || S.slotOf.count(v)) continue;
+        ++newShadows;                                      // created by this step's scheduling
+        CHECK(v->partnerType == 2 && v->partner && S.slotOf.count(v->partner), "new vehicle that is not a shadow");
+        const int ps = S.slotOf.at(v->partner);
+        const int sh = S.slot[ps].partner;
+        CHECK(sh >= 0 && S.slot[ps].type == 1 && S.slot[sh].type == 2 && S.slot[sh].partner == ps, "parent %d has no shadow in the draft", v->partner->priority);
+        if (sh >= 0) { S.slotOf[v] = sh; if ((int) S.vehOfSlot.size() <= sh) S.vehOfSlot.resize(sh + 1, nullptr); S.vehOfSlot[sh] = v; }
+    }
+    CHECK(newShadows == S.lcCtrl.nShadows, "shadows: restatement %d draft %d", newShadows, S.lcCtrl.nShadows);
+    g_shadows += newShadows;
+    // the log must be in the restatement's creation order (= RNG order): ascending shadow creation is the
+    // order of priorities drawn, which the restatement recorded implicitly in its own draws; compare by
+    // walking the draft's log and checking each parent got its shadow
+    for (int k = 0; k < S.lcCtrl.nShadows; ++k) CHECK(S.slot[S.shadowLog[k].x].partner == S.shadowLog[k].y, "shadow log entry %d inconsistent", k);
+    // lists: same vehicles in the same order on every drivable
+    for (int d = 0; d < V.nDrv; ++d) {
+        CHECK((int) o.lists[d].size() == S.count[d], "drivable %d: %zu vs %d vehicles", d, o.lists[d].size(), S.count[d]);
+        if ((int) o.lists[d].size() != S.count[d]) continue;
+        int k = 0;
+        for (Veh *v : o.lists[d]) {
+            const int p = S.off[d] + k++;
+            const int s = S.slotOf.count(v) ? S.slotOf.at(v) : -1;
+            CHECK(S.ids[p].x == s && S.pos[s] == p, "drivable %d position %d: slot %d vs %d", d, k - 1, S.ids[p].x, s);
+            CHECK(S.kin[p].x == v->dis && S.kin[p].y == v->t.speed, "drivable %d position %d: kinematics differ", d, k - 1);
+            if (!o.isLink(d)) CHECK(S.segIdx[p] == (int) v->segIndex, "segment index of prio %d: %d vs %zu", v->priority, S.segIdx[p], v->segIndex);
+            ++g_checked;
+        }
+        if (S.count[d] > 0) {
+            const Tail &t = S.tail[d];
+            Veh *last = o.lists[d].back();
+            CHECK(t.pos == S.off[d] + S.count[d] - 1 && t.dis == last->dis && t.len == last->t.len, "tail record of drivable %d", d);
+        }
+    }
+    // per-vehicle lane-change state
+    int cands = 0;
+    for (auto &kv : S.slotOf) {
+        Veh *v = kv.first;
+        const LcSlot &L = S.slot[kv.second];
+        const bool send = v->sigSend != nullptr;
+        CHECK(send == lcSendValid(L, epoch), "prio %d: signalSend %d vs %d", v->priority, send, lcSendValid(L, epoch));
+        if (send && lcSendValid(L, epoch)) {
+            CHECK(v->sigSend->target == L.sendTarget && v->sigSend->direction == L.sendDir, "prio %d: target %d/%d dir %d/%d", v->priority,
+                  v->sigSend->target, L.sendTarget, v->sigSend->direction, L.sendDir);
+        }
+        const bool recv = v->sigRecv != nullptr;
+        CHECK(recv == lcRecvValid(L, epoch), "prio %d: signalRecv %d vs %d", v->priority, recv, lcRecvValid(L, epoch));
+        if (recv && lcRecvValid(L, epoch)) CHECK(S.slotOf.at(v->sigRecv->source) == L.recvSrc, "prio %d: signal source", v->priority);
+        CHECK((int) v->changing == L.changing && v->partnerType == L.type, "prio %d: changing %d/%d type %d/%d", v->priority, v->changing, L.changing, v->partnerType, L.type);
+        CHECK((v->partner ? S.slotOf.at(v->partner) : -1) == L.partner, "prio %d: partner", v->priority);
+        CHECK(v->waitingTime == L.waiting, "prio %d: waiting time %g vs %g", v->priority, v->waitingTime, L.waiting);
+        if (v->planChange() && v->isReal()) {   // a candidate: neighbours and gaps were computed
+            ++cands;
+            const int tl = v->targetLeader ? S.slotOf.at(v->targetLeader) : -1, tf = v->targetFollower ? S.slotOf.at(v->targetFollower) : -1;
+            CHECK(L.tgtEpoch == epoch && L.tgtLeader == tl && L.tgtFollower == tf, "prio %d: target leader %d/%d follower %d/%d", v->priority, tl, L.tgtLeader, tf, L.tgtFollower);
+            CHECK(L.leaderGap == v->leaderGap && L.followerGap == v->followerGap, "prio %d: gaps %g/%g %g/%g", v->priority, v->leaderGap, L.leaderGap, v->followerGap, L.followerGap);
+        }
+        if (v->partnerType == 2 && !v->sigSend) {   // a shadow: plan continues the parent's route from the new lane
+            const int p = S.pos[kv.second];
+            const int want = o.nextDrivable(*v);
+            CHECK(S.ids[p].w == want || (S.ids[p].w < 0 && want < 0), "shadow prio %d: next drivable %d vs %d", v->priority, S.ids[p].w, want);
+        }
+    }
+    CHECK(cands == S.lcCtrl.nCand, "candidates: restatement %d draft %d", cands, S.lcCtrl.nCand);
+    g_candidates += cands;
+}
+
+void probe(Oracle &o, int phase) { if (phase == 0) before(o); else after(o); }
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: lc_device_probe config.json steps\n"); return 64; }
+    Oracle o;
+    if (!o.load(argv[1]) || !o.laneChange) { fprintf(stderr, "cannot load %s (laneChange must be true)\n", argv[1]); return 2; }
+    o.routing->enableLanePlans();
+    o.lcProbe = probe;
+    const int steps = atoi(argv[2]);
+    for (int s = 0; s < steps && g_fail == 0; ++s) o.nextStep();
+    printf("%s %lld steps, %lld list entries, %lld candidates, %lld shadows checked, %d failures\n", g_fail ? "FAIL" : "OK", g_steps, g_checked,
+           g_candidates, g_shadows, g_fail);
+    return g_fail ? 1 : 0;
+}
