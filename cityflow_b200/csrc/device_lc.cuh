@@ -458,7 +458,11 @@ __device__ void lcControlTail(const View &V, const LcView &C, int epoch) {
         V.nbuf[p] = make_int2(end ? -2 : newDrv, L.headBlocker);
         if (!end && newDrv >= 0) lcStageMover(V, d, idv, nv, nd, v, newDrv, L.headBlocker, hops, epoch);
     }
-    // Engine::threadUpdateAction -> clearSignal for the involved vehicles that are still running
+}
+// Engine::threadUpdateAction -> clearSignal (engine.cpp:424) for the involved vehicles (the plain ones took
+// their lastDir in k_control; their epoch-stamped signals expire by themselves)
+__device__ void lcClearInvolved(const LcView &C, int epoch) {
+    const int n = min(C.ctrl->nInvolved, LC_MAX_CAND);
     for (int i = 0; i < n; ++i) lcClearSignal(C.slot[C.involved[i]], epoch);
 }
 
@@ -533,7 +537,10 @@ __global__ void __launch_bounds__(256) k_lc_leader(View V, LcView C) {
     }
 }
 __global__ void k_lc_control_tail(View V, LcView C) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) lcControlTail(V, C, V.ctrl->step + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        lcControlTail(V, C, V.ctrl->step + 1);
+        lcClearInvolved(C, V.ctrl->step + 1);
+    }
 }
 // per-step reset of the small counters (before k_lc_signal)
 __global__ void k_lc_begin(LcView C) {

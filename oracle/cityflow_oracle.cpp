@@ -670,6 +670,7 @@ struct Oracle {
     void controlDeviceForm() {
         for (auto it = pool.rbegin(); it != pool.rend(); ++it)
             if (it->second->running) it->second->ctlHead = nextSpeedHead(*it->second);
+        if (lcProbe) lcProbe(*this, 2);        // tests/lc_device_probe.cpp: heads computed, nothing finished yet
         std::vector<Veh *> involved;
         for (auto it = pool.rbegin(); it != pool.rend(); ++it) {
             Veh *v = it->second;
@@ -681,6 +682,7 @@ struct Oracle {
         statMaxInvolved = std::max(statMaxInvolved, (int) involved.size());
         statRunning += (long long) activeCount;
         for (auto it = involved.rbegin(); it != involved.rend(); ++it) vehicleControl(**it);   // ascending priority
+        if (lcProbe) lcProbe(*this, 3);
     }
     // LaneChange::finishChanging lanechange.cpp:115-127 + Vehicle::finishChanging vehicle.cpp:378-381
     void finishChanging(Veh &v) {

@@ -3,7 +3,8 @@
 // on structure-of-arrays built from the restatement's state right before its own lane-change phases, and
 // compares what they decide with what the restatement decides in the reference's order -- every step:
 // who signals where, who receives whose signal, target leader / follower and gaps, who starts changing,
-// and the exact list position of every new shadow.  (The restatement itself is pinned against
+// and the exact list position of every new shadow; then lcControlTail on the vehicles involved in a lane
+// change (next speed and distance bit for bit, offset progress, finish / abort, partner links, mover staging).  (The restatement itself is pinned against
 // oracle/_ref/refdump_lcorder.)  This checks the LOGIC of the draft on the lane-bucket layout; it says
 // nothing about the kernels' launch plumbing, which needs a GPU.
 //
@@ -51,7 +52,9 @@ struct Soa {   // the arrays the draft's functions touch, sized for this step
     std::vector<int> off, count, pos, leader, laneOutBeg, laneOutLinks, planBeg, planData, segIdx, posDrv, segBeg,
         laneIdx, laneRoadN, planRoute, planRoadPos, lpRoad, lpBeg, lpId, cand, involved, spare, act[2], blk, extra, entCnt, ent;
     std::vector<double> drvLength, gap, cust, segStart, laneWidth;
-    std::vector<double2> kin, mkin;
+    std::vector<double2> kin, mkin, nkin;
+    std::vector<int2> nbuf;
+    std::vector<Veh *> involvedVeh;
     std::vector<int4> ids, nav, mids, mnav;
     std::vector<int2> veh[2], shadowLog;
     std::vector<Tail> tail;
@@ -66,7 +69,7 @@ struct Soa {   // the arrays the draft's functions touch, sized for this step
 };
 
 Soa *g = nullptr;
-long long g_checked = 0, g_candidates = 0, g_shadows = 0, g_steps = 0;
+long long g_checked = 0, g_candidates = 0, g_shadows = 0, g_steps = 0, g_involved = 0;
 int g_fail = 0;
 
 #define CHECK(cond, ...)                                  \
@@ -149,6 +152,12 @@ void build(Oracle &o) {
             L.type = v->partnerType; L.changing = v->changing; L.finished = v->lcFinished;
             if (v->sigSend) { L.sendTarget = v->sigSend->target; L.sendDir = v->sigSend->direction; }   // only changing vehicles still hold one here
             L.offset = v->offset; L.waiting = v->waitingTime; L.lastChange = v->lastChangeTime; L.gap = v->gap; L.lastDir = v->lastDir;
+            // (only meaningful when built after scheduling, for the control phase)
+            if (v->sigSend && !v->changing) L.sendEpoch = S.epoch;
+            if (v->sigRecv) { L.recvEpoch = S.epoch; }
+            L.leaderGap = v->leaderGap; L.followerGap = v->followerGap;
+            L.head = v->ctlHead;
+            t.maxPosAcc = v->t.maxPosAcc; S.tmpl[s] = t;
         }
         S.count[d] = k;
     }
@@ -166,6 +175,9 @@ void build(Oracle &o) {
     }
     for (int par = 0; par < 2; ++par) { S.veh[par].assign(P + 64, make_int2(0, 0)); S.act[par].assign(nD + 8, 0); }
     S.cand.assign(LC_MAX_CAND, 0); S.involved.assign(LC_MAX_CAND, 0); S.shadowLog.assign(LC_MAX_CAND, make_int2(0, 0));
+    S.nkin.assign(P, make_double2(0, 0)); S.nbuf.assign(P, make_int2(-1, -1));
+    S.mkin.assign(8192, make_double2(0, 0)); S.mids.assign(8192, make_int4(0, 0, 0, 0)); S.mnav.assign(8192, make_int4(0, 0, 0, 0));
+    S.entCnt.assign(nD, 0); S.ent.assign((size_t) nD * ENT_CAP, 0); S.extra.assign(nD + 8, 0);
     View &V = S.V;
     V.nLanes = nL; V.nLinks = net.nLinks(); V.nDrv = nD; V.dt = o.interval; V.par = 0; V.vehCap = P + 64;
     V.drvLength = S.drvLength.data(); V.off = S.off.data(); V.laneOutBeg = S.laneOutBeg.data(); V.laneOutLinks = S.laneOutLinks.data();
@@ -175,6 +187,8 @@ void build(Oracle &o) {
     V.vehList[0] = S.veh[0].data(); V.vehList[1] = S.veh[1].data(); V.actList[0] = S.act[0].data(); V.actList[1] = S.act[1].data();
     S.ctrl.step = (int) o.step;
     V.ctrl = &S.ctrl;
+    V.nkin = S.nkin.data(); V.nbuf = S.nbuf.data(); V.mkin = S.mkin.data(); V.mids = S.mids.data(); V.mnav = S.mnav.data();
+    V.entCnt = S.entCnt.data(); V.ent = S.ent.data(); V.extraList = S.extra.data(); V.moverCap = 8192;
     V.lcOn = 1;
     LcView &C = V.lc;
     C.slot = S.slot.data(); C.segIdx = S.segIdx.data(); C.posDrv = S.posDrv.data(); C.segBeg = S.segBeg.data(); C.segStart = S.segStart.data();
@@ -271,7 +285,68 @@ void after(Oracle &o) {
     g_candidates += cands;
 }
 
-void probe(Oracle &o, int phase) { if (phase == 0) before(o); else after(o); }
+// ---- control tail: engine.cpp:195-244 for the vehicles involved in a lane change ------------------------
+void beforeControl(Oracle &o) {
+    build(o);
+    Soa &S = *g;
+    View &V = S.V;
+    const int epoch = S.epoch;
+    // second pass over the slots: the fields that refer to other vehicles, and this step's neighbours
+    for (auto &kv : S.slotOf) {
+        Veh *v = kv.first;
+        LcSlot &L = S.slot[kv.second];
+        if (v->sigRecv) L.recvSrc = S.slotOf.at(v->sigRecv->source);
+        if (v->isReal() && v->planChange()) {
+            L.tgtEpoch = epoch;
+            L.tgtLeader = v->targetLeader ? S.slotOf.at(v->targetLeader) : -1;
+            L.tgtFollower = v->targetFollower ? S.slotOf.at(v->targetFollower) : -1;
+        }
+        L.headBlocker = v->bBlockerSet && v->bBlocker ? S.slotOf.at(v->bBlocker) : -1;
+        if (L.partner >= 0 || lcRecvValid(L, epoch) || L.type != 0 || L.changing) {   // the predicate of the k_control hook
+            S.involved[S.lcCtrl.nInvolved++] = kv.second;
+            S.involvedVeh.push_back(v);
+        }
+    }
+    lcControlTail(V, V.lc, epoch);
+}
+
+void afterControl(Oracle &o) {
+    Soa &S = *g;
+    for (Veh *v : S.involvedVeh) {
+        const int s = S.slotOf.at(v);
+        const LcSlot &L = S.slot[s];
+        const int p = S.pos[s];
+        const double2 nk = S.nkin[p];
+        const int2 nb = S.nbuf[p];
+        CHECK(v->bSpeedSet && nk.y == v->bSpeed, "prio %d: next speed %.17g vs %.17g", v->priority, v->bSpeed, nk.y);
+        CHECK(v->bDisSet && nk.x == v->bDis, "prio %d: next distance %.17g vs %.17g", v->priority, v->bDis, nk.x);
+        const int want = v->bEndSet ? -2 : (v->bDrvSet && v->bDrv >= 0 ? v->bDrv : -1);
+        CHECK(nb.x == want, "prio %d: next drivable %d vs %d", v->priority, want, nb.x);
+        CHECK(nb.y == (v->bBlockerSet && v->bBlocker ? S.slotOf.at(v->bBlocker) : -1), "prio %d: blocker buffer", v->priority);
+        CHECK(v->offset == L.offset && (int) v->changing == L.changing && (int) v->lcFinished == L.finished, "prio %d: offset %g/%g changing %d/%d finished %d/%d",
+              v->priority, v->offset, L.offset, v->changing, L.changing, v->lcFinished, L.finished);
+        CHECK(v->partnerType == L.type && (v->partner ? S.slotOf.at(v->partner) : -1) == L.partner, "prio %d: partner link after control", v->priority);
+        CHECK(v->waitingTime == L.waiting && v->lastChangeTime == L.lastChange, "prio %d: waiting %g/%g last change %g/%g", v->priority, v->waitingTime,
+              L.waiting, v->lastChangeTime, L.lastChange);
+        if (want >= 0) {   // staged for its new drivable (engine.cpp:247-249)
+            bool found = false;
+            for (int k = 0; k < S.entCnt[want] && k < ENT_CAP; ++k) {
+                const int m = S.ent[(size_t) want * ENT_CAP + k];
+                if (S.mids[m].x == s) { found = S.mkin[m].x == v->bDis && S.mkin[m].y == v->bSpeed && S.mnav[m].y == v->drivable; }
+            }
+            CHECK(found, "prio %d: not staged for drivable %d", v->priority, want);
+        }
+        ++g_involved;
+    }
+    CHECK(S.ctrl.error == 0, "device error flags %d", S.ctrl.error);
+}
+
+void probe(Oracle &o, int phase) {
+    if (phase == 0) before(o);
+    else if (phase == 1) after(o);
+    else if (phase == 2) beforeControl(o);
+    else afterControl(o);
+}
 
 }  // namespace
 
@@ -281,9 +356,10 @@ int main(int argc, char **argv) {
     if (!o.load(argv[1]) || !o.laneChange) { fprintf(stderr, "cannot load %s (laneChange must be true)\n", argv[1]); return 2; }
     o.routing->enableLanePlans();
     o.lcProbe = probe;
+    o.deviceForm = true;   // (proven equal to the reference order; gives the hook between the two control passes)
     const int steps = atoi(argv[2]);
     for (int s = 0; s < steps && g_fail == 0; ++s) o.nextStep();
-    printf("%s %lld steps, %lld list entries, %lld candidates, %lld shadows checked, %d failures\n", g_fail ? "FAIL" : "OK", g_steps, g_checked,
-           g_candidates, g_shadows, g_fail);
+    printf("%s %lld steps, %lld list entries, %lld candidates, %lld shadows checked, %lld control tails, %d failures\n", g_fail ? "FAIL" : "OK", g_steps,
+           g_checked, g_candidates, g_shadows, g_involved, g_fail);
     return g_fail ? 1 : 0;
 }
