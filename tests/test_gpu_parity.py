@@ -448,3 +448,39 @@ def test_replay_files_written_by_the_engine(cfg_replay):
     assert first[:-1] == expect[:150]
     assert second[:-1] == expect[160:]
     assert len(expect[-1].split(",")) > 100
+
+
+def _lc_library():
+    from cityflow_b200.capi import load_library
+    lib = load_library()
+    return lib if hasattr(lib, "cfb_debug_lc_vehicles") else None
+
+
+@pytest.mark.skipif(_lc_library() is None, reason="the library was not built with EXTRA=-DCFB_LANE_CHANGE (lane change is a draft, DESIGN.md section 10)")
+def test_lane_change_draft_vs_restatement(tmp_path):
+    """Only with `make -C cityflow_b200/csrc EXTRA=-DCFB_LANE_CHANGE`: laneChange=true on the GPU against the
+    restatement (pinned to oracle/_ref/refdump_lcorder): every running vehicle including shadows, every field."""
+    import ctypes
+    from cityflow_b200 import scenario
+    from cityflow_b200.capi import CEngine
+    cfg = scenario.make_grid_scenario(str(tmp_path), 4, 4, dense=dict(frac=1.0, interval=3.0, seed=2), name="lc", lane_change=True)
+    eng, ora = CEngine(cfg), H.PortOracle(cfg)
+    lib = eng.lib
+    lib.cfb_debug_lc_vehicles.restype = ctypes.c_int64
+    lib.cfb_debug_lc_vehicles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    shadows = 0
+    for s in range(1, 401):
+        eng.next_step()
+        ora.next_step()
+        want = ora.lc_snapshot()
+        n = int(lib.cfb_debug_lc_vehicles(eng.h, None, 0))
+        got = np.zeros(n, H.LC_DTYPE)
+        if n:
+            lib.cfb_debug_lc_vehicles(eng.h, got.ctypes.data, n)
+        assert eng.vehicle_count() == want.vehicle_count, "step %d" % s
+        assert np.array_equal(eng.lane_vehicle_count(), want.lane_count), "lane counts, step %d" % s
+        assert len(got) == len(want.vehicles), "step %d" % s
+        for f in H.LC_DTYPE.names:
+            assert np.array_equal(got[f], want.vehicles[f]), "step %d field %s" % (s, f)
+        shadows += int((want.vehicles["partner_type"] == 2).sum())
+    assert shadows > 300
