@@ -451,8 +451,11 @@ def test_replay_files_written_by_the_engine(cfg_replay):
 
 
 def _lc_library():
-    from cityflow_b200.capi import load_library
-    lib = load_library()
+    try:
+        from cityflow_b200.capi import load_library
+        lib = load_library()
+    except Exception:  # noqa: BLE001  (library missing: every GPU test will say so itself)
+        return None
     return lib if hasattr(lib, "cfb_debug_lc_vehicles") else None
 
 
