@@ -1,14 +1,21 @@
-// CPU probe for the lane-change DRAFT's device functions (cityflow_b200/csrc/device_lc.cuh):
-// compiles lcInitSegments / lcMakeSignal / lcSchedule (shadow insertion included) for the HOST, runs them
-// on structure-of-arrays built from the restatement's state right before its own lane-change phases, and
-// compares what they decide with what the restatement decides in the reference's order -- every step:
-// who signals where, who receives whose signal, target leader / follower and gaps, who starts changing,
-// and the exact list position of every new shadow; then lcControlTail on the vehicles involved in a lane
-// change (next speed and distance bit for bit, offset progress, finish / abort, partner links, mover staging).  (The restatement itself is pinned against
-// oracle/_ref/refdump_lcorder.)  This checks the LOGIC of the draft on the lane-bucket layout; it says
-// nothing about the kernels' launch plumbing, which needs a GPU.
+// CPU probe: the device code of the control phase and of the lane-change DRAFT, compiled for the HOST.
 //
-//   g++ -std=c++17 -O1 -I/usr/local/cuda/include -Icityflow_b200/csrc tests/lc_device_probe.cpp \
+// csrc/device_control.cuh (canPass, phase_control = the body of k_control) and csrc/device_lc.cuh
+// (lcInitSegments, lcMakeSignal, lcSchedule incl. shadow insertion, lcControlTail) are plain functions over
+// the lane-bucket arrays of csrc/device_view.cuh.  With the CUDA keywords defined away and one-thread
+// stand-ins for the few execution-model calls they use (atomics, coalesced_threads, __ffs), they run here
+// on arrays built from the restatement's state, hooked into its step (oracle/cityflow_oracle.cpp, device
+// form), and must decide exactly what the restatement decides, every step:
+//   * before / after its lane-change phases: who signals where, who receives whose signal, target leader /
+//     follower and gaps, who starts changing, list position and route plan of every new shadow;
+//   * before / after its control pass: next speed and next distance (bit for bit), next drivable, blocker
+//     and mover staging of EVERY vehicle -- through phase_control itself, with this step's Cross::notify
+//     results taken from the restatement -- plus, with lane change, offset progress, finish / abort and
+//     partner links of the involved vehicles (the sequential tail).
+// The restatement is pinned against the compiled reference (and against oracle/_ref/refdump_lcorder for lane
+// change).  What this does NOT cover: k_notify / k_move / k_leader, launch plumbing, host bookkeeping.
+//
+//   g++ -std=c++17 -O1 -ffp-contract=off -I/usr/local/cuda/include -Icityflow_b200/csrc tests/lc_device_probe.cpp \
 //       cityflow_b200/csrc/roadnet.cpp cityflow_b200/csrc/flows.cpp -o probe && ./probe config.json steps
 #include <algorithm>
 #include <climits>
@@ -31,16 +38,28 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define CFB_LANE_CHANGE 1
+#define CFB_DEAD_END_STOP 1
 #define CFB_LC_HOST_PROBE 1
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
 static inline int atomicSub(int *p, int v) { int o = *p; *p -= v; return o; }
 static inline int atomicOr(int *p, int v) { int o = *p; *p |= v; return o; }
 using std::max;
 using std::min;
+// what the control phase uses of the CUDA execution model, for ONE thread at a time
+static struct { unsigned x = 1, y = 1, z = 1; } blockDim;
+static struct { unsigned x = 0, y = 0, z = 0; } threadIdx;
+static inline long long clock64() { return 0; }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+namespace cooperative_groups {
+struct lone_thread { unsigned size() const { return 1; } unsigned thread_rank() const { return 0; } template <class T> T shfl(T v, int) const { return v; } };
+inline lone_thread coalesced_threads() { return lone_thread(); }
+}  // namespace cooperative_groups
+namespace cfb { namespace cg = cooperative_groups; }
 
 #include "device_sim.h"
 #include "device_view.cuh"
-#include "device_lc.cuh"
+#include "device_control.cuh"   // canPass, phase_control (+ device_lc.cuh)
 
 #include "../oracle/cityflow_oracle.cpp"   // Oracle / Veh (anonymous namespace: visible in this translation unit)
 
@@ -51,7 +70,13 @@ using namespace cfb;
 struct Soa {   // the arrays the draft's functions touch, sized for this step
     std::vector<int> off, count, pos, leader, laneOutBeg, laneOutLinks, planBeg, planData, segIdx, posDrv, segBeg,
         laneIdx, laneRoadN, planRoute, planRoadPos, lpRoad, lpBeg, lpId, cand, involved, spare, act[2], blk, extra, entCnt, ent;
-    std::vector<double> drvLength, gap, cust, segStart, laneWidth;
+    std::vector<double> drvLength, gap, cust, segStart, laneWidth, drvMaxSpeed, lcDist;
+    std::vector<int> llCrossBeg, lcIdx, csLink, delStep;
+    std::vector<int4> linkInfo;
+    std::vector<unsigned> foeMask;
+    std::vector<Notify> notify;
+    std::vector<unsigned char> rlAvail;
+    std::vector<Veh *> allVeh;
     std::vector<double2> kin, mkin, nkin;
     std::vector<int2> nbuf;
     std::vector<Veh *> involvedVeh;
@@ -69,7 +94,12 @@ struct Soa {   // the arrays the draft's functions touch, sized for this step
 };
 
 Soa *g = nullptr;
-long long g_checked = 0, g_candidates = 0, g_shadows = 0, g_steps = 0, g_involved = 0;
+static int slotAt(Soa &S, Veh *v, const char *what) {
+    auto it = S.slotOf.find(v);
+    if (it == S.slotOf.end()) { printf("PROBE: %s refers to a vehicle that is not running (prio %d, running %d)\n", what, v->priority, (int) v->running); fflush(stdout); abort(); }
+    return it->second;
+}
+long long g_checked = 0, g_candidates = 0, g_shadows = 0, g_steps = 0, g_involved = 0, g_controls = 0;
 int g_fail = 0;
 
 #define CHECK(cond, ...)                                  \
@@ -80,7 +110,7 @@ int g_fail = 0;
         }                                                 \
     } while (0)
 
-void build(Oracle &o) {
+void build(Oracle &o, bool forControl) {
     delete g;
     g = new Soa();
     Soa &S = *g;
@@ -134,21 +164,30 @@ void build(Oracle &o) {
                 next = R.planData()[planIdx + 1];
                 const int want = o.nextDrivable(*v);
                 if (!(next == want || (next < 0 && want < 0))) { printf("PROBE: plan disagrees with the router (%d vs %d)\n", next, want); ++g_fail; }
-            } else {
-                next = o.nextDrivable(*v);
+            } else {   // on a laneLink: second entry of the plan from the lane it came from
+                const int route = R.intern(v->route);
+                plan = R.lanePlan(route, v->iCur, net.laneIdx[v->prevDrivable]);
+                planIdx = R.planBeg()[plan] + 1;
+                next = R.planData()[planIdx + 1];
+                if (R.planData()[planIdx] != d || next != o.nextDrivable(*v)) { printf("PROBE: link plan disagrees with the router\n"); ++g_fail; }
             }
             S.kin[p] = make_double2(v->dis, v->t.speed);
             S.ids[p] = make_int4(s, s, v->priority, next);
-            S.nav[p] = make_int4(planIdx, v->prevDrivable, v->blocker ? S.slotOf.at(v->blocker) : -1, (int) v->enterLaneLinkTime);
+            S.nav[p] = make_int4(planIdx, v->prevDrivable, v->blocker ? slotAt(S, v->blocker, "blocker(nav)") : -1, (int) v->enterLaneLinkTime);
             S.gap[p] = v->gap;
             S.cust[p] = v->bCustomSet ? v->bCustom : NAN;
             S.pos[s] = p;
-            DTmpl t{};
-            t.len = v->t.len; t.maxNegAcc = v->t.maxNegAcc; t.maxSpeed = v->t.maxSpeed; t.minGap = v->t.minGap;
+            DTmpl t{};   // toDevice() of device_sim.cu
+            t.len = v->t.len; t.maxPosAcc = v->t.maxPosAcc; t.maxNegAcc = v->t.maxNegAcc; t.usualPosAcc = v->t.usualPosAcc;
+            t.usualNegAcc = v->t.usualNegAcc; t.minGap = v->t.minGap; t.maxSpeed = v->t.maxSpeed; t.headwayTime = v->t.headwayTime;
+            t.yieldDistance = v->t.yieldDistance; t.turnSpeed = v->t.turnSpeed;
+            t.approachDist = v->t.maxSpeed * v->t.maxSpeed / v->t.usualNegAcc / 2 + v->t.maxSpeed * o.interval * 2;
+            t.speed0 = v->t.speed;
             S.tmpl[s] = t;
+            S.allVeh.push_back(v);
             LcSlot &L = S.slot[s];
             lcResetSlot(L, plan);
-            L.partner = v->partner ? S.slotOf.at(v->partner) : -1;
+            L.partner = v->partner ? slotAt(S, v->partner, "partner") : -1;
             L.type = v->partnerType; L.changing = v->changing; L.finished = v->lcFinished;
             if (v->sigSend) { L.sendTarget = v->sigSend->target; L.sendDir = v->sigSend->direction; }   // only changing vehicles still hold one here
             L.offset = v->offset; L.waiting = v->waitingTime; L.lastChange = v->lastChangeTime; L.gap = v->gap; L.lastDir = v->lastDir;
@@ -157,7 +196,6 @@ void build(Oracle &o) {
             if (v->sigRecv) { L.recvEpoch = S.epoch; }
             L.leaderGap = v->leaderGap; L.followerGap = v->followerGap;
             L.head = v->ctlHead;
-            t.maxPosAcc = v->t.maxPosAcc; S.tmpl[s] = t;
         }
         S.count[d] = k;
     }
@@ -197,10 +235,67 @@ void build(Oracle &o) {
     C.lanePlanRoad = S.lpRoad.data(); C.lanePlanBeg = S.lpBeg.data(); C.lanePlanId = S.lpId.data();
     C.cand = S.cand.data(); C.involved = S.involved.data(); C.spare = S.spare.data(); C.nSpare = nSpare;
     C.shadowLog = S.shadowLog.data(); C.ctrl = &S.lcCtrl;
+
+    // ---- what the control phase needs on top (static tables as in DeviceSim::DeviceSim) ----
+    const int nK = net.nLinks();
+    S.drvMaxSpeed.resize(nD);
+    for (int d = 0; d < nD; ++d) S.drvMaxSpeed[d] = d < nL ? net.laneMaxSpeed[d] : 10000.0;
+    S.llCrossBeg.assign(nK + 1, 0);
+    for (int k = 0; k < nK; ++k) {
+        for (const CrossRef &c : net.llCrosses[k]) { S.lcIdx.push_back(c.cross * 2 + c.side); S.lcDist.push_back(net.crossDist[c.side][c.cross]); }
+        S.llCrossBeg[k + 1] = (int) S.lcIdx.size();
+    }
+    S.csLink.assign(std::max(2 * net.nCross(), 1), 0);
+    for (int c = 0; c < net.nCross(); ++c) { S.csLink[2 * c] = net.crossLink[0][c]; S.csLink[2 * c + 1] = net.crossLink[1][c]; }
+    std::vector<int> flatOf(std::max(2 * net.nCross(), 1), 0);
+    int maxCross = 1;
+    for (int k = 0; k < nK; ++k) {
+        maxCross = std::max(maxCross, S.llCrossBeg[k + 1] - S.llCrossBeg[k]);
+        for (int q = S.llCrossBeg[k]; q < S.llCrossBeg[k + 1]; ++q) flatOf[S.lcIdx[q]] = q;
+    }
+    V.maskWords = (maxCross + 31) / 32;
+    S.linkInfo.assign(std::max(nK, 1), make_int4(0, 0, 0, 0));
+    for (int k = 0; k < nK; ++k)
+        S.linkInfo[k] = make_int4(net.llRoadLink[k], net.llEndLane[k], S.llCrossBeg[k], (net.linkIsTurn(k) ? 1 : 0) | (net.rlType[net.llRoadLink[k]] << 8));
+    if (S.lcIdx.empty()) { S.lcIdx.push_back(0); S.lcDist.push_back(0); }
+    // this step's notifications (Cross::notify, engine.cpp:317-372) straight from the restatement
+    // (before notifyCross has run they are last step's and may point to vehicles that are gone)
+    S.notify.assign(std::max(2 * net.nCross(), 1), Notify{0.0, -1, -1});
+    S.foeMask.assign((size_t) std::max(nK, 1) * V.maskWords, 0u);
+    for (int c = 0; forControl && c < net.nCross(); ++c)
+        for (int side = 0; side < 2; ++side) {
+            Veh *nv = o.notifyVeh[side][c];
+            if (!nv) continue;
+            const int cs = 2 * c + side;
+            S.notify[cs] = Notify{o.notifyDist[side][c], S.pos[slotAt(S, nv, "notify")], S.epoch};
+            const int foeLink = S.csLink[cs ^ 1];
+            const int bit = flatOf[cs ^ 1] - S.llCrossBeg[foeLink];
+            S.foeMask[(size_t) foeLink * V.maskWords + (bit >> 5)] |= 1u << (bit & 31);
+        }
+    S.rlAvail.assign(std::max(net.nRoadLinks(), 1), 0);
+    for (int k = 0; k < nK; ++k) S.rlAvail[net.llRoadLink[k]] = o.linkAvailable(k) ? 1 : 0;
+    S.delStep.assign(S.pos.size(), INT_MIN);
+    int nVeh = 0, nCustom = 0;
+    for (int d = 0; d < nD; ++d) {
+        int k = 0;
+        for (Veh *v : o.lists[d]) {
+            const int p = S.off[d] + k++;
+            S.leader[p] = v->leader ? S.pos[slotAt(S, v->leader, "leader")] : -1;
+            S.blk[S.slotOf.at(v)] = v->blocker ? slotAt(S, v->blocker, "blocker") : -1;
+            S.veh[0][nVeh++] = make_int2(p, d);
+            nCustom += v->bCustomSet;
+        }
+    }
+    S.ctrl.nVeh[0] = nVeh;
+    S.ctrl.nCustom = nCustom;
+    V.drvMaxSpeed = S.drvMaxSpeed.data(); V.linkInfo = S.linkInfo.data(); V.llCrossBeg = S.llCrossBeg.data(); V.lcIdx = S.lcIdx.data();
+    V.lcDist = S.lcDist.data(); V.csLink = S.csLink.data(); V.foeMask = S.foeMask.data(); V.notify = S.notify.data();
+    V.rlAvail = S.rlAvail.data(); V.delStep = S.delStep.data(); V.nCross = net.nCross();
+    V.lcOn = o.laneChange ? 1 : 0;
 }
 
 void before(Oracle &o) {
-    build(o);
+    build(o, false);
     Soa &S = *g;
     View &V = S.V;
     for (int l = 0; l < V.nLanes; ++l) lcInitSegments(V, V.lc, l);
@@ -287,7 +382,7 @@ void after(Oracle &o) {
 
 // ---- control tail: engine.cpp:195-244 for the vehicles involved in a lane change ------------------------
 void beforeControl(Oracle &o) {
-    build(o);
+    build(o, true);
     Soa &S = *g;
     View &V = S.V;
     const int epoch = S.epoch;
@@ -301,17 +396,30 @@ void beforeControl(Oracle &o) {
             L.tgtLeader = v->targetLeader ? S.slotOf.at(v->targetLeader) : -1;
             L.tgtFollower = v->targetFollower ? S.slotOf.at(v->targetFollower) : -1;
         }
-        L.headBlocker = v->bBlockerSet && v->bBlocker ? S.slotOf.at(v->bBlocker) : -1;
-        if (L.partner >= 0 || lcRecvValid(L, epoch) || L.type != 0 || L.changing) {   // the predicate of the k_control hook
-            S.involved[S.lcCtrl.nInvolved++] = kv.second;
-            S.involvedVeh.push_back(v);
-        }
     }
-    lcControlTail(V, V.lc, epoch);
+    // the real control phase, one vehicle after the other: the lane-change hook leaves the involved ones to the tail
+    blockDim.x = 1; threadIdx.x = 0;
+    phase_control(V, 0, 1);
+    for (int k = 0; k < S.lcCtrl.nInvolved; ++k) S.involvedVeh.push_back(S.vehOfSlot[S.involved[k]]);
+    if (o.laneChange) lcControlTail(V, V.lc, epoch);
 }
 
 void afterControl(Oracle &o) {
     Soa &S = *g;
+    for (Veh *v : S.allVeh) {   // every running vehicle: the buffers k_move will commit
+        const int s = S.slotOf.at(v);
+        const int p = S.pos[s];
+        const double2 nk = S.nkin[p];
+        const int2 nb = S.nbuf[p];
+        CHECK(v->bSpeedSet && nk.y == v->bSpeed, "prio %d: next speed %.17g vs %.17g", v->priority, v->bSpeed, nk.y);
+        CHECK(v->bDisSet && nk.x == v->bDis, "prio %d: next distance %.17g vs %.17g", v->priority, v->bDis, nk.x);
+        const int want = v->bEndSet ? -2 : (v->bDrvSet && v->bDrv >= 0 ? v->bDrv : -1);
+        CHECK(nb.x == want, "prio %d: next drivable %d vs %d (on drivable %d of %d lanes, dis %.3f, plan next %d, plan %d idx %d)", v->priority, want, nb.x,
+              v->drivable, S.V.nLanes, v->dis, S.ids[p].w, S.slot[s].plan, S.nav[p].x);
+        CHECK(nb.y == (v->bBlockerSet && v->bBlocker ? S.slotOf.at(v->bBlocker) : -1), "prio %d: blocker buffer", v->priority);
+        if (o.laneChange) CHECK(v->waitingTime == S.slot[s].waiting, "prio %d: waiting time %g vs %g", v->priority, v->waitingTime, S.slot[s].waiting);
+        ++g_controls;
+    }
     for (Veh *v : S.involvedVeh) {
         const int s = S.slotOf.at(v);
         const LcSlot &L = S.slot[s];
@@ -353,13 +461,13 @@ void probe(Oracle &o, int phase) {
 int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: lc_device_probe config.json steps\n"); return 64; }
     Oracle o;
-    if (!o.load(argv[1]) || !o.laneChange) { fprintf(stderr, "cannot load %s (laneChange must be true)\n", argv[1]); return 2; }
+    if (!o.load(argv[1])) { fprintf(stderr, "cannot load %s\n", argv[1]); return 2; }
     o.routing->enableLanePlans();
     o.lcProbe = probe;
     o.deviceForm = true;   // (proven equal to the reference order; gives the hook between the two control passes)
     const int steps = atoi(argv[2]);
     for (int s = 0; s < steps && g_fail == 0; ++s) o.nextStep();
-    printf("%s %lld steps, %lld list entries, %lld candidates, %lld shadows checked, %lld control tails, %d failures\n", g_fail ? "FAIL" : "OK", g_steps,
-           g_checked, g_candidates, g_shadows, g_involved, g_fail);
+    printf("%s %lld steps, %lld list entries, %lld candidates, %lld shadows checked, %lld control tails, %lld controls, %d failures\n",
+           g_fail ? "FAIL" : "OK", g_steps, g_checked, g_candidates, g_shadows, g_involved, g_controls, g_fail);
     return g_fail ? 1 : 0;
 }
