@@ -94,7 +94,9 @@ __device__ void lcMakeSignal(const View &V, const LcView &C, int p, int d, int e
             if (go) {
                 const int planIdx = V.nav[p].x;
                 const int roadPos = lcRoadPos(V, C, L.plan, planIdx);
-                const bool onLast = idv.w == -1;               // PLAN_END: the current lane is on the route's last road
+                // Router::onLastRoad (router.cpp:131-138) compares the road with route.back(): true on EVERY visit of that
+                // road, e.g. on the first road of a route that returns to it
+                const bool onLast = C.laneRoad[d] == C.routeLastRoad[C.planRoute[L.plan]];
                 const int seg = C.segIdx[p];
                 if (C.laneIdx[d] < C.laneRoadN[d] - 1) {
                     const int outer = d + 1;
@@ -274,6 +276,30 @@ __device__ void lcInsertShadow(const View &V, const LcView &C, int slot, int epo
     LcSlot &S = C.slot[sh];
     lcResetSlot(S, np);
     S.gap = L.gap;
+    // The two immediate updates of LaneChange::insertShadow (lanechange.cpp:98-100).  The full leader pass that
+    // follows (engine.cpp:573) recomputes leaders, but a vehicle keeps its last gap VALUE when that pass finds
+    // no leader for it, and a later candidate of this same scheduling pass may copy that value into its own
+    // shadow (the follower updated here can be the next parent) -- so both are applied as the reference does.
+    {   // shadow->updateLeaderAndGap(targetLeader), vehicle.cpp:157-196
+        const int tlp = L.tgtLeader >= 0 ? V.pos[L.tgtLeader] : -1;
+        if (tlp >= 0 && C.posDrv[tlp] == target) {
+            S.gap = V.kin[tlp].x - V.tmpl[V.ids[tlp].y].len - V.kin[q].x;
+            V.gap[q] = S.gap;
+        } else {
+            int ld = -1;
+            double g = 0;
+            headSearch(V, target, V.kin[q].x, V.ids[q].w, V.nav[q].x, V.tmpl[V.ids[q].y], -1, ld, g);
+            if (ld >= 0) { S.gap = g; V.gap[q] = g; }
+        }
+    }
+    if (L.tgtFollower >= 0) {   // targetFollower->updateLeaderAndGap(shadow): same lane by construction
+        const int fp = V.pos[L.tgtFollower];
+        if (C.posDrv[fp] == target) {
+            const double g = V.kin[q].x - V.tmpl[V.ids[q].y].len - V.kin[fp].x;
+            C.slot[L.tgtFollower].gap = g;
+            V.gap[fp] = g;
+        }
+    }
     S.type = 2; S.partner = slot;                                   // setParent
     L.type = 1; L.partner = sh;                                     // setShadow
     L.changing = 1;

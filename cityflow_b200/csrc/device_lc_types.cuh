@@ -47,6 +47,8 @@ struct LcView {
     const int *posDrv;         // per position: its drivable (static)
     const int *segBeg;         // per lane: first entry of its segments in segStart (nLanes + 1)
     const double *segStart;    // Segment::startPos
+    const int *laneRoad;       // per lane: its road
+    const int *routeLastRoad;  // per route: route.back() -- Router::isLastRoad is an identity test (router.cpp:131-134)
     const int *laneIdx;        // per lane: index in its road
     const int *laneRoadN;      // per lane: number of lanes of its road
     const double *laneWidth;

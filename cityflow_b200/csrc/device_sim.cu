@@ -404,6 +404,7 @@ struct DeviceSim::Impl {
 
 #ifdef CFB_LANE_CHANGE
     DevBuf<LcSlot> lcSlot;
+    DevBuf<int> lcLaneRoad, lcRouteLastRoad;
     DevBuf<int> lcSegIdx, lcPosDrv, lcSegBeg, lcLaneIdx, lcLaneRoadN, lcPlanRoute, lcPlanRoadPos, lcLanePlanRoad,
         lcLanePlanBeg, lcLanePlanId, lcCand, lcInvolved, lcSpare, lcPrio;
     DevBuf<double> lcSegStart, lcLaneWidth;
@@ -1508,9 +1509,15 @@ void DeviceSim::uploadLanePlans(const Routing &routing) {
     up(I.lcLanePlanRoad, routing.lanePlanRoadTable());
     up(I.lcLanePlanBeg, routing.lanePlanBegTable());
     up(I.lcLanePlanId, routing.lanePlanIdTable());
+    {
+        std::vector<int> last(std::max(routing.numRoutes(), 1), -1);
+        for (int r = 0; r < routing.numRoutes(); ++r) if (routing.route(r).valid) last[r] = routing.route(r).roads.back();
+        I.lcRouteLastRoad.upload(last);
+    }
     LcView &C = I.V.lc;
     C.planRoute = I.lcPlanRoute.p; C.planRoadPos = I.lcPlanRoadPos.p;
     C.lanePlanRoad = I.lcLanePlanRoad.p; C.lanePlanBeg = I.lcLanePlanBeg.p; C.lanePlanId = I.lcLanePlanId.p;
+    C.routeLastRoad = I.lcRouteLastRoad.p;
     legacySync();
 }
 
@@ -1545,6 +1552,8 @@ void DeviceSim::enableLaneChange(const RoadNet &net, const Routing &routing) {
         for (int p = I.offHost[d]; p < I.offHost[d + 1]; ++p) posDrv[p] = d;
     I.lcSegBeg.upload(segBeg); I.lcSegStart.upload(segStart); I.lcLaneIdx.upload(laneIdx); I.lcLaneRoadN.upload(laneRoadN);
     I.lcLaneWidth.upload(laneWidth); I.lcPosDrv.upload(posDrv);
+    I.lcLaneRoad.upload(net.laneRoad);
+    V.lc.laneRoad = I.lcLaneRoad.p;
     I.lcSegIdx.alloc(I.P); I.lcSegIdx.fill(0);
     I.lcCand.alloc(LC_MAX_CAND); I.lcInvolved.alloc(LC_MAX_CAND); I.lcShadowLog.alloc(LC_MAX_CAND); I.lcPrio.alloc(LC_MAX_CAND);
     I.lcCtrl.alloc(1); I.lcCtrl.fill(0);
@@ -1626,6 +1635,10 @@ void DeviceSim::debugDumpLc(std::vector<LcDebugRec> &out) {
     std::vector<double2> kin(P);
     std::vector<int4> ids(P), nav(P);
     std::vector<LcSlot> lc(I.slotCap);
+    std::vector<int> del(I.slotCap);
+    CFB_CUDA(cudaMemcpy(del.data(), I.V.delStep, del.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    readCtrlImpl(I.stream, I.hCtrl, I.V.ctrl);
+    const int lastStep = I.hCtrl->step - 1;
     CFB_CUDA(cudaMemcpy(count.data(), I.V.count, count.size() * sizeof(int), cudaMemcpyDeviceToHost));
     CFB_CUDA(cudaMemcpy(leader.data(), I.V.leader, P * sizeof(int), cudaMemcpyDeviceToHost));
     CFB_CUDA(cudaMemcpy(kin.data(), I.V.kin, P * sizeof(double2), cudaMemcpyDeviceToHost));
@@ -1641,6 +1654,7 @@ void DeviceSim::debugDumpLc(std::vector<LcDebugRec> &out) {
             r.slot = ids[p].x; r.priority = ids[p].z; r.partnerType = L.type; r.partnerSlot = L.partner; r.drivable = d;
             r.leaderSlot = leader[p] >= 0 ? ids[leader[p]].x : -1;
             r.blockerSlot = nav[p].z;
+            if (r.blockerSlot >= 0 && del[r.blockerSlot] == lastStep) r.blockerSlot = -1;   // dropped lazily on the device
             r.flags = L.changing | (L.finished << 1);
             r.lastDir = L.lastDir;
             r.dis = kin[p].x; r.speed = kin[p].y; r.gap = leader[p] >= 0 ? L.gap : 0.0;

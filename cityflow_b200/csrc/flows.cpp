@@ -107,6 +107,11 @@ int Routing::buildPlan(const std::vector<int> &roads, int startLane, int roadPos
     for (int r = roadPos;; ++r) {
         planData_.push_back(lane);
         int ll = chooseLink(lane, roads, r);
+        // Router::isLastRoad compares the ROAD with route.back() (router.cpp:131-134), not the position: on a
+        // route that returns to its first road a lane that cannot continue counts as "on the last road" --
+        // the vehicle is not stopped (router.h:66-68) and leaves the network at the end of that lane
+        // (vehicle.cpp:58-61).  Found by the fuzz tests on the emulated device step.
+        if (ll == PLAN_DEAD && roads[r] == roads.back()) ll = PLAN_END;
         if (ll < 0) {
             planData_.push_back(ll);  // PLAN_END or PLAN_DEAD
             break;

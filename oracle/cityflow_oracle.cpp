@@ -98,6 +98,8 @@ struct Veh {
     bool changing = false, lcFinished = false;
     double lastChangeTime = 0;
     double ctlHead = 0;              // device form: order-independent part of the next speed
+    int firstLaneForProbe = -1;      // tests/device_step_probe.cpp: the lane whose waiting queue the vehicle joined
+    double initialSpeedForProbe = 0; //                               VehicleInfo::speed at creation
     bool isReal() const { return partnerType != 2; }                                   // vehicle.h:278
     bool planChange() const { return (sigSend && sigSend->target >= 0 && sigSend->target != drivable) || changing; }  // lanechange.cpp:23-25
 };
@@ -567,6 +569,7 @@ struct Oracle {
         else {
             do { sh->priority = (int) rnd(); } while (pool.count(sh->priority));
             pool.emplace(sh->priority, sh);
+            shadowsThisStep.emplace_back(&v, sh->priority);
         }
         // LaneChange::insertShadow
         v.changing = true;
@@ -659,6 +662,10 @@ struct Oracle {
     }
     bool deferShadowPriority = false;
     void (*lcProbe)(Oracle &, int) = nullptr;
+    // for tests/device_step_probe.cpp (the device code emulated on the host): this step's spawns in
+    // planRoute order and this step's shadows (parent, priority drawn) in creation order
+    std::vector<Veh *> spawnedThisStep;
+    std::vector<std::pair<Veh *, int>> shadowsThisStep;
     long long segOrderMismatch = 0;
     // sizes of the sequential parts of the device form, summed / maximised over the steps so far
     long long statCandidates = 0, statInvolved = 0, statRunning = 0;
@@ -863,6 +870,9 @@ struct Oracle {
                     }
                     v->drivable = cand[rnd() % cand.size()];
                     waiting[v->drivable].push_back(v);
+                    v->firstLaneForProbe = v->drivable;
+                    v->initialSpeedForProbe = v->t.speed;
+                    spawnedThisStep.push_back(v);
                 } else {
                     if (v->flow >= 0) {
                         if (flows[v->flow].valid)
@@ -1016,6 +1026,8 @@ struct Oracle {
     }
     // engine.cpp:566-594
     void nextStep() {
+        spawnedThisStep.clear();
+        shadowsThisStep.clear();
         for (size_t i = 0; i < flows.size(); ++i) flowStep(flows[i], (int) i);
         planRoute();
         handleWaiting();

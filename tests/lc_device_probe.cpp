@@ -25,40 +25,17 @@
 #include <map>
 #include <vector>
 
-#include <vector_types.h>
-#include <vector_functions.h>
-#undef __device__
-#undef __global__
-#undef __forceinline__
-#undef __launch_bounds__
-#undef __align__
-#define __device__
-#define __global__
-#define __forceinline__ inline
-#define __launch_bounds__(...)
-#define __align__(n) __attribute__((aligned(n)))
+#include "device_emu.h"   // CUDA keywords defined away + stand-ins; this probe runs everything as ONE thread, no fibers
 #define CFB_LANE_CHANGE 1
 #define CFB_DEAD_END_STOP 1
 #define CFB_LC_HOST_PROBE 1
-static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
-static inline int atomicSub(int *p, int v) { int o = *p; *p -= v; return o; }
-static inline int atomicOr(int *p, int v) { int o = *p; *p |= v; return o; }
 using std::max;
 using std::min;
-// what the control phase uses of the CUDA execution model, for ONE thread at a time
-static struct { unsigned x = 1, y = 1, z = 1; } blockDim;
-static struct { unsigned x = 0, y = 0, z = 0; } threadIdx;
-static inline long long clock64() { return 0; }
-static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
-static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
-namespace cooperative_groups {
-struct lone_thread { unsigned size() const { return 1; } unsigned thread_rank() const { return 0; } template <class T> T shfl(T v, int) const { return v; } };
-inline lone_thread coalesced_threads() { return lone_thread(); }
-}  // namespace cooperative_groups
 namespace cfb { namespace cg = cooperative_groups; }
 
 #include "device_sim.h"
 #include "device_view.cuh"
+#include "device_phases_a.cuh"   // headSearch (the warp code in there is not run by this probe)
 #include "device_control.cuh"   // canPass, phase_control (+ device_lc.cuh)
 
 #include "../oracle/cityflow_oracle.cpp"   // Oracle / Veh (anonymous namespace: visible in this translation unit)
@@ -71,7 +48,7 @@ struct Soa {   // the arrays the draft's functions touch, sized for this step
     std::vector<int> off, count, pos, leader, laneOutBeg, laneOutLinks, planBeg, planData, segIdx, posDrv, segBeg,
         laneIdx, laneRoadN, planRoute, planRoadPos, lpRoad, lpBeg, lpId, cand, involved, spare, act[2], blk, extra, entCnt, ent;
     std::vector<double> drvLength, gap, cust, segStart, laneWidth, drvMaxSpeed, lcDist;
-    std::vector<int> llCrossBeg, lcIdx, csLink, delStep;
+    std::vector<int> llCrossBeg, lcIdx, csLink, delStep, llStartLane, routeLast, laneRoadT;
     std::vector<int4> linkInfo;
     std::vector<unsigned> foeMask;
     std::vector<Notify> notify;
@@ -202,6 +179,9 @@ void build(Oracle &o, bool forControl) {
     S.planBeg = R.planBeg(); S.planData = R.planData();
     S.planRoute = R.planRouteTable(); S.planRoadPos = R.planRoadPosTable();
     S.lpRoad = R.lanePlanRoadTable(); S.lpBeg = R.lanePlanBegTable(); S.lpId = R.lanePlanIdTable();
+    S.routeLast.assign(std::max(R.numRoutes(), 1), -1);
+    for (int r = 0; r < R.numRoutes(); ++r) if (R.route(r).valid) S.routeLast[r] = R.route(r).roads.back();
+    S.laneRoadT.assign(net.laneRoad.begin(), net.laneRoad.end());
     S.tail.resize(nD);
     for (int d = 0; d < nD; ++d) {
         Tail t{}; t.pos = -1; t.prev = -1;
@@ -219,6 +199,9 @@ void build(Oracle &o, bool forControl) {
     View &V = S.V;
     V.nLanes = nL; V.nLinks = net.nLinks(); V.nDrv = nD; V.dt = o.interval; V.par = 0; V.vehCap = P + 64;
     V.drvLength = S.drvLength.data(); V.off = S.off.data(); V.laneOutBeg = S.laneOutBeg.data(); V.laneOutLinks = S.laneOutLinks.data();
+    S.llStartLane.assign(net.llStartLane.begin(), net.llStartLane.end());
+    if (S.llStartLane.empty()) S.llStartLane.push_back(0);
+    V.llStartLane = S.llStartLane.data();   // headSearch (the shadow's immediate leader update)
     V.tmpl = S.tmpl.data(); V.planBeg = S.planBeg.data(); V.planData = S.planData.data();
     V.kin = S.kin.data(); V.gap = S.gap.data(); V.leader = S.leader.data(); V.ids = S.ids.data(); V.nav = S.nav.data();
     V.count = S.count.data(); V.pos = S.pos.data(); V.tail = S.tail.data(); V.cust = S.cust.data(); V.blk = S.blk.data();
@@ -233,6 +216,7 @@ void build(Oracle &o, bool forControl) {
     C.laneIdx = S.laneIdx.data(); C.laneRoadN = S.laneRoadN.data(); C.laneWidth = S.laneWidth.data();
     C.planRoute = S.planRoute.data(); C.planRoadPos = S.planRoadPos.data();
     C.lanePlanRoad = S.lpRoad.data(); C.lanePlanBeg = S.lpBeg.data(); C.lanePlanId = S.lpId.data();
+    C.routeLastRoad = S.routeLast.data(); C.laneRoad = S.laneRoadT.data();
     C.cand = S.cand.data(); C.involved = S.involved.data(); C.spare = S.spare.data(); C.nSpare = nSpare;
     C.shadowLog = S.shadowLog.data(); C.ctrl = &S.lcCtrl;
 
@@ -398,7 +382,7 @@ void beforeControl(Oracle &o) {
         }
     }
     // the real control phase, one vehicle after the other: the lane-change hook leaves the involved ones to the tail
-    blockDim.x = 1; threadIdx.x = 0;
+    blockDim.x = 1; threadIdx.x = 0;   // one vehicle after the other
     phase_control(V, 0, 1);
     for (int k = 0; k < S.lcCtrl.nInvolved; ++k) S.involvedVeh.push_back(S.vehOfSlot[S.involved[k]]);
     if (o.laneChange) lcControlTail(V, V.lc, epoch);
