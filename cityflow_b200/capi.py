@@ -29,10 +29,13 @@ def declared_symbols() -> list:
     return sorted(set(re.findall(r"\b(cfb_[a-z0-9_]+)\s*\(", txt)))
 
 
-def load_library() -> ctypes.CDLL:
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError("cityflow_b200: %s is missing -- build it first (__graft_entry__.build())" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+def load_library(path: str = None) -> ctypes.CDLL:
+    """The product library; `path` is for the test suite only (the same C-ABI built over the emulated device,
+    tests/device_sim_emu.cpp -- never a product path)."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError("cityflow_b200: %s is missing -- build it first (__graft_entry__.build())" % path)
+    lib = ctypes.CDLL(path)
     c = ctypes
     vp, i32, i64, dbl, cp = c.c_void_p, c.c_int, c.c_int64, c.c_double, c.c_char_p
     sig = {
@@ -74,10 +77,13 @@ def load_library() -> ctypes.CDLL:
         "cfb_replay_destroy": (None, [vp]),
         "cfb_replay_roadnet_json": (i64, [vp, vp, i64]),
         "cfb_replay_format_step": (i64, [vp, vp, i64, vp, vp, i64]),
+        "cfb_push_vehicle": (i32, [vp, vp, vp, i32]),
         "cfb_set_replay_file": (i32, [vp, cp]),
         "cfb_set_save_replay": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
+        if not hasattr(lib, name):
+            continue   # (a test build may lack optional entry points)
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -87,8 +93,8 @@ def load_library() -> ctypes.CDLL:
 class CEngine:
     """Minimal object wrapper over the raw C calls (numpy in / out)."""
 
-    def __init__(self, config: str, device: int = 0):
-        self.lib = load_library()
+    def __init__(self, config: str, device: int = 0, lib_path: str = None):
+        self.lib = load_library(lib_path)
         self.h = self.lib.cfb_engine_create(config.encode(), 1, device)
         if not self.h:
             raise RuntimeError("cfb_engine_create failed: %s" % self.lib.cfb_last_error(None).decode())
@@ -147,6 +153,16 @@ class CEngine:
 
     def reset(self, seed: bool = False):
         self._check(self.lib.cfb_reset(self.h, int(seed)))
+
+    def set_random_seed(self, seed: int):
+        self._check(self.lib.cfb_set_random_seed(self.h, seed))
+
+    def push_vehicle(self, info: dict, roads: list):
+        """Engine::pushVehicle (engine.cpp:693-717); missing keys keep the reference's defaults."""
+        names = ["speed", "length", "width", "maxPosAcc", "maxNegAcc", "usualPosAcc", "usualNegAcc", "minGap", "maxSpeed", "headwayTime"]
+        v = np.array([info.get(k, float("nan")) for k in names], np.float64)
+        arr = (ctypes.c_char_p * len(roads))(*[r.encode() for r in roads])
+        self._check(self.lib.cfb_push_vehicle(self.h, v.ctypes.data, arr, len(roads)))
 
     def average_travel_time(self) -> float:
         return float(self.lib.cfb_get_average_travel_time(self.h))
