@@ -154,6 +154,25 @@ class CEngine:
     def reset(self, seed: bool = False):
         self._check(self.lib.cfb_reset(self.h, int(seed)))
 
+    def set_vehicle_speed(self, flow: int, index: int, speed: float) -> bool:
+        """Engine::setVehicleSpeed (engine.cpp:827-834); False = no such vehicle."""
+        class Ref(ctypes.Structure):
+            _fields_ = [("flow", ctypes.c_int32), ("index", ctypes.c_int32)]
+        self.lib.cfb_set_vehicle_speed.restype = ctypes.c_int
+        self.lib.cfb_set_vehicle_speed.argtypes = [ctypes.c_void_p, Ref, ctypes.c_double]
+        return self.lib.cfb_set_vehicle_speed(self.h, Ref(flow, index), speed) >= 0
+
+    def set_vehicle_route(self, flow: int, index: int, roads: list) -> bool:
+        """Engine::setRoute (engine.cpp:852-866)."""
+        class Ref(ctypes.Structure):
+            _fields_ = [("flow", ctypes.c_int32), ("index", ctypes.c_int32)]
+        arr = (ctypes.c_char_p * len(roads))(*[r.encode() for r in roads])
+        ok = ctypes.c_int(0)
+        self.lib.cfb_set_vehicle_route.restype = ctypes.c_int
+        self.lib.cfb_set_vehicle_route.argtypes = [ctypes.c_void_p, Ref, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        self._check(self.lib.cfb_set_vehicle_route(self.h, Ref(flow, index), arr, len(roads), ctypes.byref(ok)))
+        return ok.value == 1
+
     def set_random_seed(self, seed: int):
         self._check(self.lib.cfb_set_random_seed(self.h, seed))
 
