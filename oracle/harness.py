@@ -39,6 +39,9 @@ LC_DTYPE = np.dtype([   # `refdump runlc` / cfo_lc_vehicles: every running vehic
 REFDUMP_LC = os.path.join(os.path.dirname(REFDUMP), "refdump_lcorder")
 
 
+REF_TIMEOUT = 900   # seconds: a reference run that does not come back fails the test instead of blocking the suite
+
+
 def have_lc_ref() -> bool:
     return os.path.exists(REFDUMP_LC)
 
@@ -194,13 +197,13 @@ class RefDump:
     @staticmethod
     def static(config: str) -> dict:
         with tempfile.NamedTemporaryFile(suffix=".bin") as f:
-            subprocess.check_call([REFDUMP, "static", config, f.name])
+            subprocess.check_call([REFDUMP, "static", config, f.name], timeout=REF_TIMEOUT)
             return parse_static(f.name)
 
     @staticmethod
     def run(config: str, steps: int, threads: int = 1, every: int = 1, *, n_inter: int, n_drivables: int):
         with tempfile.NamedTemporaryFile(suffix=".bin") as f:
-            subprocess.check_call([REFDUMP, "run", config, str(steps), str(threads), f.name, str(every)])
+            subprocess.check_call([REFDUMP, "run", config, str(steps), str(threads), f.name, str(every)], timeout=REF_TIMEOUT)
             return parse_run(f.name, n_inter, n_drivables)
 
     @staticmethod
@@ -208,12 +211,12 @@ class RefDump:
         """laneChange=true run of the reference with the priority-ordered worker set (`patched`,
         oracle/lc_order_patch.sh) or of the unmodified build; states incl. shadows."""
         with tempfile.NamedTemporaryFile(suffix=".bin") as f:
-            subprocess.check_call([REFDUMP_LC if patched else REFDUMP, "runlc", config, str(steps), str(threads), f.name, str(every)])
+            subprocess.check_call([REFDUMP_LC if patched else REFDUMP, "runlc", config, str(steps), str(threads), f.name, str(every)], timeout=REF_TIMEOUT)
             return parse_runlc(f.name, n_inter, n_drivables)
 
     @staticmethod
     def bench(config: str, steps: int, threads: int, warmup: int = 0) -> dict:
-        out = subprocess.check_output([REFDUMP, "bench", config, str(steps), str(threads), str(warmup)])
+        out = subprocess.check_output([REFDUMP, "bench", config, str(steps), str(threads), str(warmup)], timeout=3600)
         return json.loads(out.decode().strip().splitlines()[-1])
 
 

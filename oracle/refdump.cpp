@@ -57,7 +57,8 @@ struct Out {
     explicit Out(const char *path) : fp(fopen(path, "wb")) {
         if (!fp) { perror(path); exit(2); }
     }
-    ~Out() { fclose(fp); }
+    ~Out() { if (fp) fclose(fp); }
+    void close() { if (fp) { fclose(fp); fp = nullptr; } }
     void i32(int32_t v) { fwrite(&v, 4, 1, fp); }
     void i64(int64_t v) { fwrite(&v, 8, 1, fp); }
     void f64(double v) { fwrite(&v, 8, 1, fp); }
@@ -146,6 +147,9 @@ int dumpStatic(const char *cfg, const char *outPath) {
             for (size_t k = 0; k < in.getRoadLinks().size(); ++k) o.i32(ph.roadLinkAvailable[k] ? 1 : 0);
         }
     }
+    o.close();
+    fflush(stdout);
+    _exit(0);   // (no ~Engine, see dumpRun)
     return 0;
 }
 
@@ -201,6 +205,11 @@ int dumpRun(const char *cfg, int steps, int threads, const char *outPath, int ev
             }
         }
     }
+    // The reference's ~Engine (engine.cpp:762-771) can fail to return when worker threads are still parked
+    // on its barriers (seen with 8 threads): the dump is complete, so close it and leave without the destructor.
+    o.close();
+    fflush(stdout);
+    _exit(0);
     return 0;
 }
 
@@ -255,6 +264,11 @@ int dumpRunLC(const char *cfg, int steps, int threads, const char *outPath, int 
             for (Vehicle *v : d->getVehicles()) o.i32(v->getPriority());
         }
     }
+    // The reference's ~Engine (engine.cpp:762-771) can fail to return when worker threads are still parked
+    // on its barriers (seen with 8 threads): the dump is complete, so close it and leave without the destructor.
+    o.close();
+    fflush(stdout);
+    _exit(0);
     return 0;
 }
 
