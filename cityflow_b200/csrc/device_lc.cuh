@@ -225,15 +225,16 @@ __device__ void lcUpdateLeaderAndFollower(const View &V, const LcView &C, int sl
 // Engine::insertShadow engine.cpp:811-819 + LaneChange::insertShadow lanechange.cpp:73-102.
 // The shadow becomes a vehicle of its own in the target lane's bucket, right before targetFollower
 // (or at the end); the records behind it move back by one position.
-__device__ void lcInsertShadow(const View &V, const LcView &C, int slot, int epoch) {
+// Returns the shadow's slot (-1: no room).  Safe to run for different ROADS at the same time: it touches the
+// target lane's bucket, per-slot records of vehicles on that road, and shared counters through atomics.
+__device__ int lcInsertShadow(const View &V, const LcView &C, int slot, int epoch) {
     LcSlot &L = C.slot[slot];
-    const int u = C.ctrl->spareUsed;
-    if (u >= C.nSpare) { C.ctrl->error |= 2; return; }
-    const int sh = C.spare[u];
     const int target = L.sendTarget;
     const int base = V.off[target], n = V.count[target];
-    if (n >= V.off[target + 1] - base) { atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW); return; }
-    C.ctrl->spareUsed = u + 1;
+    if (n >= V.off[target + 1] - base) { atomicOr(&V.ctrl->error, ERR_BUCKET_OVERFLOW); return -1; }
+    const int u = atomicAdd(&C.ctrl->spareUsed, 1);
+    if (u >= C.nSpare) { atomicOr(&C.ctrl->error, 2); return -1; }
+    const int sh = C.spare[u];
     const int pv = V.pos[slot];
     int at = n;                                                    // list position (0-based) of the shadow
     if (L.tgtFollower >= 0) {
@@ -310,28 +311,34 @@ __device__ void lcInsertShadow(const View &V, const LcView &C, int slot, int epo
     if (vi < V.vehCap) V.vehList[cpar][vi] = make_int2(base + n, target);   // the position that became occupied
     if (n == 0) V.actList[cpar][atomicAdd(&V.ctrl->nAct[cpar], 1)] = target;
     atomicAdd(&V.ctrl->active, 1);                                  // activeVehicleCount++ (engine.cpp:818)
-    const int k = C.ctrl->nShadows;
-    C.shadowLog[k] = make_int2(slot, sh);
-    C.ctrl->nShadows = k + 1;
+    return sh;
 }
 
+// one candidate of Engine::scheduleLaneChange's loop (engine.cpp:795-807); returns the shadow's slot or -1
+__device__ int lcScheduleOne(const View &V, const LcView &C, int slot, int epoch) {
+    LcSlot &L = C.slot[slot];
+    lcUpdateLeaderAndFollower(V, C, slot, epoch);
+    if (L.tgtLeader >= 0) lcReceiveSignal(V, C, L.tgtLeader, slot, epoch);      // SimpleLaneChange::sendSignal
+    if (L.tgtFollower >= 0) lcReceiveSignal(V, C, L.tgtFollower, slot, epoch);
+    const int p = V.pos[slot];
+    const int d = C.posDrv[p];
+    if (lcPlanChange(L, d, epoch) && lcSendValid(L, epoch) && !lcRecvValid(L, epoch) && !L.changing) {
+        const bool gapValid = L.leaderGap >= lcMinBrake(V, p) && L.followerGap >= lcSafeGapBefore(V, L, epoch);
+        if (gapValid && d < V.nLanes) return lcInsertShadow(V, C, slot, epoch);
+    }
+    return -1;
+}
+// the whole loop in one thread, in the reference's order (kept for the host probe and as a debugging fallback)
 __device__ void lcSchedule(const View &V, const LcView &C, int epoch) {
     int n = min(C.ctrl->nCand, LC_MAX_CAND);
     lcSortByPriority(V, C.cand, n);          // threadVehiclePool order (priority-ordered reference, oracle/lc_order_patch.sh)
     lcAllEqualSortPermute(C.cand, n);        // std::sort by urgency, all equal
+    int k = 0;
     for (int i = 0; i < n; ++i) {
-        const int slot = C.cand[i];
-        LcSlot &L = C.slot[slot];
-        lcUpdateLeaderAndFollower(V, C, slot, epoch);
-        if (L.tgtLeader >= 0) lcReceiveSignal(V, C, L.tgtLeader, slot, epoch);      // SimpleLaneChange::sendSignal
-        if (L.tgtFollower >= 0) lcReceiveSignal(V, C, L.tgtFollower, slot, epoch);
-        const int p = V.pos[slot];
-        const int d = C.posDrv[p];
-        if (lcPlanChange(L, d, epoch) && lcSendValid(L, epoch) && !lcRecvValid(L, epoch) && !L.changing) {
-            const bool gapValid = L.leaderGap >= lcMinBrake(V, p) && L.followerGap >= lcSafeGapBefore(V, L, epoch);
-            if (gapValid && d < V.nLanes) lcInsertShadow(V, C, slot, epoch);
-        }
+        const int sh = lcScheduleOne(V, C, C.cand[i], epoch);
+        if (sh >= 0) C.shadowLog[k++] = make_int2(C.cand[i], sh);
     }
+    C.ctrl->nShadows = k;
 }
 
 // ---- control tail (Engine::vehicleControl engine.cpp:188-251 for the involved vehicles), one thread -----
@@ -416,13 +423,11 @@ __device__ void lcAbort(const LcView &C, int slot, int epoch) {
     lcClearSignal(L, epoch);
 }
 
-__device__ void lcControlTail(const View &V, const LcView &C, int epoch) {
-    const int n = min(C.ctrl->nInvolved, LC_MAX_CAND);
-    lcSortByPriority(V, C.involved, n);      // the order one worker walks its vehicles in (ascending priority)
+// Engine::vehicleControl (engine.cpp:188-251) for ONE vehicle involved in a lane change, given its head
+__device__ void lcControlOne(const View &V, const LcView &C, int slot, int epoch) {
     const double dt = V.dt;
     const double now = (epoch - 1) * dt;
-    for (int i = 0; i < n; ++i) {
-        const int slot = C.involved[i];
+    {
         LcSlot &L = C.slot[slot];
         const int p = V.pos[slot];
         const int d = C.posDrv[p];
@@ -484,6 +489,13 @@ __device__ void lcControlTail(const View &V, const LcView &C, int epoch) {
         V.nbuf[p] = make_int2(end ? -2 : newDrv, L.headBlocker);
         if (!end && newDrv >= 0) lcStageMover(V, d, idv, nv, nd, v, newDrv, L.headBlocker, hops, epoch);
     }
+}
+// all involved vehicles in one thread, ascending priority = the order one worker walks its vehicles in
+// (kept for the host probe and as a debugging fallback)
+__device__ void lcControlTail(const View &V, const LcView &C, int epoch) {
+    const int n = min(C.ctrl->nInvolved, LC_MAX_CAND);
+    lcSortByPriority(V, C.involved, n);
+    for (int i = 0; i < n; ++i) lcControlOne(V, C, C.involved[i], epoch);
 }
 // Engine::threadUpdateAction -> clearSignal (engine.cpp:424) for the involved vehicles (the plain ones took
 // their lastDir in k_control; their epoch-stamped signals expire by themselves)
@@ -568,6 +580,85 @@ __global__ void k_lc_control_tail(View V, LcView C) {
         lcClearInvolved(C, V.ctrl->step + 1);
     }
 }
+// ---- the same two phases, spread over the roads ---------------------------------------------------------
+// Candidates (and involved vehicles) of different roads never interact (checked on the
+// CPU), so each road walks ITS entries in the global order while the roads run side by side.  Three small
+// kernels per phase: order (one block), roads (one thread per entry; the first entry of a road serves the
+// whole road), log / clear (one thread).
+// k_lc_order: global order of `list[0..n)` = ascending priority (rank sort, priorities are unique) and, for
+// the candidates, libstdc++'s all-equal-keys permutation on top; then the group of every entry.
+__device__ void lcOrderBlock(const View &V, const LcView &C, int *list, int n, bool candidates, int epoch) {
+    int *key = C.scratchA, *sorted = C.scratchB, *group = C.scratchC, *created = C.scratchD;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) key[i] = lcPriorityOf(V, list[i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int r = 0;
+        const int k = key[i];
+        for (int j = 0; j < n; ++j) r += key[j] < k;
+        sorted[r] = list[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) list[i] = sorted[i];
+    __syncthreads();
+    if (candidates && threadIdx.x == 0) lcAllEqualSortPermute(list, n);   // std::sort by urgency, all equal (engine.cpp:793)
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int slot = list[i];
+        const int d = C.posDrv[V.pos[slot]];
+        int g;
+        if (d < V.nLanes) g = C.laneRoad[d];
+        else {   // on a laneLink: only the road its signal source is on can matter to it
+            const LcSlot &X = C.slot[slot];
+            g = lcRecvValid(X, epoch) ? C.laneRoad[C.posDrv[V.pos[X.recvSrc]]] : -1 - i;
+        }
+        group[i] = g;
+        created[i] = -1;
+    }
+}
+__global__ void __launch_bounds__(256) k_lc_order(View V, LcView C) {
+    if (blockIdx.x == 0) lcOrderBlock(V, C, C.cand, min(C.ctrl->nCand, LC_MAX_CAND), true, V.ctrl->step + 1);
+}
+__global__ void __launch_bounds__(128) k_lc_schedule_roads(View V, LcView C) {
+    const int n = min(C.ctrl->nCand, LC_MAX_CAND), epoch = V.ctrl->step + 1;
+    const int *group = C.scratchC;
+    int *created = C.scratchD;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int g = group[i];
+        bool first = true;
+        for (int j = 0; j < i && first; ++j) first = group[j] != g;
+        if (!first) continue;
+        for (int j = i; j < n; ++j)
+            if (group[j] == g) created[j] = lcScheduleOne(V, C, C.cand[j], epoch);
+    }
+}
+// shadows in the global schedule order = the order their priorities are drawn in (vehicle.cpp:33)
+__global__ void k_lc_log(View V, LcView C) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const int n = min(C.ctrl->nCand, LC_MAX_CAND);
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+        if (C.scratchD[i] >= 0) C.shadowLog[k++] = make_int2(C.cand[i], C.scratchD[i]);
+    C.ctrl->nShadows = k;
+}
+__global__ void __launch_bounds__(256) k_lc_tail_order(View V, LcView C) {
+    if (blockIdx.x == 0) lcOrderBlock(V, C, C.involved, min(C.ctrl->nInvolved, LC_MAX_CAND), false, V.ctrl->step + 1);
+}
+__global__ void __launch_bounds__(128) k_lc_tail_roads(View V, LcView C) {
+    const int n = min(C.ctrl->nInvolved, LC_MAX_CAND), epoch = V.ctrl->step + 1;
+    const int *group = C.scratchC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int g = group[i];
+        bool first = true;
+        for (int j = 0; j < i && first; ++j) first = group[j] != g;
+        if (!first) continue;
+        for (int j = i; j < n; ++j)
+            if (group[j] == g) lcControlOne(V, C, C.involved[j], epoch);
+    }
+}
+__global__ void k_lc_tail_clear(View V, LcView C) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) lcClearInvolved(C, V.ctrl->step + 1);
+}
+
 // per-step reset of the small counters (before k_lc_signal)
 __global__ void k_lc_begin(LcView C) {
     C.ctrl->nCand = 0; C.ctrl->nInvolved = 0; C.ctrl->nShadows = 0; C.ctrl->spareUsed = 0;

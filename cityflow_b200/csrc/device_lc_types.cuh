@@ -55,6 +55,7 @@ struct LcView {
     const int *planRoute, *planRoadPos;                 // per plan
     const int *lanePlanRoad, *lanePlanBeg, *lanePlanId; // Routing::lanePlan tables
     int *cand, *involved;      // slots
+    int *scratchA, *scratchB, *scratchC, *scratchD;   // LC_MAX_CAND ints each: keys / sorted copy / road of entry / shadow created
     const int *spare;          // free slots the host lent for this step's shadows
     int nSpare;
     int2 *shadowLog;           // (parent slot, shadow slot), schedule order = RNG order of their priorities

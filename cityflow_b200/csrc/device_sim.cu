@@ -404,7 +404,8 @@ struct DeviceSim::Impl {
 
 #ifdef CFB_LANE_CHANGE
     DevBuf<LcSlot> lcSlot;
-    DevBuf<int> lcLaneRoad, lcRouteLastRoad;
+    DevBuf<int> lcLaneRoad, lcRouteLastRoad, lcScratch;
+    bool lcSerial = false;            // CITYFLOW_B200_LC_SERIAL=1: scheduling / control tail in one thread each (debugging)
     DevBuf<int> lcSegIdx, lcPosDrv, lcSegBeg, lcLaneIdx, lcLaneRoadN, lcPlanRoute, lcPlanRoadPos, lcLanePlanRoad,
         lcLanePlanBeg, lcLanePlanId, lcCand, lcInvolved, lcSpare, lcPrio;
     DevBuf<double> lcSegStart, lcLaneWidth;
@@ -1557,12 +1558,16 @@ void DeviceSim::enableLaneChange(const RoadNet &net, const Routing &routing) {
     I.lcSegIdx.alloc(I.P); I.lcSegIdx.fill(0);
     I.lcCand.alloc(LC_MAX_CAND); I.lcInvolved.alloc(LC_MAX_CAND); I.lcShadowLog.alloc(LC_MAX_CAND); I.lcPrio.alloc(LC_MAX_CAND);
     I.lcCtrl.alloc(1); I.lcCtrl.fill(0);
+    I.lcScratch.alloc((size_t) 4 * LC_MAX_CAND); I.lcScratch.fill(0);
+    if (const char *g = getenv("CITYFLOW_B200_LC_SERIAL")) I.lcSerial = g[0] == '1';
     I.lcSlot.alloc(std::max(I.slotCap, 1)); I.lcSlot.fill(0);
     CFB_CUDA(cudaMallocHost(&I.hLcCtrl, sizeof(LcCtrl)));
     LcView &C = V.lc;
     C.slot = I.lcSlot.p; C.segIdx = I.lcSegIdx.p; C.posDrv = I.lcPosDrv.p; C.segBeg = I.lcSegBeg.p; C.segStart = I.lcSegStart.p;
     C.laneIdx = I.lcLaneIdx.p; C.laneRoadN = I.lcLaneRoadN.p; C.laneWidth = I.lcLaneWidth.p;
     C.cand = I.lcCand.p; C.involved = I.lcInvolved.p; C.shadowLog = I.lcShadowLog.p; C.ctrl = I.lcCtrl.p;
+    C.scratchA = I.lcScratch.p; C.scratchB = I.lcScratch.p + LC_MAX_CAND; C.scratchC = I.lcScratch.p + 2 * LC_MAX_CAND;
+    C.scratchD = I.lcScratch.p + 3 * LC_MAX_CAND;
     C.spare = nullptr; C.nSpare = 0;
     V.lcOn = 1;
     I.useGraph = false;   // the step has a host round trip in the middle (shadow priorities come from the engine RNG)
@@ -1592,7 +1597,13 @@ void DeviceSim::stepLcBegin(const SpawnRec *recs, int n, const int32_t *spare, i
     k_lc_admitted<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
     k_lc_segments<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
     k_lc_signal<<<I.gridControl, TPB, 0, s>>>(V, V.lc);
-    k_lc_schedule<<<1, 32, 0, s>>>(V, V.lc);
+    if (I.lcSerial) {
+        k_lc_schedule<<<1, 32, 0, s>>>(V, V.lc);
+    } else {
+        k_lc_order<<<1, 256, 0, s>>>(V, V.lc);
+        k_lc_schedule_roads<<<LC_MAX_CAND / 128, 128, 0, s>>>(V, V.lc);
+        k_lc_log<<<1, 32, 0, s>>>(V, V.lc);
+    }
     CFB_CUDA(cudaMemcpyAsync(I.hLcCtrl, I.lcCtrl.p, sizeof(LcCtrl), cudaMemcpyDeviceToHost, s));
     CFB_CUDA(cudaStreamSynchronize(s));
     CFB_CUDA(cudaGetLastError());
@@ -1619,7 +1630,13 @@ void DeviceSim::stepLcEnd(const int32_t *priorities, int n) {
     k_lc_leader<<<I.gridNotify, TPB, 0, s>>>(V, V.lc);
     k_notify<<<I.gridNotify, TPB, 0, s>>>(V);
     k_control<<<I.gridControl, 256, 0, s>>>(V);
-    k_lc_control_tail<<<1, 32, 0, s>>>(V, V.lc);
+    if (I.lcSerial) {
+        k_lc_control_tail<<<1, 32, 0, s>>>(V, V.lc);
+    } else {
+        k_lc_tail_order<<<1, 256, 0, s>>>(V, V.lc);
+        k_lc_tail_roads<<<LC_MAX_CAND / 128, 128, 0, s>>>(V, V.lc);
+        k_lc_tail_clear<<<1, 32, 0, s>>>(V, V.lc);
+    }
     k_move<<<I.gridMove, TPB, 0, s>>>(V);
     k_leader<<<I.gridLeader, TPB, 0, s>>>(V);
     CFB_CUDA(cudaGetLastError());

@@ -37,7 +37,7 @@ struct HostSim {   // DeviceSim's arrays (device_sim.cu constructor), on the hos
     Buf<int> off, laneOutBeg, laneOutLinks, llStartLane, llEndLane, llRoadLink, llCrossBeg, lcIdx, csLink, lcPeer, interPhaseBeg,
         interRLBeg, phaseAvailBeg, rlInter, planBeg, planData, leader, count, pos, waitHead, waitTail, waitNext, curPhase, entCnt, ent,
         act0, act1, extra, blk, delStep, segIdx, posDrv, segBeg, laneIdx, laneRoadN, planRoute, planRoadPos, lpRoad, lpBeg, lpId, cand,
-        involved, spare, prio, routeLast, laneRoadT;
+        involved, spare, prio, routeLast, laneRoadT, scratch;
     Buf<unsigned char> phaseAvail, interVirtual, inserted, rlAvail;
     Buf<DTmpl> tmpl;
     Buf<double2> kin, nkin, mkin;
@@ -148,6 +148,8 @@ struct HostSim {   // DeviceSim's arrays (device_sim.cu constructor), on the hos
         laneRoadT.assign(net.laneRoad.begin(), net.laneRoad.end()); C.laneRoad = laneRoadT.p();
         C.laneIdx = laneIdx.p(); C.laneRoadN = laneRoadN.p(); C.laneWidth = laneWidth.p(); C.cand = cand.p(); C.involved = involved.p();
         C.spare = spare.p(); C.nSpare = 0; C.shadowLog = shadowLog.p(); C.ctrl = &lcCtrl;
+        scratch.assign((size_t) 4 * LC_MAX_CAND, 0);
+        C.scratchA = scratch.p(); C.scratchB = scratch.p() + LC_MAX_CAND; C.scratchC = scratch.p() + 2 * LC_MAX_CAND; C.scratchD = scratch.p() + 3 * LC_MAX_CAND;
     }
     void setPlans(const Routing &R) {
         planBeg.assign(R.planBeg().begin(), R.planBeg().end()); planData.assign(R.planData().begin(), R.planData().end());

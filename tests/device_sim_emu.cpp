@@ -127,7 +127,12 @@ void DeviceSim::stepLcBegin(const SpawnRec *recs, int n, const int32_t *spare, i
     H.run(G, [&](int, int) { k_lc_admitted(V, V.lc); });
     H.run(G, [&](int, int) { k_lc_segments(V, V.lc); });
     H.run(G, [&](int, int) { k_lc_signal(V, V.lc); });
-    H.run(1, [&](int, int) { k_lc_schedule(V, V.lc); });
+    if (getenv("CITYFLOW_B200_LC_SERIAL")) H.run(1, [&](int, int) { k_lc_schedule(V, V.lc); });
+        else {   // the per-road form DeviceSim launches by default
+            H.run(1, [&](int, int) { k_lc_order(V, V.lc); });
+            H.run(G, [&](int, int) { k_lc_schedule_roads(V, V.lc); });
+            H.run(1, [&](int, int) { k_lc_log(V, V.lc); });
+        }
     if (H.lcCtrl.error) throw std::runtime_error("cityflow_b200: lane-change capacity exceeded (candidates per step or spare slots)");
     created.resize(H.lcCtrl.nShadows);
     for (int k = 0; k < H.lcCtrl.nShadows; ++k) created[k] = LcShadow{H.shadowLog[k].x, H.shadowLog[k].y};
@@ -143,7 +148,12 @@ void DeviceSim::stepLcEnd(const int32_t *priorities, int n) {
     H.run(G, [&](int, int) { k_lc_leader(V, V.lc); });
     H.run(G, [&](int b, int nb) { phase_notify(V, b, nb); });
     H.run(G, [&](int b, int nb) { phase_control(V, b, nb); });
-    H.run(1, [&](int, int) { k_lc_control_tail(V, V.lc); });
+    if (getenv("CITYFLOW_B200_LC_SERIAL")) H.run(1, [&](int, int) { k_lc_control_tail(V, V.lc); });
+    else {
+        H.run(1, [&](int, int) { k_lc_tail_order(V, V.lc); });
+        H.run(G, [&](int, int) { k_lc_tail_roads(V, V.lc); });
+        H.run(1, [&](int, int) { k_lc_tail_clear(V, V.lc); });
+    }
     H.run(G, [&](int b, int nb) { phase_move(V, b, nb); });
     H.run(G, [&](int b, int nb) { phase_leader(V, b, nb); });
     launches_ += 6 + (n > 0);

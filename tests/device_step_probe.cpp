@@ -116,7 +116,12 @@ void deviceStep(Oracle &o) {
                 }
             }
         }
-        H.run(1, [&](int, int) { k_lc_schedule(V, V.lc); });
+        if (getenv("CITYFLOW_B200_LC_SERIAL")) H.run(1, [&](int, int) { k_lc_schedule(V, V.lc); });
+        else {   // the per-road form DeviceSim launches by default
+            H.run(1, [&](int, int) { k_lc_order(V, V.lc); });
+            H.run(G, [&](int, int) { k_lc_schedule_roads(V, V.lc); });
+            H.run(1, [&](int, int) { k_lc_log(V, V.lc); });
+        }
         // host round trip: the shadows' priorities, in schedule order (HostEngine::nextStepLaneChange); here they
         // come from the restatement's own draws, matched by parent
         const int ns = H.lcCtrl.nShadows;
@@ -167,7 +172,14 @@ void deviceStep(Oracle &o) {
     }
     H.run(G, [&](int b, int n) { phase_notify(V, b, n); });
     H.run(G, [&](int b, int n) { phase_control(V, b, n); });
-    if (V.lcOn) H.run(1, [&](int, int) { k_lc_control_tail(V, V.lc); });
+    if (V.lcOn) {
+        if (getenv("CITYFLOW_B200_LC_SERIAL")) H.run(1, [&](int, int) { k_lc_control_tail(V, V.lc); });
+        else {
+            H.run(1, [&](int, int) { k_lc_tail_order(V, V.lc); });
+            H.run(G, [&](int, int) { k_lc_tail_roads(V, V.lc); });
+            H.run(1, [&](int, int) { k_lc_tail_clear(V, V.lc); });
+        }
+    }
     H.run(G, [&](int b, int n) { phase_move(V, b, n); });
     H.run(G, [&](int b, int n) { phase_leader(V, b, n); });
     H.steps += 1;
