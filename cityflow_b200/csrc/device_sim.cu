@@ -71,7 +71,14 @@ __global__ void __launch_bounds__(256) k_notify(View V) { phase_notify(V, blockI
 #include "device_control.cuh"
 namespace cfb {
 
+#ifdef CFB_CONTROL_COOP
+}  // namespace cfb
+#include "device_control_coop.cuh"   // EXPERIMENT: the warp evaluates its vehicles' crosses side by side
+namespace cfb {
+__global__ void __launch_bounds__(256, 4) k_control(View V) { phase_control_coop(V, blockIdx.x, gridDim.x); }
+#else
 __global__ void __launch_bounds__(256, 4) k_control(View V) { phase_control(V, blockIdx.x, gridDim.x); }
+#endif
 
 }  // namespace cfb
 #include "device_phases_b.cuh"

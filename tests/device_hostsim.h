@@ -20,7 +20,11 @@ namespace cfb { namespace cg = cooperative_groups; }
 #include "device_sim.h"
 #include "device_view.cuh"
 #include "device_phases_a.cuh"
-#include "device_control.cuh"   // (+ device_lc.cuh, kernels included: blockIdx / gridDim are globals here)
+#include "device_control.cuh"
+#ifdef CFB_CONTROL_COOP
+#include "device_control_coop.cuh"
+#define phase_control phase_control_coop   // the probes then run the cooperative variant as k_control's body
+#endif   // (+ device_lc.cuh, kernels included: blockIdx / gridDim are globals here)
 #include "device_phases_b.cuh"
 
 
