@@ -973,7 +973,13 @@ struct Oracle {
         // tie order inside std::sort is unspecified in the reference; here: stable, pool order
         for (size_t a = 0; a + 1 < pushBuffer.size(); ++a)
             for (size_t b = a + 1; b < pushBuffer.size(); ++b)
-                if (pushBuffer[a].second == pushBuffer[b].second && pushBuffer[a].first->bDrv == pushBuffer[b].first->bDrv) ++ties;
+                if (pushBuffer[a].second == pushBuffer[b].second && pushBuffer[a].first->bDrv == pushBuffer[b].first->bDrv) {
+                    ++ties;
+                    if (getenv("CFO_PRINT_TIES"))
+                        fprintf(stderr, "[oracle] tie at step %zu: drivable %d dis %.17g  flow_%d_%d (from %d, speed %.17g) vs flow_%d_%d (from %d, speed %.17g)\n", step,
+                                pushBuffer[a].first->bDrv, pushBuffer[a].second, pushBuffer[a].first->flow, pushBuffer[a].first->cnt, pushBuffer[a].first->drivable, pushBuffer[a].first->bSpeed,
+                                pushBuffer[b].first->flow, pushBuffer[b].first->cnt, pushBuffer[b].first->drivable, pushBuffer[b].first->bSpeed);
+                }
         std::stable_sort(pushBuffer.begin(), pushBuffer.end(),
                          [](const std::pair<Veh *, double> &a, const std::pair<Veh *, double> &b) { return a.second > b.second; });
         for (auto &pr : pushBuffer) {

@@ -191,8 +191,41 @@ def parse_runlc(path: str, n_inter: int, n_drivables: int):
     return out
 
 
+def parse_counts(path: str) -> dict:
+    """`refdump counts`: {"vehicle_count": int32[steps], "dumps": {step: (lane_count, lane_waiting, lane_speed_sum)}}"""
+    buf = open(path, "rb").read()
+    magic, n_lanes, steps, every = (int(x) for x in np.frombuffer(buf, "<i4", 4, 0))
+    assert magic == 0x43464E31
+    off = 16
+    vc = np.zeros(steps, np.int64)
+    dumps = {}
+    for s in range(steps):
+        vc[s] = int(np.frombuffer(buf, "<i4", 1, off)[0]); off += 4
+        if (s + 1) % every != 0 and s + 1 != steps:
+            continue
+        st = int(np.frombuffer(buf, "<i4", 1, off)[0]); off += 4
+        assert st == s + 1
+        cnt = np.frombuffer(buf, "<i4", n_lanes, off); off += 4 * n_lanes
+        wait = np.frombuffer(buf, "<i4", n_lanes, off); off += 4 * n_lanes
+        ssum = np.frombuffer(buf, "<f8", n_lanes, off); off += 8 * n_lanes
+        dumps[st] = (cnt, wait, ssum)
+    assert off == len(buf)
+    return {"vehicle_count": vc, "dumps": dumps, "n_lanes": n_lanes}
+
+
 class RefDump:
     """The compiled reference (oracle/_ref/refdump)."""
+
+    @staticmethod
+    def counts(config: str, steps: int, threads: int = 1, every: int = 25, out_path: str = None) -> dict:
+        """Vehicle count after every step + per-lane observables every `every` steps (cheap at 1e6 vehicles)."""
+        path = out_path or tempfile.mktemp(suffix=".bin")
+        try:
+            subprocess.check_call([REFDUMP, "counts", config, str(steps), str(threads), path, str(every)], timeout=3600)
+            return parse_counts(path)
+        finally:
+            if out_path is None and os.path.exists(path):
+                os.unlink(path)
 
     @staticmethod
     def static(config: str) -> dict:

@@ -13,6 +13,10 @@
 //   refdump runlc <config.json> <steps> <threads> <out.bin> [every]
 //       the same for laneChange=true runs: every running vehicle including shadows, keyed by
 //       priority, with the lane-change state (partner, offset, changing, waiting time).
+//   refdump counts <config.json> <steps> <threads> <out.bin> [every]
+//       light-weight observables for long / large runs (the multi-GPU parity tests): the vehicle count
+//       after EVERY step, and every `every` steps the per-lane vehicle count, per-lane waiting count
+//       (speed < 0.1) and per-lane sum of speeds.
 //   refdump bench <config.json> <steps> <threads> [warmup]
 //       timing loop in the shape of tools/debug/simple_run.cpp:42-57, prints one
 //       JSON line -> the `--impl reference` arm of bench.py.
@@ -272,6 +276,38 @@ int dumpRunLC(const char *cfg, int steps, int threads, const char *outPath, int 
     return 0;
 }
 
+// Observables only (engine.cpp:615-648 as the Python getters compute them), cheap enough for 1e6 vehicles.
+int dumpCounts(const char *cfg, int steps, int threads, const char *outPath, int every) {
+    Engine e(cfg, threads);
+    Out o(outPath);
+    const auto &lanes = e.roadnet.getLanes();
+    o.i32(0x43464E31);  // 'CFN1'
+    o.i32((int32_t) lanes.size());
+    o.i32(steps);
+    o.i32(every);
+    for (int s = 0; s < steps; ++s) {
+        e.nextStep();
+        o.i32((int32_t) e.getVehicleCount());
+        if ((s + 1) % every != 0 && s + 1 != steps) continue;
+        o.i32(s + 1);
+        for (Lane *l : lanes) o.i32((int32_t) l->getVehicleCount());
+        for (Lane *l : lanes) {
+            int c = 0;
+            for (Vehicle *v : l->getVehicles()) c += v->getSpeed() < 0.1;
+            o.i32(c);
+        }
+        for (Lane *l : lanes) {
+            double sum = 0;
+            for (Vehicle *v : l->getVehicles()) sum += v->getSpeed();
+            o.f64(sum);
+        }
+    }
+    o.close();
+    fflush(stdout);
+    _exit(0);   // (no ~Engine, see dumpRun)
+    return 0;
+}
+
 int bench(const char *cfg, int steps, int threads, int warmup) {
     auto t0 = std::chrono::steady_clock::now();
     Engine e(cfg, threads);
@@ -304,8 +340,10 @@ int main(int argc, char **argv) {
         return dumpRun(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
     if (argc >= 6 && !strcmp(argv[1], "runlc"))
         return dumpRunLC(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
+    if (argc >= 6 && !strcmp(argv[1], "counts"))
+        return dumpCounts(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
     if (argc >= 5 && !strcmp(argv[1], "bench"))
         return bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0);
-    fprintf(stderr, "usage: refdump static|run|runlc|bench ...\n");
+    fprintf(stderr, "usage: refdump static|run|runlc|counts|bench ...\n");
     return 64;
 }
