@@ -62,6 +62,7 @@ def load_library(path: str = None) -> ctypes.CDLL:
         "cfb_reset": (i32, [vp, i32]),
         "cfb_debug_vehicles": (i64, [vp, vp, i64]),
         "cfb_gpu_launches": (i64, [vp]),
+        "cfb_tie_count": (i64, [vp]),
         "cfb_enable_kernel_timing": (i32, [vp, i32]),
         "cfb_kernel_times": (i32, [vp, vp, vp]),
         "cfb_synchronize": (i32, [vp]),
@@ -188,6 +189,9 @@ class CEngine:
 
     def gpu_launches(self) -> int:
         return int(self.lib.cfb_gpu_launches(self.h))
+
+    def tie_count(self) -> int:
+        return int(self._check(self.lib.cfb_tie_count(self.h)))
 
 
 class CShardGroup:

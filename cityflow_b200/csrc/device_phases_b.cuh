@@ -92,6 +92,7 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 const double od = __shfl_sync(0xffffffffu, myDis, j);
                 const int op = __shfl_sync(0xffffffffu, myPrio, j);
                 if (lane < m && j != lane && (od > myDis || (od == myDis && op < myPrio))) ++rank;
+                if (lane < m && j < lane && od == myDis) atomicAdd(&V.ctrl->ties, 1);   // (never in the tested scenarios up to 30x30)
             }
             if (lane < m) {
                 const int q = base + nsurv + rank;
@@ -155,6 +156,7 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
     const int nAct = V.ctrl->nAct[npar];
     if (gtid == 0) {  // nothing in this kernel reads these (list parity is the host-provided V.par)
         V.ctrl->step += 1;                                             // Engine::step (engine.cpp:593)
+        V.ctrl->epoch += 1;
         V.ctrl->vehicleSteps += (unsigned long long) (long long) V.ctrl->active;   // may be negative on one rank of a sharded run  // all finishes of this step are in
     }
     if (!V.rl) {

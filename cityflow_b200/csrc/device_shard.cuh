@@ -1,0 +1,254 @@
+// device_shard.cuh -- the seam protocol of a sharded run over PEER MEMORY (NVLink / NVSwitch).
+// Part of device_sim.cu.  The reference has no counterpart (its threads share one address space).
+//
+// Every rank owns one "arena" (one cudaMalloc, exported with cudaIpc and mapped by every peer):
+//
+//   flags   [3][world] int    flags[k][src] = last epoch for which rank `src` completed its writes of kind k
+//                              k = 0 movers of the step, 1 tails + blocker list of the step, 2 finished-vehicle marks
+//   delStep [slotCap]   int   step at which the vehicle of a slot left the network (every rank writes here)
+//   blkIn   [2][world][1 + BLK_IN_CAP] int2   this step's blocker changes of a NEIGHBOUR rank, count in [0].x
+//   moverIn [2][nBoundIn]  MoverMsg            entrants of the lanes this rank owns and a peer feeds
+//   tailIn  [2][nBoundOut] TailMsg             tail records of the lanes this rank feeds and a peer owns
+//
+// A sender stores its records straight into the receiver's arena (posted writes over NVLink), fences, and the
+// last block of the sending kernel publishes the epoch in the receiver's flag word; the receiving kernel spins on
+// its LOCAL flag word and then reads its LOCAL mailbox.  No collective, no host involvement, two dependent
+// NVLink hops per step (movers after k_control, tails after k_move).  The [2] is the parity of the epoch: a
+// sender can be at most one step ahead of a neighbour that still reads the previous message (shard.h).
+//
+// Deadlock freedom: a kernel only ever waits for data whose producing kernel depends on nothing later than what the
+// waiting rank has already sent (movers(t) <- k_control(t) <- tails(t-1) <- k_move(t-1) <- movers(t-1) ...).  Every wait
+// has a time-out (ERR_SHARD_TIMEOUT) so a crashed peer cannot hang the GPU.
+#pragma once
+
+namespace cfb {
+
+constexpr int BLK_IN_CAP = 1 << 13;     // blocker changes per step sent to one neighbour (8 bytes each)
+constexpr int SHARD_FLAG_KINDS = 3;
+constexpr long long SHARD_SPIN_LIMIT_NS = 4000000000LL;   // 4 s
+
+struct __align__(16) TailMsg {     // owner -> feeder: Drivable::getLastVehicle of a boundary lane
+    Tail tail;
+    int count, inserted, pad0, pad1;
+    double2 kin;
+    int4 ids, nav;
+};
+struct __align__(16) MoverRec {
+    double2 kin;
+    int4 ids, nav;
+};
+struct __align__(16) MoverMsg {    // feeder -> owner: this step's entrants of a boundary lane
+    int n, pad0, pad1, pad2;
+    MoverRec rec[ENT_CAP];
+};
+
+struct ShardPeer {                 // rank q's arena as mapped into this process (all null for q == me)
+    int *flags;
+    int *delStep;
+    int2 *blkIn;                   // q's blkIn[0][me]; parity 1 is `blkStride` further
+    MoverMsg *moverIn;             // q's moverIn[0]; parity 1 is nIn further
+    TailMsg *tailIn;
+    int nIn, nOut;                 // q's nBoundIn / nBoundOut (strides of the parity halves)
+};
+
+struct ShardP2P {                  // by-value kernel argument
+    const ShardPeer *peers;        // [world]
+    int me, world;
+    const int *nbr;                // ranks that share a seam lane with me
+    int nNbr;
+    const int *outPeer, *outDst;   // per boundOut entry: owner rank, index in the owner's moverIn
+    const int *inPeer, *inDst;     // per boundIn entry: feeder rank, index in the feeder's tailIn
+    int *flags;                    // my own arena
+    int2 *blkIn;
+    MoverMsg *moverIn;
+    TailMsg *tailIn;
+    int *ticket;                   // 2 ints: block tickets of the two sending kernels
+};
+
+__device__ __forceinline__ unsigned long long shardNow() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Block-wide: wait until every neighbour's flag of `kind` has reached epoch E.
+__device__ __forceinline__ void shardWait(const View &V, const ShardP2P &S, int kind, int E, bool allRanks) {
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = shardNow();
+        const int n = allRanks ? S.world : S.nNbr;
+        for (int k = 0; k < n; ++k) {
+            const int q = allRanks ? k : S.nbr[k];
+            if (q == S.me) continue;
+            volatile int *f = S.flags + kind * S.world + q;
+            while (*f < E) {
+                if (shardNow() - t0 > (unsigned long long) SHARD_SPIN_LIMIT_NS) {
+                    atomicOr(&V.ctrl->error, ERR_SHARD_TIMEOUT);
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __threadfence_system();   // acquire: the mailbox reads below come after the flag reads
+    }
+    __syncthreads();
+}
+
+// Called by every thread after its remote stores: the last block to arrive publishes the epoch.
+__device__ __forceinline__ bool shardLastBlock(int *ticket) {
+    __shared__ int sLast;
+    __threadfence_system();       // release: my remote stores are performed before the ticket / the flag
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        sLast = (t == (int) gridDim.x - 1);
+        if (sLast) *ticket = 0;
+    }
+    __syncthreads();
+    if (sLast) __threadfence_system();
+    return sLast != 0;
+}
+
+// After k_control: one warp per boundary lane this rank feeds; the record goes straight into the owner's arena.
+__global__ void __launch_bounds__(128) k_send_movers(View V, ShardP2P S) {
+    const int E = V.ctrl->epoch + 1, par = E & 1;
+    const int lane = threadIdx.x & 31;
+    const int nW = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < V.nBoundOut; j += nW) {
+        const int L = V.boundOut[j];
+        const ShardPeer &P = S.peers[S.outPeer[j]];
+        MoverMsg *out = P.moverIn + (size_t) par * P.nIn + S.outDst[j];
+        const int n = min(V.entCnt[L], ENT_CAP);
+        if (lane == 0) { out->n = n; out->pad0 = out->pad1 = out->pad2 = 0; }
+        if (lane < n) {
+            const int m = V.ent[L * ENT_CAP + lane];
+            MoverRec r;
+            r.kin = V.mkin[m];
+            r.ids = V.mids[m];
+            r.nav = V.mnav[m];
+            out->rec[lane] = r;
+        }
+        __syncwarp();
+        if (lane == 0) V.entCnt[L] = 0;
+    }
+    if (shardLastBlock(S.ticket) && threadIdx.x < S.nNbr)
+        *(volatile int *) (S.peers[S.nbr[threadIdx.x]].flags + 0 * S.world + S.me) = E;
+}
+
+// Before k_move: wait for the feeders, then stage their entrants like local movers (cf. k_unpack_movers).
+__global__ void __launch_bounds__(128) k_recv_movers(View V, ShardP2P S) {
+    const int E = V.ctrl->epoch + 1, par = E & 1;
+    shardWait(V, S, 0, E, false);
+    const int lane = threadIdx.x & 31;
+    const int nW = (gridDim.x * blockDim.x) >> 5;
+    const MoverMsg *in = S.moverIn + (size_t) par * V.nBoundIn;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < V.nBoundIn; j += nW) {
+        const int L = V.boundIn[j];
+        const int n = in[j].n;
+        if (n == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&V.ctrl->moverCount, n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n) {
+            const int m = base + lane;
+            if (m < V.moverCap) {
+                const MoverRec r = in[j].rec[lane];
+                V.mkin[m] = r.kin;
+                V.mids[m] = r.ids;
+                V.mnav[m] = r.nav;
+                V.ent[L * ENT_CAP + lane] = m;
+            } else {
+                atomicOr(&V.ctrl->error, ERR_MOVER_OVERFLOW);
+            }
+        }
+        if (lane == 0) {
+            V.entCnt[L] = n;
+            if (V.count[L] == 0) V.extraList[atomicAdd(&V.ctrl->nExtra, 1)] = L;
+        }
+    }
+}
+
+// After k_move: tail records to the feeders, this step's blocker changes to the neighbours, finished-vehicle marks
+// to everybody.
+__global__ void __launch_bounds__(128) k_send_tails(View V, ShardP2P S) {
+    const int E = V.ctrl->epoch + 1, par = E & 1;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int j = gtid; j < V.nBoundIn; j += stride) {
+        const int L = V.boundIn[j];
+        TailMsg m;
+        m.tail = V.tail[L];
+        m.count = V.count[L];
+        m.inserted = V.inserted[L];
+        m.pad0 = m.pad1 = 0;
+        m.kin = make_double2(0, 0);
+        m.ids = m.nav = make_int4(0, 0, 0, 0);
+        if (m.tail.pos >= 0) {
+            m.kin = V.kin[m.tail.pos];
+            m.ids = V.ids[m.tail.pos];
+            m.nav = V.nav[m.tail.pos];
+        }
+        const ShardPeer &P = S.peers[S.inPeer[j]];
+        P.tailIn[(size_t) par * P.nOut + S.inDst[j]] = m;
+    }
+    const int nUpd = V.ctrl->nBlkUpd;
+    if (nUpd > BLK_IN_CAP) atomicOr(&V.ctrl->error, ERR_MOVER_OVERFLOW);
+    const int n = min(nUpd, BLK_IN_CAP);
+    const size_t blkStride = (size_t) S.world * (1 + BLK_IN_CAP);
+    for (int k = 0; k < S.nNbr; ++k) {
+        int2 *dst = S.peers[S.nbr[k]].blkIn + (size_t) par * blkStride;
+        for (int i = gtid; i < n; i += stride) dst[1 + i] = V.blkUpd[1 + i];
+        if (gtid == 0) dst[0] = make_int2(n, E);
+    }
+    const int step = V.ctrl->step;
+    for (int i = gtid; i < n; i += stride) {
+        const int2 u = V.blkUpd[1 + i];
+        if (u.y != -2) continue;
+        for (int q = 0; q < S.world; ++q)
+            if (q != S.me) S.peers[q].delStep[u.x] = step;
+    }
+    if (shardLastBlock(S.ticket + 1)) {
+        if (threadIdx.x == 0) V.ctrl->nBlkUpd = 0;
+        if (threadIdx.x < S.nNbr) *(volatile int *) (S.peers[S.nbr[threadIdx.x]].flags + 1 * S.world + S.me) = E;
+        if (threadIdx.x < S.world && threadIdx.x != S.me)
+            *(volatile int *) (S.peers[threadIdx.x].flags + 2 * S.world + S.me) = E;
+    }
+}
+
+// Before k_leader: wait for the owners / neighbours, refresh the ghost copies, apply the neighbours' blocker changes.
+__global__ void __launch_bounds__(128) k_recv_tails(View V, ShardP2P S) {
+    const int E = V.ctrl->epoch + 1, par = E & 1;
+    shardWait(V, S, 1, E, false);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const TailMsg *in = S.tailIn + (size_t) par * V.nBoundOut;
+    for (int j = gtid; j < V.nBoundOut; j += stride) {
+        const int L = V.boundOut[j];
+        const TailMsg m = in[j];
+        V.tail[L] = m.tail;
+        V.count[L] = m.count;
+        V.inserted[L] = (unsigned char) m.inserted;
+        if (m.tail.pos >= 0) {  // ghost copy of the one vehicle this rank may look at
+            V.kin[m.tail.pos] = m.kin;
+            V.ids[m.tail.pos] = m.ids;
+            V.nav[m.tail.pos] = m.nav;
+        }
+    }
+    const size_t blkStride = (size_t) S.world * (1 + BLK_IN_CAP);
+    const int step = V.ctrl->step;
+    for (int k = 0; k < S.nNbr; ++k) {
+        const int2 *src = S.blkIn + (size_t) par * blkStride + (size_t) S.nbr[k] * (1 + BLK_IN_CAP);
+        const int n = src[0].x;
+        for (int i = gtid; i < n; i += stride) {
+            const int2 u = src[1 + i];
+            if (u.y == -2) {
+                V.blk[u.x] = -1;
+                V.delStep[u.x] = step;
+            } else {
+                V.blk[u.x] = u.y;
+            }
+        }
+    }
+}
+
+// Host query support: every rank's finished-vehicle marks through the last completed step have landed here.
+__global__ void k_wait_fin(View V, ShardP2P S) { shardWait(V, S, 2, V.ctrl->epoch, true); }
+
+}  // namespace cfb

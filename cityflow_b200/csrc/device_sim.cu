@@ -105,21 +105,12 @@ __global__ void __launch_bounds__(256, 4) k_step(View V) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Sharded mode: what crosses a seam (partition.h).  Fixed-size messages, one entry per boundary lane.
-struct __align__(16) TailMsg {     // owner -> feeder: Drivable::getLastVehicle of a boundary lane
-    Tail tail;
-    int count, inserted, pad0, pad1;
-    double2 kin;
-    int4 ids, nav;
-};
-struct __align__(16) MoverRec {
-    double2 kin;
-    int4 ids, nav;
-};
-struct __align__(16) MoverMsg {    // feeder -> owner: this step's entrants of a boundary lane
-    int n, pad0, pad1, pad2;
-    MoverRec rec[ENT_CAP];
-};
+// Sharded mode: what crosses a seam (partition.h).  Fixed-size messages, one entry per boundary lane
+// (TailMsg / MoverMsg in device_shard.cuh, with the peer-memory transport).  The k_pack / k_unpack / k_seal /
+// k_apply kernels below are the staging form used with the NCCL transport (CITYFLOW_B200_SHARD_TRANSPORT=nccl).
+}  // namespace cfb
+#include "device_shard.cuh"
+namespace cfb {
 
 __global__ void k_pack_tails(View V, TailMsg *out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,6 +363,28 @@ struct DeviceSim::Impl {
     bool shardGraphOk = true;    // whole sharded step (kernels + NCCL groups) replayed as one graph per parity
     DevBuf<int> shardScratch;
     DevBuf<unsigned char> finGather;
+    // peer-memory transport (device_shard.cuh)
+    DevBuf<unsigned char> arena;
+    DevBuf<ShardPeer> peers;
+    DevBuf<int> p2pInts;              // nbr | outPeer | outDst | inPeer | inDst | ticket[2]
+    ShardP2P S{};
+    bool p2p = false;
+    std::vector<std::vector<int>> bsize;   // bsize[a][b] = lanes rank a feeds and rank b owns
+    static constexpr int SHARD_SLOT_CAP = 1 << 22;   // slot-indexed arrays are fixed once peers have mapped delStep
+    struct ArenaLayout { size_t flags, delStep, blkIn, moverIn, tailIn, total; };
+    static ArenaLayout arenaLayout(int world, int nIn, int nOut) {
+        auto up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+        ArenaLayout L;
+        L.flags = 0;
+        L.delStep = up((size_t) SHARD_FLAG_KINDS * world * sizeof(int));
+        L.blkIn = L.delStep + up((size_t) SHARD_SLOT_CAP * sizeof(int));
+        L.moverIn = L.blkIn + up((size_t) 2 * world * (1 + BLK_IN_CAP) * sizeof(int2));
+        L.tailIn = L.moverIn + up((size_t) 2 * std::max(nIn, 1) * sizeof(MoverMsg));
+        L.total = L.tailIn + up((size_t) 2 * std::max(nOut, 1) * sizeof(TailMsg));
+        return L;
+    }
+    int nInOf(int q) const { int n = 0; for (int p = 0; p < shardWorld; ++p) n += bsize[p][q]; return n; }
+    int nOutOf(int q) const { int n = 0; for (int p = 0; p < shardWorld; ++p) n += bsize[q][p]; return n; }
     DevBuf<Tail> tail;
     DevBuf<unsigned> dbgCyc, dbgPath;
     DevBuf<int4> linkInfo;
@@ -656,6 +669,7 @@ void DeviceSim::uploadPlans(const Routing &routing) {
 void DeviceSim::ensureSlotCapacity(int slots) {
     Impl &I = *impl_;
     if (slots <= I.slotCap) return;
+    if (I.arena.p) throw std::runtime_error("cityflow_b200: slot capacity of a sharded run exceeded (4 M vehicles alive or waiting)");
     int cap = std::max(I.slotCap, 1024);
     while (cap < slots) cap *= 2;
     CFB_CUDA(cudaStreamSynchronize(I.stream));
@@ -705,6 +719,7 @@ void DeviceSim::reset() {
     I.waitHead.fill(0xff); I.waitTail.fill(0xff); I.inserted.fill(0);
     I.pos.fill(0xff); I.waitNext.fill(0xff); I.cust.fill(0xff); I.slotCust.fill(0xff);
     I.blk.fill(0xff); I.delStep.fill(0x80);
+    if (I.arena.p) CFB_CUDA(cudaMemset(I.V.delStep, 0x80, (size_t) Impl::SHARD_SLOT_CAP * sizeof(int)));   // (lives in the arena)
     I.notify.fill(0);
     I.tail.fill(0xff);   // pos = -1: every drivable empty
     I.foeMask.fill(0);
@@ -714,7 +729,11 @@ void DeviceSim::reset() {
     I.hPhaseStale = false;
     CFB_CUDA(cudaMemcpy(I.remain.p, I.phase0Time.data(), I.phase0Time.size() * sizeof(double), cudaMemcpyHostToDevice));
     I.rlAvail.fill(0);
+    int epoch = 0;   // the seam messages of a sharded run are stamped with it: it never goes back
+    CFB_CUDA(cudaMemcpy(&epoch, &I.V.ctrl->epoch, sizeof(int), cudaMemcpyDeviceToHost));
     I.ctrl.fill(0);
+    legacySync();
+    CFB_CUDA(cudaMemcpy(&I.V.ctrl->epoch, &epoch, sizeof(int), cudaMemcpyHostToDevice));
     // leader = -1 everywhere is not required (only occupied positions are read)
     steps_ = 0;
     legacySync();
@@ -838,12 +857,14 @@ void DeviceSim::synchronize() { CFB_CUDA(cudaStreamSynchronize(impl_->stream)); 
 // (performed by a ShardTransport on this engine's stream) in between.
 void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned char> &owned,
                                const std::vector<std::vector<int>> &feedPerPeer,
-                               const std::vector<std::vector<int>> &ownPerPeer) {
+                               const std::vector<std::vector<int>> &ownPerPeer,
+                               const std::vector<std::vector<int>> &boundarySize) {
     Impl &I = *impl_;
     View &V = I.V;
     CFB_CUDA(cudaStreamSynchronize(I.stream));
     I.shardRank = rank;
     I.shardWorld = world;
+    I.bsize = boundarySize;
     std::vector<unsigned char> own3 = owned;
     for (int q = 0; q < world; ++q)
         for (int l : feedPerPeer[q]) own3[l] = 2;   // ghost lanes: admitted into locally, never listed as work
@@ -956,6 +977,110 @@ void DeviceSim::applyBlk() {
     k_apply_blk<<<grid, 256, 0, I.stream>>>(I.V, I.blkAll.p, I.shardWorld, I.shardRank, 1 + I.V.blkUpdCap);
     launches_ += 1;
 }
+// ---- peer-memory transport (device_shard.cuh) ----
+// The arena other ranks write into.  From here on the slot-indexed arrays have their final size (delStep lives in
+// the arena and is mapped by the peers).
+DeviceSim::ShardArena DeviceSim::shardArena() {
+    Impl &I = *impl_;
+    if (!I.arena.p) {
+        ensureSlotCapacity(Impl::SHARD_SLOT_CAP);
+        CFB_CUDA(cudaStreamSynchronize(I.stream));
+        const Impl::ArenaLayout L = Impl::arenaLayout(I.shardWorld, I.V.nBoundIn, I.V.nBoundOut);
+        I.arena.alloc(L.total);
+        I.arena.fill(0);
+        legacySync();
+        CFB_CUDA(cudaMemcpy(I.arena.p + L.delStep, I.V.delStep, (size_t) Impl::SHARD_SLOT_CAP * sizeof(int), cudaMemcpyDeviceToDevice));
+        legacySync();
+        I.delStep.release();
+        I.V.delStep = (int *) (I.arena.p + L.delStep);
+        I.graphDirty = true;
+        I.dropShardGraphs();
+    }
+    return ShardArena{I.arena.p, I.arena.n};
+}
+
+// `peerBase[q]` = rank q's arena as mapped into this process (ignored for q == me).
+void DeviceSim::shardConnect(const std::vector<void *> &peerBase) {
+    Impl &I = *impl_;
+    View &V = I.V;
+    const int W = I.shardWorld, me = I.shardRank;
+    if (!I.arena.p || (int) peerBase.size() != W) throw std::runtime_error("shardConnect: arena missing / wrong world size");
+    CFB_CUDA(cudaStreamSynchronize(I.stream));
+    std::vector<ShardPeer> peers(W);
+    for (int q = 0; q < W; ++q) {
+        unsigned char *base = q == me ? I.arena.p : (unsigned char *) peerBase[q];
+        const Impl::ArenaLayout L = Impl::arenaLayout(W, I.nInOf(q), I.nOutOf(q));
+        ShardPeer &P = peers[q];
+        P.flags = (int *) (base + L.flags);
+        P.delStep = (int *) (base + L.delStep);
+        P.blkIn = (int2 *) (base + L.blkIn) + (size_t) me * (1 + BLK_IN_CAP);
+        P.moverIn = (MoverMsg *) (base + L.moverIn);
+        P.tailIn = (TailMsg *) (base + L.tailIn);
+        P.nIn = std::max(I.nInOf(q), 1);
+        P.nOut = std::max(I.nOutOf(q), 1);
+    }
+    I.peers.upload(peers);
+    // index tables: where my messages land in the receivers' mailboxes
+    std::vector<int> nbr, outPeer, outDst, inPeer, inDst;
+    for (int q = 0; q < W; ++q) {
+        if (q == me) continue;
+        if (I.bsize[me][q] + I.bsize[q][me] > 0) nbr.push_back(q);
+        int inBegAtQ = 0, outBegAtQ = 0;   // q's inBeg[me], q's outBeg[me]
+        for (int p = 0; p < me; ++p) { inBegAtQ += I.bsize[p][q]; outBegAtQ += I.bsize[q][p]; }
+        for (int k = 0; k < I.bsize[me][q]; ++k) { outPeer.push_back(q); outDst.push_back(inBegAtQ + k); }
+        for (int k = 0; k < I.bsize[q][me]; ++k) { inPeer.push_back(q); inDst.push_back(outBegAtQ + k); }
+    }
+    if ((int) outPeer.size() != V.nBoundOut || (int) inPeer.size() != V.nBoundIn) throw std::runtime_error("shardConnect: boundary tables disagree");
+    if ((int) nbr.size() > 120) throw std::runtime_error("shardConnect: too many neighbour ranks");
+    std::vector<int> all;
+    const size_t oN = 0, oOP = oN + nbr.size(), oOD = oOP + outPeer.size(), oIP = oOD + outDst.size(), oID = oIP + inPeer.size(), oT = oID + inDst.size();
+    all.insert(all.end(), nbr.begin(), nbr.end());
+    all.insert(all.end(), outPeer.begin(), outPeer.end());
+    all.insert(all.end(), outDst.begin(), outDst.end());
+    all.insert(all.end(), inPeer.begin(), inPeer.end());
+    all.insert(all.end(), inDst.begin(), inDst.end());
+    all.push_back(0); all.push_back(0);
+    I.p2pInts.upload(all);
+    const Impl::ArenaLayout L = Impl::arenaLayout(W, V.nBoundIn, V.nBoundOut);
+    ShardP2P &S = I.S;
+    S.peers = I.peers.p; S.me = me; S.world = W;
+    S.nbr = I.p2pInts.p + oN; S.nNbr = (int) nbr.size();
+    S.outPeer = I.p2pInts.p + oOP; S.outDst = I.p2pInts.p + oOD; S.inPeer = I.p2pInts.p + oIP; S.inDst = I.p2pInts.p + oID;
+    S.ticket = I.p2pInts.p + oT;
+    S.flags = (int *) (I.arena.p + L.flags);
+    S.blkIn = (int2 *) (I.arena.p + L.blkIn);
+    S.moverIn = (MoverMsg *) (I.arena.p + L.moverIn);
+    S.tailIn = (TailMsg *) (I.arena.p + L.tailIn);
+    if (V.blkUpdCap > BLK_IN_CAP) V.blkUpdCap = BLK_IN_CAP;
+    I.p2p = true;
+    I.dropShardGraphs();
+    legacySync();
+}
+bool DeviceSim::shardIsP2P() const { return impl_->p2p; }
+
+void DeviceSim::sendMovers() {
+    Impl &I = *impl_;
+    const int g = std::max(1, std::min(64, (I.V.nBoundOut * 32 + 127) / 128));
+    k_send_movers<<<g, 128, 0, I.stream>>>(I.V, I.S);
+    launches_ += 1;
+}
+void DeviceSim::recvMovers() {
+    Impl &I = *impl_;
+    const int g = std::max(1, std::min(64, (I.V.nBoundIn * 32 + 127) / 128));
+    k_recv_movers<<<g, 128, 0, I.stream>>>(I.V, I.S);
+    launches_ += 1;
+}
+void DeviceSim::sendTails() {
+    Impl &I = *impl_;
+    k_send_tails<<<16, 128, 0, I.stream>>>(I.V, I.S);
+    launches_ += 1;
+}
+void DeviceSim::recvTails() {
+    Impl &I = *impl_;
+    k_recv_tails<<<16, 128, 0, I.stream>>>(I.V, I.S);
+    launches_ += 1;
+}
+
 void DeviceSim::shardCounts(ShardTransport *t, int32_t *laneOut, int *activeOut) {
     Impl &I = *impl_;
     const int n = laneOut ? 1 + I.V.nLanes : 1;   // the vehicle count alone is a 4-byte all-reduce
@@ -1130,6 +1255,11 @@ static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src) {
 int DeviceSim::vehicleCount() {
     readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
     return impl_->hCtrl->active;
+}
+
+int DeviceSim::tieCount() {
+    readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
+    return impl_->hCtrl->ties;
 }
 
 int DeviceSim::errorFlags() {
@@ -1434,6 +1564,10 @@ int DeviceSim::slotDelStep(int slot) {
     Impl &I = *impl_;
     if (slot < 0 || slot >= I.slotCap) return INT_MIN;
     int d = INT_MIN;
+    if (I.p2p) {   // every rank's finished-vehicle marks through the last completed step (they arrive as peer stores)
+        k_wait_fin<<<1, 32, 0, I.stream>>>(I.V, I.S);
+        CFB_CUDA(cudaStreamSynchronize(I.stream));
+    }
     CFB_CUDA(cudaMemcpy(&d, I.V.delStep + slot, sizeof(int), cudaMemcpyDeviceToHost));
     return d;
 }

@@ -49,6 +49,7 @@ enum DeviceError : int {
     ERR_ROUTE_DEAD_END = 8,     // lane cannot reach the next road of the route (reference asserts)
     ERR_FINISHED_OVERFLOW = 16,
     ERR_PHASE_RANGE = 32,       // a phase index handed over on the device is outside the intersection's phase list
+    ERR_SHARD_TIMEOUT = 64,     // sharded run: a peer's seam message did not arrive (peer crashed or stopped stepping)
 };
 
 struct DeviceSimOptions {
@@ -99,7 +100,17 @@ public:
 
     // ---- sharded mode: the step phase by phase (see shard.h for the protocol) ----
     void configureShard(int rank, int world, const std::vector<unsigned char> &owned,
-                        const std::vector<std::vector<int>> &feedPerPeer, const std::vector<std::vector<int>> &ownPerPeer);
+                        const std::vector<std::vector<int>> &feedPerPeer, const std::vector<std::vector<int>> &ownPerPeer,
+                        const std::vector<std::vector<int>> &boundarySize);
+    // peer-memory transport (device_shard.cuh): the arena peers write into; connect once every rank's arena is mapped
+    struct ShardArena { void *base; size_t bytes; };
+    ShardArena shardArena();
+    void shardConnect(const std::vector<void *> &peerBase);
+    bool shardIsP2P() const;
+    void sendMovers();
+    void recvMovers();
+    void sendTails();
+    void recvTails();
     ShardBuffers shardBuffers();
     void stageStep(const SpawnRec *recs, int n);
     int shardStepBegin();            // 0 plain, 1 replayed (skip the phases), 2 capturing
@@ -135,6 +146,7 @@ public:
     // Observations (synchronise the stream).
     int vehicleCount();
     int errorFlags();
+    int tieCount();                               // see cfb_tie_count
     long long stepsDone() const { return steps_; }
     void laneVehicleCount(int32_t *out);          // nLanes * replicas
     void laneWaitingVehicleCount(int32_t *out);   // speed < 0.1

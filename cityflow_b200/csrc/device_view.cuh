@@ -29,12 +29,14 @@ struct Ctrl {
     int moverCount;
     int finCount;
     int error;
-    int reserved0;   // (layout: keeps the counters below 8-byte aligned)
+    int ties;        // same-step entrants of one drivable with EQUAL new distance: their order is unspecified in the
+                     // reference (non-stable std::sort over a thread-interleaved buffer, engine.cpp:480); here: priority
     int nVeh[2];     // work lists, double-buffered on step parity
     int nAct[2];
     int nExtra;
     int nBlkUpd;     // sharded mode: blocker changes of this step (see blkUpd)
     int nCustom;     // outstanding set_vehicle_speed requests (Vehicle::setCustomSpeed, vehicle.h:128)
+    int epoch;       // steps completed since the engine was created (never reset): stamps the seam messages (device_shard.cuh)
     unsigned long long vehicleSteps;  // sum over steps of activeVehicleCount after the step (the bench metric)
     unsigned long long dbg[8];        // CFB_DEBUG_COUNTERS builds: in-kernel cycle / trip-count maxima
 };

@@ -237,6 +237,7 @@ public:
             if (err & ERR_MOVER_OVERFLOW) m += " mover staging overflow;";
             if (err & ERR_ROUTE_DEAD_END) m += " a vehicle reached a lane that cannot continue its route (the reference asserts here, vehicle.cpp:60);";
             if (err & ERR_FINISHED_OVERFLOW) m += " finished ring overflow;";
+            if (err & ERR_SHARD_TIMEOUT) m += " a peer rank's seam message did not arrive within 4 s (every rank of a sharded run must step in lock step);";
             if (err & ERR_PHASE_RANGE) m += " a phase index set from the device is out of range (the reference throws from phases.at(), trafficlight.cpp:17);";
             throw std::runtime_error(m);
         }
@@ -516,7 +517,18 @@ public:
             dev->stageStep(batch.data(), (int) batch.size());
             for (int attempt = 0; attempt < 2; ++attempt) {
                 const int st = dev->shardStepBegin();
-                if (st != 1) try {
+                if (st != 1 && dev->shardIsP2P()) {
+                    // peer-memory data plane (device_shard.cuh): the seam records are stored straight into the
+                    // neighbours' mailboxes by the send kernels; nothing but kernels on the stream
+                    dev->runIngest();
+                    dev->runNotifyControl();
+                    dev->sendMovers();                                                                     // X1
+                    dev->recvMovers();
+                    dev->runMove();
+                    dev->sendTails();                                                                      // X2
+                    dev->recvTails();
+                    dev->runLeader();
+                } else if (st != 1) try {
                     ShardBuffers b = dev->shardBuffers();
                     dev->runIngest();
                     dev->runNotifyControl();
@@ -549,12 +561,13 @@ public:
         if (!bad.empty()) return bad;
         std::vector<unsigned char> owned(part.drvOwner.size());
         for (size_t d = 0; d < owned.size(); ++d) owned[d] = part.drvOwner[d] == rank;
-        std::vector<std::vector<int>> feed(world), own(world);
+        std::vector<std::vector<int>> feed(world), own(world), bsize(world, std::vector<int>(world, 0));
         for (int q = 0; q < world; ++q) {
             feed[q] = part.boundary[rank][q];   // lanes I feed, q owns
             own[q] = part.boundary[q][rank];    // lanes q feeds, I own
+            for (int p2 = 0; p2 < world; ++p2) bsize[q][p2] = (int) part.boundary[q][p2].size();
         }
-        dev->configureShard(rank, world, owned, feed, own);
+        dev->configureShard(rank, world, owned, feed, own, bsize);
         return "";
     }
 
@@ -999,6 +1012,9 @@ int64_t cfb_vehicle_steps(cfb_engine *e) {
 }
 
 int64_t cfb_gpu_launches(const cfb_engine *e) { return e->h.dev->launchesDone(); }
+int64_t cfb_tie_count(cfb_engine *e) {
+    CFB_TRY(e, return (int64_t) e->h.dev->tieCount();)
+}
 int cfb_enable_kernel_timing(cfb_engine *e, int on) { e->h.dev->enableKernelTiming(on != 0); return CFB_OK; }
 int cfb_kernel_times(cfb_engine *e, double ms[5], int64_t *steps) {
     auto t = e->h.dev->kernelTimes();
@@ -1280,6 +1296,23 @@ cfb_engine *cfb_engine_create_sharded(const char *config_file, int thread_num, i
         return nullptr;
     }
     e->h.transport = st->transport.get();
+    // data plane: peer memory over NVLink unless it is unavailable or CITYFLOW_B200_SHARD_TRANSPORT=nccl asks for
+    // the staged NCCL send/recv form (kept for comparison)
+    const char *tr = getenv("CITYFLOW_B200_SHARD_TRANSPORT");
+    if (!(tr && !strcmp(tr, "nccl"))) {
+        try {
+            cfb::DeviceSim::ShardArena a = e->h.dev->shardArena();
+            std::vector<void *> peers;
+            std::string why;
+            if (st->transport->shareArena(a.base, a.bytes, peers, why)) e->h.dev->shardConnect(peers);
+            else std::cerr << "[cityflow_b200] sharded run falls back to NCCL send/recv: " << why << std::endl;
+        } catch (const std::exception &ex) {
+            g_createError = std::string("sharded engine: ") + ex.what();
+            e->h.transport = nullptr;
+            cfb_engine_destroy(e);
+            return nullptr;
+        }
+    }
     g_shards[e] = std::move(st);
     return e;
 }
@@ -1311,6 +1344,7 @@ int cfb_shard_lane_vehicle_count(cfb_engine *e, int32_t *out, int n, int waiting
 struct cfb_shard_group {
     std::vector<cfb_engine *> ranks;
     std::string lastError;
+    bool p2p = false;
 };
 
 namespace {
@@ -1354,6 +1388,15 @@ cfb_shard_group *cfb_shard_group_create(const char *config_file, int world, int 
         std::string err = e->h.configureShard(r, world);
         if (!err.empty()) { g_createError = "sharded engine: " + err; for (auto *x : g->ranks) cfb_engine_destroy(x); return nullptr; }
     }
+    {   // same process: the "peer mappings" are the arenas themselves
+        const char *tr = getenv("CITYFLOW_B200_SHARD_TRANSPORT");
+        g->p2p = !(tr && !strcmp(tr, "nccl"));
+        if (g->p2p) {
+            std::vector<void *> bases;
+            for (auto *e : g->ranks) bases.push_back(e->h.dev->shardArena().base);
+            for (auto *e : g->ranks) e->h.dev->shardConnect(bases);
+        }
+    }
     // finished vehicles: union over the ranks (the hook sees each rank's local list in turn)
     cfb_shard_group *gp = g.get();
     for (int r = 0; r < world; ++r) {
@@ -1387,12 +1430,23 @@ int cfb_shard_group_step(cfb_shard_group *g, int n) {
             std::vector<cfb::ShardBuffers> B;
             for (auto *e : g->ranks) { e->h.prepareStep(); B.push_back(e->h.dev->shardBuffers()); }
             for (auto *e : g->ranks) { e->h.dev->stageStep(e->h.batch.data(), (int) e->h.batch.size()); e->h.dev->runIngest(); }
-            for (auto *e : g->ranks) { e->h.dev->runNotifyControl(); e->h.dev->packMovers(); }
-            loopExchange(B, false);
-            for (auto *e : g->ranks) e->h.shardPhase(2);
-            loopExchange(B, true);
-            loopAllGatherBlk(B);
-            for (auto *e : g->ranks) { e->h.shardPhase(3); e->h.dev->shardStepEnd(0); }
+            if (g->p2p) {
+                // the ranks' streams are drained between the phases, so a receive kernel never has to spin here:
+                // what this checks is the protocol (indices, parities, epochs), not the waiting
+                auto syncAll = [&]() { for (auto *e : g->ranks) e->h.dev->synchronize(); };
+                for (auto *e : g->ranks) { e->h.dev->runNotifyControl(); e->h.dev->sendMovers(); }
+                syncAll();
+                for (auto *e : g->ranks) { e->h.dev->recvMovers(); e->h.dev->runMove(); e->h.dev->sendTails(); }
+                syncAll();
+                for (auto *e : g->ranks) { e->h.dev->recvTails(); e->h.dev->runLeader(); e->h.dev->shardStepEnd(0); }
+            } else {
+                for (auto *e : g->ranks) { e->h.dev->runNotifyControl(); e->h.dev->packMovers(); }
+                loopExchange(B, false);
+                for (auto *e : g->ranks) e->h.shardPhase(2);
+                loopExchange(B, true);
+                loopAllGatherBlk(B);
+                for (auto *e : g->ranks) { e->h.shardPhase(3); e->h.dev->shardStepEnd(0); }
+            }
             for (int r = 0; r < W; ++r) g->ranks[r]->h.finishStep();   // rank 0 first: its drain collects all lists
         }
         for (auto *e : g->ranks) e->h.checkDevice();

@@ -260,6 +260,7 @@ public:
     }
     // measurement helpers (not part of the reference surface)
     int64_t gpuLaunches() const { return cfb_gpu_launches(e_); }
+    int64_t tieCount() { return cfb_tie_count(e_); }
     void enableKernelTiming(bool on) { cfb_enable_kernel_timing(e_, on); }
     py::tuple kernelTimes() {
         double ms[5];
@@ -332,6 +333,7 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         // extras
         .def("next_steps", &Engine::nextSteps, "n"_a)
         .def("gpu_launches", &Engine::gpuLaunches)
+        .def("tie_count", &Engine::tieCount)
         .def("enable_kernel_timing", &Engine::enableKernelTiming, "on"_a = true)
         .def("kernel_times", &Engine::kernelTimes)
         .def("timed_steps", &Engine::timedSteps, "n"_a, "flush_l2"_a = false)

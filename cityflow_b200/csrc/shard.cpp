@@ -6,6 +6,7 @@
 
 #include <cstring>
 #include <stdexcept>
+#include <vector>
 
 namespace cfb {
 namespace {
@@ -68,6 +69,7 @@ public:
         CFB_NCCL(api().CommInitRank(&comm_, world, uid, rank));
     }
     ~NcclTransport() override {
+        for (void *p : opened_) cudaIpcCloseMemHandle(p);
         if (comm_) api().CommDestroy(comm_);
     }
     int rank() const override { return rank_; }
@@ -104,10 +106,60 @@ public:
     void allReduceSumInt(void *stream, int *devBuf, int n) override {
         CFB_NCCL(api().AllReduce(devBuf, devBuf, (size_t) n, ncclInt, ncclSum, comm_, (cudaStream_t) stream));
     }
+    // cudaIpc handles travel through one NCCL all-gather (the only bootstrap channel this library has); whether
+    // every rank could map every arena is agreed on with an all-reduce, so all ranks pick the same data plane.
+    bool shareArena(void *localBase, size_t bytes, std::vector<void *> &peerBase, std::string &err) override {
+        (void) bytes;
+        peerBase.assign(world_, nullptr);
+        peerBase[rank_] = localBase;
+        cudaIpcMemHandle_t mine;
+        int ok = cudaIpcGetMemHandle(&mine, localBase) == cudaSuccess ? 1 : 0;
+        if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+        unsigned char *dSend = nullptr, *dAll = nullptr;
+        int *dOk = nullptr;
+        cudaStream_t s = nullptr;
+        if (cudaMalloc(&dSend, 64) != cudaSuccess || cudaMalloc(&dAll, (size_t) 64 * world_) != cudaSuccess ||
+            cudaMalloc(&dOk, sizeof(int)) != cudaSuccess || cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+            err = "shareArena: cudaMalloc failed";
+            return false;
+        }
+        std::vector<cudaIpcMemHandle_t> all(world_);
+        cudaMemcpyAsync(dSend, &mine, 64, cudaMemcpyHostToDevice, s);
+        CFB_NCCL(api().AllGather(dSend, dAll, 64, ncclChar, comm_, s));
+        cudaMemcpyAsync(all.data(), dAll, (size_t) 64 * world_, cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        for (int q = 0; q < world_ && ok; ++q) {
+            if (q == rank_) continue;
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            peerBase[q] = p;
+            opened_.push_back(p);
+        }
+        cudaMemcpyAsync(dOk, &ok, sizeof(int), cudaMemcpyHostToDevice, s);
+        CFB_NCCL(api().AllReduce(dOk, dOk, 1, ncclInt, ncclMin, comm_, s));
+        int allOk = 0;
+        cudaMemcpyAsync(&allOk, dOk, sizeof(int), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        cudaFree(dSend); cudaFree(dAll); cudaFree(dOk);
+        cudaStreamDestroy(s);
+        if (!allOk) {
+            for (void *p : opened_) cudaIpcCloseMemHandle(p);
+            opened_.clear();
+            err = "peer access between the GPUs of this run is not available (cudaIpcOpenMemHandle failed on some rank)";
+            return false;
+        }
+        return true;
+    }
 
 private:
     int rank_, world_;
     ncclComm_t comm_ = nullptr;
+    std::vector<void *> opened_;   // peers' arenas mapped with cudaIpcOpenMemHandle
 };
 
 }  // namespace

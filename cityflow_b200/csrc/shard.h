@@ -35,6 +35,10 @@ public:
                                    const std::vector<int> &recvBeg, size_t bytes, const void *gSend, void *gRecvAll,
                                    size_t gBytesPerRank) = 0;
     virtual void allReduceSumInt(void *stream, int *devBuf, int n) = 0;   // in place, device ints
+    // Peer-memory data plane (device_shard.cuh): make `localBase` (one cudaMalloc of `bytes`) writable by every other
+    // rank and map theirs.  peerBase[q] = rank q's arena in this process's address space (own entry = localBase).
+    // Returns false (with `err`) when some pair of GPUs cannot reach each other; every rank gets the same answer.
+    virtual bool shareArena(void *localBase, size_t bytes, std::vector<void *> &peerBase, std::string &err) = 0;
 };
 
 // NCCL transport (libnccl is loaded at run time with dlopen, so the single-GPU engine has no

@@ -242,10 +242,17 @@ def grid_straight_flows(rows: int, cols: int, interval=2.0, vehicle: Optional[di
 
 
 def random_walk_flows(roadnet: dict, frac=0.5, interval=10.0, max_len=12, seed=1,
-                      vehicle: Optional[dict] = None) -> list:
+                      vehicle: Optional[dict] = None, fleet_spread=0.0) -> list:
     """Dense demand: for every road with a successor, with probability
-    ``frac`` one flow following a seeded random walk over roadLink successors (<= max_len roads)."""
+    ``frac`` one flow following a seeded random walk over roadLink successors (<= max_len roads).
+
+    ``fleet_spread`` > 0 gives every flow its own vehicle parameters, drawn (from a second seeded stream, so
+    the routes do not change) within +-fleet_spread of the template: a heterogeneous fleet.  With identical
+    vehicles two queue heads that start from rest in the same step enter a lane with bit-equal distances now
+    and then, and the reference orders such a pair by thread timing (engine.cpp:247-249, :480) -- its own result is
+    then not defined; distinct parameters make that coincidence vanish."""
     vehicle = dict(vehicle or DEFAULT_VEHICLE)
+    fleet = random.Random(seed * 7919 + 17)
     nxt: Dict[str, set] = {}
     for inter in roadnet["intersections"]:
         for rl in inter.get("roadLinks", []):
@@ -262,7 +269,12 @@ def random_walk_flows(roadnet: dict, frac=0.5, interval=10.0, max_len=12, seed=1
         while len(route) < max_len and route[-1] in nxt:
             route.append(rng.choice(sorted(nxt[route[-1]])))
         if len(route) >= 2:
-            flows.append({"vehicle": vehicle, "route": route, "interval": float(interval),
+            veh = vehicle
+            if fleet_spread > 0:
+                veh = dict(vehicle)
+                for k in ("length", "maxPosAcc", "maxNegAcc", "usualPosAcc", "usualNegAcc", "minGap", "maxSpeed", "headwayTime"):
+                    veh[k] = vehicle[k] * (1.0 + fleet_spread * (2.0 * fleet.random() - 1.0))
+            flows.append({"vehicle": veh, "route": route, "interval": float(interval),
                           "startTime": 0, "endTime": -1})
     return flows
 

@@ -177,6 +177,11 @@ int64_t cfb_debug_vehicles(cfb_engine *e, void *out, int64_t cap);
 /* Measurement support (bench.py): number of our kernels launched so far, per-kernel CUDA-event
  * time accumulators (ms) when enabled, and device-side size figures. */
 int64_t cfb_gpu_launches(const cfb_engine *e);
+/* Same-step entrants of one drivable with EQUAL new distance seen so far (summed over the rank's drivables).  The
+ * reference orders such a pair by a non-stable std::sort over a buffer its worker threads fill in arrival order
+ * (engine.cpp:247-249, :480), i.e. its result is not defined there -- two runs of the reference with different
+ * thread_num differ from the first tie on.  This engine orders them by priority.  0 = the run is comparable bit for bit. */
+int64_t cfb_tie_count(cfb_engine *e);
 /* n steps, each bracketed by CUDA events on the engine's stream (optionally with a 256 MiB L2
  * flush before each bracket); *ms = summed device time, *vehicle_steps = sum of vehicle counts */
 int cfb_timed_steps(cfb_engine *e, int n, int flush_l2, double *ms, int64_t *vehicle_steps);

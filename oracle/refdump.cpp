@@ -17,7 +17,11 @@
 //       light-weight observables for long / large runs (the multi-GPU parity tests): the vehicle count
 //       after EVERY step, and every `every` steps the per-lane vehicle count, per-lane waiting count
 //       (speed < 0.1) and per-lane sum of speeds.
-//   refdump bench <config.json> <steps> <threads> [warmup]
+//   refdump sweep <config.json> <steps> <warmup> <t1,t2,...>
+//       thread sweep at ONE operating point: the first thread count runs the warm-up
+//       steps, its state goes through the reference's own Archive (dump / loadFromFile) into one engine per
+//       further thread count, each is timed over <steps> steps; prints one JSON line.
+//   refdump bench <config.json> <steps> <threads> [warmup] [counts.bin]
 //       timing loop in the shape of tools/debug/simple_run.cpp:42-57, prints one
 //       JSON line -> the `--impl reference` arm of bench.py.
 //
@@ -308,18 +312,69 @@ int dumpCounts(const char *cfg, int steps, int threads, const char *outPath, int
     return 0;
 }
 
-int bench(const char *cfg, int steps, int threads, int warmup) {
+int sweep(const char *cfg, int steps, int warmup, const char *list) {
+    std::vector<int> threads;
+    for (const char *p = list; *p;) {
+        threads.push_back(atoi(p));
+        while (*p && *p != ',') ++p;
+        if (*p == ',') ++p;
+    }
+    if (threads.empty()) return 64;
+    char path[] = "/tmp/refdump_sweep_XXXXXX";
+    int fd = mkstemp(path);
+    if (fd >= 0) close(fd);
+    std::string out = "{\"steps\": " + std::to_string(steps) + ", \"warmup\": " + std::to_string(warmup) + ", \"sweep\": {";
+    size_t vehicles = 0;
+    for (size_t k = 0; k < threads.size(); ++k) {
+        Engine *e = new Engine(cfg, threads[k]);   // never destroyed (see dumpRun)
+        if (k == 0) {
+            for (int s = 0; s < warmup; ++s) e->nextStep();
+            if (threads.size() > 1) e->snapshot().dump(path);
+        } else {
+            e->loadFromFile(path);
+        }
+        long long vs = 0;
+        auto t2 = std::chrono::steady_clock::now();
+        for (int s = 0; s < steps; ++s) {
+            e->nextStep();
+            vs += (long long) e->getVehicleCount();
+        }
+        auto t3 = std::chrono::steady_clock::now();
+        const double sec = std::chrono::duration<double>(t3 - t2).count();
+        vehicles = e->getVehicleCount();
+        char buf[160];
+        snprintf(buf, sizeof buf, "%s\"%d\": {\"seconds\": %.6f, \"vehicle_steps\": %lld, \"vehicle_steps_per_s\": %.3f}", k ? ", " : "", threads[k], sec, vs,
+                 sec > 0 ? vs / sec : 0.0);
+        out += buf;
+    }
+    unlink(path);
+    printf("%s}, \"final_vehicles\": %zu}\n", out.c_str(), vehicles);
+    fflush(stdout);
+    _exit(0);
+    return 0;
+}
+
+int bench(const char *cfg, int steps, int threads, int warmup, const char *countsPath) {
     auto t0 = std::chrono::steady_clock::now();
     Engine e(cfg, threads);
     auto t1 = std::chrono::steady_clock::now();
-    for (int s = 0; s < warmup; ++s) e.nextStep();
+    std::vector<int32_t> counts;   // get_vehicle_count() after every step, warm-up included (parity_check of bench.py)
+    counts.reserve((size_t) warmup + steps);
+    for (int s = 0; s < warmup; ++s) { e.nextStep(); counts.push_back((int32_t) e.getVehicleCount()); }
     long long vs = 0;
     auto t2 = std::chrono::steady_clock::now();
     for (int s = 0; s < steps; ++s) {
         e.nextStep();
-        vs += (long long) e.getVehicleCount();
+        const long long c = (long long) e.getVehicleCount();
+        vs += c;
+        counts.push_back((int32_t) c);
     }
     auto t3 = std::chrono::steady_clock::now();
+    if (countsPath) {
+        Out o(countsPath);
+        for (int32_t c : counts) o.i32(c);
+        o.close();
+    }
     double load = std::chrono::duration<double>(t1 - t0).count();
     double sec = std::chrono::duration<double>(t3 - t2).count();
     printf("{\"steps\": %d, \"warmup\": %d, \"threads\": %d, \"load_s\": %.6f, \"seconds\": %.6f, "
@@ -343,7 +398,8 @@ int main(int argc, char **argv) {
     if (argc >= 6 && !strcmp(argv[1], "counts"))
         return dumpCounts(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
     if (argc >= 5 && !strcmp(argv[1], "bench"))
-        return bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0);
-    fprintf(stderr, "usage: refdump static|run|runlc|counts|bench ...\n");
+        return bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0, argc >= 7 ? argv[6] : nullptr);
+    if (argc >= 6 && !strcmp(argv[1], "sweep")) return sweep(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
+    fprintf(stderr, "usage: refdump static|run|runlc|counts|sweep|bench ...\n");
     return 64;
 }

@@ -163,6 +163,7 @@ void DeviceSim::synchronize() {}
 
 int DeviceSim::vehicleCount() { return impl_->H.ctrl.active; }
 int DeviceSim::errorFlags() { return impl_->H.ctrl.error; }
+int DeviceSim::tieCount() { return impl_->H.ctrl.ties; }
 void DeviceSim::laneVehicleCount(int32_t *out) { for (int l = 0; l < impl_->H.V.nLanes; ++l) out[l] = impl_->H.count[l]; }
 void DeviceSim::laneWaitingVehicleCount(int32_t *out) {
     HostSim &H = impl_->H;
@@ -294,7 +295,15 @@ void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
 }
 
 // ---- not emulated ----
-void DeviceSim::configureShard(int, int, const std::vector<unsigned char> &, const std::vector<std::vector<int>> &, const std::vector<std::vector<int>> &) { notEmulated("sharding"); }
+void DeviceSim::configureShard(int, int, const std::vector<unsigned char> &, const std::vector<std::vector<int>> &, const std::vector<std::vector<int>> &,
+                               const std::vector<std::vector<int>> &) { notEmulated("sharding"); }
+DeviceSim::ShardArena DeviceSim::shardArena() { notEmulated("sharding"); return ShardArena{nullptr, 0}; }
+void DeviceSim::shardConnect(const std::vector<void *> &) { notEmulated("sharding"); }
+bool DeviceSim::shardIsP2P() const { return false; }
+void DeviceSim::sendMovers() { notEmulated("sharding"); }
+void DeviceSim::recvMovers() { notEmulated("sharding"); }
+void DeviceSim::sendTails() { notEmulated("sharding"); }
+void DeviceSim::recvTails() { notEmulated("sharding"); }
 ShardBuffers DeviceSim::shardBuffers() { notEmulated("sharding"); return ShardBuffers(); }
 int DeviceSim::shardStepBegin() { notEmulated("sharding"); return 0; }
 bool DeviceSim::shardStepEnd(int) { notEmulated("sharding"); return false; }
