@@ -375,8 +375,17 @@ def run_ours(args):
 
     eng_steps_total = args.prefill + warm + 3 * args.steps
     # ---- per-kernel device time (CUDA events around every kernel; separate pass, serialised) ----
-    if sharded:   # per-kernel events are only wired for the single-engine launch path
+    shard_phases = None
+    if sharded:   # phase by phase (CUDA events between the phases; plain launches, serialised): where a sharded step's time goes
         (k_ing, k_not, k_ctl, k_mov, k_led), kn = (0.0, 0.0, 0.0, 0.0, 0.0), 1
+        eng.enable_kernel_timing(True)
+        for _ in range(min(args.steps, 50)):
+            eng.next_step()
+        ph, pn = eng.shard_phase_times()
+        eng.enable_kernel_timing(False)
+        names = ["k_ingest", "k_notify+k_control", "send_movers", "recv_movers(+wait)", "k_move", "send_tails", "recv_tails(+wait)", "k_leader"]
+        shard_phases = {"rank0_ms": {n: v / max(pn, 1) for n, v in zip(names, ph)},
+                        "max_over_ranks_ms": {n: reduce_max(v / max(pn, 1)) for n, v in zip(names, ph)}}
     else:
         eng.enable_kernel_timing(True)
         ksteps = min(args.steps, 50)
@@ -440,6 +449,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "kernel_ms": kms,
             "host_ms_per_step": {"spawn_generation": host_gen_ms / max(eng_steps_total, 1), "enqueue": host_enq_ms / max(eng_steps_total, 1)},
+            "shard_phase_ms": shard_phases,
             "roofline": roof(dominant) if not sharded else None,
             "roofline_leader_scan": roof("k_leader") if not sharded else None,
             "clocks": clocks,

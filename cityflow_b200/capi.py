@@ -29,13 +29,15 @@ def declared_symbols() -> list:
     return sorted(set(re.findall(r"\b(cfb_[a-z0-9_]+)\s*\(", txt)))
 
 
-def load_library(path: str = None) -> ctypes.CDLL:
-    """The product library; `path` is for the test suite only (the same C-ABI built over the emulated device,
-    tests/device_sim_emu.cpp -- never a product path)."""
-    path = path or LIB_PATH
-    if not os.path.exists(path):
-        raise RuntimeError("cityflow_b200: %s is missing -- build it first (__graft_entry__.build())" % path)
-    lib = ctypes.CDLL(path)
+def load_library() -> ctypes.CDLL:
+    """The product library (libcityflow_b200.so next to this file); there is no other path to load from."""
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("cityflow_b200: %s is missing -- build it first (__graft_entry__.build())" % LIB_PATH)
+    return bind(ctypes.CDLL(LIB_PATH))
+
+
+def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
+    """Attach the argument / result types of include/cityflow_b200.h to an opened library."""
     c = ctypes
     vp, i32, i64, dbl, cp = c.c_void_p, c.c_int, c.c_int64, c.c_double, c.c_char_p
     sig = {
@@ -94,8 +96,11 @@ def load_library(path: str = None) -> ctypes.CDLL:
 class CEngine:
     """Minimal object wrapper over the raw C calls (numpy in / out)."""
 
-    def __init__(self, config: str, device: int = 0, lib_path: str = None):
-        self.lib = load_library(lib_path)
+    def _library(self) -> ctypes.CDLL:
+        return load_library()
+
+    def __init__(self, config: str, device: int = 0):
+        self.lib = self._library()
         self.h = self.lib.cfb_engine_create(config.encode(), 1, device)
         if not self.h:
             raise RuntimeError("cfb_engine_create failed: %s" % self.lib.cfb_last_error(None).decode())

@@ -6,71 +6,81 @@
 namespace cfb {
 
 // ------------------------------------------------------------------------------------------
-// Cross::canPass roadnet.cpp:603-676.  `cs` = 2*cross + side of the asking vehicle's laneLink.
-__device__ bool canPass(const View &V, int cs, const Notify &f, const DTmpl &T, double mySpeed, int myEnterLL,
-                        int myPriority, double distanceToLaneLinkStart, double distOnLane, int &foeSlot) {
-    const int fp = f.pos;
+// Cross::canPass roadnet.cpp:603-676, split at the line between what depends on the foe alone and what depends on
+// the asking vehicle.  foeTerms() is the foe half: called by k_notify for every cross side it notifies (`n.dist`,
+// `n.pos` set; `foeLinkW` = linkInfo.w of the notified vehicle's laneLink: turn | type << 8).  Same FP64
+// expressions as the reference, evaluated on the same committed state (nothing between k_notify and k_control
+// changes a vehicle, a blocker or delStep).
+__device__ __forceinline__ void foeTerms(const View &V, Notify &n, int foeLinkW) {
+    const int fp = n.pos;
     const int4 fid = V.ids[fp];
-    foeSlot = fid.x;
-    const int myLink = V.csLink[cs], foeLink = V.csLink[cs ^ 1];
-    const int f1 = V.linkInfo[myLink].w, f2 = V.linkInfo[foeLink].w;
-    const int t1 = f1 >> 8, t2 = f2 >> 8;
+    const DTmpl &FT = V.tmpl[fid.y];
+    const double foeSpeed = V.kin[fp].y, d2 = n.dist;
+    n.slot = fid.x;
+    n.prio = fid.z;
+    n.enterLL = V.nav[fp].w;          // a size_t compared as double in the reference (vehicle.h:262)
+    int fl = (foeLinkW >> 8) << 8;
+    if (canYield(FT, foeSpeed, d2)) fl |= NF_CAN_YIELD;
+    if (d2 + FT.len < 0) fl |= NF_PASSED;
+    n.steps = d2 > 0 ? reachSteps(foeSpeed, d2, (foeLinkW & 1) ? FT.turnSpeed : FT.maxSpeed, FT.usualPosAcc, V.dt) : 0;
+    // deadlock detection over the committed blocker chain (Floyd), roadnet.cpp:662-674.  A reference to a vehicle
+    // that left the network in the previous step counts as null (Engine::threadUpdateAction drops it,
+    // engine.cpp:419-421): evaluated lazily here.
+    const int prevStep = V.ctrl->step - 1;
+    auto blockerOf = [&](int s) -> int {
+        int b = V.blk[s];
+        if (b >= 0 && V.delStep[b] == prevStep) b = -1;
+        return b;
+    };
+    int fast = fid.x, slow = fid.x;
+    while (fast >= 0) {
+        int fb = blockerOf(fast);
+        if (fb < 0) break;
+        slow = blockerOf(slow);
+        fast = blockerOf(fb);
+        if (slow == fast) {
+            fl |= NF_CYCLE;
+            break;
+        }
+    }
+    n.flags = fl;
+    n.pad0 = n.pad1 = n.pad2 = 0;
+}
+
+// The asking half.  `myLinkW` = linkInfo.w of the asking vehicle's laneLink; `f` = the other side's record.
+__device__ __forceinline__ bool canPass(const View &V, const Notify &f, int myLinkW, const DTmpl &T, double mySpeed, int myEnterLL,
+                                        int myPriority, double distanceToLaneLinkStart, double distOnLane, int &foeSlot) {
+    foeSlot = f.slot;
+    const int t1 = myLinkW >> 8, t2 = f.flags >> 8;
     const double d1 = distOnLane - distanceToLaneLinkStart, d2 = f.dist;
     if (!canYield(T, mySpeed, d1)) return true;
-    const DTmpl &FT = V.tmpl[fid.y];
-    const double foeSpeed = V.kin[fp].y;
     int yield = 0;
-    if (!canYield(FT, foeSpeed, d2)) yield = 1;
+    if (!(f.flags & NF_CAN_YIELD)) yield = 1;
     if (yield == 0) {
         if (t1 > t2) {
             yield = -1;
         } else {
-            const double dt = V.dt;
             if (d2 > 0) {
-                int foeSteps = reachSteps(foeSpeed, d2, (f2 & 1) ? FT.turnSpeed : FT.maxSpeed, FT.usualPosAcc, dt);
-                int mySteps = reachSteps(mySpeed, d1, (f1 & 1) ? T.turnSpeed : T.maxSpeed, T.usualPosAcc, dt);
+                const int foeSteps = f.steps;
+                const int mySteps = reachSteps(mySpeed, d1, (myLinkW & 1) ? T.turnSpeed : T.maxSpeed, T.usualPosAcc, V.dt);
                 if (foeSteps > mySteps) yield = -1;
                 else if (t1 < t2) yield = 1;
                 else if (foeSteps < mySteps) yield = 1;
                 else {
-                    // enterLaneLinkTime is a size_t compared as double (vehicle.h:262)
-                    const int foeEnter = V.nav[fp].w;
+                    const int foeEnter = f.enterLL;
                     if (myEnterLL == foeEnter) {
-                        if (d1 == d2) yield = myPriority > fid.z ? -1 : 1;
+                        if (d1 == d2) yield = myPriority > f.prio ? -1 : 1;
                         else yield = d1 < d2 ? -1 : 1;
                     } else {
                         yield = myEnterLL < foeEnter ? -1 : 1;
                     }
                 }
             } else {
-                yield = d2 + FT.len < 0 ? -1 : 1;
+                yield = (f.flags & NF_PASSED) ? -1 : 1;
             }
         }
     }
-    if (yield == 1) {
-        // deadlock detection over the committed blocker chain (Floyd), roadnet.cpp:662-674
-        // A reference to a vehicle that left the network in the previous step counts as null
-        // (Engine::threadUpdateAction drops it, engine.cpp:419-421): evaluated lazily here.
-        const int prevStep = V.ctrl->step - 1;
-        auto blockerOf = [&](int s) -> int {
-            int b = V.blk[s];
-            if (b >= 0 && V.delStep[b] == prevStep) b = -1;
-            return b;
-        };
-        int fast = fid.x, slow = fid.x;
-        int trips = 0;
-        while (fast >= 0) {
-            ++trips;
-            int fb = blockerOf(fast);
-            if (fb < 0) break;
-            slow = blockerOf(slow);
-            fast = blockerOf(fb);
-            if (slow == fast) {
-                yield = -1;
-                break;
-            }
-        }
-    }
+    if (yield == 1 && (f.flags & NF_CYCLE)) yield = -1;
     return yield == -1;
 }
 
@@ -190,7 +200,7 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
                         if (f.epoch != epoch) continue;
                         pathBits |= 4u;
                         int foeSlot;
-                        if (!canPass(V, cs, f, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
+                        if (!canPass(V, f, li.w, T, speed, nv.w, idv.z, toStart, dOn, foeSlot)) {
                             s = min2(s, stopBeforeSpeed(T, speed, dOn - toStart - T.yieldDistance, dt));
                             newBlocker = foeSlot;
                             stop = true;

@@ -166,7 +166,7 @@ __device__ __forceinline__ void phase_control_coop(const View &V, const int bid,
                 const int cs = V.lcIdx[q2];
                 const Notify f = V.notify[cs ^ 1];
                 int foeSlot = -1;
-                const bool pass = canPass(V, cs, f, V.tmpl[id2.y], V.kin[p2].y, V.nav[p2].w, id2.z, sItemStart[wib][k], V.lcDist[q2], foeSlot);
+                const bool pass = canPass(V, f, V.linkInfo[V.csLink[cs]].w, V.tmpl[id2.y], V.kin[p2].y, V.nav[p2].w, id2.z, sItemStart[wib][k], V.lcDist[q2], foeSlot);
                 sRes[wib][k] = pass ? -1 : foeSlot;
             }
             __syncwarp();

@@ -21,6 +21,7 @@ __device__ __forceinline__ void blkSet(const View &V, int slot, int val) {
 }
 
 __device__ __forceinline__ int planAt(const View &V, int plan, int idx) { return V.planData[V.planBeg[plan] + idx]; }
+__device__ __forceinline__ void foeTerms(const View &V, Notify &n, int foeLinkW);   // device_control.cuh
 
 // Cross-drivable leader search for the head of a list (Vehicle::updateLeaderAndGap, else-branch,
 // vehicle.cpp:162-195).  Candidates are read from the per-drivable tail records.  `myLane >= 0`
@@ -89,19 +90,28 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
     if (staged)
         for (int k = threadIdx.x; k < nSpawn; k += blockDim.x) sLane[k] = V.spawn[k].lane;
     __syncthreads();
-    for (int r = i; r < V.nRL; r += nblk * blockDim.x) {
+    const int nRLmine = V.ingRL ? V.nIngRL : V.nRL;
+    for (int x = i; x < nRLmine; x += nblk * blockDim.x) {
+        const int r = V.ingRL ? V.ingRL[x] : x;
         int in = V.rlInter[r];
         int ph = V.interPhaseBeg[in] + V.curPhase[in];
         V.rlAvail[r] = V.phaseAvail[V.phaseAvailBeg[ph] + (r - V.interRLBeg[in])];
     }
-    for (int k = i; k < V.nLinks * V.maskWords; k += nblk * blockDim.x) V.foeMask[k] = 0u;
+    if (V.ingLinks) {
+        for (int x = i; x < V.nIngLinks * V.maskWords; x += nblk * blockDim.x)
+            V.foeMask[V.ingLinks[x / V.maskWords] * V.maskWords + x % V.maskWords] = 0u;
+    } else {
+        for (int k = i; k < V.nLinks * V.maskWords; k += nblk * blockDim.x) V.foeMask[k] = 0u;
+    }
     if (i == 0) {  // lists of the other parity are rebuilt by this step's k_move
         V.ctrl->moverCount = 0;
         V.ctrl->nVeh[cpar ^ 1] = 0;
         V.ctrl->nAct[cpar ^ 1] = 0;
         V.ctrl->nExtra = 0;
     }
-    for (i = gtid0; i < V.nLanes; i += nblk * blockDim.x) {
+    const int nLanesMine = V.ingLanes ? V.nIngLanes : V.nLanes;
+    for (int x = gtid0; x < nLanesMine; x += nblk * blockDim.x) {
+    i = V.ingLanes ? V.ingLanes[x] : x;
     // Sharded: a lane this rank FEEDS is admitted into here as well, on the ghost copy, with the same
     // inputs as on its owner (spawn records and queue are replicated, the ghost tail is exact after
     // the previous step's exchange) -- so the owner need not report the admission.
@@ -227,6 +237,7 @@ __device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
     const int c2 = V.count[linkDrv], base2 = V.off[linkDrv];
     if (!has1 && !has3 && c2 == 0) return;
     const double L = V.drvLength[linkDrv];
+    const int linkW = V.linkInfo[ll].w;
     for (int k0 = 0; k0 < nc; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < nc;
@@ -269,6 +280,7 @@ __device__ void notifyLink(const View &V, int ll, int lane, int epoch) {
             n.dist = ndist;
             n.pos = owner;
             n.epoch = epoch;
+            foeTerms(V, n, linkW);
             V.notify[V.lcIdx[cb + k]] = n;
             // tell the crossing link which of ITS crosses now has a foe (k_control visits only those)
             const int peer = V.lcPeer[cb + k];

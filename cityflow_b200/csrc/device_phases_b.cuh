@@ -31,6 +31,12 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
         base = V.off[d];
         const int cap = V.off[d + 1] - base;
         int nsurv = 0;
+        // Leader / gap of every vehicle that is not the head of the list (Vehicle::updateLeaderAndGap, vehicle.cpp:158-160:
+        // leader = list predecessor, gap = leader.dis - leader.len - dis on the committed values) is settled right here:
+        // the warp that compacts the bucket holds every survivor's new distance in registers, the predecessor's arrive by
+        // shuffle, and `carry` hands the last committed vehicle over to the next chunk / to the entrants.  Only list heads
+        // (cross-drivable search) are left to k_leader.
+        double carryDis = 0, carryLen = 0;
         for (int c0 = 0; c0 < n; c0 += 32) {
             const int k = c0 + lane;
             const bool valid = k < n;
@@ -46,7 +52,13 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
             }
             const bool keep = valid && nb.x == -1;
             const unsigned mask = __ballot_sync(0xffffffffu, keep);
-            const int dst = nsurv + __popc(mask & ((1u << lane) - 1));
+            const unsigned below = mask & ((1u << lane) - 1);
+            const int dst = nsurv + __popc(below);
+            const double myLen = keep ? V.tmpl[idv.y].len : 0.0;
+            const int predLane = below ? 31 - __clz(below) : 0;    // nearest survivor in front of me inside this chunk
+            double pd = __shfl_sync(0xffffffffu, nk.x, predLane);
+            double pl = __shfl_sync(0xffffffffu, myLen, predLane);
+            if (!below) { pd = carryDis; pl = carryLen; }
             __syncwarp();
             if (keep) {
                 const int q = base + dst;
@@ -57,6 +69,13 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 if (dst != k) {
                     V.ids[q] = idv;
                     V.pos[idv.x] = q;
+                }
+                if (dst > 0) {
+                    V.leader[q] = q - 1;
+                    V.gap[q] = pd - pl - nk.x;
+#ifdef CFB_LANE_CHANGE
+                    if (V.lcOn) V.lc.slot[idv.x].gap = pd - pl - nk.x;
+#endif
                 }
             } else if (valid && nb.x == -2) {                      // finished (engine.cpp:296-310)
                 V.pos[idv.x] = -1;
@@ -71,6 +90,11 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
 #endif
                 atomicSub(&V.ctrl->active, 1);
             }
+            if (mask) {
+                const int last = 31 - __clz(mask);
+                carryDis = __shfl_sync(0xffffffffu, nk.x, last);
+                carryLen = __shfl_sync(0xffffffffu, myLen, last);
+            }
             nsurv += __popc(mask);
         }
         if (m > 0) {
@@ -80,12 +104,14 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 m = max(0, cap - nsurv);
             }
             int mi = -1;
-            double myDis = 0;
+            double myDis = 0, myLen = 0;
             int myPrio = 0;
             if (lane < m) {
                 mi = V.ent[d * ENT_CAP + lane];
                 myDis = V.mkin[mi].x;
-                myPrio = V.mids[mi].z;
+                const int4 mid = V.mids[mi];
+                myPrio = mid.z;
+                myLen = V.tmpl[mid.y].len;
             }
             int rank = 0;
             for (int j = 0; j < m; ++j) {
@@ -93,6 +119,13 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 const int op = __shfl_sync(0xffffffffu, myPrio, j);
                 if (lane < m && j != lane && (od > myDis || (od == myDis && op < myPrio))) ++rank;
                 if (lane < m && j < lane && od == myDis) atomicAdd(&V.ctrl->ties, 1);   // (never in the tested scenarios up to 30x30)
+            }
+            double pd = carryDis, pl = carryLen;                   // list predecessor of the first entrant: the last survivor
+            for (int j = 0; j < m; ++j) {
+                const double od = __shfl_sync(0xffffffffu, myDis, j);
+                const double ol = __shfl_sync(0xffffffffu, myLen, j);
+                const int orank = __shfl_sync(0xffffffffu, rank, j);
+                if (lane < m && orank == rank - 1) { pd = od; pl = ol; }
             }
             if (lane < m) {
                 const int q = base + nsurv + rank;
@@ -103,6 +136,13 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 V.nav[q] = mnv;
                 blkSet(V, idv.x, mnv.z);
                 V.pos[idv.x] = q;
+                if (nsurv + rank > 0) {
+                    V.leader[q] = q - 1;
+                    V.gap[q] = pd - pl - myDis;
+#ifdef CFB_LANE_CHANGE
+                    if (V.lcOn) V.lc.slot[idv.x].gap = pd - pl - myDis;
+#endif
+                }
             }
             if (lane == 0) V.entCnt[d] = 0;
         }
@@ -142,11 +182,10 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
 }
 
 // ------------------------------------------------------------------------------------------
-// k_leader: warp per occupied drivable (the list k_move just wrote).  Non-heads: leader = list
-// predecessor, gap = leader.dis - leader.len - dis (vehicle.cpp:158-160), predecessor values
-// arrive by warp shuffle.  Heads: cross-drivable search.  Also drops blockers that left the
-// network this step (engine.cpp:419-421) and, in the leading threads, advances the traffic
-// lights (TrafficLight::passTime, trafficlight.cpp:29-37) and the step counter.
+// k_leader: thread per occupied drivable (the list k_move just wrote): the cross-drivable leader search of the list
+// HEAD (vehicle.cpp:162-195).  Everybody else's leader / gap was settled by k_move while it had the bucket in
+// registers.  In the leading threads: the traffic lights (TrafficLight::passTime, trafficlight.cpp:29-37) and the
+// step counter.
 __device__ __forceinline__ void phase_leader(const View &V, const int bid, const int nblk) {
     const int gtid = bid * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -173,44 +212,8 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
             V.curPhase[in] = cur;
         }
     }
-    // flat pass over the position list k_move just wrote (bucket order: a thread's list
-    // predecessor usually sits in the previous lane, its dis/len arrive by shuffle)
-    (void) warp; (void) nWarps;
-    const int nVeh = min(V.ctrl->nVeh[npar], V.vehCap);
     const int stride = nblk * blockDim.x;
-    for (int it0 = gtid - lane; it0 < nVeh; it0 += stride) {
-        const int it = it0 + lane;
-        const bool valid = it < nVeh;
-        int p = -2, d = 0;
-        bool head = true;
-        double dis = 0, len = 0;
-        int4 idv = make_int4(0, 0, 0, 0);
-        if (valid) {
-            const int2 vd = V.vehList[npar][it];
-            p = vd.x;
-            d = vd.y & ~HEAD_BIT;
-            head = (vd.y & HEAD_BIT) != 0;
-            dis = V.kin[p].x;
-            idv = V.ids[p];
-            len = V.tmpl[idv.y].len;
-        }
-        const int pp = __shfl_up_sync(0xffffffffu, p, 1);
-        double pd = __shfl_up_sync(0xffffffffu, dis, 1);
-        double pl = __shfl_up_sync(0xffffffffu, len, 1);
-        if (valid) {
-            if (!head) {
-                if (lane == 0 || pp != p - 1) {  // predecessor handled by another warp
-                    pd = V.kin[p - 1].x;
-                    pl = V.tmpl[V.ids[p - 1].y].len;
-                }
-                V.leader[p] = p - 1;
-                V.gap[p] = pd - pl - dis;
-#ifdef CFB_LANE_CHANGE
-                if (V.lcOn) V.lc.slot[idv.x].gap = pd - pl - dis;
-#endif
-            }
-        }
-    }
+    (void) lane; (void) warp; (void) nWarps;
     // list heads: dense pass, one thread per occupied drivable (their cross-drivable search is a
     // chain of dependent loads; keeping it out of the streaming pass above avoids one slow lane
     // per warp)

@@ -352,14 +352,21 @@ struct DeviceSim::Impl {
     DevBuf<int2> finSlots, vehList0, vehList1;
     DevBuf<int> act0, act1, extra, lcPeer, blk, delStep, boundOut, boundIn;
     DevBuf<unsigned char> owned;
+    DevBuf<int> ingBuf;
+    std::vector<int> ingLists;
     DevBuf<TailMsg> tailSend, tailRecv;
     DevBuf<MoverMsg> moverSend, moverRecv;
     DevBuf<int2> blkUpd, blkAll;
     std::vector<int> outBeg, inBeg;
     std::vector<unsigned char> ownedHost;
     int shardRank = 0, shardWorld = 1;
-    cudaGraphExec_t shardGraph[2] = {nullptr, nullptr};
-    cudaEvent_t shardGraphDone[2] = {nullptr, nullptr};
+    // A step is replayed as ONE graph per list parity.  Re-launching an executable graph whose previous launch has not
+    // finished makes the driver wait on the host, so each parity has a small ring of instances of the same graph: the
+    // host may run 2 * GRING steps ahead of the device before a step falls back to plain launches.
+    static constexpr int GRING = 4;
+    cudaGraph_t shardTemplate[2] = {nullptr, nullptr};
+    cudaGraphExec_t shardGraph[2][GRING] = {};
+    cudaEvent_t shardGraphDone[2][GRING] = {};
     bool shardGraphOk = true;    // whole sharded step (kernels + NCCL groups) replayed as one graph per parity
     DevBuf<int> shardScratch;
     DevBuf<unsigned char> finGather;
@@ -369,6 +376,7 @@ struct DeviceSim::Impl {
     DevBuf<int> p2pInts;              // nbr | outPeer | outDst | inPeer | inDst | ticket[2]
     ShardP2P S{};
     bool p2p = false;
+    bool arenaShared = false;         // mapped by other PROCESSES (as opposed to the in-process loop-back group)
     std::vector<std::vector<int>> bsize;   // bsize[a][b] = lanes rank a feeds and rank b owns
     static constexpr int SHARD_SLOT_CAP = 1 << 22;   // slot-indexed arrays are fixed once peers have mapped delStep
     struct ArenaLayout { size_t flags, delStep, blkIn, moverIn, tailIn, total; };
@@ -421,6 +429,9 @@ struct DeviceSim::Impl {
     size_t stepEvUsed = 0;
     DevBuf<unsigned char> flushBuf;
     KernelTimes times;
+    cudaEvent_t shardEv[SHARD_PHASES + 1] = {};
+    double shardMs[SHARD_PHASES] = {};
+    long long shardTimedSteps = 0;
 
 #ifdef CFB_LANE_CHANGE
     DevBuf<LcSlot> lcSlot;
@@ -438,13 +449,24 @@ struct DeviceSim::Impl {
     int numSMs = 148;
     int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
     bool useGraph = true, graphDirty = false, useCoop = false;   // cooperative k_step measured slower
-    cudaEvent_t graphDone[2] = {nullptr, nullptr};
+    cudaEvent_t graphDone[2][GRING] = {};
+    cudaGraph_t graphTemplate[2] = {nullptr, nullptr};
     int gridStep = 0;
-    cudaGraphExec_t graphExec[2] = {nullptr, nullptr};
+    cudaGraphExec_t graphExec[2][GRING] = {};
 
     void dropShardGraphs() {
-        for (int k = 0; k < 2; ++k)
-            if (shardGraph[k]) { cudaStreamSynchronize(stream); cudaGraphExecDestroy(shardGraph[k]); shardGraph[k] = nullptr; }
+        for (int k = 0; k < 2; ++k) {
+            for (int r = 0; r < GRING; ++r)
+                if (shardGraph[k][r]) { cudaStreamSynchronize(stream); cudaGraphExecDestroy(shardGraph[k][r]); shardGraph[k][r] = nullptr; }
+            if (shardTemplate[k]) { cudaGraphDestroy(shardTemplate[k]); shardTemplate[k] = nullptr; }
+        }
+    }
+    void dropGraphs() {
+        for (int k = 0; k < 2; ++k) {
+            for (int r = 0; r < GRING; ++r)
+                if (graphExec[k][r]) { cudaStreamSynchronize(stream); cudaGraphExecDestroy(graphExec[k][r]); graphExec[k][r] = nullptr; }
+            if (graphTemplate[k]) { cudaGraphDestroy(graphTemplate[k]); graphTemplate[k] = nullptr; }
+        }
     }
     void ensureHostInts(size_t n) {
         if (n <= hIntsCap) return;
@@ -630,11 +652,20 @@ DeviceSim::~DeviceSim() {
     }
     for (auto &ev : I.ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : I.stepEv) cudaEventDestroy(ev);
-    for (int k = 0; k < 2; ++k) if (I.graphExec[k]) cudaGraphExecDestroy(I.graphExec[k]);
-    for (int k = 0; k < 2; ++k) if (I.graphDone[k]) cudaEventDestroy(I.graphDone[k]);
+    I.dropGraphs();
+    I.dropShardGraphs();
+    for (int k = 0; k < 2; ++k)
+        for (int r = 0; r < Impl::GRING; ++r) {
+            if (I.graphDone[k][r]) cudaEventDestroy(I.graphDone[k][r]);
+            if (I.shardGraphDone[k][r]) cudaEventDestroy(I.shardGraphDone[k][r]);
+        }
     if (I.hCtrl) cudaFreeHost(I.hCtrl);
     if (I.hInts) cudaFreeHost(I.hInts);
     if (I.stream) cudaStreamDestroy(I.stream);
+    // A peer process may still have the arena mapped (cudaIpcOpenMemHandle): freeing exported memory before every
+    // importer has closed it is undefined, and a barrier in a destructor can hang on a rank that died -- the arena of a
+    // multi-process run is left to process exit.
+    if (I.arena.p && I.p2p && I.shardWorld > 1 && I.arenaShared) { I.arena.p = nullptr; I.arena.n = 0; }
     delete impl_;
 }
 
@@ -814,26 +845,28 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
         // The five kernels of one step are replayed as one CUDA graph per list parity: one launch
         // call per step instead of five, and no host-paced gaps between the kernels.
         if (I.graphDirty) {
-            for (int k = 0; k < 2; ++k)
-                if (I.graphExec[k]) { cudaGraphExecDestroy(I.graphExec[k]); I.graphExec[k] = nullptr; }
+            I.dropGraphs();
             I.graphDirty = false;
         }
-        cudaGraphExec_t &ge = I.graphExec[V.par];
+        const int ring = (int) ((steps_ >> 1) % Impl::GRING);
+        cudaGraphExec_t &ge = I.graphExec[V.par][ring];
         if (!ge) {
-            cudaGraph_t g = nullptr;
-            CFB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            launchAll(false);
-            CFB_CUDA(cudaStreamEndCapture(s, &g));
+            cudaGraph_t &g = I.graphTemplate[V.par];
+            if (!g) {
+                CFB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                launchAll(false);
+                CFB_CUDA(cudaStreamEndCapture(s, &g));
+            }
             CFB_CUDA(cudaGraphInstantiate(&ge, g, 0));
-            cudaGraphDestroy(g);
         }
         // Re-launching an executable graph whose previous launch has not finished makes the driver
-        // wait on the host (observed: ~1 ms per step once the host runs more than two steps ahead).
-        // When that is the case fall back to the five plain launches, which only enqueue.
-        if (!I.graphDone[V.par]) CFB_CUDA(cudaEventCreateWithFlags(&I.graphDone[V.par], cudaEventDisableTiming));
-        else if (cudaEventQuery(I.graphDone[V.par]) != cudaSuccess) { launchAll(false); goto launched; }
+        // wait on the host (observed: ~1 ms per step), hence the ring of instances; when even the ring
+        // is exhausted fall back to the five plain launches, which only enqueue.
+        cudaEvent_t &done = I.graphDone[V.par][ring];
+        if (!done) CFB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        else if (cudaEventQuery(done) != cudaSuccess) { launchAll(false); goto launched; }
         CFB_CUDA(cudaGraphLaunch(ge, s));
-        CFB_CUDA(cudaEventRecord(I.graphDone[V.par], s));
+        CFB_CUDA(cudaEventRecord(done, s));
     }
 launched:
     CFB_CUDA(cudaGetLastError());
@@ -858,7 +891,8 @@ void DeviceSim::synchronize() { CFB_CUDA(cudaStreamSynchronize(impl_->stream)); 
 void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned char> &owned,
                                const std::vector<std::vector<int>> &feedPerPeer,
                                const std::vector<std::vector<int>> &ownPerPeer,
-                               const std::vector<std::vector<int>> &boundarySize) {
+                               const std::vector<std::vector<int>> &boundarySize,
+                               const std::vector<unsigned char> &ownedRoadLinks) {
     Impl &I = *impl_;
     View &V = I.V;
     CFB_CUDA(cudaStreamSynchronize(I.stream));
@@ -871,6 +905,20 @@ void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned c
     I.owned.upload(own3);
     I.ownedHost = owned;
     V.owned = I.owned.p;
+    {   // k_ingest walks these instead of every lane / laneLink / roadLink of the whole network
+        std::vector<int> lanes, links, rls;
+        for (int l = 0; l < V.nLanes; ++l) if (own3[l]) lanes.push_back(l);
+        for (int k = 0; k < V.nLinks; ++k) if (owned[V.nLanes + k]) links.push_back(k);
+        for (int r = 0; r < (int) ownedRoadLinks.size(); ++r) if (ownedRoadLinks[r]) rls.push_back(r);
+        V.nIngLanes = (int) lanes.size(); V.nIngLinks = (int) links.size(); V.nIngRL = (int) rls.size();
+        I.ingLists.clear();
+        I.ingLists.insert(I.ingLists.end(), lanes.begin(), lanes.end());
+        I.ingLists.insert(I.ingLists.end(), links.begin(), links.end());
+        I.ingLists.insert(I.ingLists.end(), rls.begin(), rls.end());
+        I.ingLists.push_back(0);
+        I.ingBuf.upload(I.ingLists);
+        V.ingLanes = I.ingBuf.p; V.ingLinks = I.ingBuf.p + lanes.size(); V.ingRL = I.ingBuf.p + lanes.size() + links.size();
+    }
     std::vector<int> out, in;
     I.outBeg.assign(1, 0);
     I.inBeg.assign(1, 0);
@@ -923,7 +971,7 @@ ShardBuffers DeviceSim::shardBuffers() {
 void DeviceSim::runIngest() {
     Impl &I = *impl_;
     const int TPB = 256;
-    const int g = (std::max(I.V.nLanes, I.V.nRL) + TPB - 1) / TPB;
+    const int g = ((I.V.ingLanes ? std::max(std::max(I.V.nIngLanes, I.V.nIngRL), I.V.nIngLinks * I.V.maskWords / 4) : std::max(I.V.nLanes, I.V.nRL)) + TPB - 1) / TPB;
     k_ingest<<<std::max(g, 1), TPB, 0, I.stream>>>(I.V);
     launches_ += 1;
 }
@@ -1000,6 +1048,7 @@ DeviceSim::ShardArena DeviceSim::shardArena() {
 }
 
 // `peerBase[q]` = rank q's arena as mapped into this process (ignored for q == me).
+void DeviceSim::shardMarkArenaExported() { impl_->arenaShared = true; }
 void DeviceSim::shardConnect(const std::vector<void *> &peerBase) {
     Impl &I = *impl_;
     View &V = I.V;
@@ -1137,11 +1186,16 @@ void DeviceSim::shardGatherFinished(ShardTransport *t, std::vector<FinRec> &inou
 int DeviceSim::shardStepBegin() {
     Impl &I = *impl_;
     const int par = I.V.par;
-    if (!I.shardGraphOk || steps_ < 8) return 0;                       // plain
-    if (I.shardGraph[par]) {
-        if (cudaEventQuery(I.shardGraphDone[par]) != cudaSuccess) return 0;  // previous replay still running: just enqueue
-        CFB_CUDA(cudaGraphLaunch(I.shardGraph[par], I.stream));
-        CFB_CUDA(cudaEventRecord(I.shardGraphDone[par], I.stream));
+    if (!I.shardGraphOk || steps_ < 8 || I.timing) return 0;           // plain
+    const int ring = (int) ((steps_ >> 1) % Impl::GRING);
+    cudaGraphExec_t &ge = I.shardGraph[par][ring];
+    cudaEvent_t &done = I.shardGraphDone[par][ring];
+    if (!done) CFB_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    if (ge || I.shardTemplate[par]) {
+        if (!ge && cudaGraphInstantiate(&ge, I.shardTemplate[par], 0) != cudaSuccess) { cudaGetLastError(); ge = nullptr; return 0; }
+        else if (cudaEventQuery(done) != cudaSuccess) { cudaGetLastError(); return 0; }   // this instance is still running: just enqueue
+        CFB_CUDA(cudaGraphLaunch(ge, I.stream));
+        CFB_CUDA(cudaEventRecord(done, I.stream));
         return 1;                                                     // replayed: the caller skips the phases
     }
     if (cudaStreamBeginCapture(I.stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
@@ -1157,19 +1211,20 @@ bool DeviceSim::shardStepEnd(int state) {
     bool ok = true;
     if (state == 2) {
         const int par = I.V.par;
+        const int ring = (int) ((steps_ >> 1) % Impl::GRING);
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamEndCapture(I.stream, &g);
-        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&I.shardGraph[par], g, 0);
-        if (g) cudaGraphDestroy(g);
-        if (e != cudaSuccess || !I.shardGraph[par]) {
+        if (e == cudaSuccess && g) e = cudaGraphInstantiate(&I.shardGraph[par][ring], g, 0);
+        if (e != cudaSuccess || !I.shardGraph[par][ring]) {
+            if (g) cudaGraphDestroy(g);
             cudaGetLastError();
-            I.shardGraph[par] = nullptr;
+            I.shardGraph[par][ring] = nullptr;
             I.shardGraphOk = false;
             ok = false;                                                // nothing ran: the caller repeats the step plainly
         } else {
-            if (!I.shardGraphDone[par]) CFB_CUDA(cudaEventCreateWithFlags(&I.shardGraphDone[par], cudaEventDisableTiming));
-            CFB_CUDA(cudaGraphLaunch(I.shardGraph[par], I.stream));
-            CFB_CUDA(cudaEventRecord(I.shardGraphDone[par], I.stream));
+            I.shardTemplate[par] = g;
+            CFB_CUDA(cudaGraphLaunch(I.shardGraph[par][ring], I.stream));
+            CFB_CUDA(cudaEventRecord(I.shardGraphDone[par][ring], I.stream));
         }
     }
     if (ok) {
@@ -1243,6 +1298,30 @@ unsigned long long DeviceSim::vehicleSteps() {
 void DeviceSim::enableKernelTiming(bool on) {
     impl_->timing = on;
     impl_->times = KernelTimes();
+    for (double &x : impl_->shardMs) x = 0;
+    impl_->shardTimedSteps = 0;
+}
+bool DeviceSim::timingOn() const { return impl_->timing; }
+void DeviceSim::shardTimeMark(int k) {
+    Impl &I = *impl_;
+    if (!I.timing) return;
+    if (!I.shardEv[k]) CFB_CUDA(cudaEventCreate(&I.shardEv[k]));
+    CFB_CUDA(cudaEventRecord(I.shardEv[k], I.stream));
+}
+void DeviceSim::shardTimeCollect() {
+    Impl &I = *impl_;
+    if (!I.timing) return;
+    CFB_CUDA(cudaEventSynchronize(I.shardEv[SHARD_PHASES]));
+    for (int k = 0; k < SHARD_PHASES; ++k) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, I.shardEv[k], I.shardEv[k + 1]);
+        I.shardMs[k] += ms;
+    }
+    I.shardTimedSteps += 1;
+}
+void DeviceSim::shardPhaseTimes(double ms[SHARD_PHASES], long long *steps) {
+    for (int k = 0; k < SHARD_PHASES; ++k) ms[k] = impl_->shardMs[k];
+    if (steps) *steps = impl_->shardTimedSteps;
 }
 DeviceSim::KernelTimes DeviceSim::kernelTimes() { return impl_->times; }
 

@@ -101,11 +101,12 @@ public:
     // ---- sharded mode: the step phase by phase (see shard.h for the protocol) ----
     void configureShard(int rank, int world, const std::vector<unsigned char> &owned,
                         const std::vector<std::vector<int>> &feedPerPeer, const std::vector<std::vector<int>> &ownPerPeer,
-                        const std::vector<std::vector<int>> &boundarySize);
+                        const std::vector<std::vector<int>> &boundarySize, const std::vector<unsigned char> &ownedRoadLinks);
     // peer-memory transport (device_shard.cuh): the arena peers write into; connect once every rank's arena is mapped
     struct ShardArena { void *base; size_t bytes; };
     ShardArena shardArena();
     void shardConnect(const std::vector<void *> &peerBase);
+    void shardMarkArenaExported();   // other processes map the arena: it must outlive them (never freed)
     bool shardIsP2P() const;
     void sendMovers();
     void recvMovers();
@@ -177,6 +178,12 @@ public:
     // Measurement support for bench.py / profiles (CUDA-event timing of one kernel across launches).
     struct KernelTimes { double ingest = 0, notify = 0, control = 0, move = 0, leader = 0; long long launches = 0; };
     void enableKernelTiming(bool on);
+    // sharded step, phase by phase: ingest | notify+control | send movers | recv movers | move | send tails | recv tails | leader
+    static constexpr int SHARD_PHASES = 8;
+    bool timingOn() const;
+    void shardTimeMark(int k);                       // records event k (0..SHARD_PHASES) when timing is on
+    void shardTimeCollect();                         // after mark SHARD_PHASES: accumulates the phase durations
+    void shardPhaseTimes(double ms[SHARD_PHASES], long long *steps);
     void flushL2();                 // 256 MiB memset on the engine stream
     void markTimed();               // record an event; brackets are (even, odd) pairs
     double collectTimedMs();        // sync; sum of bracket durations; clears the brackets

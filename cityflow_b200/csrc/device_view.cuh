@@ -16,7 +16,16 @@ struct __align__(16) Notify {  // one side of one Cross (roadnet.h:122-124), epo
     double dist;
     int pos;
     int epoch;
+    // The terms of Cross::canPass (roadnet.cpp:603-676) that depend on the NOTIFIED vehicle alone -- it is the foe of
+    // everybody asking from the crossing link -- evaluated once here by k_notify (one lane per cross, no divergence)
+    // instead of once per asking vehicle at the end of k_control's dependent-load chain: see foeTerms().
+    int slot, prio, enterLL, steps;   // foe vehicle handle, Vehicle::priority, enterLaneLinkTime, reach steps (dist > 0)
+    int flags;                        // NF_* | RoadLinkType of the foe's link << 8
+    int pad0, pad1, pad2;
 };
+constexpr int NF_CAN_YIELD = 1;       // Vehicle::canYield(dist) of the foe (vehicle.cpp:284-287)
+constexpr int NF_PASSED = 2;          // dist + len < 0: the foe's tail has cleared the cross (roadnet.cpp:657)
+constexpr int NF_CYCLE = 4;           // the foe's committed blocker chain runs into a cycle (Floyd, roadnet.cpp:662-674)
 
 struct __align__(16) Tail {  // last vehicle of a drivable (Drivable::getLastVehicle), pos < 0 when empty
     double dis, len, speed;
@@ -111,6 +120,8 @@ struct View {
     int *delStep;        // per slot: step at which the vehicle in that slot left the network
     // ---- sharded mode (partition.h): null / 0 when the engine owns the whole network ----
     const unsigned char *owned;   // per drivable: 1 = this rank owns it, 2 = a lane it feeds (ghost copy kept in step), 0 = foreign
+    const int *ingLanes, *ingLinks, *ingRL;   // k_ingest's index lists: lanes owned or fed, laneLinks / roadLinks owned
+    int nIngLanes, nIngLinks, nIngRL;         // (a rank's per-step work must not grow with the size of the WHOLE network)
     const int *boundOut;          // lanes this rank feeds but does not own (all peers, concatenated)
     const int *boundIn;           // lanes this rank owns but a peer feeds
     int nBoundOut, nBoundIn;

@@ -157,6 +157,7 @@ int Routing::intern(const std::vector<int> &anchors) {
     }
     routes_.push_back(std::move(rt));
     byAnchors_[anchors] = id;
+    anchorsOf_.push_back(anchors);
     return id;
 }
 

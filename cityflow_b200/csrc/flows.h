@@ -58,6 +58,7 @@ public:
     // Interns the route; builds plans for every candidate start lane. Returns route id.
     int intern(const std::vector<int> &anchors);
     const Route &route(int id) const { return routes_[id]; }
+    const std::vector<int> &anchorsOf(int id) const { return anchorsOf_[id]; }   // what intern() was called with (archives)
     int numRoutes() const { return (int) routes_.size(); }
     // plan storage (flat, PLAN_END terminated)
     const std::vector<int> &planData() const { return planData_; }
@@ -88,6 +89,7 @@ private:
     const RoadNet &net_;
     std::vector<Route> routes_;
     std::map<std::vector<int>, int> byAnchors_;
+    std::vector<std::vector<int>> anchorsOf_;
     std::vector<int> planData_, planBeg_;
     bool lanePlans_ = false;
     std::vector<int> planRoute_, planRoadPos_;            // per plan

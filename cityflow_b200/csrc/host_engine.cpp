@@ -520,14 +520,24 @@ public:
                 if (st != 1 && dev->shardIsP2P()) {
                     // peer-memory data plane (device_shard.cuh): the seam records are stored straight into the
                     // neighbours' mailboxes by the send kernels; nothing but kernels on the stream
+                    dev->shardTimeMark(0);
                     dev->runIngest();
+                    dev->shardTimeMark(1);
                     dev->runNotifyControl();
+                    dev->shardTimeMark(2);
                     dev->sendMovers();                                                                     // X1
+                    dev->shardTimeMark(3);
                     dev->recvMovers();
+                    dev->shardTimeMark(4);
                     dev->runMove();
+                    dev->shardTimeMark(5);
                     dev->sendTails();                                                                      // X2
+                    dev->shardTimeMark(6);
                     dev->recvTails();
+                    dev->shardTimeMark(7);
                     dev->runLeader();
+                    dev->shardTimeMark(8);
+                    dev->shardTimeCollect();
                 } else if (st != 1) try {
                     ShardBuffers b = dev->shardBuffers();
                     dev->runIngest();
@@ -567,7 +577,10 @@ public:
             own[q] = part.boundary[q][rank];    // lanes q feeds, I own
             for (int p2 = 0; p2 < world; ++p2) bsize[q][p2] = (int) part.boundary[q][p2].size();
         }
-        dev->configureShard(rank, world, owned, feed, own, bsize);
+        std::vector<unsigned char> ownedRL(net.nRoadLinks(), 0);
+        for (int k = 0; k < net.nLinks(); ++k)
+            if (part.drvOwner[net.nLanes() + k] == rank) ownedRL[net.llRoadLink[k]] = 1;
+        dev->configureShard(rank, world, owned, feed, own, bsize, ownedRL);
         return "";
     }
 
@@ -616,6 +629,11 @@ public:
         std::vector<SlotInfo> slots;
         std::vector<int> freeSlots;
         std::vector<Pending> pending;
+        // Slot records and the device image hold INDICES into the route / plan / template tables, which grow at run
+        // time (push_vehicle, set_vehicle_route): the archive carries what was interned, in order, and load() re-interns
+        // it -- an engine whose tables are not a prefix-compatible continuation refuses the archive.
+        std::vector<std::vector<int>> routeAnchors;
+        std::vector<VehicleTemplate> templates;
     };
     void saveHost(HostState &s) {
         drain();
@@ -624,9 +642,22 @@ public:
         s.flowNow.clear(); s.flowCur.clear(); s.flowCnt.clear(); s.flowValid.clear();
         for (auto &f : hot) { s.flowNow.push_back(f.nowTime); s.flowCur.push_back(f.currentTime); s.flowCnt.push_back(f.cnt); s.flowValid.push_back((uint8_t) f.valid); }
         s.slots = slots; s.freeSlots = freeSlots; s.pending = pending;
+        s.routeAnchors.clear();
+        for (int r = 0; r < routing->numRoutes(); ++r) s.routeAnchors.push_back(routing->anchorsOf(r));
+        s.templates = templates;
     }
     void loadHost(const HostState &s) {
         if (s.flowNow.size() != flows.size()) throw std::runtime_error("archive does not match this engine (flows)");
+        for (size_t r = 0; r < s.routeAnchors.size(); ++r) {
+            if (r < (size_t) routing->numRoutes() ? routing->anchorsOf((int) r) != s.routeAnchors[r] : routing->intern(s.routeAnchors[r]) != (int) r)
+                throw std::runtime_error("archive does not match this engine (route table)");
+        }
+        for (size_t t = 0; t < s.templates.size(); ++t) {
+            const bool same = t < templates.size() ? (!(templates[t] < s.templates[t]) && !(s.templates[t] < templates[t])) : internTemplate(s.templates[t]) == (int) t;
+            if (!same) throw std::runtime_error("archive does not match this engine (vehicle template table)");
+        }
+        if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
+        if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
         rnd = s.rnd; step = s.step; manuallyPushCnt = s.manuallyPushCnt; finishedCnt = s.finishedCnt;
         cumulativeTravelTime = s.cumulativeTravelTime;
         for (size_t i = 0; i < hot.size(); ++i) { hot[i].nowTime = s.flowNow[i]; hot[i].currentTime = s.flowCur[i]; hot[i].cnt = s.flowCnt[i]; hot[i].valid = s.flowValid[i]; }
@@ -648,12 +679,29 @@ struct cfb_engine {
     cfb::HostEngine h;
     std::string lastError;
     std::vector<cfb::SpeedRec> recs;
+    std::unique_ptr<cfb::ShardTransport> transport;   // sharded run: destroyed before the device (see cfb_engine_destroy)
 };
+
+namespace {
+// Every entry point runs with the engine's GPU current and leaves the caller's device as it found it: the engine may sit
+// on another GPU than torch's current one, a second engine may sit on a third, and a fresh host thread starts on device 0.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(const cfb_engine *e) {
+        if (!e || !e->h.dev) return;
+        const int want = e->h.dev->device();
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != want) cudaSetDevice(want); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
 
 static thread_local std::string g_createError;
 
 #define CFB_TRY(e, ...)                                    \
     try {                                                  \
+        DeviceGuard guard_(e);                             \
         __VA_ARGS__                                        \
     } catch (const std::exception &ex) {                   \
         (e)->lastError = ex.what();                        \
@@ -668,6 +716,9 @@ extern "C" {
 cfb_engine *cfb_engine_create(const char *config_file, int thread_num, int device) {
     (void) thread_num;
     cfb_engine *e = nullptr;
+    int prevDevice = -1;   // the DeviceSim constructor selects the engine's GPU: the caller's current device is put back
+    if (cudaGetDevice(&prevDevice) != cudaSuccess) { prevDevice = -1; cudaGetLastError(); }
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prevDevice};
     try {
         e = new cfb_engine();
         int dev = device;
@@ -686,7 +737,13 @@ cfb_engine *cfb_engine_create(const char *config_file, int thread_num, int devic
     }
 }
 
-void cfb_engine_destroy(cfb_engine *e) { delete e; }
+void cfb_engine_destroy(cfb_engine *e) {
+    if (!e) return;
+    DeviceGuard guard(e);
+    e->h.transport = nullptr;
+    e->transport.reset();   // NCCL communicator + peer mappings go before the device state
+    delete e;
+}
 
 const char *cfb_last_error(const cfb_engine *e) { return e ? e->lastError.c_str() : g_createError.c_str(); }
 
@@ -708,6 +765,7 @@ double cfb_get_current_time(const cfb_engine *e) { return e->h.currentTime(); }
 
 double cfb_get_average_travel_time(cfb_engine *e) {
     try {
+        DeviceGuard guard(e);
         cfb::HostEngine &h = e->h;
         h.drain();
         double tt = h.cumulativeTravelTime;
@@ -1022,6 +1080,12 @@ int cfb_kernel_times(cfb_engine *e, double ms[5], int64_t *steps) {
     if (steps) *steps = t.launches;
     return CFB_OK;
 }
+int cfb_shard_phase_times(cfb_engine *e, double ms[8], int64_t *steps) {
+    long long n = 0;
+    e->h.dev->shardPhaseTimes(ms, &n);
+    if (steps) *steps = n;
+    return CFB_OK;
+}
 int cfb_synchronize(cfb_engine *e) {
     CFB_TRY(e, e->h.dev->synchronize();)
     return CFB_OK;
@@ -1183,6 +1247,7 @@ extern "C" {
 
 cfb_archive *cfb_snapshot(cfb_engine *e) {
     try {
+        DeviceGuard guard(e);
         cfb_archive *a = new cfb_archive();
         e->h.saveHost(a->host);
         a->dev = e->h.dev->snapshot();
@@ -1198,8 +1263,8 @@ void cfb_archive_destroy(cfb_archive *a) { delete a; }
 int cfb_load(cfb_engine *e, const cfb_archive *a) {
     CFB_TRY(e,
         e->h.dev->synchronize();
+        e->h.loadHost(a->host);          // (re-interns routes / templates first: may re-upload tables)
         e->h.dev->restore(a->dev);
-        e->h.loadHost(a->host);
     )
     return CFB_OK;
 }
@@ -1209,7 +1274,7 @@ int cfb_archive_dump(const cfb_archive *a, const char *path) {
         std::ofstream o(path, std::ios::binary);
         if (!o) return CFB_ERR_ARGUMENT;
         const auto &s = a->host;
-        const uint64_t magic = 0x3142464341ULL;  // "ACFB1"
+        const uint64_t magic = 0x3242464341ULL;  // "ACFB2"
         o.write((const char *) &magic, 8);
         std::ostringstream r;
         r << s.rnd;
@@ -1223,6 +1288,13 @@ int cfb_archive_dump(const cfb_archive *a, const char *path) {
         o.write((const char *) &s.cumulativeTravelTime, 8);
         putVec(o, s.flowNow); putVec(o, s.flowCur); putVec(o, s.flowCnt); putVec(o, s.flowValid);
         putVec(o, s.slots); putVec(o, s.freeSlots); putVec(o, s.pending);
+        {
+            std::vector<int> flat;   // routes: count, then (length, anchors...) each
+            flat.push_back((int) s.routeAnchors.size());
+            for (const auto &a : s.routeAnchors) { flat.push_back((int) a.size()); flat.insert(flat.end(), a.begin(), a.end()); }
+            putVec(o, flat);
+            putVec(o, s.templates);
+        }
         std::vector<unsigned char> blob;
         cfb::DeviceSim::snapshotToHost(a->dev, blob);
         putVec(o, blob);
@@ -1238,7 +1310,7 @@ int cfb_load_from_file(cfb_engine *e, const char *path) {
         if (!i) throw std::runtime_error(std::string("cannot open archive file ") + path);
         uint64_t magic = 0;
         i.read((char *) &magic, 8);
-        if (magic != 0x3142464341ULL) throw std::runtime_error("not an archive written by cityflow_b200 (the reference's JSON archive format is not supported)");
+        if (magic != 0x3242464341ULL) throw std::runtime_error("not an archive written by cityflow_b200 (the reference's JSON archive format is not supported)");
         cfb_archive a;
         auto &s = a.host;
         std::vector<char> rv;
@@ -1253,13 +1325,26 @@ int cfb_load_from_file(cfb_engine *e, const char *path) {
         i.read((char *) &s.cumulativeTravelTime, 8);
         getVec(i, s.flowNow); getVec(i, s.flowCur); getVec(i, s.flowCnt); getVec(i, s.flowValid);
         getVec(i, s.slots); getVec(i, s.freeSlots); getVec(i, s.pending);
+        {
+            std::vector<int> flat;
+            getVec(i, flat);
+            size_t k = 0;
+            const int nr = flat.empty() ? 0 : flat[k++];
+            for (int r = 0; r < nr && k < flat.size(); ++r) {
+                const int n = flat[k++];
+                if (k + n > flat.size()) throw std::runtime_error("truncated archive file");
+                s.routeAnchors.emplace_back(flat.begin() + k, flat.begin() + k + n);
+                k += n;
+            }
+            getVec(i, s.templates);
+        }
         std::vector<unsigned char> blob;
         getVec(i, blob);
         if (!i) throw std::runtime_error("truncated archive file");
         a.dev = cfb::DeviceSim::snapshotFromHost(blob.data(), blob.size());
         e->h.dev->synchronize();
-        e->h.dev->restore(a.dev);
         e->h.loadHost(a.host);
+        e->h.dev->restore(a.dev);
     )
     return CFB_OK;
 }
@@ -1270,10 +1355,6 @@ int cfb_load_from_file(cfb_engine *e, const char *path) {
 // Sharded execution: one rank of a multi-GPU run over NCCL, and an in-process
 // loop-back group (several ranks on one GPU, exchanges by device copies) that the parity tests use
 // to check the seam protocol against the unsharded engine.
-struct cfb_engine_shard_state {
-    std::unique_ptr<cfb::ShardTransport> transport;
-};
-static std::map<cfb_engine *, std::unique_ptr<cfb_engine_shard_state>> g_shards;
 
 extern "C" {
 
@@ -1287,15 +1368,15 @@ cfb_engine *cfb_engine_create_sharded(const char *config_file, int thread_num, i
                                       const unsigned char nccl_id[128]) {
     cfb_engine *e = cfb_engine_create(config_file, thread_num, device);
     if (!e || world <= 1) return e;
+    DeviceGuard guard(e);
     std::string err = e->h.configureShard(rank, world);
-    std::unique_ptr<cfb_engine_shard_state> st(new cfb_engine_shard_state());
-    if (err.empty()) st->transport.reset(cfb::createNcclTransport(rank, world, nccl_id, device < 0 ? 0 : device, err));
-    if (!err.empty() || !st->transport) {
+    if (err.empty()) e->transport.reset(cfb::createNcclTransport(rank, world, nccl_id, device < 0 ? 0 : device, err));
+    if (!err.empty() || !e->transport) {
         g_createError = "sharded engine: " + err;
         cfb_engine_destroy(e);
         return nullptr;
     }
-    e->h.transport = st->transport.get();
+    e->h.transport = e->transport.get();
     // data plane: peer memory over NVLink unless it is unavailable or CITYFLOW_B200_SHARD_TRANSPORT=nccl asks for
     // the staged NCCL send/recv form (kept for comparison)
     const char *tr = getenv("CITYFLOW_B200_SHARD_TRANSPORT");
@@ -1304,7 +1385,8 @@ cfb_engine *cfb_engine_create_sharded(const char *config_file, int thread_num, i
             cfb::DeviceSim::ShardArena a = e->h.dev->shardArena();
             std::vector<void *> peers;
             std::string why;
-            if (st->transport->shareArena(a.base, a.bytes, peers, why)) e->h.dev->shardConnect(peers);
+            e->h.dev->shardMarkArenaExported();
+            if (e->transport->shareArena(a.base, a.bytes, peers, why)) e->h.dev->shardConnect(peers);
             else std::cerr << "[cityflow_b200] sharded run falls back to NCCL send/recv: " << why << std::endl;
         } catch (const std::exception &ex) {
             g_createError = std::string("sharded engine: ") + ex.what();
@@ -1313,7 +1395,6 @@ cfb_engine *cfb_engine_create_sharded(const char *config_file, int thread_num, i
             return nullptr;
         }
     }
-    g_shards[e] = std::move(st);
     return e;
 }
 

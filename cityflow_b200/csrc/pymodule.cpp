@@ -334,6 +334,11 @@ PYBIND11_MODULE(_cityflow_b200, m) {
         .def("next_steps", &Engine::nextSteps, "n"_a)
         .def("gpu_launches", &Engine::gpuLaunches)
         .def("tie_count", &Engine::tieCount)
+        .def("shard_phase_times", [](Engine &e) {
+            double ms[8] = {0}; int64_t n = 0;
+            cfb_shard_phase_times(e.raw(), ms, &n);
+            return py::make_tuple(std::vector<double>(ms, ms + 8), n);
+        })
         .def("enable_kernel_timing", &Engine::enableKernelTiming, "on"_a = true)
         .def("kernel_times", &Engine::kernelTimes)
         .def("timed_steps", &Engine::timedSteps, "n"_a, "flush_l2"_a = false)

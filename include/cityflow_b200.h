@@ -197,6 +197,10 @@ int cfb_debug_counters(cfb_engine *e, uint64_t out[8], int clear);
 int64_t cfb_debug_arrays(cfb_engine *e, uint32_t *cyc, uint32_t *path, int64_t cap);
 int cfb_enable_kernel_timing(cfb_engine *e, int on);
 int cfb_kernel_times(cfb_engine *e, double ms_out[5], int64_t *steps_timed);
+/* sharded run with cfb_enable_kernel_timing: accumulated device time (ms) of the eight phases of a step -- ingest, notify +
+ * control, send movers, receive movers (includes waiting for the feeders), move, send tails, receive tails (includes
+ * waiting for the owners), leader */
+int cfb_shard_phase_times(cfb_engine *e, double ms_out[8], int64_t *steps_timed);
 int cfb_synchronize(cfb_engine *e);
 int64_t cfb_num_drivables(const cfb_engine *e);
 /* CUDA device ordinal the engine was created on */

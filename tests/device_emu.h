@@ -141,6 +141,7 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
 static inline void __syncthreads() { emu::barrier(); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline long long clock64() { return 0; }
 static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }

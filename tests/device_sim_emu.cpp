@@ -296,10 +296,15 @@ void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
 
 // ---- not emulated ----
 void DeviceSim::configureShard(int, int, const std::vector<unsigned char> &, const std::vector<std::vector<int>> &, const std::vector<std::vector<int>> &,
-                               const std::vector<std::vector<int>> &) { notEmulated("sharding"); }
+                               const std::vector<std::vector<int>> &, const std::vector<unsigned char> &) { notEmulated("sharding"); }
 DeviceSim::ShardArena DeviceSim::shardArena() { notEmulated("sharding"); return ShardArena{nullptr, 0}; }
 void DeviceSim::shardConnect(const std::vector<void *> &) { notEmulated("sharding"); }
 bool DeviceSim::shardIsP2P() const { return false; }
+bool DeviceSim::timingOn() const { return false; }
+void DeviceSim::shardTimeMark(int) {}
+void DeviceSim::shardTimeCollect() {}
+void DeviceSim::shardPhaseTimes(double *ms, long long *steps) { for (int k = 0; k < SHARD_PHASES; ++k) ms[k] = 0; if (steps) *steps = 0; }
+void DeviceSim::shardMarkArenaExported() {}
 void DeviceSim::sendMovers() { notEmulated("sharding"); }
 void DeviceSim::recvMovers() { notEmulated("sharding"); }
 void DeviceSim::sendTails() { notEmulated("sharding"); }

@@ -276,6 +276,9 @@ void build(Oracle &o, bool forControl) {
     V.lcDist = S.lcDist.data(); V.csLink = S.csLink.data(); V.foeMask = S.foeMask.data(); V.notify = S.notify.data();
     V.rlAvail = S.rlAvail.data(); V.delStep = S.delStep.data(); V.nCross = net.nCross();
     V.lcOn = o.laneChange ? 1 : 0;
+    // the foe half of Cross::canPass, as k_notify attaches it to every notification (device_control.cuh foeTerms)
+    for (int cs = 0; forControl && cs < 2 * net.nCross(); ++cs)
+        if (S.notify[cs].epoch == S.epoch && S.notify[cs].pos >= 0) foeTerms(V, S.notify[cs], S.linkInfo[S.csLink[cs]].w);
 }
 
 void before(Oracle &o) {

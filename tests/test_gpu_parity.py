@@ -487,3 +487,112 @@ def test_lane_change_draft_vs_restatement(tmp_path):
             assert np.array_equal(got[f], want.vehicles[f]), "step %d field %s" % (s, f)
         shadows += int((want.vehicles["partner_type"] == 2).sum())
     assert shadows > 300
+
+
+# ------------------------------------------------------------------------------------------
+# Irregular networks (tests/randnet.py): missing streets, 1-3 lanes, bent roads, sparse laneLink sets -- including first
+# lanes that cannot continue the route two roads ahead, where Vehicle::getNextSpeed's `if (laneChange)` block
+# (vehicle.cpp:323-329, it tests the LaneChange OBJECT and so runs with laneChange=false too) parks the vehicle at the end
+# of the lane.  Full state every step against the restatement (which is pinned to the compiled reference on the same
+# generator, tests/test_cpu.py::test_random_network_loader_and_oracle_vs_reference).
+@pytest.mark.parametrize("seed", [1, 2, 3, 5, 8, 11])
+def test_fuzzed_irregular_networks_vs_port(seed, tmp_path):
+    import randnet
+    from cityflow_b200 import scenario
+    net = randnet.random_roadnet(seed, rows=2 + seed % 3, cols=3 + seed % 2)
+    flows = randnet.random_flows(net, seed + 100, n_flows=40 + seed % 50)
+    cfg = scenario.write_scenario(str(tmp_path), net, flows, seed=seed, interval=[1.0, 0.5, 2.0, 1.0][seed % 4], name="g%d" % seed)
+    _run_against_port(cfg, 500)
+
+
+def test_fuzzed_network_vs_compiled_reference(tmp_path):
+    """The same kind of network straight against the UNMODIFIED reference (oracle/_ref/refdump): the restatement shares the
+    product's loader, the compiled reference does not -- a loader / routing bug cannot hide behind it here."""
+    if not H.have_ref():
+        pytest.skip("oracle/_ref was not built")
+    import randnet
+    from cityflow_b200 import scenario
+    from cityflow_b200.capi import CEngine
+    net = randnet.random_roadnet(4, rows=3, cols=4)
+    flows = randnet.random_flows(net, 104, n_flows=70)
+    cfg = scenario.write_scenario(str(tmp_path), net, flows, seed=4, interval=1.0, name="gref")
+    eng = CEngine(cfg)
+    ref = H.RefDump.run(cfg, 500, threads=2, every=10, n_inter=eng.n_inter, n_drivables=eng.n_drivables)
+    done = 0
+    for st in ref:
+        eng.next_step(st.step - done)
+        done = st.step
+        bad = H.compare_states(_relax(st), _gpu_state(eng, st.step), check_order=False)
+        assert not bad, "step %d: %s" % (st.step, "; ".join(bad[:6]))
+    assert eng.tie_count() == 0
+
+
+def test_vehicle_setters_step_by_step_vs_port(tmp_path):
+    """set_vehicle_speed / set_vehicle_route (engine.cpp:827-866) applied identically to the GPU engine and to the
+    restatement (itself pinned to the reference's Python module): every speed of every vehicle after every step."""
+    import json
+    import os
+    import cityflow
+    from cityflow_b200 import scenario
+    cfg = scenario.make_grid_scenario(str(tmp_path), 4, 4, dense=dict(frac=1.0, interval=3.0, seed=2), name="api")
+    flows = json.load(open(os.path.join(str(tmp_path), "flow_api.json")))
+    eng, ora = cityflow.Engine(cfg, thread_num=1), H.PortOracle(cfg)
+
+    def vid(f, k):
+        return "manually_pushed_%d" % k if f == -2 else "flow_%d_%d" % (f, k)
+
+    for s in range(1, 401):
+        v = ora.vehicles()
+        if s % 20 == 3:
+            for j in range(0, len(v), max(1, len(v) // 6)):
+                f, k, sp = int(v["flow"][j]), int(v["cnt"][j]), float(v["speed"][j]) * 0.5
+                eng.set_vehicle_speed(vid(f, k), sp)
+                assert ora.set_vehicle_speed(f, k, sp)
+        if s % 30 == 7:
+            for j in range(1, len(v), max(1, len(v) // 8)):
+                f, k = int(v["flow"][j]), int(v["cnt"][j])
+                target = flows[(s + j) % len(flows)]["route"][-1:]
+                assert eng.set_vehicle_route(vid(f, k), target) == ora.set_vehicle_route(f, k, target), (s, vid(f, k))
+        eng.next_step()
+        ora.next_step()
+        v = ora.vehicles()
+        mine = eng.get_vehicle_speed()
+        theirs = {vid(f, k): sp for f, k, sp in zip(v["flow"], v["cnt"], v["speed"])}
+        assert mine == theirs, "step %d: %s" % (s, [(k, mine.get(k), theirs[k]) for k in theirs if mine.get(k) != theirs[k]][:3])
+
+
+def test_30x30_through_the_bench_window_vs_compiled_reference(scenario_dir):
+    """The bench operating point itself: BASELINE.json configs[2] (30x30, ~1.3e5 vehicles, gridlock) against the UNMODIFIED
+    reference -- vehicle count after every step, per-lane counts, per-lane waiting counts (speed < 0.1) and per-lane speed
+    sums (within 1e-6 per vehicle) every 50 steps and at steps 1200, 1210, 1220, 1230 (the vehicle count at every step of
+    the window 1200..1230)."""
+    if not H.have_ref():
+        pytest.skip("oracle/_ref was not built")
+    import os
+    from cityflow_b200 import scenario
+    from cityflow_b200.capi import CEngine
+    cfg = scenario.make_grid_scenario(scenario_dir, 30, 30, name="g30w", dense=dict(frac=0.5, interval=10.0, seed=1))
+    ref = H.RefDump.counts(cfg, 1230, os.cpu_count() or 8, 10)
+    eng = CEngine(cfg)
+    for s in range(1, 1231):
+        eng.next_step()
+        if s >= 1200 or s % 5 == 0:
+            assert eng.vehicle_count() == int(ref["vehicle_count"][s - 1]), s
+        if s % 10 or (s % 50 and s < 1200):
+            continue
+        rc, rw, rs = ref["dumps"][s]
+        assert eng.vehicle_count() == int(ref["vehicle_count"][s - 1]), s
+        mc, mw = eng.lane_vehicle_count(), eng.lane_waiting_count()
+        assert np.array_equal(mc, rc), "step %d: %d lane counts differ" % (s, int((mc != rc).sum()))
+        assert np.array_equal(mw, rw), "step %d: %d lane waiting counts differ" % (s, int((mw != rw).sum()))
+    # per-vehicle speeds at the end, through the per-lane speed sums (bar: 1e-6 per vehicle; the sums differ by summation order only)
+    v = eng.debug_vehicles()
+    on = v[v["drivable"] < eng.n_lanes]
+    mine = np.bincount(on["drivable"], weights=on["speed"], minlength=eng.n_lanes)
+    assert np.all(np.abs(mine - rs) <= 1e-6 * np.maximum(mc, 1)), "per-lane speed sums differ"
+    assert eng.vehicle_count() > 120000
+
+
+def test_6x6_3600_steps_vs_port(cfg_6x6):
+    """BASELINE.json configs[1] length: the generator's default 6x6 scenario for the full 3600 steps, full state every 100."""
+    _run_against_port(cfg_6x6, 3600, every=100)
