@@ -64,8 +64,17 @@ namespace cfb {
 }  // namespace cfb
 #include "device_phases_a.cuh"
 namespace cfb {
-__global__ void __launch_bounds__(256) k_ingest(View V) { phase_ingest(V, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(256) k_notify(View V) { phase_notify(V, blockIdx.x, gridDim.x); }
+// Programmatic dependent launch: the five step kernels are chained with programmatic stream serialisation, so the next
+// kernel's launch, block scheduling and prologue overlap the tail of the previous one (each kernel is latency-bound and
+// drains unevenly).  `griddepcontrol.wait` returns once the whole previous grid has completed and its memory operations
+// are visible -- the data dependence between the phases is unchanged -- and `launch_dependents` right behind it lets the
+// kernel after this one be scheduled as early as possible.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdlEnter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__global__ void __launch_bounds__(256) k_ingest(View V) { pdlEnter(); phase_ingest(V, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_notify(View V) { pdlEnter(); phase_notify(V, blockIdx.x, gridDim.x); }
 
 }  // namespace cfb
 #include "device_control.cuh"
@@ -75,16 +84,16 @@ namespace cfb {
 }  // namespace cfb
 #include "device_control_coop.cuh"   // EXPERIMENT: the warp evaluates its vehicles' crosses side by side
 namespace cfb {
-__global__ void __launch_bounds__(256, 4) k_control(View V) { phase_control_coop(V, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256, 4) k_control(View V) { pdlEnter(); phase_control_coop(V, blockIdx.x, gridDim.x); }
 #else
-__global__ void __launch_bounds__(256, 4) k_control(View V) { phase_control(V, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256, 4) k_control(View V) { pdlEnter(); phase_control(V, blockIdx.x, gridDim.x); }
 #endif
 
 }  // namespace cfb
 #include "device_phases_b.cuh"
 namespace cfb {
-__global__ void __launch_bounds__(256) k_move(View V) { phase_move(V, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(256) k_leader(View V) { phase_leader(V, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_move(View V) { pdlEnter(); phase_move(V, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_leader(View V) { pdlEnter(); phase_leader(V, blockIdx.x, gridDim.x); }
 
 // ------------------------------------------------------------------------------------------
 // k_step: the whole step as ONE cooperative kernel -- the five phases separated by grid-wide
@@ -332,6 +341,21 @@ struct DevBuf {
 // state that way ends with this barrier, before anything can be enqueued on the engine's stream.
 static void legacySync() { CFB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); }
 
+// A step kernel, optionally with programmatic stream serialisation (see pdlEnter()).
+static void launchStepKernel(void (*k)(View), int grid, int block, cudaStream_t s, bool pdl, const View &V) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, k, V));
+}
+
 struct DeviceSim::Impl {
     DeviceSimOptions opt;
     View V{};
@@ -448,6 +472,7 @@ struct DeviceSim::Impl {
     int slotCap = 0;
     int numSMs = 148;
     int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
+    bool usePdl = true;   // CITYFLOW_B200_NO_PDL=1: plain stream order between the step kernels
     bool useGraph = true, graphDirty = false, useCoop = false;   // cooperative k_step measured slower
     cudaEvent_t graphDone[2][GRING] = {};
     cudaGraph_t graphTemplate[2] = {nullptr, nullptr};
@@ -513,6 +538,7 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     CFB_CUDA(cudaDeviceGetAttribute(&I.numSMs, cudaDevAttrMultiProcessorCount, opt.device));
     if (const char *g = getenv("CITYFLOW_B200_NO_GRAPH")) I.useGraph = !(g[0] == '1');
     if (const char *g = getenv("CITYFLOW_B200_COOP")) I.useCoop = (g[0] == '1');
+    if (const char *g = getenv("CITYFLOW_B200_NO_PDL")) I.usePdl = !(g[0] == '1');
     {
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, opt.device);
@@ -819,16 +845,17 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     ensureGrids();   // one resident wave per kernel (occupancy x #SM blocks)
     const bool tm = I.timing;
     auto launchAll = [&](bool withEvents) {
+        const bool pdl = I.usePdl && !withEvents;   // (events between the kernels would serialise them anyway)
         if (withEvents) cudaEventRecord(I.ev[0], s);
-        k_ingest<<<std::max(gLaneRL, 1), TPB, 0, s>>>(V);
+        launchStepKernel(k_ingest, std::max(gLaneRL, 1), TPB, s, false, V);   // follows a copy, not a kernel
         if (withEvents) cudaEventRecord(I.ev[1], s);
-        k_notify<<<I.gridNotify, TPB, 0, s>>>(V);
+        launchStepKernel(k_notify, I.gridNotify, TPB, s, pdl, V);
         if (withEvents) cudaEventRecord(I.ev[2], s);
-        k_control<<<I.gridControl, 256, 0, s>>>(V);
+        launchStepKernel(k_control, I.gridControl, 256, s, pdl, V);
         if (withEvents) cudaEventRecord(I.ev[3], s);
-        k_move<<<I.gridMove, TPB, 0, s>>>(V);
+        launchStepKernel(k_move, I.gridMove, TPB, s, pdl, V);
         if (withEvents) cudaEventRecord(I.ev[4], s);
-        k_leader<<<I.gridLeader, TPB, 0, s>>>(V);
+        launchStepKernel(k_leader, I.gridLeader, TPB, s, pdl, V);
         if (withEvents) cudaEventRecord(I.ev[5], s);
     };
     if (!tm && I.useCoop) {
@@ -852,12 +879,21 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
         cudaGraphExec_t &ge = I.graphExec[V.par][ring];
         if (!ge) {
             cudaGraph_t &g = I.graphTemplate[V.par];
-            if (!g) {
-                CFB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                launchAll(false);
-                CFB_CUDA(cudaStreamEndCapture(s, &g));
+            for (int attempt = 0; attempt < 2 && !ge; ++attempt) {
+                if (!g) {
+                    CFB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                    launchAll(false);
+                    if (cudaStreamEndCapture(s, &g) != cudaSuccess) g = nullptr;
+                }
+                if (!g || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) {
+                    // a driver that cannot put programmatic dependencies into a graph: plain edges instead
+                    cudaGetLastError();
+                    if (g) { cudaGraphDestroy(g); g = nullptr; }
+                    ge = nullptr;
+                    if (!I.usePdl) throw std::runtime_error("cityflow_b200: cannot capture the step into a CUDA graph");
+                    I.usePdl = false;
+                }
             }
-            CFB_CUDA(cudaGraphInstantiate(&ge, g, 0));
         }
         // Re-launching an executable graph whose previous launch has not finished makes the driver
         // wait on the host (observed: ~1 ms per step), hence the ring of instances; when even the ring
@@ -978,8 +1014,8 @@ void DeviceSim::runIngest() {
 void DeviceSim::runNotifyControl() {
     Impl &I = *impl_;
     ensureGrids();
-    k_notify<<<I.gridNotify, 256, 0, I.stream>>>(I.V);
-    k_control<<<I.gridControl, 256, 0, I.stream>>>(I.V);
+    launchStepKernel(k_notify, I.gridNotify, 256, I.stream, I.usePdl && !I.timing, I.V);   // behind k_ingest
+    launchStepKernel(k_control, I.gridControl, 256, I.stream, I.usePdl && !I.timing, I.V);
     launches_ += 2;
 }
 void DeviceSim::runMove() {

@@ -124,6 +124,26 @@ public:
     std::vector<std::string> laneIds;
     size_t uploadedPlans = 0, uploadedTemplates = 0;
     bool finishedDirty = false;                              // steps enqueued since the last drain
+    // ---- the spawner runs ONE STEP AHEAD of the device ----
+    // Flow::nextStep / planRoute of step t+1 (prepareStep) depend on nothing step t computes -- except whether the holder of
+    // a colliding priority has left, which createVehicle asks the device about -- so next_step() enqueues step t and then
+    // prepares step t+1 while the GPU is busy: the host work disappears from a loop that waits for the device every step
+    // (next_step(); get_vehicle_count()).  Every API call that could observe or change what the preparation touched
+    // (push_vehicle, set_random_seed, reset, archives, id-based getters / setters, get_vehicles(include_waiting),
+    // get_average_travel_time) first takes it back (cancelAhead), so results are those of the reference's order of events.
+    std::vector<unsigned char> laneLocal;                     // sharded: lanes this rank owns or feeds
+    bool ahead = false;
+    bool aheadEnabled = true;
+    bool undoLog = false;
+    struct Undo {
+        std::mt19937 rnd;
+        std::vector<FlowHot> hot;
+        std::vector<int> freeSlots, allocated, inserted;
+        std::vector<std::pair<int, int>> erased;
+        std::vector<Pending> pending;
+        size_t slotsSize = 0;
+        int manuallyPushCnt = 0;
+    } undo;
     long long h2dBytes = 0, d2hBytes = 0;                    // host<->device traffic of the public calls (bench e2e)
 
     static uint64_t key(int flow, int index) { return ((uint64_t) (uint32_t) flow << 32) | (uint32_t) index; }
@@ -223,6 +243,7 @@ public:
 #endif
         uploadedPlans = routing->numPlans();
         uploadedTemplates = templates.size();
+        if (const char *na = getenv("CITYFLOW_B200_NO_AHEAD")) aheadEnabled = !(na[0] == '1');
         return true;
     }
 
@@ -311,6 +332,7 @@ public:
             dev->synchronize();
             if (dev->slotDelStep(other) >= slots[other].spawnStep) {
                 pool.erase(priority);
+                if (undoLog) undo.erased.emplace_back(priority, other);
                 break;
             }
         }
@@ -327,6 +349,7 @@ public:
         s.tmplId = tmplId;
         s.live = true;
         pool.insert(priority, slot);
+        if (undoLog) { undo.inserted.push_back(priority); undo.allocated.push_back(slot); }
         idMapValid = false;
         pending.push_back({slot, firstRoad, routeId, tmplId, flow});
         return slot;
@@ -388,12 +411,16 @@ public:
         if (!pending.empty()) {
             // Engine::planRoute walks roads in file order, each road's buffer in spawn order
             // (road, arrival index) keys: same order as a stable sort by road, cheaper than moving structs
-            sortKeys.resize(pending.size());
-            for (size_t k = 0; k < pending.size(); ++k) sortKeys[k] = ((uint64_t) (uint32_t) pending[k].road << 32) | (uint32_t) k;
-            std::sort(sortKeys.begin(), sortKeys.end());
-            pendingSorted.resize(pending.size());
-            for (size_t k = 0; k < pending.size(); ++k) pendingSorted[k] = pending[(uint32_t) sortKeys[k]];
-            for (const Pending &p : pendingSorted) {
+            bool inRoadOrder = true;   // (flows written road by road -- every generated scenario -- arrive in that order already)
+            for (size_t k = 1; k < pending.size() && inRoadOrder; ++k) inRoadOrder = pending[k - 1].road <= pending[k].road;
+            if (!inRoadOrder) {
+                sortKeys.resize(pending.size());
+                for (size_t k = 0; k < pending.size(); ++k) sortKeys[k] = ((uint64_t) (uint32_t) pending[k].road << 32) | (uint32_t) k;
+                std::sort(sortKeys.begin(), sortKeys.end());
+                pendingSorted.resize(pending.size());
+                for (size_t k = 0; k < pending.size(); ++k) pendingSorted[k] = pending[(uint32_t) sortKeys[k]];
+            }
+            for (const Pending &p : inRoadOrder ? pending : pendingSorted) {
                 const RouteHot &rt = hotRoute(p.routeId);
                 if (rt.valid) {
                     SpawnRec r{};
@@ -411,7 +438,8 @@ public:
                     r.tmpl = p.tmplId;
                     r.priority = slots[p.slot].priority;
                     slots[p.slot].firstLane = r.lane;
-                    batch.push_back(r);
+                    // one rank of a sharded run ingests only the lanes it owns or feeds (k_ingest skips the others anyway)
+                    if (laneLocal.empty() || laneLocal[r.lane]) batch.push_back(r);
                 } else {
                     if (p.flow >= 0) {
                         if (hot[p.flow].valid)
@@ -426,12 +454,16 @@ public:
                 }
             }
             pending.clear();
-            sortKeys.resize(batch.size());
-            for (size_t k = 0; k < batch.size(); ++k) sortKeys[k] = ((uint64_t) (uint32_t) batch[k].lane << 32) | (uint32_t) k;
-            std::sort(sortKeys.begin(), sortKeys.end());
-            batchTmp.resize(batch.size());
-            for (size_t k = 0; k < batch.size(); ++k) batchTmp[k] = batch[(uint32_t) sortKeys[k]];
-            batch.swap(batchTmp);
+            bool inLaneOrder = true;
+            for (size_t k = 1; k < batch.size() && inLaneOrder; ++k) inLaneOrder = batch[k - 1].lane <= batch[k].lane;
+            if (!inLaneOrder) {
+                sortKeys.resize(batch.size());
+                for (size_t k = 0; k < batch.size(); ++k) sortKeys[k] = ((uint64_t) (uint32_t) batch[k].lane << 32) | (uint32_t) k;
+                std::sort(sortKeys.begin(), sortKeys.end());
+                batchTmp.resize(batch.size());
+                for (size_t k = 0; k < batch.size(); ++k) batchTmp[k] = batch[(uint32_t) sortKeys[k]];
+                batch.swap(batchTmp);
+            }
         }
         if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
         if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
@@ -509,7 +541,8 @@ public:
 #ifdef CFB_LANE_CHANGE
         if (laneChange) { nextStepLaneChange(); return; }
 #endif
-        prepareStep();
+        if (!ahead) prepareStep();
+        ahead = false;
         const auto t1 = std::chrono::steady_clock::now();
         if (!transport) {
             dev->step(batch.data(), (int) batch.size());
@@ -557,6 +590,35 @@ public:
         }
         hostEnqueueNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
         finishStep();
+        prepareAhead();
+    }
+    void prepareAhead() {
+        if (!aheadEnabled || ahead || laneChange) return;
+        undo.rnd = rnd;
+        undo.hot = hot;
+        undo.freeSlots = freeSlots;
+        undo.pending = pending;
+        undo.slotsSize = slots.size();
+        undo.allocated.clear(); undo.inserted.clear(); undo.erased.clear();
+        undoLog = true;
+        prepareStep();
+        undoLog = false;
+        ahead = true;
+    }
+    // Take the preparation of the coming step back: afterwards the host state is what it was right after the last step.
+    void cancelAhead() {
+        if (!ahead) return;
+        ahead = false;
+        rnd = undo.rnd;
+        hot.swap(undo.hot);
+        for (int p : undo.inserted) pool.erase(p);
+        for (auto &pr : undo.erased) pool.insert(pr.first, pr.second);
+        for (int s : undo.allocated) if ((size_t) s < undo.slotsSize) slots[s].live = false;
+        slots.resize(undo.slotsSize);
+        freeSlots = undo.freeSlots;
+        pending = undo.pending;
+        batch.clear();
+        idMapValid = false;
     }
     // Cut the network and tell the device which part is ours (before the first step).
     std::string configureShard(int rank, int world) {
@@ -577,6 +639,9 @@ public:
             own[q] = part.boundary[q][rank];    // lanes q feeds, I own
             for (int p2 = 0; p2 < world; ++p2) bsize[q][p2] = (int) part.boundary[q][p2].size();
         }
+        laneLocal.assign(net.nLanes(), 0);
+        for (int l = 0; l < net.nLanes(); ++l) laneLocal[l] = owned[l];
+        for (int q = 0; q < world; ++q) for (int l : feed[q]) laneLocal[l] = 1;
         std::vector<unsigned char> ownedRL(net.nRoadLinks(), 0);
         for (int k = 0; k < net.nLinks(); ++k)
             if (part.drvOwner[net.nLanes() + k] == rank) ownedRL[net.llRoadLink[k]] = 1;
@@ -586,6 +651,7 @@ public:
 
     // Engine::reset engine.cpp:744-760
     void reset(bool resetRnd) {
+        cancelAhead();
         dev->synchronize();
         dev->reset();
         slots.clear();
@@ -636,6 +702,7 @@ public:
         std::vector<VehicleTemplate> templates;
     };
     void saveHost(HostState &s) {
+        cancelAhead();
         drain();
         s.rnd = rnd; s.step = step; s.manuallyPushCnt = manuallyPushCnt; s.finishedCnt = finishedCnt;
         s.cumulativeTravelTime = cumulativeTravelTime;
@@ -647,6 +714,7 @@ public:
         s.templates = templates;
     }
     void loadHost(const HostState &s) {
+        cancelAhead();
         if (s.flowNow.size() != flows.size()) throw std::runtime_error("archive does not match this engine (flows)");
         for (size_t r = 0; r < s.routeAnchors.size(); ++r) {
             if (r < (size_t) routing->numRoutes() ? routing->anchorsOf((int) r) != s.routeAnchors[r] : routing->intern(s.routeAnchors[r]) != (int) r)
@@ -767,6 +835,7 @@ double cfb_get_average_travel_time(cfb_engine *e) {
     try {
         DeviceGuard guard(e);
         cfb::HostEngine &h = e->h;
+        h.cancelAhead();
         h.drain();
         double tt = h.cumulativeTravelTime;
         int n = h.finishedCnt;
@@ -836,6 +905,7 @@ int64_t cfb_get_vehicles(cfb_engine *e, int include_waiting, cfb_vehicle_ref *id
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
         if (!include_waiting) return cfb_get_vehicle_speed(e, ids, nullptr, nullptr, cap);
+        h.cancelAhead();
         h.drain();
         int64_t n = 0;
         for (auto &kv : h.pool.sorted()) {
@@ -860,6 +930,7 @@ int64_t cfb_get_lane_vehicles(cfb_engine *e, int64_t *lane_begin, int n_lanes_pl
 int cfb_get_leader(cfb_engine *e, cfb_vehicle_ref v, cfb_vehicle_ref *leader, int *found) {
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
+        h.cancelAhead();
         h.drain();
         const int vs = h.slotOfId(v.flow, v.index);
         if (vs < 0) throw std::runtime_error("Vehicle not found");
@@ -986,6 +1057,7 @@ int64_t cfb_debug_lc_vehicles(cfb_engine *e, cfb_lc_vehicle *out, int64_t cap) {
 #endif
 
 int cfb_set_random_seed(cfb_engine *e, int seed) {
+    e->h.cancelAhead();
     e->h.rnd.seed(seed);
     return CFB_OK;
 }
@@ -998,6 +1070,7 @@ int cfb_reset(cfb_engine *e, int reset_rnd) {
 int cfb_push_vehicle(cfb_engine *e, const double v[10], const char *const *roads, int n_roads) {
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
+        h.cancelAhead();
         cfb::VehicleTemplate t;
         double *f[10] = {&t.speed, &t.len, &t.width, &t.maxPosAcc, &t.maxNegAcc, &t.usualPosAcc, &t.usualNegAcc,
                          &t.minGap, &t.maxSpeed, &t.headwayTime};
@@ -1099,6 +1172,7 @@ int cfb_device(const cfb_engine *e) { return e->h.dev->device(); }
 extern "C" int cfb_set_vehicle_speed(cfb_engine *e, cfb_vehicle_ref v, double speed) {
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
+        h.cancelAhead();
         h.drain();
         const int s = h.slotOfId(v.flow, v.index);
         if (s < 0) throw std::runtime_error("Vehicle not found");
@@ -1113,6 +1187,7 @@ extern "C" int cfb_set_vehicle_route(cfb_engine *e, cfb_vehicle_ref v, const cha
     *ok = 0;
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
+        h.cancelAhead();
         h.drain();
         const int s = h.slotOfId(v.flow, v.index);
         if (s < 0) return CFB_OK;                       // unknown vehicle: false
@@ -1158,6 +1233,7 @@ extern "C" int cfb_set_vehicle_route(cfb_engine *e, cfb_vehicle_ref v, const cha
 extern "C" int64_t cfb_get_vehicle_info(cfb_engine *e, cfb_vehicle_ref v, char *out, int64_t cap) {
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
+        h.cancelAhead();
         h.drain();
         const int s = h.slotOfId(v.flow, v.index);
         if (s < 0) throw std::runtime_error("Vehicle not found");
