@@ -67,6 +67,9 @@ def parse_args():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-parity", action="store_true", help="skip the reference run behind parity_check")
     p.add_argument("--no-sweep", action="store_true", help="cpu_baseline: thread_num = nproc only, no thread sweep")
+    p.add_argument("--lane-change", action="store_true",
+                   help='the same workload with "laneChange": true (no parity_check: the reference\'s lane-change schedule '
+                        "follows heap addresses, its result is only defined statistically)")
     p.add_argument("--multi", default="weak", choices=["weak", "sharded", "strong", "replicas"],
                    help="N>1, see the module docstring ('sharded' = 'weak')")
     p.add_argument("--clock-ms", type=int, default=50, help="nvidia-smi sampling period (0 = off)")
@@ -76,6 +79,10 @@ def parse_args():
     a = p.parse_args()
     if a.multi == "sharded":
         a.multi = "weak"
+    if a.lane_change:
+        a.no_parity = True
+        if a.gpus > 1:
+            a.multi = "replicas"   # the lane-change path is single-GPU (its scheduling kernels are not sharded)
     return a
 
 
@@ -107,7 +114,7 @@ def make_scenario(args, directory):
     sc = scenario_module()
     if args.config == "rl":
         return sc.make_grid_scenario(directory, 6, 6, name="rl", rl_traffic_light=True, dense=dict(frac=1.0, interval=5.0, seed=2))
-    return sc.make_grid_scenario(directory, args.rows, grid_cols(args), name="bench",
+    return sc.make_grid_scenario(directory, args.rows, grid_cols(args), name="bench", lane_change=args.lane_change,
                                  dense=dict(frac=args.frac, interval=args.flow_interval, seed=flow_seed(args), fleet_spread=fleet_spread(args)))
 
 
@@ -117,7 +124,8 @@ def workload_name(args):
     fs = fleet_spread(args)
     return "%dx%d grid (tools/generator layout), random-walk flows frac=%g interval=%gs seed=%d%s, interval=1.0s, seed=0" % (
         args.rows, grid_cols(args), args.frac, args.flow_interval, flow_seed(args),
-        (", vehicle parameters per flow within +-%g%% of the template" % (100 * fs)) if fs > 0 else "")
+        (", vehicle parameters per flow within +-%g%% of the template" % (100 * fs)) if fs > 0 else "") + (
+        ", laneChange=true" if args.lane_change else "")
 
 
 def scaling_of(args):

@@ -84,11 +84,9 @@ __device__ __forceinline__ bool canPass(const View &V, const Notify &f, int myLi
     return yield == -1;
 }
 
-#ifdef CFB_LANE_CHANGE
 }  // namespace cfb
 #include "device_lc.cuh"
 namespace cfb {
-#endif
 
 // k_control: one thread per running vehicle (grid-stride over the position list).
 // Vehicle::getNextSpeed vehicle.cpp:308-335, getCarFollowSpeed :212-238, getIntersectionRelatedSpeed
@@ -211,7 +209,6 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
             }
             v = min2(v, s);
         }
-#ifdef CFB_LANE_CHANGE
         if (V.lcOn) {   // vehicle.cpp:323-329 / engine.cpp:195-244, see device_lc.cuh
             LcSlot &L = V.lc.slot[idv.x];
             if (L.partner >= 0 || lcRecvValid(L, epoch) || L.type != 0 || L.changing) {
@@ -231,8 +228,6 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
             // follower, so only lastDir is taken here; the epoch-stamped signals expire by themselves
             L.lastDir = lcSendValid(L, epoch) ? L.sendDir : 0;
         }
-#endif
-#ifdef CFB_DEAD_END_STOP
         // vehicle.cpp:323-329 runs with laneChange=false too (the `if` there tests the LaneChange OBJECT):
         // yieldSpeed() is 100 without signals, and a vehicle whose lane cannot continue its route stops
         // at the end of the lane.  Found by the fuzz tests; NOT compiled in by
@@ -240,7 +235,6 @@ __device__ __forceinline__ void phase_control(const View &V, const int bid, cons
         v = min2(v, 100.0);
         if (!onLink && nd0 == PLAN_DEAD)
             v = min2(v, noCollisionSpeed(0, 1, speed, T.maxNegAcc, dLen - dis, dt, T.minGap));
-#endif
         v = max2(v, speed - T.maxNegAcc * dt);
         // ---- Engine::vehicleControl ----
         double deltaDis;

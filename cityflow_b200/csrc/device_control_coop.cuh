@@ -185,7 +185,6 @@ __device__ __forceinline__ void phase_control_coop(const View &V, const int bid,
             }
             v = min2(v, s);
         }
-#ifdef CFB_LANE_CHANGE
         if (V.lcOn) {   // vehicle.cpp:323-329 / engine.cpp:195-244, see device_lc.cuh
             LcSlot &L = V.lc.slot[idv.x];
             if (L.partner >= 0 || lcRecvValid(L, epoch) || L.type != 0 || L.changing) {
@@ -205,8 +204,6 @@ __device__ __forceinline__ void phase_control_coop(const View &V, const int bid,
             // follower, so only lastDir is taken here; the epoch-stamped signals expire by themselves
             L.lastDir = lcSendValid(L, epoch) ? L.sendDir : 0;
         }
-#endif
-#ifdef CFB_DEAD_END_STOP
         // vehicle.cpp:323-329 runs with laneChange=false too (the `if` there tests the LaneChange OBJECT):
         // yieldSpeed() is 100 without signals, and a vehicle whose lane cannot continue its route stops
         // at the end of the lane.  Found by the fuzz tests; NOT compiled in by
@@ -214,7 +211,6 @@ __device__ __forceinline__ void phase_control_coop(const View &V, const int bid,
         v = min2(v, 100.0);
         if (!onLink && nd0 == PLAN_DEAD)
             v = min2(v, noCollisionSpeed(0, 1, speed, T.maxNegAcc, dLen - dis, dt, T.minGap));
-#endif
         v = max2(v, speed - T.maxNegAcc * dt);
         // ---- Engine::vehicleControl ----
         double deltaDis;

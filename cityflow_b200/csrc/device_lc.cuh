@@ -1,18 +1,19 @@
-// device_lc.cuh -- lane change on the device.  DRAFT, compiled only with -DCFB_LANE_CHANGE.
+// device_lc.cuh -- lane change on the device ("laneChange": true): SimpleLaneChange::makeSignal (lanechange.cpp:151-184),
+// Engine::scheduleLaneChange / insertShadow (engine.cpp:792-820, lanechange.cpp:71-102), yieldSpeed (:186-206) and the
+// partner coupling of Engine::vehicleControl (engine.cpp:195-244).
 //
-// STATUS: written at the end of round 1 when no GPU was left; it compiles for sm_100a but has NOT
-// run.  The default build does not contain it (its SASS is byte-identical to the validated
-// library) and the engine still rejects "laneChange": true.  Validation plan: GPU engine built
-// with -DCFB_LANE_CHANGE vs the restatement's lane-change states (oracle, PortOracle.lc_snapshot),
-// which are pinned against oracle/_ref/refdump_lcorder.
+// STATUS: part of the library.  On a B200 it is bit-equal, every field of every vehicle including shadows, every step,
+// to the restatement -- which is pinned against oracle/_ref/refdump_lcorder, the reference with its per-worker vehicle
+// sets ordered by priority instead of by heap address (tests/test_gpu_parity.py::test_lane_change_vs_restatement,
+// tools/lc_gpu_check.py; compute-sanitizer racecheck clean) -- and statistically equal to the unmodified reference.
 //
 // The algorithm is the "device form" that tests/test_cpu.py::test_lane_change_device_form_is_equivalent
 // proves equal to the reference-ordered restatement, in its simplest shape:
 //   * everything that does not depend on processing order stays in the parallel kernels;
 //   * the two order-dependent parts -- Engine::scheduleLaneChange (engine.cpp:792-809) and the tail of
 //     Engine::vehicleControl for the few vehicles involved in a lane change (engine.cpp:195-244) -- run
-//     in ONE thread each, in exactly the reference's order (first cut: correctness before speed; both
-//     split per road).
+//     per ROAD (one thread serves one road's candidates in the global order; roads are independent),
+//     CITYFLOW_B200_LC_SERIAL=1 selects the one-thread-for-everything form.
 // Included by device_sim.cu after its helpers (min2, noCollisionSpeed, Tail, View ...).
 #pragma once
 

@@ -1,5 +1,5 @@
-// device_lc_types.cuh -- data layout of the lane-change draft (see device_lc.cuh).  Only compiled with
-// -DCFB_LANE_CHANGE; included by device_sim.cu before its View struct.
+// device_lc_types.cuh -- data layout of the lane-change path (see device_lc.cuh); included by device_view.cuh before the
+// View struct.
 #pragma once
 
 namespace cfb {

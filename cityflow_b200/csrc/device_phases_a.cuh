@@ -157,15 +157,11 @@ __device__ __forceinline__ void phase_ingest(const View &V, const int bid, const
                 Tail nt;
                 nt.dis = 0.0; nt.len = T.len; nt.speed = T.speed0; nt.pos = p; nt.prev = -1;
                 V.tail[i] = nt;
-#ifdef CFB_LANE_CHANGE
                 if (V.lcOn) lcResetSlot(V.lc.slot[h], info.z);
-#endif
                 if (n > 0) {
                     V.leader[p] = p - 1;
                     V.gap[p] = tl.dis - tl.len - 0.0;
-#ifdef CFB_LANE_CHANGE
                     if (V.lcOn) V.lc.slot[h].gap = tl.dis - tl.len - 0.0;
-#endif
                     ins = 1;
                 } else {
                     V.leader[p] = -1;
@@ -309,22 +305,16 @@ __device__ __forceinline__ void phase_notify(const View &V, const int bid, const
         }
         const int c = V.count[d], base = V.off[d];
         if (c == 0) continue;
-#ifdef CFB_LANE_CHANGE
         // with lane change the search already ran before the signals (k_lc_admitted) and the full leader
         // pass after scheduling (k_lc_leader) has the final word
         if ((V.inserted[d] & 2) && lane == 0 && !V.lcOn) {
-#else
-        if ((V.inserted[d] & 2) && lane == 0) {  // vehicle admitted to an empty lane this step
-#endif
             const int4 idv = V.ids[base];
             int ld = -1;
             double g = 0;
             headSearch(V, d, 0.0, idv.w, V.nav[base].x, V.tmpl[idv.y], d, ld, g);
             V.leader[base] = ld;
             if (ld >= 0) V.gap[base] = g;
-#ifdef CFB_LANE_CHANGE
             if (V.lcOn && ld >= 0) V.lc.slot[idv.x].gap = g;
-#endif
         }
         // the link the tail came out of, if it is empty now (otherwise it is on the list itself)
         const int prev = V.nav[base + c - 1].y;

@@ -73,21 +73,15 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 if (dst > 0) {
                     V.leader[q] = q - 1;
                     V.gap[q] = pd - pl - nk.x;
-#ifdef CFB_LANE_CHANGE
                     if (V.lcOn) V.lc.slot[idv.x].gap = pd - pl - nk.x;
-#endif
                 }
             } else if (valid && nb.x == -2) {                      // finished (engine.cpp:296-310)
                 V.pos[idv.x] = -1;
                 blkSet(V, idv.x, -2);
                 const int f = atomicAdd(&V.ctrl->finCount, 1);
-#ifdef CFB_LANE_CHANGE
                 // a vehicle replaced by its shadow is not a "finished vehicle" (engine.cpp:297-301): flagged for the host
                 const int finTag = (V.lcOn && V.lc.slot[idv.x].finished) ? (idv.x | 0x40000000) : idv.x;
                 if (f < V.finCap) V.finSlots[f] = make_int2(finTag, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
-#else
-                if (f < V.finCap) V.finSlots[f] = make_int2(idv.x, V.ctrl->step); else atomicOr(&V.ctrl->error, ERR_FINISHED_OVERFLOW);
-#endif
                 atomicSub(&V.ctrl->active, 1);
             }
             if (mask) {
@@ -139,9 +133,7 @@ __device__ __forceinline__ void phase_move(const View &V, const int bid, const i
                 if (nsurv + rank > 0) {
                     V.leader[q] = q - 1;
                     V.gap[q] = pd - pl - myDis;
-#ifdef CFB_LANE_CHANGE
                     if (V.lcOn) V.lc.slot[idv.x].gap = pd - pl - myDis;
-#endif
                 }
             }
             if (lane == 0) V.entCnt[d] = 0;
@@ -226,9 +218,7 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
         headSearch(V, d, V.kin[p].x, idv.w, V.nav[p].x, V.tmpl[idv.y], -1, ld, g);
         V.leader[p] = ld;
         if (ld >= 0) V.gap[p] = g;
-#ifdef CFB_LANE_CHANGE
         if (V.lcOn && ld >= 0) V.lc.slot[idv.x].gap = g;
-#endif
     }
 }
 

@@ -93,23 +93,33 @@ __device__ __forceinline__ void shardWait(const View &V, const ShardP2P &S, int 
     __syncthreads();
 }
 
-// Called by every thread after its remote stores: the last block to arrive publishes the epoch.
+// Called by every thread after its remote stores: the last block to arrive publishes the epoch.  Ordering: every
+// thread's stores -> its device-scope fence -> the block barrier -> the ticket (device-scope atomic) -> observed by the
+// last block -> ONE system-scope fence (fences are cumulative: it orders everything that happened before it against the
+// flag stores that follow, for every observer in the system) -> the flag.  A system-scope fence in every thread instead
+// measured ~15 us per send kernel (r02d), which is why there is exactly one.
 __device__ __forceinline__ bool shardLastBlock(int *ticket) {
     __shared__ int sLast;
-    __threadfence_system();       // release: my remote stores are performed before the ticket / the flag
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const int t = atomicAdd(ticket, 1);
         sLast = (t == (int) gridDim.x - 1);
         if (sLast) *ticket = 0;
+        if (sLast) __threadfence_system();
     }
     __syncthreads();
-    if (sLast) __threadfence_system();
     return sLast != 0;
+}
+// programmatic dependent launch (see pdlEnter() in device_sim.cu)
+__device__ __forceinline__ void shardPdlEnter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // After k_control: one warp per boundary lane this rank feeds; the record goes straight into the owner's arena.
 __global__ void __launch_bounds__(128) k_send_movers(View V, ShardP2P S) {
+    shardPdlEnter();
     const int E = V.ctrl->epoch + 1, par = E & 1;
     const int lane = threadIdx.x & 31;
     const int nW = (gridDim.x * blockDim.x) >> 5;
@@ -130,12 +140,13 @@ __global__ void __launch_bounds__(128) k_send_movers(View V, ShardP2P S) {
         __syncwarp();
         if (lane == 0) V.entCnt[L] = 0;
     }
-    if (shardLastBlock(S.ticket) && threadIdx.x < S.nNbr)
-        *(volatile int *) (S.peers[S.nbr[threadIdx.x]].flags + 0 * S.world + S.me) = E;
+    if (shardLastBlock(S.ticket) && threadIdx.x == 0)   // (the thread that issued the system fence)
+        for (int k = 0; k < S.nNbr; ++k) *(volatile int *) (S.peers[S.nbr[k]].flags + 0 * S.world + S.me) = E;
 }
 
 // Before k_move: wait for the feeders, then stage their entrants like local movers (cf. k_unpack_movers).
 __global__ void __launch_bounds__(128) k_recv_movers(View V, ShardP2P S) {
+    shardPdlEnter();
     const int E = V.ctrl->epoch + 1, par = E & 1;
     shardWait(V, S, 0, E, false);
     const int lane = threadIdx.x & 31;
@@ -170,6 +181,7 @@ __global__ void __launch_bounds__(128) k_recv_movers(View V, ShardP2P S) {
 // After k_move: tail records to the feeders, this step's blocker changes to the neighbours, finished-vehicle marks
 // to everybody.
 __global__ void __launch_bounds__(128) k_send_tails(View V, ShardP2P S) {
+    shardPdlEnter();
     const int E = V.ctrl->epoch + 1, par = E & 1;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (int j = gtid; j < V.nBoundIn; j += stride) {
@@ -205,16 +217,17 @@ __global__ void __launch_bounds__(128) k_send_tails(View V, ShardP2P S) {
         for (int q = 0; q < S.world; ++q)
             if (q != S.me) S.peers[q].delStep[u.x] = step;
     }
-    if (shardLastBlock(S.ticket + 1)) {
-        if (threadIdx.x == 0) V.ctrl->nBlkUpd = 0;
-        if (threadIdx.x < S.nNbr) *(volatile int *) (S.peers[S.nbr[threadIdx.x]].flags + 1 * S.world + S.me) = E;
-        if (threadIdx.x < S.world && threadIdx.x != S.me)
-            *(volatile int *) (S.peers[threadIdx.x].flags + 2 * S.world + S.me) = E;
+    if (shardLastBlock(S.ticket + 1) && threadIdx.x == 0) {   // (the thread that issued the system fence)
+        V.ctrl->nBlkUpd = 0;
+        for (int k = 0; k < S.nNbr; ++k) *(volatile int *) (S.peers[S.nbr[k]].flags + 1 * S.world + S.me) = E;
+        for (int q = 0; q < S.world; ++q)
+            if (q != S.me) *(volatile int *) (S.peers[q].flags + 2 * S.world + S.me) = E;
     }
 }
 
 // Before k_leader: wait for the owners / neighbours, refresh the ghost copies, apply the neighbours' blocker changes.
 __global__ void __launch_bounds__(128) k_recv_tails(View V, ShardP2P S) {
+    shardPdlEnter();
     const int E = V.ctrl->epoch + 1, par = E & 1;
     shardWait(V, S, 1, E, false);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;

@@ -342,6 +342,20 @@ struct DevBuf {
 static void legacySync() { CFB_CUDA(cudaStreamSynchronize(cudaStreamLegacy)); }
 
 // A step kernel, optionally with programmatic stream serialisation (see pdlEnter()).
+template <class... A>
+static void launchPdl(void (*k)(A...), int grid, int block, cudaStream_t s, bool pdl, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, k, args...));
+}
 static void launchStepKernel(void (*k)(View), int grid, int block, cudaStream_t s, bool pdl, const View &V) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -457,7 +471,6 @@ struct DeviceSim::Impl {
     double shardMs[SHARD_PHASES] = {};
     long long shardTimedSteps = 0;
 
-#ifdef CFB_LANE_CHANGE
     DevBuf<LcSlot> lcSlot;
     DevBuf<int> lcLaneRoad, lcRouteLastRoad, lcScratch;
     bool lcSerial = false;            // CITYFLOW_B200_LC_SERIAL=1: scheduling / control tail in one thread each (debugging)
@@ -468,7 +481,6 @@ struct DeviceSim::Impl {
     DevBuf<LcCtrl> lcCtrl;
     LcCtrl *hLcCtrl = nullptr;        // pinned readback
     int lcSpareCap = 0;
-#endif
     int slotCap = 0;
     int numSMs = 148;
     int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
@@ -752,7 +764,6 @@ void DeviceSim::ensureSlotCapacity(int slots) {
     std::swap(I.slotCust.p, ncust.p); std::swap(I.slotCust.n, ncust.n);
     std::swap(I.blk.p, nblk.p); std::swap(I.blk.n, nblk.n);
     std::swap(I.delStep.p, ndel.p); std::swap(I.delStep.n, ndel.n);
-#ifdef CFB_LANE_CHANGE
     if (I.V.lcOn) {
         DevBuf<LcSlot> nlc;
         nlc.alloc(cap);
@@ -761,7 +772,6 @@ void DeviceSim::ensureSlotCapacity(int slots) {
         std::swap(I.lcSlot.p, nlc.p); std::swap(I.lcSlot.n, nlc.n);
         I.V.lc.slot = I.lcSlot.p;
     }
-#endif
     legacySync();   // ... and the copies before the old buffers are freed / the new ones are used
     I.slotCap = cap;
     I.V.pos = I.pos.p; I.V.waitNext = I.waitNext.p; I.V.slotInfo = I.slotInfo.p; I.V.slotCust = I.slotCust.p; I.V.blk = I.blk.p; I.V.delStep = I.delStep.p;
@@ -1021,13 +1031,13 @@ void DeviceSim::runNotifyControl() {
 void DeviceSim::runMove() {
     Impl &I = *impl_;
     ensureGrids();
-    k_move<<<I.gridMove, 256, 0, I.stream>>>(I.V);
+    launchStepKernel(k_move, I.gridMove, 256, I.stream, I.usePdl && !I.timing, I.V);
     launches_ += 1;
 }
 void DeviceSim::runLeader() {
     Impl &I = *impl_;
     ensureGrids();
-    k_leader<<<I.gridLeader, 256, 0, I.stream>>>(I.V);
+    launchStepKernel(k_leader, I.gridLeader, 256, I.stream, I.usePdl && !I.timing, I.V);
     launches_ += 1;
 }
 void DeviceSim::packTails() {
@@ -1146,23 +1156,23 @@ bool DeviceSim::shardIsP2P() const { return impl_->p2p; }
 void DeviceSim::sendMovers() {
     Impl &I = *impl_;
     const int g = std::max(1, std::min(64, (I.V.nBoundOut * 32 + 127) / 128));
-    k_send_movers<<<g, 128, 0, I.stream>>>(I.V, I.S);
+    launchPdl(k_send_movers, g, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
     launches_ += 1;
 }
 void DeviceSim::recvMovers() {
     Impl &I = *impl_;
     const int g = std::max(1, std::min(64, (I.V.nBoundIn * 32 + 127) / 128));
-    k_recv_movers<<<g, 128, 0, I.stream>>>(I.V, I.S);
+    launchPdl(k_recv_movers, g, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
     launches_ += 1;
 }
 void DeviceSim::sendTails() {
     Impl &I = *impl_;
-    k_send_tails<<<16, 128, 0, I.stream>>>(I.V, I.S);
+    launchPdl(k_send_tails, 16, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
     launches_ += 1;
 }
 void DeviceSim::recvTails() {
     Impl &I = *impl_;
-    k_recv_tails<<<16, 128, 0, I.stream>>>(I.V, I.S);
+    launchPdl(k_recv_tails, 16, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
     launches_ += 1;
 }
 
@@ -1754,9 +1764,8 @@ void DeviceSim::setPhase(int intersection, int phase) {
     I.phaseDirty = true;
 }
 
-#ifdef CFB_LANE_CHANGE
 // ------------------------------------------------------------------------------------------
-// Lane change, DRAFT (device_lc.cuh).  Not validated on a GPU yet; not compiled by default.
+// Lane change (device_lc.cuh).
 void DeviceSim::uploadLanePlans(const Routing &routing) {
     Impl &I = *impl_;
     CFB_CUDA(cudaStreamSynchronize(I.stream));
@@ -1935,6 +1944,5 @@ void DeviceSim::debugDumpLc(std::vector<LcDebugRec> &out) {
             out.push_back(r);
         }
 }
-#endif  // CFB_LANE_CHANGE
 
 }  // namespace cfb

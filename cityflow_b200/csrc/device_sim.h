@@ -196,8 +196,7 @@ public:
     int numDrivables() const;
     int device() const;   // CUDA device ordinal the engine lives on
 
-#ifdef CFB_LANE_CHANGE
-    // ---- lane change, DRAFT (device_lc.cuh): not validated on a GPU yet ----
+    // ---- lane change (device_lc.cuh) ----
     struct LcShadow { int32_t parentSlot, shadowSlot; };
     struct LcDebugRec {   // every running vehicle incl. shadows; mirrors oracle/harness.py LC_DTYPE with slots for identities
         int32_t slot, priority, partnerType, partnerSlot, drivable, leaderSlot, blockerSlot, flags, lastDir, pad;
@@ -213,7 +212,6 @@ public:
     // Second half: the drawn priorities, then leader pass, notify, control (+ sequential tail), move, leader.
     void stepLcEnd(const int32_t *priorities, int n);
     void debugDumpLc(std::vector<LcDebugRec> &out);
-#endif
 
     struct Impl;
 

@@ -54,11 +54,9 @@ struct Ctrl {
 // (per-vehicle cycle / path samples of k_control are recorded in this build: tools/dbg_control_cycles.py)
 #endif
 
-#ifdef CFB_LANE_CHANGE
 }  // namespace cfb
 #include "device_lc_types.cuh"
 namespace cfb {
-#endif
 
 constexpr int HEAD_BIT = 0x40000000;   // in vehList[].y: the vehicle is the first of its drivable's list
 constexpr int ENT_CAP = 16;   // entrants staged per drivable per step
@@ -130,10 +128,8 @@ struct View {
     unsigned *dbgCyc, *dbgPath;   // CFB_DEBUG_COUNTERS builds: per-position cycles / path bits of k_control
     Ctrl *ctrl;
     const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
-#ifdef CFB_LANE_CHANGE
     int lcOn;                   // "laneChange": true
     LcView lc;
-#endif
 };
 
 // ------------------------------------------------------------------------------------------

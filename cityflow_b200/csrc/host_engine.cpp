@@ -201,19 +201,11 @@ public:
             error = e.what();
             return false;
         }
-#ifndef CFB_LANE_CHANGE
-        if (laneChange) {
-            error = "laneChange=true is not supported by the B200 engine yet";
-            return false;
-        }
-#endif
         if (!net.load(dir + roadnetFile)) { error = "loading roadnet file error!"; return false; }
         std::vector<FlowDef> defs;
         if (!loadFlows(dir + flowFile, net, defs)) { error = "loading flow file error!"; return false; }
         routing.reset(new Routing(net));
-#ifdef CFB_LANE_CHANGE
         if (laneChange) routing->enableLanePlans();   // a shadow continues the route from the lane it was inserted into
-#endif
         for (auto &d : defs) {
             FlowRun f;
             f.def = d;
@@ -238,9 +230,7 @@ public:
         opt.interval = interval;
         opt.rlTrafficLight = rlTrafficLight;
         dev.reset(new DeviceSim(net, templates, *routing, opt));
-#ifdef CFB_LANE_CHANGE
-        if (laneChange) dev->enableLaneChange(net, *routing);   // DRAFT, see device_lc.cuh
-#endif
+        if (laneChange) dev->enableLaneChange(net, *routing);   // device_lc.cuh
         uploadedPlans = routing->numPlans();
         uploadedTemplates = templates.size();
         if (const char *na = getenv("CITYFLOW_B200_NO_AHEAD")) aheadEnabled = !(na[0] == '1');
@@ -273,7 +263,6 @@ public:
         if (transport) dev->shardGatherFinished(transport, fin);
         else if (finishedHook) finishedHook(fin);
         // deterministic accumulation order for the travel-time sum (ring order is atomics order)
-#ifdef CFB_LANE_CHANGE
         // a vehicle replaced by its shadow is tagged by the device (engine.cpp:297-301): it is not a
         // finished vehicle, its shadow (same name) carries on as the real one
         std::vector<char> replaced(fin.size(), 0);
@@ -290,7 +279,6 @@ public:
                 freeSlots.push_back(fin[k].slot);
                 idMapValid = false;
             }
-#endif
         std::sort(fin.begin(), fin.end(), [this](const FinRec &a, const FinRec &b) {
             return a.step != b.step ? a.step < b.step : slots[a.slot].priority < slots[b.slot].priority;
         });
@@ -503,8 +491,7 @@ public:
             case 3: dev->unpackTails(); dev->applyBlk(); dev->runLeader(); break;
         }
     }
-#ifdef CFB_LANE_CHANGE
-    // One step with lane change (DRAFT): the shadows' priorities come from the engine RNG right after
+    // One step with lane change: the shadows' priorities come from the engine RNG right after
     // this step's spawn draws (vehicle.cpp:33), so the step has a host round trip in the middle.
     void nextStepLaneChange() {
         std::vector<int32_t> spare(256);
@@ -536,11 +523,8 @@ public:
         dev->stepLcEnd(prio.data(), (int) prio.size());
         finishStep();
     }
-#endif
     void nextStep() {
-#ifdef CFB_LANE_CHANGE
         if (laneChange) { nextStepLaneChange(); return; }
-#endif
         if (!ahead) prepareStep();
         ahead = false;
         const auto t1 = std::chrono::steady_clock::now();
@@ -1028,13 +1012,7 @@ int64_t cfb_replay_format_step(cfb_replay *r, const cfb_replay_vehicle *v, int64
     return copyOut(r->buf, out, cap);
 }
 
-#ifdef CFB_LANE_CHANGE
-// DRAFT (include/cityflow_b200_lc_draft.h): every running vehicle including shadows in vehiclePool
-// (priority) order, in the layout of oracle/harness.py LC_DTYPE, for the parity tests of the lane-change path.
-struct cfb_lc_vehicle {
-    int32_t flow, cnt, priority, partner_type, partner, drivable, leader, blocker, flags, last_dir;
-    double dis, speed, gap, offset, waiting_time, last_change_time;
-};
+// Test support (include/cityflow_b200.h): every running vehicle including shadows, LC_DTYPE layout.
 int64_t cfb_debug_lc_vehicles(cfb_engine *e, cfb_lc_vehicle *out, int64_t cap) {
     CFB_TRY(e,
         cfb::HostEngine &h = e->h;
@@ -1054,7 +1032,6 @@ int64_t cfb_debug_lc_vehicles(cfb_engine *e, cfb_lc_vehicle *out, int64_t cap) {
         return (int64_t) recs.size();
     )
 }
-#endif
 
 int cfb_set_random_seed(cfb_engine *e, int seed) {
     e->h.cancelAhead();
@@ -1142,6 +1119,9 @@ int64_t cfb_vehicle_steps(cfb_engine *e) {
     CFB_TRY(e, return (int64_t) e->h.dev->vehicleSteps();)
 }
 
+int64_t cfb_finished_vehicle_count(cfb_engine *e) {
+    CFB_TRY(e, e->h.cancelAhead(); e->h.drain(); return (int64_t) e->h.finishedCnt;)
+}
 int64_t cfb_gpu_launches(const cfb_engine *e) { return e->h.dev->launchesDone(); }
 int64_t cfb_tie_count(cfb_engine *e) {
     CFB_TRY(e, return (int64_t) e->h.dev->tieCount();)

@@ -173,10 +173,20 @@ int64_t cfb_shard_group_debug_vehicles(cfb_shard_group *g, void *out, int64_t ca
  * Record = 8 x int32 {flow, index, priority, drivable, leader flow, leader index, blocker flow,
  * blocker index}, 3 x double {distance, speed, gap}, 1 x int64 {enterLaneLinkTime}; 64 bytes. */
 int64_t cfb_debug_vehicles(cfb_engine *e, void *out, int64_t cap);
+/* Test support, laneChange=true runs: every running vehicle INCLUDING shadows (Vehicle::isReal() == false,
+ * lanechange.cpp:71-102) in vehiclePool (priority) order; partner / leader / blocker are given as priorities (-1 none).
+ * Same layout as oracle/harness.py LC_DTYPE (refdump runlc). */
+typedef struct {
+    int32_t flow, cnt, priority, partner_type, partner, drivable, leader, blocker, flags, last_dir;
+    double dis, speed, gap, offset, waiting_time, last_change_time;
+} cfb_lc_vehicle;
+int64_t cfb_debug_lc_vehicles(cfb_engine *e, cfb_lc_vehicle *out, int64_t cap);
 
 /* Measurement support (bench.py): number of our kernels launched so far, per-kernel CUDA-event
  * time accumulators (ms) when enabled, and device-side size figures. */
 int64_t cfb_gpu_launches(const cfb_engine *e);
+/* Engine::finishedVehicleCnt (engine.h:58; the denominator part of get_average_travel_time): vehicles that completed their route */
+int64_t cfb_finished_vehicle_count(cfb_engine *e);
 /* Same-step entrants of one drivable with EQUAL new distance seen so far (summed over the rank's drivables).  The
  * reference orders such a pair by a non-stable std::sort over a buffer its worker threads fill in arrival order
  * (engine.cpp:247-249, :480), i.e. its result is not defined there -- two runs of the reference with different

@@ -11,8 +11,6 @@
 #include "device_emu.h"
 static struct { unsigned x = 0, y = 0, z = 0; } blockIdx;
 static struct { unsigned x = 1, y = 1, z = 1; } gridDim;
-#define CFB_LANE_CHANGE 1
-#define CFB_DEAD_END_STOP 1
 using std::max;
 using std::min;
 namespace cfb { namespace cg = cooperative_groups; }

@@ -26,8 +26,6 @@
 #include <vector>
 
 #include "device_emu.h"   // CUDA keywords defined away + stand-ins; this probe runs everything as ONE thread, no fibers
-#define CFB_LANE_CHANGE 1
-#define CFB_DEAD_END_STOP 1
 #define CFB_LC_HOST_PROBE 1
 using std::max;
 using std::min;

@@ -1,13 +1,11 @@
-"""Lane change on the GPU, DRAFT -- first thing to run next round (the path has never executed):
+"""Lane change on the GPU against the restatement, every field of every vehicle (shadows included), every step:
 
-    make -C cityflow_b200/csrc clean && make -C cityflow_b200/csrc EXTRA=-DCFB_LANE_CHANGE
     python tools/lc_gpu_check.py [rows cols steps]
-    make -C cityflow_b200/csrc clean && make -C cityflow_b200/csrc          # back to the default library
 
-Compares, every step, the engine's running vehicles INCLUDING shadows (cfb_debug_lc_vehicles: partner,
-offset, waiting time, leader, blocker, ...) and the per-lane counts with the restatement's
-(PortOracle.lc_snapshot), which is pinned against oracle/_ref/refdump_lcorder.  Prints the first
-difference per field and stops."""
+Compares the engine's running vehicles INCLUDING shadows (cfb_debug_lc_vehicles: partner, offset, waiting time, leader,
+blocker, ...) and the per-lane counts with the restatement's (PortOracle.lc_snapshot), which is pinned against
+oracle/_ref/refdump_lcorder.  Prints the first difference per field and stops.  CITYFLOW_B200_LC_SERIAL=1 selects the
+one-thread forms of the scheduling / control-tail kernels."""
 import ctypes
 import os
 import sys
@@ -26,10 +24,8 @@ def main():
     rows, cols, steps = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (3, 3, 600)))
     d = tempfile.mkdtemp()
     cfg = scenario.make_grid_scenario(d, rows, cols, dense=dict(frac=1.0, interval=3.0, seed=2), name="lc", lane_change=True)
-    eng = CEngine(cfg)          # raises unless the library was built with -DCFB_LANE_CHANGE
+    eng = CEngine(cfg)
     lib = eng.lib
-    if not hasattr(lib, "cfb_debug_lc_vehicles"):
-        raise SystemExit("this libcityflow_b200.so was not built with EXTRA=-DCFB_LANE_CHANGE")
     lib.cfb_debug_lc_vehicles.restype = ctypes.c_int64
     lib.cfb_debug_lc_vehicles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     ora = H.PortOracle(cfg)

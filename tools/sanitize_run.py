@@ -6,7 +6,7 @@
 
 Small networks so the instrumented kernels finish in seconds: single engine (step kernels, spawn
 ring, observation kernels, archive, vehicle setters), rlTrafficLight engine (host and device phase
-setting, device-resident observations), the lane-change draft when the library has it (its per-road
+setting, device-resident observations), lane change (its per-road
 kernels run roads concurrently: racecheck is the interesting tool there) and a 2-rank loop-back shard group
 (pack/unpack/seal kernels).
 Exit code 0 and the sanitizer's "ERROR SUMMARY: 0 errors" are the result."""
@@ -73,16 +73,13 @@ def main():
         rl.next_step()
     print("rl ok, vehicles", rl.get_vehicle_count())
 
-    # lane change (only in a library built with EXTRA=-DCFB_LANE_CHANGE; the default one rejects the config)
-    from cityflow_b200.capi import CEngine, load_library
-    if hasattr(load_library(), "cfb_debug_lc_vehicles"):
-        cfg_lc = scenario.make_grid_scenario(d, 3, 3, dense=dict(frac=1.0, interval=2.0, seed=6), name="sanlc", lane_change=True)
-        lc = CEngine(cfg_lc)
-        for _ in range(steps):
-            lc.next_step()
-        print("lane change ok, vehicles (shadows included)", lc.vehicle_count())
-    else:
-        print("lane change: not in this library (draft, EXTRA=-DCFB_LANE_CHANGE)")
+    # lane change: its per-road kernels run roads concurrently (racecheck is the interesting tool here)
+    from cityflow_b200.capi import CEngine
+    cfg_lc = scenario.make_grid_scenario(d, 3, 3, dense=dict(frac=1.0, interval=2.0, seed=6), name="sanlc", lane_change=True)
+    lc = CEngine(cfg_lc)
+    for _ in range(steps):
+        lc.next_step()
+    print("lane change ok, vehicles (shadows included)", lc.vehicle_count())
 
     grp = CShardGroup(cfg_sh, 2)
     grp.next_step(steps)
