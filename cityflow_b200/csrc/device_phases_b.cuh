@@ -189,6 +189,14 @@ __device__ __forceinline__ void phase_leader(const View &V, const int bid, const
         V.ctrl->step += 1;                                             // Engine::step (engine.cpp:593)
         V.ctrl->epoch += 1;
         V.ctrl->vehicleSteps += (unsigned long long) (long long) V.ctrl->active;   // may be negative on one rank of a sharded run  // all finishes of this step are in
+        if (V.hostMirror) {   // the step's result, stored straight into host memory: get_vehicle_count() needs no copy
+            volatile int *m = V.hostMirror;
+            m[1] = V.ctrl->active;
+            m[2] = V.ctrl->error;
+            m[3] = V.ctrl->ties;
+            __threadfence_system();
+            m[0] = V.ctrl->epoch;
+        }
     }
     if (!V.rl) {
         for (int in = gtid; in < V.nInter; in += nblk * blockDim.x) {

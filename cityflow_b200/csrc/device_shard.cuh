@@ -118,8 +118,7 @@ __device__ __forceinline__ void shardPdlEnter() {
 }
 
 // After k_control: one warp per boundary lane this rank feeds; the record goes straight into the owner's arena.
-__global__ void __launch_bounds__(128) k_send_movers(View V, ShardP2P S) {
-    shardPdlEnter();
+__device__ __forceinline__ void sendMoversBody(const View &V, const ShardP2P &S) {
     const int E = V.ctrl->epoch + 1, par = E & 1;
     const int lane = threadIdx.x & 31;
     const int nW = (gridDim.x * blockDim.x) >> 5;
@@ -143,10 +142,10 @@ __global__ void __launch_bounds__(128) k_send_movers(View V, ShardP2P S) {
     if (shardLastBlock(S.ticket) && threadIdx.x == 0)   // (the thread that issued the system fence)
         for (int k = 0; k < S.nNbr; ++k) *(volatile int *) (S.peers[S.nbr[k]].flags + 0 * S.world + S.me) = E;
 }
+__global__ void __launch_bounds__(128) k_send_movers(View V, ShardP2P S) { shardPdlEnter(); sendMoversBody(V, S); }
 
 // Before k_move: wait for the feeders, then stage their entrants like local movers (cf. k_unpack_movers).
-__global__ void __launch_bounds__(128) k_recv_movers(View V, ShardP2P S) {
-    shardPdlEnter();
+__device__ __forceinline__ void recvMoversBody(const View &V, const ShardP2P &S) {
     const int E = V.ctrl->epoch + 1, par = E & 1;
     shardWait(V, S, 0, E, false);
     const int lane = threadIdx.x & 31;
@@ -177,11 +176,14 @@ __global__ void __launch_bounds__(128) k_recv_movers(View V, ShardP2P S) {
         }
     }
 }
+__global__ void __launch_bounds__(128) k_recv_movers(View V, ShardP2P S) { shardPdlEnter(); recvMoversBody(V, S); }
+// Both halves in one launch (the default): this rank's sends do not depend on what it receives, so the kernel first
+// stores and publishes its own records and then waits for the neighbours' -- one launch and one ramp less per exchange.
+__global__ void __launch_bounds__(128) k_xchg_movers(View V, ShardP2P S) { shardPdlEnter(); sendMoversBody(V, S); recvMoversBody(V, S); }
 
 // After k_move: tail records to the feeders, this step's blocker changes to the neighbours, finished-vehicle marks
 // to everybody.
-__global__ void __launch_bounds__(128) k_send_tails(View V, ShardP2P S) {
-    shardPdlEnter();
+__device__ __forceinline__ void sendTailsBody(const View &V, const ShardP2P &S) {
     const int E = V.ctrl->epoch + 1, par = E & 1;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     for (int j = gtid; j < V.nBoundIn; j += stride) {
@@ -224,10 +226,10 @@ __global__ void __launch_bounds__(128) k_send_tails(View V, ShardP2P S) {
             if (q != S.me) *(volatile int *) (S.peers[q].flags + 2 * S.world + S.me) = E;
     }
 }
+__global__ void __launch_bounds__(128) k_send_tails(View V, ShardP2P S) { shardPdlEnter(); sendTailsBody(V, S); }
 
 // Before k_leader: wait for the owners / neighbours, refresh the ghost copies, apply the neighbours' blocker changes.
-__global__ void __launch_bounds__(128) k_recv_tails(View V, ShardP2P S) {
-    shardPdlEnter();
+__device__ __forceinline__ void recvTailsBody(const View &V, const ShardP2P &S) {
     const int E = V.ctrl->epoch + 1, par = E & 1;
     shardWait(V, S, 1, E, false);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -260,6 +262,8 @@ __global__ void __launch_bounds__(128) k_recv_tails(View V, ShardP2P S) {
         }
     }
 }
+__global__ void __launch_bounds__(128) k_recv_tails(View V, ShardP2P S) { shardPdlEnter(); recvTailsBody(V, S); }
+__global__ void __launch_bounds__(128) k_xchg_tails(View V, ShardP2P S) { shardPdlEnter(); sendTailsBody(V, S); recvTailsBody(V, S); }
 
 // Host query support: every rank's finished-vehicle marks through the last completed step have landed here.
 __global__ void k_wait_fin(View V, ShardP2P S) { shardWait(V, S, 2, V.ctrl->epoch, true); }

@@ -35,6 +35,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -414,6 +415,7 @@ struct DeviceSim::Impl {
     DevBuf<int> p2pInts;              // nbr | outPeer | outDst | inPeer | inDst | ticket[2]
     ShardP2P S{};
     bool p2p = false;
+    bool shardSplit = false;          // CITYFLOW_B200_SHARD_SPLIT=1: separate send / receive kernels (also used for the per-phase timing)
     bool arenaShared = false;         // mapped by other PROCESSES (as opposed to the in-process loop-back group)
     std::vector<std::vector<int>> bsize;   // bsize[a][b] = lanes rank a feeds and rank b owns
     static constexpr int SHARD_SLOT_CAP = 1 << 22;   // slot-indexed arrays are fixed once peers have mapped delStep
@@ -453,6 +455,8 @@ struct DeviceSim::Impl {
     int *hPhaseRing[RING] = {};         // pinned staging, one per ring slot
     bool phaseDirty = false;
     Ctrl *hCtrl = nullptr;  // pinned readback
+    volatile int *hMirror = nullptr;   // pinned + mapped: {epoch, active, error, ties}, written by k_leader (device_phases_b.cuh)
+    long long epochHost = 0;           // steps enqueued since the engine was created (what hMirror[0] will reach)
     int *hInts = nullptr;   // pinned readback (lanes)
     size_t hIntsCap = 0;
     // timing
@@ -484,6 +488,7 @@ struct DeviceSim::Impl {
     int slotCap = 0;
     int numSMs = 148;
     int gridNotify = 0, gridMove = 0, gridLeader = 0, gridControl = 0;
+    bool mirrorStale = false;   // something other than a step changed active / error (reset, restore, a setter): read the device
     bool usePdl = true;   // CITYFLOW_B200_NO_PDL=1: plain stream order between the step kernels
     bool useGraph = true, graphDirty = false, useCoop = false;   // cooperative k_step measured slower
     cudaEvent_t graphDone[2][GRING] = {};
@@ -668,6 +673,15 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     I.finSlots.alloc(V.finCap);
     I.ctrl.alloc(1);
     CFB_CUDA(cudaMallocHost(&I.hCtrl, sizeof(Ctrl)));
+    {
+        int *hm = nullptr, *dm = nullptr;
+        CFB_CUDA(cudaHostAlloc(&hm, 64, cudaHostAllocMapped));
+        memset(hm, 0, 64);
+        CFB_CUDA(cudaHostGetDevicePointer(&dm, hm, 0));
+        I.hMirror = hm;
+        V.hostMirror = dm;
+        if (const char *g = getenv("CITYFLOW_B200_NO_MIRROR")) if (g[0] == '1') V.hostMirror = nullptr;
+    }
     V.kin = I.kin.p; V.nkin = I.nkin.p; V.gap = I.gap.p; V.leader = I.leader.p; V.ids = I.ids.p; V.nav = I.nav.p;
     V.nbuf = I.nbuf.p; V.count = I.count.p; V.entCnt = I.entCnt.p; V.ent = I.ent.p;
     V.waitHead = I.waitHead.p; V.waitTail = I.waitTail.p; V.inserted = I.inserted.p; V.notify = I.notify.p;
@@ -698,6 +712,7 @@ DeviceSim::~DeviceSim() {
             if (I.shardGraphDone[k][r]) cudaEventDestroy(I.shardGraphDone[k][r]);
         }
     if (I.hCtrl) cudaFreeHost(I.hCtrl);
+    if (I.hMirror) cudaFreeHost((void *) I.hMirror);
     if (I.hInts) cudaFreeHost(I.hInts);
     if (I.stream) cudaStreamDestroy(I.stream);
     // A peer process may still have the arena mapped (cudaIpcOpenMemHandle): freeing exported memory before every
@@ -801,6 +816,8 @@ void DeviceSim::reset() {
     I.ctrl.fill(0);
     legacySync();
     CFB_CUDA(cudaMemcpy(&I.V.ctrl->epoch, &epoch, sizeof(int), cudaMemcpyHostToDevice));
+    if (I.hMirror) { I.hMirror[1] = 0; I.hMirror[2] = 0; I.hMirror[3] = 0; }   // (the stream is idle: nothing else writes it now)
+    I.mirrorStale = false;
     // leader = -1 everywhere is not required (only occupied positions are read)
     steps_ = 0;
     legacySync();
@@ -918,6 +935,8 @@ launched:
     CFB_CUDA(cudaGetLastError());
     launches_ += (!tm && I.useCoop) ? 1 : 5;
     steps_ += 1;
+    I.epochHost += 1;
+    I.mirrorStale = false;
     if (tm) {
         CFB_CUDA(cudaEventSynchronize(I.ev[5]));
         float ms[5];
@@ -1147,6 +1166,7 @@ void DeviceSim::shardConnect(const std::vector<void *> &peerBase) {
     S.moverIn = (MoverMsg *) (I.arena.p + L.moverIn);
     S.tailIn = (TailMsg *) (I.arena.p + L.tailIn);
     if (V.blkUpdCap > BLK_IN_CAP) V.blkUpdCap = BLK_IN_CAP;
+    if (const char *g = getenv("CITYFLOW_B200_SHARD_SPLIT")) I.shardSplit = g[0] == '1';
     I.p2p = true;
     I.dropShardGraphs();
     legacySync();
@@ -1165,6 +1185,18 @@ void DeviceSim::recvMovers() {
     launchPdl(k_recv_movers, g, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
     launches_ += 1;
 }
+void DeviceSim::xchgMovers() {
+    Impl &I = *impl_;
+    const int g = std::max(1, std::min(64, (std::max(I.V.nBoundOut, I.V.nBoundIn) * 32 + 127) / 128));
+    launchPdl(k_xchg_movers, g, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
+    launches_ += 1;
+}
+void DeviceSim::xchgTails() {
+    Impl &I = *impl_;
+    launchPdl(k_xchg_tails, 16, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
+    launches_ += 1;
+}
+bool DeviceSim::shardSplitKernels() const { return impl_->shardSplit || impl_->timing; }
 void DeviceSim::sendTails() {
     Impl &I = *impl_;
     launchPdl(k_send_tails, 16, 128, I.stream, I.usePdl && !I.timing, I.V, I.S);
@@ -1276,6 +1308,7 @@ bool DeviceSim::shardStepEnd(int state) {
     if (ok) {
         CFB_CUDA(cudaGetLastError());
         steps_ += 1;
+        I.epochHost += 1;
     }
     return ok;
 }
@@ -1377,7 +1410,22 @@ static void readCtrlImpl(cudaStream_t s, Ctrl *dst, const Ctrl *src) {
     CFB_CUDA(cudaStreamSynchronize(s));
 }
 
+// The last enqueued step's {active, error, ties} as k_leader stored them in host memory: wait for the epoch stamp instead
+// of enqueuing a copy behind the step and synchronising the stream (saves a D2H round trip per get_vehicle_count()).
+static bool mirrorCurrent(DeviceSim::Impl &I) {
+    if (!I.V.hostMirror || I.mirrorStale) return false;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (long spin = 0; I.hMirror[0] < (int) I.epochHost; ++spin) {
+        if ((spin & 1023) == 1023) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) return false;   // let the caller synchronise
+        }
+        __builtin_ia32_pause();
+    }
+    return true;
+}
+
 int DeviceSim::vehicleCount() {
+    if (mirrorCurrent(*impl_)) return impl_->hMirror[1];
     readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
     return impl_->hCtrl->active;
 }
@@ -1388,6 +1436,7 @@ int DeviceSim::tieCount() {
 }
 
 int DeviceSim::errorFlags() {
+    if (mirrorCurrent(*impl_)) return impl_->hMirror[2];
     readCtrlImpl(impl_->stream, impl_->hCtrl, impl_->V.ctrl);
     return impl_->hCtrl->error;
 }
@@ -1428,6 +1477,7 @@ void DeviceSim::setPhasesFromDevice(const int32_t *phases, void *producerStream)
     CFB_CUDA(cudaStreamWaitEvent(ps, I.actTaken, 0));
     I.phaseDirty = false;    // every light was just overwritten: pending host-side changes are superseded
     I.hPhaseStale = true;
+    I.mirrorStale = true;    // k_set_phases may raise ERR_PHASE_RANGE outside a step
     launches_ += 1;
 }
 
@@ -1649,6 +1699,12 @@ void DeviceSim::restore(const Snapshot *s) {
     }
     I.phaseDirty = false;
     I.hPhaseStale = false;
+    {   // the restored control block decides what the host mirror shows until the next step
+        readCtrlImpl(I.stream, I.hCtrl, I.V.ctrl);
+        I.epochHost = I.hCtrl->epoch;
+        if (I.hMirror) { I.hMirror[1] = I.hCtrl->active; I.hMirror[2] = I.hCtrl->error; I.hMirror[3] = I.hCtrl->ties; I.hMirror[0] = I.hCtrl->epoch; }
+        I.mirrorStale = false;
+    }
     I.notify.fill(0);      // epoch-stamped scratch: nothing of an older timeline may match
     I.foeMask.fill(0);
     CFB_CUDA(cudaStreamSynchronize(I.stream));
@@ -1907,6 +1963,7 @@ void DeviceSim::stepLcEnd(const int32_t *priorities, int n) {
     CFB_CUDA(cudaGetLastError());
     launches_ += 6 + (n > 0);
     steps_ += 1;
+    I.epochHost += 1;
 }
 
 void DeviceSim::debugDumpLc(std::vector<LcDebugRec> &out) {

@@ -112,6 +112,9 @@ public:
     void recvMovers();
     void sendTails();
     void recvTails();
+    void xchgMovers();               // send + receive in one kernel (default)
+    void xchgTails();
+    bool shardSplitKernels() const;
     ShardBuffers shardBuffers();
     void stageStep(const SpawnRec *recs, int n);
     int shardStepBegin();            // 0 plain, 1 replayed (skip the phases), 2 capturing

@@ -127,6 +127,7 @@ struct View {
     int blkUpdCap;
     unsigned *dbgCyc, *dbgPath;   // CFB_DEBUG_COUNTERS builds: per-position cycles / path bits of k_control
     Ctrl *ctrl;
+    int *hostMirror;            // pinned, host-mapped: {epoch, active, error, ties} written by k_leader at the end of every step
     const SpawnRec *spawn;      // this step's records (lane-sorted); spawn[-1].slot holds their number
     int lcOn;                   // "laneChange": true
     LcView lc;

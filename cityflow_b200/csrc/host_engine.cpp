@@ -537,6 +537,15 @@ public:
                 if (st != 1 && dev->shardIsP2P()) {
                     // peer-memory data plane (device_shard.cuh): the seam records are stored straight into the
                     // neighbours' mailboxes by the send kernels; nothing but kernels on the stream
+                    const bool split = dev->shardSplitKernels();
+                    if (!split) {   // 7 kernels: ingest, notify, control, exchange movers, move, exchange tails, leader
+                        dev->runIngest();
+                        dev->runNotifyControl();
+                        dev->xchgMovers();                                                                 // X1
+                        dev->runMove();
+                        dev->xchgTails();                                                                  // X2
+                        dev->runLeader();
+                    } else {
                     dev->shardTimeMark(0);
                     dev->runIngest();
                     dev->shardTimeMark(1);
@@ -555,6 +564,7 @@ public:
                     dev->runLeader();
                     dev->shardTimeMark(8);
                     dev->shardTimeCollect();
+                    }
                 } else if (st != 1) try {
                     ShardBuffers b = dev->shardBuffers();
                     dev->runIngest();
@@ -810,7 +820,7 @@ int cfb_next_steps(cfb_engine *e, int n) {
 }
 
 int64_t cfb_get_vehicle_count(cfb_engine *e) {
-    CFB_TRY(e, int c = e->h.dev->vehicleCount(); e->h.checkDevice(); e->h.d2hBytes += 64; return c;)
+    CFB_TRY(e, int c = e->h.dev->vehicleCount(); e->h.checkDevice(); e->h.d2hBytes += 16; return c;)   // {epoch, active, error, ties}: stored by k_leader into mapped host memory
 }
 
 double cfb_get_current_time(const cfb_engine *e) { return e->h.currentTime(); }

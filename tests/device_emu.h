@@ -139,6 +139,8 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier(); }
 static inline void __syncthreads() { emu::barrier(); }
+static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int) v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }

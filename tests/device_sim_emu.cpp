@@ -309,6 +309,9 @@ void DeviceSim::sendMovers() { notEmulated("sharding"); }
 void DeviceSim::recvMovers() { notEmulated("sharding"); }
 void DeviceSim::sendTails() { notEmulated("sharding"); }
 void DeviceSim::recvTails() { notEmulated("sharding"); }
+void DeviceSim::xchgMovers() { notEmulated("sharding"); }
+void DeviceSim::xchgTails() { notEmulated("sharding"); }
+bool DeviceSim::shardSplitKernels() const { return true; }
 ShardBuffers DeviceSim::shardBuffers() { notEmulated("sharding"); return ShardBuffers(); }
 int DeviceSim::shardStepBegin() { notEmulated("sharding"); return 0; }
 bool DeviceSim::shardStepEnd(int) { notEmulated("sharding"); return false; }

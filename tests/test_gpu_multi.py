@@ -20,7 +20,7 @@ def _gpus():
         return 0
 
 
-def _run(world, args, port, env=None, timeout=1500):
+def _run(world, args, port, env=None, timeout=600):
     e = dict(os.environ)
     e.update(env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
@@ -41,7 +41,8 @@ def test_two_ranks_30x60_through_the_bench_window_vs_reference():
     _run(2, [30, 60, 1230, 25, 0.5, 10, 1, 0.02], 29531)
 
 
-@pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.skipif(_gpus() < 2 or os.environ.get("CFB_TEST_NCCL_TRANSPORT") != "1",
+                    reason="needs 2 GPUs; opt-in (CFB_TEST_NCCL_TRANSPORT=1): the staged NCCL send/recv form is kept for comparison only")
 def test_two_ranks_nccl_transport_vs_reference():
     _run(2, [8, 12, 400, 25, 1.0, 4, 1], 29532, env={"CITYFLOW_B200_SHARD_TRANSPORT": "nccl"})
 
