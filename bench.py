@@ -38,14 +38,15 @@ sys.path.insert(0, ROOT)
 METRIC = "vehicle_steps_per_sec"
 UNIT = "vehicle-steps/s"
 
-# The weak-scaling grids (30 x 30N, N > 1) use a HETEROGENEOUS fleet: every flow's vehicle parameters lie within +-2 % of
-# the generator's template.  Reason: the reference orders two vehicles that enter the same lane in the same step with
-# bit-EQUAL distance by a non-stable sort over a buffer its worker threads fill in arrival order (engine.cpp:247-249,
-# :403-409, :480), so from the first such tie on its own result depends on thread timing -- measured: thread_num 3 vs 8,
-# and two runs at 8, give different vehicle counts on the 30x60 grid from step 468 on (profiles/r02_reference_ties.md).
-# With identical vehicles such ties occur about once per 3e8 vehicle-steps (none on 30x30 within the bench window, 1 on
-# 30x60, 8 on 30x120 before step 1300); with distinct parameters none (oracle tie counter), so parity_check is defined.
-WEAK_FLEET_SPREAD = 0.02
+# The bench grids use a HETEROGENEOUS fleet: every flow's vehicle parameters lie within +-2 % of the generator's
+# template.  Reason: the reference orders two vehicles that enter the same lane in the same step with bit-EQUAL distance by
+# a non-stable sort over a buffer its worker threads fill in completion order (engine.cpp:247-249, :403-409, :480), so from
+# the first such tie on its own result depends on thread timing -- measured: thread_num 3 vs 8, and two runs at 8, give
+# different vehicle counts on the 30x60 grid from step 468 on (profiles/r02_reference_ties.md).  With identical vehicles
+# such ties occur about once per 3e8 vehicle-steps (1 on 30x30 and on 30x60, 8 on 30x120 before step 1300); with distinct
+# parameters none on 30x30 ... 30x240 (oracle tie counter), so parity_check is well defined.  `--fleet-spread 0` gives the
+# generator's identical vehicles.
+FLEET_SPREAD = 0.02
 
 
 def parse_args():
@@ -61,7 +62,7 @@ def parse_args():
     p.add_argument("--frac", type=float, default=0.5)
     p.add_argument("--flow-interval", type=float, default=10.0)
     p.add_argument("--flow-seed", type=int, default=1)
-    p.add_argument("--fleet-spread", type=float, default=-1.0, help="per-flow vehicle parameter spread; default: 0 (N=1, strong, replicas), 0.02 (weak, N>1)")
+    p.add_argument("--fleet-spread", type=float, default=-1.0, help="per-flow vehicle parameter spread (default 0.02, see FLEET_SPREAD; 0 = identical vehicles)")
     p.add_argument("--threads", type=int, default=0, help="reference arm: thread_num (default nproc)")
     p.add_argument("--cpu-steps", type=int, default=100, help="cpu_baseline sample: timed steps after the prefill")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -105,9 +106,7 @@ def flow_seed(args):
 
 
 def fleet_spread(args):
-    if args.fleet_spread >= 0:
-        return args.fleet_spread
-    return WEAK_FLEET_SPREAD if (max(args.gpus, 1) > 1 and args.multi == "weak") else 0.0
+    return args.fleet_spread if args.fleet_spread >= 0 else FLEET_SPREAD
 
 
 def make_scenario(args, directory):

@@ -94,19 +94,21 @@ __device__ __forceinline__ void shardWait(const View &V, const ShardP2P &S, int 
 }
 
 // Called by every thread after its remote stores: the last block to arrive publishes the epoch.  Ordering: every
-// thread's stores -> its device-scope fence -> the block barrier -> the ticket (device-scope atomic) -> observed by the
-// last block -> ONE system-scope fence (fences are cumulative: it orders everything that happened before it against the
-// flag stores that follow, for every observer in the system) -> the flag.  A system-scope fence in every thread instead
-// measured ~15 us per send kernel (r02d), which is why there is exactly one.
+// thread's stores -> the block barrier -> ONE system-scope fence per block by thread 0 (fences are cumulative: it orders
+// everything that happened before it, for every observer in the system) -> the ticket (device-scope atomic) -> observed
+// by the last block -> its fence -> the flag.  (A system-scope fence in EVERY thread cost several microseconds per send
+// kernel, r02d: each waits for the NVLink acknowledgement of the stores before it.)
 __device__ __forceinline__ bool shardLastBlock(int *ticket) {
     __shared__ int sLast;
-    __threadfence();
-    __syncthreads();
+    __syncthreads();                  // the block's stores happen before thread 0's fence (CTA barrier) ...
     if (threadIdx.x == 0) {
+        __threadfence_system();       // ... which is cumulative: one fence per block covers all of them
         const int t = atomicAdd(ticket, 1);
         sLast = (t == (int) gridDim.x - 1);
-        if (sLast) *ticket = 0;
-        if (sLast) __threadfence_system();
+        if (sLast) {
+            *ticket = 0;
+            __threadfence_system();   // acquire side of the ticket: every block's fence is ordered before the flag stores
+        }
     }
     __syncthreads();
     return sLast != 0;

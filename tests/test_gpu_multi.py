@@ -54,4 +54,4 @@ def test_four_ranks_8x12_dense_vs_reference():
 
 @pytest.mark.skipif(_gpus() < 4, reason="needs 4 GPUs")
 def test_four_ranks_strong_cut_of_30x30_vs_reference():
-    _run(4, [30, 30, 600, 50, 0.5, 10, 1], 29534)
+    _run(4, [30, 30, 600, 50, 0.5, 10, 1, 0.02], 29534)

@@ -610,7 +610,7 @@ def test_30x30_through_the_bench_window_vs_compiled_reference(scenario_dir):
     import os
     from cityflow_b200 import scenario
     from cityflow_b200.capi import CEngine
-    cfg = scenario.make_grid_scenario(scenario_dir, 30, 30, name="g30w", dense=dict(frac=0.5, interval=10.0, seed=1))
+    cfg = scenario.make_grid_scenario(scenario_dir, 30, 30, name="g30w", dense=dict(frac=0.5, interval=10.0, seed=1, fleet_spread=0.02))
     ref = H.RefDump.counts(cfg, 1230, os.cpu_count() or 8, 10)
     eng = CEngine(cfg)
     for s in range(1, 1231):
@@ -630,6 +630,7 @@ def test_30x30_through_the_bench_window_vs_compiled_reference(scenario_dir):
     mine = np.bincount(on["drivable"], weights=on["speed"], minlength=eng.n_lanes)
     assert np.all(np.abs(mine - rs) <= 1e-6 * np.maximum(mc, 1)), "per-lane speed sums differ"
     assert eng.vehicle_count() > 120000
+    assert eng.tie_count() == 0   # (the bench fleet: no entrant tie, so the reference's result is defined -- bench.py FLEET_SPREAD)
 
 
 def test_6x6_3600_steps_vs_port(cfg_6x6):
