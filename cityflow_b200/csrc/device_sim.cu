@@ -45,6 +45,7 @@
 #include <vector>
 
 #include "device_sim.h"
+#include "partition.h"
 #include "shard.h"
 
 namespace cfb {
@@ -1134,16 +1135,9 @@ void DeviceSim::shardConnect(const std::vector<void *> &peerBase) {
         P.nOut = std::max(I.nOutOf(q), 1);
     }
     I.peers.upload(peers);
-    // index tables: where my messages land in the receivers' mailboxes
-    std::vector<int> nbr, outPeer, outDst, inPeer, inDst;
-    for (int q = 0; q < W; ++q) {
-        if (q == me) continue;
-        if (I.bsize[me][q] + I.bsize[q][me] > 0) nbr.push_back(q);
-        int inBegAtQ = 0, outBegAtQ = 0;   // q's inBeg[me], q's outBeg[me]
-        for (int p = 0; p < me; ++p) { inBegAtQ += I.bsize[p][q]; outBegAtQ += I.bsize[q][p]; }
-        for (int k = 0; k < I.bsize[me][q]; ++k) { outPeer.push_back(q); outDst.push_back(inBegAtQ + k); }
-        for (int k = 0; k < I.bsize[q][me]; ++k) { inPeer.push_back(q); inDst.push_back(outBegAtQ + k); }
-    }
+    // index tables: where my messages land in the receivers' mailboxes (partition.h)
+    const SeamTables T = seamTables(I.bsize, me);
+    const std::vector<int> &nbr = T.nbr, &outPeer = T.outPeer, &outDst = T.outDst, &inPeer = T.inPeer, &inDst = T.inDst;
     if ((int) outPeer.size() != V.nBoundOut || (int) inPeer.size() != V.nBoundIn) throw std::runtime_error("shardConnect: boundary tables disagree");
     if ((int) nbr.size() > 120) throw std::runtime_error("shardConnect: too many neighbour ranks");
     std::vector<int> all;

@@ -34,4 +34,28 @@ struct Partition {
     int numBoundaryLanes() const;
 };
 
+// Where rank `me`'s seam messages land in the receivers' mailboxes (device_shard.cuh).  A rank lists the lanes it feeds
+// ("out", grouped by owner, ascending lane id inside a group) and the lanes it owns that a peer feeds ("in", grouped by
+// feeder); a mover message for out-entry j goes to entry outDst[j] of rank outPeer[j]'s IN list, a tail message for
+// in-entry j to entry inDst[j] of rank inPeer[j]'s OUT list.  Pure function of the boundary-size matrix
+// bsize[a][b] = |boundary[a][b]|, which every rank derives identically -- tests/test_dist_cpu.py lets two processes
+// compute their tables independently and checks that they meet.
+struct SeamTables {
+    std::vector<int> nbr;                         // ranks sharing a seam lane with `me`
+    std::vector<int> outPeer, outDst, inPeer, inDst;
+};
+inline SeamTables seamTables(const std::vector<std::vector<int>> &bsize, int me) {
+    SeamTables t;
+    const int W = (int) bsize.size();
+    for (int q = 0; q < W; ++q) {
+        if (q == me) continue;
+        if (bsize[me][q] + bsize[q][me] > 0) t.nbr.push_back(q);
+        int inBegAtQ = 0, outBegAtQ = 0;   // q's inBeg[me], q's outBeg[me]
+        for (int p = 0; p < me; ++p) { inBegAtQ += bsize[p][q]; outBegAtQ += bsize[q][p]; }
+        for (int k = 0; k < bsize[me][q]; ++k) { t.outPeer.push_back(q); t.outDst.push_back(inBegAtQ + k); }
+        for (int k = 0; k < bsize[q][me]; ++k) { t.inPeer.push_back(q); t.inDst.push_back(outBegAtQ + k); }
+    }
+    return t;
+}
+
 }  // namespace cfb

@@ -1,8 +1,7 @@
-"""Multi-process plumbing for bench.py (one process per GPU, launched by torch.distributed.run).
-
-Round 1 runs independent engine replicas per rank: the only cross-rank traffic is
-the barrier around the timed region and the max / sum reductions of the per-rank timings and
-vehicle-step counts.  The helpers work on any backend (nccl on GPUs, gloo in the CPU tests)."""
+"""Multi-process plumbing for bench.py (one process per GPU, launched by torch.distributed.run): the barrier around the
+timed regions and the max / sum reductions of the per-rank timings and vehicle-step counts.  The engine's own cross-rank
+traffic (seam records of a sharded run) does not go through here.  The helpers work on any backend
+(nccl on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
 import os

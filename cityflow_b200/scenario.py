@@ -5,9 +5,9 @@ flow: engine.cpp:106-164, config: engine.cpp:37-84).  BASELINE.json's configs ar
 the reference's ``tools/generator``; that tool is not available on the GPU box, so this module
 re-creates the same grid scenario from first principles (a regular lattice of 4-arm
 signalised intersections with one left / straight / right lane per approach and Hermite
-laneLink curves).  ``tests/test_scenario.py`` checks that the JSON produced here is identical,
-value for value, to what ``tools/generator/generate_grid_scenario.py`` writes (when the
-reference tree is present).
+laneLink curves).  ``tests/test_cpu.py::test_grid_generator_matches_reference_tool`` checks that the
+JSON produced here is identical, value for value, to what ``tools/generator/generate_grid_scenario.py``
+writes (when the reference tree is present).
 
 It also implements the dense "random walk" flow recipe from SURVEY.md Appendix A that reaches
 the ~1e5-vehicle operating point on the 30x30 grid.

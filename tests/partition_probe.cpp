@@ -29,6 +29,25 @@ int main(int argc, char **argv) {
         }
         printf("]");
     }
-    printf("], \"validate\": \"%s\"}\n", p.validate(n, 64.2).c_str());
+    printf("]");
+    if (argc >= 4) {   // seam tables of one rank (what DeviceSim::shardConnect uploads), with the rank's own lane lists
+        const int me = atoi(argv[3]);
+        std::vector<std::vector<int>> bsize(world, std::vector<int>(world, 0));
+        for (int a = 0; a < world; ++a) for (int b = 0; b < world; ++b) bsize[a][b] = (int) p.boundary[a][b].size();
+        const cfb::SeamTables t = cfb::seamTables(bsize, me);
+        auto arr = [](const char *name, const std::vector<int> &v) {
+            printf(", \"%s\": [", name);
+            for (size_t k = 0; k < v.size(); ++k) printf("%s%d", k ? "," : "", v[k]);
+            printf("]");
+        };
+        std::vector<int> outLanes, inLanes;   // the order DeviceSim::configureShard lists them in
+        for (int q = 0; q < world; ++q) {
+            outLanes.insert(outLanes.end(), p.boundary[me][q].begin(), p.boundary[me][q].end());
+            inLanes.insert(inLanes.end(), p.boundary[q][me].begin(), p.boundary[q][me].end());
+        }
+        arr("nbr", t.nbr); arr("out_peer", t.outPeer); arr("out_dst", t.outDst); arr("in_peer", t.inPeer); arr("in_dst", t.inDst);
+        arr("out_lanes", outLanes); arr("in_lanes", inLanes);
+    }
+    printf(", \"validate\": \"%s\"}\n", p.validate(n, 64.2).c_str());
     return 0;
 }
