@@ -88,6 +88,7 @@ public:
     std::vector<int> due;                                    // flows spawning this step, one entry per vehicle
     std::vector<FlowHot> hot;                                // hot[i] mirrors flows[i]'s runtime state (authoritative)
     std::vector<uint64_t> sortKeys;
+    std::vector<int> predicted;                              // this step's priority draws, predicted on a copy of the RNG (prefetch keys)
     std::vector<Pending> pendingSorted;
     std::vector<SpawnRec> batchTmp;
     std::unique_ptr<Routing> routing;
@@ -116,6 +117,7 @@ public:
     std::unordered_map<uint64_t, int> idToSlot;              // built lazily (get_leader)
     bool idMapValid = false;
     long long hostGenNs = 0, hostEnqueueNs = 0;
+    long long genFlowsNs = 0, genCreateNs = 0, genPlanNs = 0;   // breakdown of hostGenNs: flow clocks | vehicle creation | planRoute + records
     // sharded mode
     ShardTransport *transport = nullptr;                      // not owned
     std::function<void(std::vector<FinRec> &)> finishedHook;   // local list -> list of all ranks              // host time spent generating spawns / enqueuing
@@ -377,25 +379,36 @@ public:
             }
             f.currentTime += interval;
         }
-        if (due.size() >= 8) {
-            // Each creation costs a few cache misses (priority table, slot record) and nothing else; the
-            // keys are known in advance because the RNG can be run ahead on a copy: priority, thread
-            // index, priority, ... (engine.cpp:601-606).  A priority collision makes the real sequence
-            // leave the predicted one -- then the remaining prefetches are merely useless.
+        const auto tFlows = std::chrono::steady_clock::now();
+        genFlowsNs += std::chrono::duration_cast<std::chrono::nanoseconds>(tFlows - t0).count();
+        // Each creation costs a few cache misses (priority table, slot record) and nothing else; the keys are known in
+        // advance because the RNG can be run ahead on a copy: priority, thread index, priority, ... (engine.cpp:601-606).
+        // A priority collision makes the real sequence leave the predicted one -- then the remaining prefetches are merely
+        // useless.  The prefetches run a fixed distance ahead of the creations: a core tracks only a dozen or so outstanding
+        // line fills, so issuing all of a step's prefetches up front drops most of them (measured: 285 -> see profiles/).
+        const size_t nDue = due.size();
+        constexpr size_t PF = 12;
+        if (nDue >= 8) {
             std::mt19937 ahead = rnd;
-            const size_t nFree = freeSlots.size();
-            for (size_t k = 0; k < due.size(); ++k) {
-                pool.prefetch((int) ahead());
-                (void) ahead();
-                if (k < nFree) __builtin_prefetch(&slots[freeSlots[nFree - 1 - k]], 1);
-            }
+            predicted.resize(nDue);
+            for (size_t k = 0; k < nDue; ++k) { predicted[k] = (int) ahead(); (void) ahead(); }
         }
-        for (const int i : due) {
+        const size_t nFree = freeSlots.size();
+        auto prefetchFor = [&](size_t k) {
+            pool.prefetch(predicted[k]);
+            if (k < nFree) __builtin_prefetch(&slots[freeSlots[nFree - 1 - k]], 1);
+        };
+        if (nDue >= 8) for (size_t k = 0; k < std::min(PF, nDue); ++k) prefetchFor(k);
+        for (size_t k = 0; k < nDue; ++k) {
+            if (nDue >= 8 && k + PF < nDue) prefetchFor(k + PF);
+            const int i = due[k];
             const FlowStatic &fs = flowStatic[i];
             createVehicle(i, H[i].cnt++, fs.routeId, fs.tmplId, fs.firstRoad);
         }
         due.clear();
         batch.clear();
+        const auto tCreate = std::chrono::steady_clock::now();
+        genCreateNs += std::chrono::duration_cast<std::chrono::nanoseconds>(tCreate - tFlows).count();
         if (!pending.empty()) {
             // Engine::planRoute walks roads in file order, each road's buffer in spawn order
             // (road, arrival index) keys: same order as a stable sort by road, cheaper than moving structs
@@ -456,7 +469,9 @@ public:
         if (templates.size() != uploadedTemplates) { dev->uploadTemplates(templates); uploadedTemplates = templates.size(); }
         if ((size_t) routing->numPlans() != uploadedPlans) { dev->uploadPlans(*routing); uploadedPlans = routing->numPlans(); }
         dev->ensureSlotCapacity((int) slots.size());
-        hostGenNs += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        const auto tEnd = std::chrono::steady_clock::now();
+        genPlanNs += std::chrono::duration_cast<std::chrono::nanoseconds>(tEnd - tCreate).count();
+        hostGenNs += std::chrono::duration_cast<std::chrono::nanoseconds>(tEnd - t0).count();
     }
     // Engine::updateLog engine.cpp:518-554: positions of the running vehicles and the light states
     // after this step, one line.  Gathers from the device (synchronises), so stepping with
@@ -1272,6 +1287,9 @@ extern "C" int cfb_transfer_bytes(const cfb_engine *e, int64_t *h2d, int64_t *d2
 extern "C" int cfb_host_times(const cfb_engine *e, double *gen_ms, double *enqueue_ms) {
     if (gen_ms) *gen_ms = e->h.hostGenNs * 1e-6;
     if (enqueue_ms) *enqueue_ms = e->h.hostEnqueueNs * 1e-6;
+    if (getenv("CITYFLOW_B200_HOST_PROFILE"))
+        fprintf(stderr, "[cityflow_b200] spawner: flow clocks %.3f ms, vehicle creation %.3f ms, planRoute + records %.3f ms (totals)\n",
+                e->h.genFlowsNs * 1e-6, e->h.genCreateNs * 1e-6, e->h.genPlanNs * 1e-6);
     return CFB_OK;
 }
 

@@ -17,15 +17,29 @@ public:
     bool contains(int k) const { return find(k) >= 0; }
     int get(int k) const { long i = find(k); return i >= 0 ? cell_[i].val : -1; }
     void insert(int k, int v) {
-        if ((used_ + 1) * 2 > cap_) rehash(roomFor(size_ + 1));
+        if ((size_ + 1) * 4 > cap_) rehash(roomFor(size_ + 1));
         size_t i = hash(k);
         while (cell_[i].val >= 0) i = (i + 1) & (cap_ - 1);
-        if (cell_[i].val == EMPTY) ++used_;
         cell_[i].key = k; cell_[i].val = v; ++size_;
     }
+    // Backward-shift deletion: the entries behind the hole move up while that keeps them reachable from their home
+    // cell, so there are no tombstones and a table whose population is steady (vehicles arrive as fast as they leave)
+    // never has to be rebuilt.
     void erase(int k) {
-        long i = find(k);
-        if (i >= 0) { cell_[i].val = DELETED; --size_; }
+        long f = find(k);
+        if (f < 0) return;
+        size_t i = (size_t) f, j = i;
+        const size_t mask = cap_ - 1;
+        for (;;) {
+            j = (j + 1) & mask;
+            if (cell_[j].val < 0) break;
+            const size_t h = hash(cell_[j].key);
+            // cell j may move into the hole i unless its home h lies cyclically in (i, j]
+            const bool homeBetween = i <= j ? (h > i && h <= j) : (h > i || h <= j);
+            if (!homeBetween) { cell_[i] = cell_[j]; i = j; }
+        }
+        cell_[i].val = EMPTY;
+        --size_;
     }
     void clear() { rehash(1 << 12, false); }
     size_t size() const { return size_; }
@@ -42,19 +56,18 @@ public:
         return out;
     }
 private:
-    enum { EMPTY = -1, DELETED = -2 };
+    enum { EMPTY = -1 };
     struct Cell { int key, val; };   // val >= 0: slot; one 8-byte cell = one cache line touched per probe
     size_t hash(int k) const { return ((uint32_t) k * 2654435761u) & (cap_ - 1); }
     long find(int k) const {
         size_t i = hash(k);
         while (cell_[i].val != EMPTY) {
-            if (cell_[i].val >= 0 && cell_[i].key == k) return (long) i;
+            if (cell_[i].key == k) return (long) i;
             i = (i + 1) & (cap_ - 1);
         }
         return -1;
     }
-    // table size for n live entries: load <= 1/4 after a rehash.  Sized from the LIVE count -- cells
-    // of vehicles that left are dropped by the rehash, so a long run does not grow the table.
+    // table size for n live entries: load <= 1/4 (grown only when the population grows)
     static size_t roomFor(size_t n) {
         size_t c = 1 << 12;
         while (c < n * 4) c *= 2;
@@ -62,11 +75,11 @@ private:
     }
     void rehash(size_t n, bool keep = true) {
         std::vector<Cell> old = std::move(cell_);
-        cap_ = n; cell_.assign(n, Cell{0, EMPTY}); used_ = size_ = 0;
+        cap_ = n; cell_.assign(n, Cell{0, EMPTY}); size_ = 0;
         if (keep) for (const Cell &c : old) if (c.val >= 0) insert(c.key, c.val);
     }
     std::vector<Cell> cell_;
-    size_t cap_ = 0, used_ = 0, size_ = 0;
+    size_t cap_ = 0, size_ = 0;
 };
 
 }  // namespace cfb

@@ -84,6 +84,7 @@ void DeviceSim::uploadPlans(const Routing &routing) {
     if (H.V.lcOn) uploadLanePlans(routing);
 }
 void DeviceSim::ensureSlotCapacity(int slots) {
+    if (getenv("CFB_EMU_HOST_ONLY")) return;
     if (slots > impl_->H.slotCap) throw std::runtime_error("device_sim_emu: slot capacity of the emulated device exceeded");
 }
 void DeviceSim::uploadLanePlans(const Routing &routing) { impl_->H.setPlans(routing); }
@@ -107,6 +108,21 @@ void DeviceSim::step(const SpawnRec *recs, int n) {
     stageStep(recs, n);
     HostSim &H = impl_->H;
     View &V = H.V;
+    // Spawner microbenchmark (CFB_EMU_HOST_ONLY=<population>): no kernels; once <population> vehicles are alive the
+    // oldest ones "leave" at the rate new ones arrive, so the host's priority table / slot table sit at a steady size.
+    static const char *hostOnly = getenv("CFB_EMU_HOST_ONLY");
+    if (hostOnly) {
+        static std::vector<int> fifo;
+        static size_t head = 0;
+        const size_t target = (size_t) atol(hostOnly);
+        for (int k = 0; k < n; ++k) fifo.push_back(recs[k].slot);
+        while (fifo.size() - head > target && H.ctrl.finCount < H.V.finCap) {
+            H.finSlots[H.ctrl.finCount++] = make_int2(fifo[head++], (int) steps_);
+            H.delStep[0] = 0;
+        }
+        steps_ += 1;
+        return;
+    }
     H.run(G, [&](int b, int nb) { phase_ingest(V, b, nb); });
     H.run(G, [&](int b, int nb) { phase_notify(V, b, nb); });
     H.run(G, [&](int b, int nb) { phase_control(V, b, nb); });
