@@ -262,7 +262,7 @@ def run_reference_arm(args):
         cfg = make_scenario(args, d)
         r = reference_run(cfg, args.steps, args.prefill + args.warmup, threads)
         sweep = None
-        if not args.no_sweep and r["kind"] == "reference":
+        if not args.no_sweep and r["kind"] == "reference" and args.gpus <= 1:   # (one operating point: the N=1 workload)
             try:
                 sweep = reference_sweep(cfg, min(args.steps, 50), args.prefill + args.warmup, nproc)
             except Exception as ex:  # noqa: BLE001

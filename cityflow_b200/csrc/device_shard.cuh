@@ -5,6 +5,8 @@
 //
 //   flags   [3][world] int    flags[k][src] = last epoch for which rank `src` completed its writes of kind k
 //                              k = 0 movers of the step, 1 tails + blocker list of the step, 2 finished-vehicle marks
+//           [8][world] int    activeOf[E % 8][src] = rank `src`'s share of get_vehicle_count() after step E (every rank
+//                              stores it into every arena: the collective count needs no all-reduce, k_sum_active)
 //   delStep [slotCap]   int   step at which the vehicle of a slot left the network (every rank writes here)
 //   blkIn   [2][world][1 + BLK_IN_CAP] int2   this step's blocker changes of a NEIGHBOUR rank, count in [0].x
 //   moverIn [2][nBoundIn]  MoverMsg            entrants of the lanes this rank owns and a peer feeds
@@ -24,7 +26,8 @@
 namespace cfb {
 
 constexpr int BLK_IN_CAP = 1 << 13;     // blocker changes per step sent to one neighbour (8 bytes each)
-constexpr int SHARD_FLAG_KINDS = 3;
+constexpr int SHARD_ACT_RING = 8;       // per-step vehicle counts of the other ranks: a ring deeper than any rank can run ahead
+constexpr int SHARD_FLAG_KINDS = 3 + SHARD_ACT_RING;   // flag words 0..2, then activeOf[E % ring][src]
 constexpr long long SHARD_SPIN_LIMIT_NS = 4000000000LL;   // 4 s
 
 struct __align__(16) TailMsg {     // owner -> feeder: Drivable::getLastVehicle of a boundary lane
@@ -223,7 +226,11 @@ __device__ __forceinline__ void sendTailsBody(const View &V, const ShardP2P &S) 
     }
     if (shardLastBlock(S.ticket + 1) && threadIdx.x == 0) {   // (the thread that issued the system fence)
         V.ctrl->nBlkUpd = 0;
-        for (int k = 0; k < S.nNbr; ++k) *(volatile int *) (S.peers[S.nbr[k]].flags + 1 * S.world + S.me) = E;
+        for (int k = 0; k < S.nNbr; ++k) *(volatile int *) (S.peers[S.nbr[k]].flags + 1 * S.world + S.me) = E;   // (what the neighbours wait for goes first)
+        const int act = V.ctrl->active;                        // final for this step: k_move is done
+        for (int q = 0; q < S.world; ++q)
+            if (q != S.me) *(volatile int *) (S.peers[q].flags + (3 + E % SHARD_ACT_RING) * S.world + S.me) = act;
+        __threadfence_system();
         for (int q = 0; q < S.world; ++q)
             if (q != S.me) *(volatile int *) (S.peers[q].flags + 2 * S.world + S.me) = E;
     }
@@ -269,5 +276,23 @@ __global__ void __launch_bounds__(128) k_xchg_tails(View V, ShardP2P S) { shardP
 
 // Host query support: every rank's finished-vehicle marks through the last completed step have landed here.
 __global__ void k_wait_fin(View V, ShardP2P S) { shardWait(V, S, 2, V.ctrl->epoch, true); }
+
+// The collective get_vehicle_count() (engine.cpp:615-617 over the whole network) without a collective: every rank's share
+// of the last completed step is already in this arena; wait for the stamps, add them up, hand the sum to the host
+// through its mapped mirror (words 4, 5 = sum, epoch).
+__global__ void k_sum_active(View V, ShardP2P S) {
+    const int E = V.ctrl->epoch;
+    shardWait(V, S, 2, E, true);
+    if (threadIdx.x == 0 && V.hostMirror) {
+        long long sum = V.ctrl->active;
+        for (int q = 0; q < S.world; ++q)
+            if (q != S.me) sum += *(volatile int *) (S.flags + (3 + E % SHARD_ACT_RING) * S.world + q);
+        volatile int *m = V.hostMirror;
+        m[4] = (int) sum;
+        m[6] = V.ctrl->error;
+        __threadfence_system();
+        m[5] = E;
+    }
+}
 
 }  // namespace cfb

@@ -1202,6 +1202,24 @@ void DeviceSim::recvTails() {
     launches_ += 1;
 }
 
+// Network-wide vehicle count over the peer-memory arena (k_sum_active); false: not available, use shardCounts().
+bool DeviceSim::shardVehicleCount(int *activeOut) {
+    Impl &I = *impl_;
+    if (!I.p2p || !I.V.hostMirror) return false;
+    k_sum_active<<<1, 32, 0, I.stream>>>(I.V, I.S);
+    launches_ += 1;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (long spin = 0; I.hMirror[5] < (int) I.epochHost; ++spin) {
+        if ((spin & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+            CFB_CUDA(cudaStreamSynchronize(I.stream));
+            if (I.hMirror[5] < (int) I.epochHost) return false;
+        }
+        __builtin_ia32_pause();
+    }
+    *activeOut = I.hMirror[4];
+    return true;
+}
+
 void DeviceSim::shardCounts(ShardTransport *t, int32_t *laneOut, int *activeOut) {
     Impl &I = *impl_;
     const int n = laneOut ? 1 + I.V.nLanes : 1;   // the vehicle count alone is a 4-byte all-reduce

@@ -130,6 +130,7 @@ public:
     void sealBlk();
     void applyBlk();
     void shardCounts(ShardTransport *t, int32_t *laneOut, int *activeOut);   // global sums (collective)
+    bool shardVehicleCount(int *activeOut);        // the same count over the peer-memory arena (no all-reduce); false = unavailable
     void shardWaitingCounts(ShardTransport *t, int32_t *laneOut);
     void shardGatherFinished(ShardTransport *t, std::vector<FinRec> &inout);
 

@@ -1487,8 +1487,8 @@ int64_t cfb_shard_vehicle_count(cfb_engine *e) {
     CFB_TRY(e,
         if (!e->h.transport) return (int64_t) e->h.dev->vehicleCount();
         int a = 0;
-        e->h.dev->shardCounts(e->h.transport, nullptr, &a);
-        e->h.d2hBytes += 4;
+        if (!e->h.dev->shardVehicleCount(&a)) e->h.dev->shardCounts(e->h.transport, nullptr, &a);
+        e->h.d2hBytes += 8;
         e->h.checkDevice();
         return (int64_t) a;
     )

@@ -316,6 +316,7 @@ void DeviceSim::configureShard(int, int, const std::vector<unsigned char> &, con
 DeviceSim::ShardArena DeviceSim::shardArena() { notEmulated("sharding"); return ShardArena{nullptr, 0}; }
 void DeviceSim::shardConnect(const std::vector<void *> &) { notEmulated("sharding"); }
 bool DeviceSim::shardIsP2P() const { return false; }
+bool DeviceSim::shardVehicleCount(int *) { return false; }
 bool DeviceSim::timingOn() const { return false; }
 void DeviceSim::shardTimeMark(int) {}
 void DeviceSim::shardTimeCollect() {}
