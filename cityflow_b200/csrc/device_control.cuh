@@ -6,12 +6,15 @@
 namespace cfb {
 
 // ------------------------------------------------------------------------------------------
-// Cross::canPass roadnet.cpp:603-676.  foeTerms() gathers what it reads of the foe: called by k_notify for every cross
-// side it notifies (`n.dist`, `n.pos` set; `foeLinkW` = linkInfo.w of the notified vehicle's laneLink: turn | type << 8).
-// Same FP64 expressions as the reference, on the same committed state (nothing between k_notify and k_control changes
-// a vehicle).  (A first version also evaluated the foe's reach steps and the Floyd walk here: k_control 35 -> 24.7 us but
-// k_notify 16.9 -> 24.9 us at 1.3e5 vehicles and 97 -> 182 us at 1.5e6 -- every notification paid for what only some
-// askers need; profiles/r02e.)
+// Cross::canPass roadnet.cpp:603-676, split at the line between what depends on the foe alone and what depends on
+// the asking vehicle.  foeTerms() is the foe half: called by k_notify for every cross side it notifies (`n.dist`,
+// `n.pos` set; `foeLinkW` = linkInfo.w of the notified vehicle's laneLink: turn | type << 8).  Same FP64
+// expressions as the reference, evaluated on the same committed state (nothing between k_notify and k_control
+// changes a vehicle, a blocker or delStep).
+// Measured (profiles/): against the asker doing everything (round 1) k_control 35.0 -> 24.7 us and k_notify 16.9 ->
+// 24.9 us at 1.3e5 vehicles, step 0.0936 -> with PDL 0.0894 ms.  A lighter record (k_notify only gathers the foe's
+// fields, the asker computes the reach steps and walks the blocker chain) was tried too: k_notify 20.5 / k_control 33.2 us,
+// step 0.0963 ms at 1.3e5 vehicles, 2 % faster only at 1.5e6 -- this form stays.
 __device__ __forceinline__ void foeTerms(const View &V, Notify &n, int foeLinkW) {
     const int fp = n.pos;
     const int4 fid = V.ids[fp];
@@ -23,11 +26,29 @@ __device__ __forceinline__ void foeTerms(const View &V, Notify &n, int foeLinkW)
     int fl = (foeLinkW >> 8) << 8;
     if (canYield(FT, foeSpeed, d2)) fl |= NF_CAN_YIELD;
     if (d2 + FT.len < 0) fl |= NF_PASSED;
+    n.steps = d2 > 0 ? reachSteps(foeSpeed, d2, (foeLinkW & 1) ? FT.turnSpeed : FT.maxSpeed, FT.usualPosAcc, V.dt) : 0;
+    // deadlock detection over the committed blocker chain (Floyd), roadnet.cpp:662-674.  A reference to a vehicle
+    // that left the network in the previous step counts as null (Engine::threadUpdateAction drops it,
+    // engine.cpp:419-421): evaluated lazily here.
+    const int prevStep = V.ctrl->step - 1;
+    auto blockerOf = [&](int s) -> int {
+        int b = V.blk[s];
+        if (b >= 0 && V.delStep[b] == prevStep) b = -1;
+        return b;
+    };
+    int fast = fid.x, slow = fid.x;
+    while (fast >= 0) {
+        int fb = blockerOf(fast);
+        if (fb < 0) break;
+        slow = blockerOf(slow);
+        fast = blockerOf(fb);
+        if (slow == fast) {
+            fl |= NF_CYCLE;
+            break;
+        }
+    }
     n.flags = fl;
-    n.foeSpeed = foeSpeed;
-    n.foeAcc = FT.usualPosAcc;
-    n.foeTarget = (foeLinkW & 1) ? FT.turnSpeed : FT.maxSpeed;
-    n.pad = 0;
+    n.pad0 = n.pad1 = n.pad2 = 0;
 }
 
 // The asking half.  `myLinkW` = linkInfo.w of the asking vehicle's laneLink; `f` = the other side's record.
@@ -44,7 +65,7 @@ __device__ __forceinline__ bool canPass(const View &V, const Notify &f, int myLi
             yield = -1;
         } else {
             if (d2 > 0) {
-                const int foeSteps = reachSteps(f.foeSpeed, d2, f.foeTarget, f.foeAcc, V.dt);
+                const int foeSteps = f.steps;
                 const int mySteps = reachSteps(mySpeed, d1, (myLinkW & 1) ? T.turnSpeed : T.maxSpeed, T.usualPosAcc, V.dt);
                 if (foeSteps > mySteps) yield = -1;
                 else if (t1 < t2) yield = 1;
@@ -63,28 +84,7 @@ __device__ __forceinline__ bool canPass(const View &V, const Notify &f, int myLi
             }
         }
     }
-    if (yield == 1) {
-        // deadlock detection over the committed blocker chain (Floyd), roadnet.cpp:662-674.  A reference to a vehicle
-        // that left the network in the previous step counts as null (Engine::threadUpdateAction drops it,
-        // engine.cpp:419-421): evaluated lazily here.
-        const int prevStep = V.ctrl->step - 1;
-        auto blockerOf = [&](int s) -> int {
-            int b = V.blk[s];
-            if (b >= 0 && V.delStep[b] == prevStep) b = -1;
-            return b;
-        };
-        int fast = f.slot, slow = f.slot;
-        while (fast >= 0) {
-            int fb = blockerOf(fast);
-            if (fb < 0) break;
-            slow = blockerOf(slow);
-            fast = blockerOf(fb);
-            if (slow == fast) {
-                yield = -1;
-                break;
-            }
-        }
-    }
+    if (yield == 1 && (f.flags & NF_CYCLE)) yield = -1;
     return yield == -1;
 }
 

@@ -76,7 +76,7 @@ __device__ __forceinline__ void pdlEnter() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __global__ void __launch_bounds__(256) k_ingest(View V) { pdlEnter(); phase_ingest(V, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(256, 5) k_notify(View V) { pdlEnter(); phase_notify(V, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_notify(View V) { pdlEnter(); phase_notify(V, blockIdx.x, gridDim.x); }
 
 }  // namespace cfb
 #include "device_control.cuh"

@@ -16,18 +16,16 @@ struct __align__(16) Notify {  // one side of one Cross (roadnet.h:122-124), epo
     double dist;
     int pos;
     int epoch;
-    // Everything Cross::canPass (roadnet.cpp:603-676) reads of the NOTIFIED vehicle -- it is the foe of everybody asking
-    // from the crossing link -- gathered once here by k_notify (one lane per cross, no divergence), so that the asking
-    // vehicle in k_control finds it in ONE load instead of at the end of a chain notify -> ids / kin / nav -> template:
-    // see foeTerms().  The FP64 work that only some askers need (the foe's reach steps, the Floyd walk over its blocker
-    // chain) stays with the asker; it needs no further loads for the former.
-    int slot, prio, enterLL;          // foe vehicle handle, Vehicle::priority, enterLaneLinkTime
+    // The terms of Cross::canPass (roadnet.cpp:603-676) that depend on the NOTIFIED vehicle alone -- it is the foe of
+    // everybody asking from the crossing link -- evaluated once here by k_notify (one lane per cross, no divergence)
+    // instead of once per asking vehicle at the end of k_control's dependent-load chain: see foeTerms().
+    int slot, prio, enterLL, steps;   // foe vehicle handle, Vehicle::priority, enterLaneLinkTime, reach steps (dist > 0)
     int flags;                        // NF_* | RoadLinkType of the foe's link << 8
-    double foeSpeed, foeAcc, foeTarget;   // speed, usualPosAcc, turnSpeed or maxSpeed (the arguments of getReachSteps)
-    double pad;
+    int pad0, pad1, pad2;
 };
 constexpr int NF_CAN_YIELD = 1;       // Vehicle::canYield(dist) of the foe (vehicle.cpp:284-287)
 constexpr int NF_PASSED = 2;          // dist + len < 0: the foe's tail has cleared the cross (roadnet.cpp:657)
+constexpr int NF_CYCLE = 4;           // the foe's committed blocker chain runs into a cycle (Floyd, roadnet.cpp:662-674)
 
 struct __align__(16) Tail {  // last vehicle of a drivable (Drivable::getLastVehicle), pos < 0 when empty
     double dis, len, speed;
