@@ -3,10 +3,36 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <utility>
 #include <vector>
+#include <sys/mman.h>
 
 namespace cfb {
+
+// Allocator for the two tables the spawn loop hits at random (priority table, slot records: tens of MB at 1e6 vehicles):
+// 2 MiB-aligned blocks with MADV_HUGEPAGE, so that a random access costs a cache miss but not a TLB miss on top.
+template <class T>
+struct HugePageAllocator {
+    using value_type = T;
+    HugePageAllocator() = default;
+    template <class U> HugePageAllocator(const HugePageAllocator<U> &) {}
+    T *allocate(size_t n) {
+        const size_t bytes = n * sizeof(T);
+        if (bytes < ((size_t) 1 << 21)) return static_cast<T *>(::operator new(bytes));
+        const size_t rounded = (bytes + ((size_t) 1 << 21) - 1) & ~(((size_t) 1 << 21) - 1);
+        void *p = std::aligned_alloc((size_t) 1 << 21, rounded);
+        if (!p) throw std::bad_alloc();
+        madvise(p, rounded, MADV_HUGEPAGE);
+        return static_cast<T *>(p);
+    }
+    void deallocate(T *p, size_t n) {
+        if (n * sizeof(T) < ((size_t) 1 << 21)) ::operator delete(p); else std::free(p);
+    }
+    template <class U> bool operator==(const HugePageAllocator<U> &) const { return true; }
+    template <class U> bool operator!=(const HugePageAllocator<U> &) const { return false; }
+};
 
 // Open-addressing hash map priority -> slot: Engine::checkPriority (engine.cpp:601) is on the
 // per-spawn path; the reference's ordered std::map is only materialised (sorted) when an API call
@@ -74,12 +100,38 @@ private:
         return c;
     }
     void rehash(size_t n, bool keep = true) {
-        std::vector<Cell> old = std::move(cell_);
+        std::vector<Cell, HugePageAllocator<Cell>> old = std::move(cell_);
         cap_ = n; cell_.assign(n, Cell{0, EMPTY}); size_ = 0;
         if (keep) for (const Cell &c : old) if (c.val >= 0) insert(c.key, c.val);
     }
-    std::vector<Cell> cell_;
+    std::vector<Cell, HugePageAllocator<Cell>> cell_;
     size_t cap_ = 0, size_ = 0;
+};
+
+// The same map cut into four by the top two bits of the (uniformly random) priority, so that four threads can each own a
+// quarter of it while a step's vehicles are created (host_engine.cpp, parallel creation); everywhere else it behaves
+// like one PriorityMap.
+class PriorityMap4 {
+public:
+    static int part(int k) { return (int) ((uint32_t) k >> 30); }
+    PriorityMap &sub(int p) { return m_[p].m; }
+    bool contains(int k) const { return m_[part(k)].m.contains(k); }
+    int get(int k) const { return m_[part(k)].m.get(k); }
+    void insert(int k, int v) { m_[part(k)].m.insert(k, v); }
+    void erase(int k) { m_[part(k)].m.erase(k); }
+    void clear() { for (auto &m : m_) m.m.clear(); }
+    size_t size() const { size_t n = 0; for (auto &m : m_) n += m.m.size(); return n; }
+    size_t capacity() const { size_t n = 0; for (auto &m : m_) n += m.m.capacity(); return n; }
+    void prefetch(int k) const { m_[part(k)].m.prefetch(k); }
+    std::vector<std::pair<int, int>> sorted() const {
+        std::vector<std::pair<int, int>> out;
+        for (auto &m : m_) { auto s = m.m.sorted(); out.insert(out.end(), s.begin(), s.end()); }
+        std::sort(out.begin(), out.end());
+        return out;
+    }
+private:
+    struct alignas(128) Padded { PriorityMap m; };   // each quarter's size counter on its own cache line (four threads insert at once)
+    Padded m_[4];
 };
 
 }  // namespace cfb
