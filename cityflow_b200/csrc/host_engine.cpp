@@ -356,11 +356,12 @@ public:
         }
     };
     std::unique_ptr<Workers> workers;
-    // Opt-in (CITYFLOW_B200_PARALLEL_SPAWN_MIN=<vehicles per step from which the workers are used>; 0 = never, the
-    // default): measured on 8 cores with the tables of a 1e6-vehicle run, spawn generation 190 -> 152 us per step (1451
-    // vehicles per step), 82 -> 63 us (725 per step) -- the RNG, the slot hand-out and the flow clocks stay sequential -- which
-    // does not buy enough to put threads into the default path of a bit-exact engine.
-    int parallelSpawnMin = 0;
+    // Used for steps that spawn at least this many vehicles (CITYFLOW_B200_PARALLEL_SPAWN_MIN; 0 = never): in practice the
+    // ranks of a 4- or 8-GPU run, which replicate 725 / 1451 creations per step; the single-GPU and 2-GPU workloads stay
+    // on the sequential loop.  Measured on a B200 host (4 ranks, 30x120, profiles/r02i): spawn generation 147 -> 95 us per
+    // step, end to end 0.260 -> 0.161 ms per step, parity_check equal.  The RNG, the slot hand-out and the flow clocks stay
+    // sequential.
+    int parallelSpawnMin = 512;
     std::vector<int> parSlot, parIndex;
 
     std::vector<uint32_t> parMine[Workers::T];
