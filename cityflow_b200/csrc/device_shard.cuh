@@ -68,11 +68,19 @@ struct ShardP2P {                  // by-value kernel argument
     int *ticket;                   // 2 ints: block tickets of the two sending kernels
 };
 
+#ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long shardNow() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ __forceinline__ void shardPause() { __nanosleep(100); }
+#else   // tests/device_sim_emu.cpp runs these bodies on the host: every poll counts as a millisecond, so a flag that never
+        // comes (a protocol error) trips the time-out instead of spinning for ever
+static unsigned long long g_shardClock = 0;
+inline unsigned long long shardNow() { return g_shardClock += 1000000ULL; }
+inline void shardPause() {}
+#endif
 
 // Block-wide: wait until every neighbour's flag of `kind` has reached epoch E.
 __device__ __forceinline__ void shardWait(const View &V, const ShardP2P &S, int kind, int E, bool allRanks) {
@@ -88,7 +96,7 @@ __device__ __forceinline__ void shardWait(const View &V, const ShardP2P &S, int 
                     atomicOr(&V.ctrl->error, ERR_SHARD_TIMEOUT);
                     break;
                 }
-                __nanosleep(100);
+                shardPause();
             }
         }
         __threadfence_system();   // acquire: the mailbox reads below come after the flag reads
@@ -118,8 +126,10 @@ __device__ __forceinline__ bool shardLastBlock(int *ticket) {
 }
 // programmatic dependent launch (see pdlEnter() in device_sim.cu)
 __device__ __forceinline__ void shardPdlEnter() {
+#ifdef __CUDACC__
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 
 // After k_control: one warp per boundary lane this rank feeds; the record goes straight into the owner's arena.

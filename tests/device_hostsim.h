@@ -24,6 +24,7 @@ namespace cfb { namespace cg = cooperative_groups; }
 #define phase_control phase_control_coop   // the probes then run the cooperative variant as k_control's body
 #endif   // (+ device_lc.cuh, kernels included: blockIdx / gridDim are globals here)
 #include "device_phases_b.cuh"
+#include "device_shard.cuh"      // the seam protocol's kernel bodies (peer-memory form), run on the emulated warp too
 
 
 namespace cfbtest {

@@ -12,6 +12,7 @@
 // phases, custom speed, plans, reset).  Not emulated (throw): sharding, snapshots, device-resident
 // observations / actions, timing.
 #include "device_hostsim.h"
+#include "partition.h"
 
 #include <stdexcept>
 
@@ -26,6 +27,33 @@ struct DeviceSim::Impl {
     bool phaseDirty = false;
     std::vector<int> offHost;
 };
+
+// ---- sharding over "peer memory": the ranks of a loop-back group (host_engine.cpp cfb_shard_group_*) live in one process, a
+// peer's arena is the other engine's arrays.  Same kernel bodies as on the GPU (device_shard.cuh); what is not emulated is
+// the staged NCCL form and everything collective. ----
+struct EmuArena {   // what DeviceSim::shardArena() hands out here: where a peer finds this rank's mailboxes
+    int *flags, *delStep;
+    int2 *blkIn;
+    MoverMsg *moverIn;
+    TailMsg *tailIn;
+    int nIn, nOut;
+};
+struct ShardEmu {
+    int rank = 0, world = 1;
+    std::vector<std::vector<int>> bsize;
+    cfbtest::Buf<unsigned char> owned;
+    cfbtest::Buf<int> boundOut, boundIn, ing, flags, ints;
+    cfbtest::Buf<int2> blkUpd, blkIn;
+    cfbtest::Buf<MoverMsg> moverIn;
+    cfbtest::Buf<TailMsg> tailIn;
+    cfbtest::Buf<ShardPeer> peers;
+    std::vector<unsigned char> ownedHost;
+    EmuArena arena{};
+    ShardP2P S{};
+    bool connected = false;
+};
+static std::map<const DeviceSim *, ShardEmu> g_shardEmu;
+
 
 static void notEmulated(const char *what) { throw std::runtime_error(std::string("device_sim_emu: ") + what + " is not emulated"); }
 
@@ -243,8 +271,14 @@ void DeviceSim::debugDump(std::vector<DebugRec> &out) {
     HostSim &H = impl_->H;
     const int lastStep = H.ctrl.step - 1;
     out.clear();
+    const std::vector<unsigned char> *ownedHost = nullptr;   // one rank of a loop-back group: its own drivables only (the rest holds ghost data)
+    {
+        auto it = g_shardEmu.find(this);
+        if (it != g_shardEmu.end() && !it->second.ownedHost.empty()) ownedHost = &it->second.ownedHost;
+    }
     for (int d = 0; d < H.V.nDrv; ++d)
         for (int k = 0; k < H.count[d]; ++k) {
+            if (ownedHost && !(*ownedHost)[d]) break;
             const int p = H.off[d] + k;
             DebugRec r{};
             r.slot = H.ids[p].x; r.drivable = d;
@@ -310,38 +344,106 @@ void DeviceSim::setVehiclePlan(int slot, int planId, int planIdx, int nextDrv) {
     else H.slotInfo[slot].z = planId;
 }
 
-// ---- not emulated ----
-void DeviceSim::configureShard(int, int, const std::vector<unsigned char> &, const std::vector<std::vector<int>> &, const std::vector<std::vector<int>> &,
-                               const std::vector<std::vector<int>> &, const std::vector<unsigned char> &) { notEmulated("sharding"); }
-DeviceSim::ShardArena DeviceSim::shardArena() { notEmulated("sharding"); return ShardArena{nullptr, 0}; }
-void DeviceSim::shardConnect(const std::vector<void *> &) { notEmulated("sharding"); }
-bool DeviceSim::shardIsP2P() const { return false; }
+void DeviceSim::configureShard(int rank, int world, const std::vector<unsigned char> &owned, const std::vector<std::vector<int>> &feedPerPeer,
+                               const std::vector<std::vector<int>> &ownPerPeer, const std::vector<std::vector<int>> &boundarySize,
+                               const std::vector<unsigned char> &ownedRoadLinks) {
+    ShardEmu &E = g_shardEmu[this];
+    HostSim &H = impl_->H;
+    View &V = H.V;
+    E.rank = rank; E.world = world; E.bsize = boundarySize; E.ownedHost = owned;
+    std::vector<unsigned char> own3 = owned;
+    for (int q = 0; q < world; ++q) for (int l : feedPerPeer[q]) own3[l] = 2;
+    E.owned.assign(own3.begin(), own3.end());
+    V.owned = E.owned.p();
+    std::vector<int> lanes, links, rls;
+    for (int l = 0; l < V.nLanes; ++l) if (own3[l]) lanes.push_back(l);
+    for (int k = 0; k < V.nLinks; ++k) if (owned[V.nLanes + k]) links.push_back(k);
+    for (int r = 0; r < (int) ownedRoadLinks.size(); ++r) if (ownedRoadLinks[r]) rls.push_back(r);
+    V.nIngLanes = (int) lanes.size(); V.nIngLinks = (int) links.size(); V.nIngRL = (int) rls.size();
+    E.ing.clear();
+    E.ing.insert(E.ing.end(), lanes.begin(), lanes.end()); E.ing.insert(E.ing.end(), links.begin(), links.end()); E.ing.insert(E.ing.end(), rls.begin(), rls.end());
+    E.ing.push_back(0);
+    V.ingLanes = E.ing.p(); V.ingLinks = E.ing.p() + lanes.size(); V.ingRL = E.ing.p() + lanes.size() + links.size();
+    E.boundOut.clear(); E.boundIn.clear();
+    for (int q = 0; q < world; ++q) {
+        E.boundOut.insert(E.boundOut.end(), feedPerPeer[q].begin(), feedPerPeer[q].end());
+        E.boundIn.insert(E.boundIn.end(), ownPerPeer[q].begin(), ownPerPeer[q].end());
+    }
+    V.nBoundOut = (int) E.boundOut.size(); V.nBoundIn = (int) E.boundIn.size();
+    if (E.boundOut.empty()) E.boundOut.push_back(0);
+    if (E.boundIn.empty()) E.boundIn.push_back(0);
+    V.boundOut = E.boundOut.p(); V.boundIn = E.boundIn.p();
+    V.blkUpdCap = BLK_IN_CAP;
+    E.blkUpd.assign(1 + V.blkUpdCap, make_int2(0, 0));
+    V.blkUpd = E.blkUpd.p();
+}
+DeviceSim::ShardArena DeviceSim::shardArena() {
+    ShardEmu &E = g_shardEmu[this];
+    HostSim &H = impl_->H;
+    if (E.flags.empty()) {
+        E.flags.assign((size_t) SHARD_FLAG_KINDS * E.world, 0);
+        E.blkIn.assign((size_t) 2 * E.world * (1 + BLK_IN_CAP), make_int2(0, 0));
+        E.moverIn.assign((size_t) 2 * std::max(H.V.nBoundIn, 1), MoverMsg{});
+        E.tailIn.assign((size_t) 2 * std::max(H.V.nBoundOut, 1), TailMsg{});
+        E.arena = EmuArena{E.flags.p(), H.delStep.p(), E.blkIn.p(), E.moverIn.p(), E.tailIn.p(), std::max(H.V.nBoundIn, 1), std::max(H.V.nBoundOut, 1)};
+    }
+    return ShardArena{&E.arena, sizeof(EmuArena)};
+}
+void DeviceSim::shardConnect(const std::vector<void *> &peerBase) {
+    ShardEmu &E = g_shardEmu[this];
+    const int W = E.world, me = E.rank;
+    E.peers.assign(W, ShardPeer{});
+    for (int q = 0; q < W; ++q) {
+        const EmuArena &A = *static_cast<const EmuArena *>(peerBase[q]);
+        ShardPeer &P = E.peers[q];
+        P.flags = A.flags; P.delStep = A.delStep; P.blkIn = A.blkIn + (size_t) me * (1 + BLK_IN_CAP);
+        P.moverIn = A.moverIn; P.tailIn = A.tailIn; P.nIn = A.nIn; P.nOut = A.nOut;
+    }
+    const SeamTables T = seamTables(E.bsize, me);
+    E.ints.clear();
+    const size_t oN = 0, oOP = oN + T.nbr.size(), oOD = oOP + T.outPeer.size(), oIP = oOD + T.outDst.size(), oID = oIP + T.inPeer.size(), oT = oID + T.inDst.size();
+    for (const std::vector<int> *v : {&T.nbr, &T.outPeer, &T.outDst, &T.inPeer, &T.inDst}) E.ints.insert(E.ints.end(), v->begin(), v->end());
+    E.ints.push_back(0); E.ints.push_back(0);
+    ShardP2P &S = E.S;
+    S.peers = E.peers.p(); S.me = me; S.world = W;
+    S.nbr = E.ints.p() + oN; S.nNbr = (int) T.nbr.size();
+    S.outPeer = E.ints.p() + oOP; S.outDst = E.ints.p() + oOD; S.inPeer = E.ints.p() + oIP; S.inDst = E.ints.p() + oID;
+    S.ticket = E.ints.p() + oT;
+    S.flags = E.flags.p(); S.blkIn = E.blkIn.p(); S.moverIn = E.moverIn.p(); S.tailIn = E.tailIn.p();
+    E.connected = true;
+}
+bool DeviceSim::shardIsP2P() const { auto it = g_shardEmu.find(this); return it != g_shardEmu.end() && it->second.connected; }
 bool DeviceSim::shardVehicleCount(int *) { return false; }
 bool DeviceSim::timingOn() const { return false; }
 void DeviceSim::shardTimeMark(int) {}
 void DeviceSim::shardTimeCollect() {}
 void DeviceSim::shardPhaseTimes(double *ms, long long *steps) { for (int k = 0; k < SHARD_PHASES; ++k) ms[k] = 0; if (steps) *steps = 0; }
 void DeviceSim::shardMarkArenaExported() {}
-void DeviceSim::sendMovers() { notEmulated("sharding"); }
-void DeviceSim::recvMovers() { notEmulated("sharding"); }
-void DeviceSim::sendTails() { notEmulated("sharding"); }
-void DeviceSim::recvTails() { notEmulated("sharding"); }
-void DeviceSim::xchgMovers() { notEmulated("sharding"); }
-void DeviceSim::xchgTails() { notEmulated("sharding"); }
+void DeviceSim::sendMovers() { ShardEmu &E = g_shardEmu[this]; impl_->H.run(G, [&](int, int) { sendMoversBody(impl_->H.V, E.S); }); launches_ += 1; }
+void DeviceSim::recvMovers() { ShardEmu &E = g_shardEmu[this]; impl_->H.run(G, [&](int, int) { recvMoversBody(impl_->H.V, E.S); }); launches_ += 1; }
+void DeviceSim::sendTails() { ShardEmu &E = g_shardEmu[this]; impl_->H.run(G, [&](int, int) { sendTailsBody(impl_->H.V, E.S); }); launches_ += 1; }
+void DeviceSim::recvTails() { ShardEmu &E = g_shardEmu[this]; impl_->H.run(G, [&](int, int) { recvTailsBody(impl_->H.V, E.S); }); launches_ += 1; }
+void DeviceSim::xchgMovers() { notEmulated("the one-kernel exchange (two ranks would have to run at once)"); }
+void DeviceSim::xchgTails() { notEmulated("the one-kernel exchange (two ranks would have to run at once)"); }
 bool DeviceSim::shardSplitKernels() const { return true; }
-ShardBuffers DeviceSim::shardBuffers() { notEmulated("sharding"); return ShardBuffers(); }
-int DeviceSim::shardStepBegin() { notEmulated("sharding"); return 0; }
-bool DeviceSim::shardStepEnd(int) { notEmulated("sharding"); return false; }
-void DeviceSim::runIngest() { notEmulated("sharding"); }
-void DeviceSim::runNotifyControl() { notEmulated("sharding"); }
-void DeviceSim::runMove() { notEmulated("sharding"); }
-void DeviceSim::runLeader() { notEmulated("sharding"); }
-void DeviceSim::packTails() { notEmulated("sharding"); }
-void DeviceSim::unpackTails() { notEmulated("sharding"); }
-void DeviceSim::packMovers() { notEmulated("sharding"); }
-void DeviceSim::unpackMovers() { notEmulated("sharding"); }
-void DeviceSim::sealBlk() { notEmulated("sharding"); }
-void DeviceSim::applyBlk() { notEmulated("sharding"); }
+ShardBuffers DeviceSim::shardBuffers() { ShardBuffers b; b.rank = g_shardEmu[this].rank; b.world = g_shardEmu[this].world; return b; }
+int DeviceSim::shardStepBegin() { return 0; }
+bool DeviceSim::shardStepEnd(int) { steps_ += 1; return true; }
+void DeviceSim::runIngest() { HostSim &H = impl_->H; H.run(G, [&](int b, int nb) { phase_ingest(H.V, b, nb); }); launches_ += 1; }
+void DeviceSim::runNotifyControl() {
+    HostSim &H = impl_->H;
+    H.run(G, [&](int b, int nb) { phase_notify(H.V, b, nb); });
+    H.run(G, [&](int b, int nb) { phase_control(H.V, b, nb); });
+    launches_ += 2;
+}
+void DeviceSim::runMove() { HostSim &H = impl_->H; H.run(G, [&](int b, int nb) { phase_move(H.V, b, nb); }); launches_ += 1; }
+void DeviceSim::runLeader() { HostSim &H = impl_->H; H.run(G, [&](int b, int nb) { phase_leader(H.V, b, nb); }); launches_ += 1; }
+void DeviceSim::packTails() { notEmulated("the staged (NCCL) seam exchange"); }
+void DeviceSim::unpackTails() { notEmulated("the staged (NCCL) seam exchange"); }
+void DeviceSim::packMovers() { notEmulated("the staged (NCCL) seam exchange"); }
+void DeviceSim::unpackMovers() { notEmulated("the staged (NCCL) seam exchange"); }
+void DeviceSim::sealBlk() { notEmulated("the staged (NCCL) seam exchange"); }
+void DeviceSim::applyBlk() { notEmulated("the staged (NCCL) seam exchange"); }
 void DeviceSim::shardCounts(ShardTransport *, int32_t *, int *) { notEmulated("sharding"); }
 void DeviceSim::shardWaitingCounts(ShardTransport *, int32_t *) { notEmulated("sharding"); }
 void DeviceSim::shardGatherFinished(ShardTransport *, std::vector<FinRec> &) { notEmulated("sharding"); }
