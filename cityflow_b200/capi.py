@@ -81,6 +81,11 @@ def bind(lib: ctypes.CDLL) -> ctypes.CDLL:
         "cfb_replay_roadnet_json": (i64, [vp, vp, i64]),
         "cfb_replay_format_step": (i64, [vp, vp, i64, vp, vp, i64]),
         "cfb_push_vehicle": (i32, [vp, vp, vp, i32]),
+        "cfb_snapshot": (vp, [vp]),
+        "cfb_archive_destroy": (None, [vp]),
+        "cfb_load": (i32, [vp, vp]),
+        "cfb_archive_dump": (i32, [vp, cp]),
+        "cfb_load_from_file": (i32, [vp, cp]),
         "cfb_set_replay_file": (i32, [vp, cp]),
         "cfb_set_save_replay": (i32, [vp, i32]),
     }
@@ -188,6 +193,20 @@ class CEngine:
         v = np.array([info.get(k, float("nan")) for k in names], np.float64)
         arr = (ctypes.c_char_p * len(roads))(*[r.encode() for r in roads])
         self._check(self.lib.cfb_push_vehicle(self.h, v.ctypes.data, arr, len(roads)))
+
+    def dump(self, path: str):
+        """engine.snapshot().dump(path): the reference's JSON schema when `path` ends in .json, else the binary image."""
+        a = self.lib.cfb_snapshot(self.h)
+        if not a:
+            raise RuntimeError(self.lib.cfb_last_error(self.h).decode())
+        try:
+            if self.lib.cfb_archive_dump(a, path.encode()) < 0:
+                raise RuntimeError("cannot write archive to %s: %s" % (path, self.lib.cfb_last_error(self.h).decode()))
+        finally:
+            self.lib.cfb_archive_destroy(a)
+
+    def load_from_file(self, path: str):
+        self._check(self.lib.cfb_load_from_file(self.h, path.encode()))
 
     def average_travel_time(self) -> float:
         return float(self.lib.cfb_get_average_travel_time(self.h))

@@ -1,0 +1,193 @@
+// device_image.cuh -- the snapshot image of the dynamic state: its region list (one definition for device_sim.cu and
+// the emulated device of the tests) and the translation between the image and its decoded form (StateImage,
+// device_sim.h) that the reference-schema JSON archive is written from / read into (host_engine.cpp).  Host code only:
+// the image is brought to the host / sent to the device by DeviceSim::snapshotToHost / snapshotFromHost + restore, which
+// are the same calls the binary archive uses.
+//
+// Included after device_view.cuh by a DeviceSim implementation (device_sim.cu, tests/device_sim_emu.cpp).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+namespace cfb {
+
+struct ImageGeometry {
+    const int *off;          // host copy of View::off (nDrv + 1 entries)
+    int nDrv, nLanes, nInter;
+    size_t P;                // positions
+};
+
+// (pointer, bytes) of every array a snapshot carries, in image order; slot-indexed arrays last (their size may differ
+// between the time a snapshot is taken and the time it is restored)
+constexpr size_t IMAGE_SLOT_REGIONS = 6;
+inline std::vector<std::pair<void *, size_t>> snapshotRegions(const View &V, size_t P, size_t S) {
+    const size_t nL = (size_t) std::max(V.nLanes, 1);
+    return {
+        {V.kin, P * sizeof(double2)}, {V.gap, P * sizeof(double)}, {V.leader, P * sizeof(int)},
+        {V.ids, P * sizeof(int4)}, {V.nav, P * sizeof(int4)}, {V.cust, P * sizeof(double)},
+        {V.count, (size_t) V.nDrv * sizeof(int)}, {V.entCnt, (size_t) V.nDrv * sizeof(int)},
+        {V.tail, (size_t) V.nDrv * sizeof(Tail)},
+        {V.waitHead, nL * sizeof(int)}, {V.waitTail, nL * sizeof(int)},
+        {V.inserted, nL},
+        {V.curPhase, (size_t) V.nInter * sizeof(int)}, {V.remain, (size_t) V.nInter * sizeof(double)},
+        {V.vehList[0], P * sizeof(int2)}, {V.vehList[1], P * sizeof(int2)},
+        {V.actList[0], (size_t) V.nDrv * sizeof(int)}, {V.actList[1], (size_t) V.nDrv * sizeof(int)},
+        {V.ctrl, sizeof(Ctrl)},
+        {V.pos, S * sizeof(int)}, {V.waitNext, S * sizeof(int)}, {V.slotInfo, S * sizeof(int4)}, {V.slotCust, S * sizeof(double)},
+        {V.blk, S * sizeof(int)}, {V.delStep, S * sizeof(int)},
+    };
+}
+
+// The serialised image (snapshotToHost): {magic, steps, slotCap, #regions, region bytes...} as long long, then the
+// regions, each padded to 256 bytes.
+constexpr long long IMAGE_MAGIC = 0x43464241LL;
+inline size_t imagePad(size_t b) { return (b + 255) & ~(size_t) 255; }
+
+struct ImageArrays {   // typed pointers into a serialised image
+    double2 *kin; double *gap; int *leader; int4 *ids, *nav; double *cust; int *count, *entCnt; Tail *tail;
+    int *waitHead, *waitTail; unsigned char *inserted; int *curPhase; double *remain; int2 *vehList[2]; int *actList[2];
+    Ctrl *ctrl; int *pos, *waitNext; int4 *slotInfo; double *slotCust; int *blk, *delStep;
+    long long steps; int slotCap;
+};
+
+inline std::vector<size_t> imageRegionBytes(const ImageGeometry &G, size_t S) {
+    View V{};
+    V.nLanes = G.nLanes; V.nDrv = G.nDrv; V.nInter = G.nInter;
+    std::vector<size_t> out;
+    for (auto &r : snapshotRegions(V, G.P, S)) out.push_back(r.second);
+    return out;
+}
+
+// Lay the typed pointers over `blob`; checks the header against this engine's geometry.
+inline ImageArrays imageMap(unsigned char *blob, size_t n, const ImageGeometry &G) {
+    if (n < 4 * sizeof(long long)) throw std::runtime_error("cityflow_b200: truncated archive");
+    const long long *h = reinterpret_cast<const long long *>(blob);
+    if (h[0] != IMAGE_MAGIC) throw std::runtime_error("cityflow_b200: not an archive of this engine");
+    ImageArrays A{};
+    A.steps = h[1];
+    A.slotCap = (int) h[2];
+    const std::vector<size_t> want = imageRegionBytes(G, (size_t) A.slotCap);
+    if ((size_t) h[3] != want.size()) throw std::runtime_error("cityflow_b200: archive does not match this engine");
+    size_t off = (4 + want.size()) * sizeof(long long);
+    void *ptr[32];
+    for (size_t k = 0; k < want.size(); ++k) {
+        if ((size_t) h[4 + k] != want[k]) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
+        ptr[k] = blob + off;
+        off += imagePad(want[k]);
+    }
+    if (off > n) throw std::runtime_error("cityflow_b200: truncated archive");
+    int k = 0;
+    A.kin = (double2 *) ptr[k++]; A.gap = (double *) ptr[k++]; A.leader = (int *) ptr[k++]; A.ids = (int4 *) ptr[k++];
+    A.nav = (int4 *) ptr[k++]; A.cust = (double *) ptr[k++]; A.count = (int *) ptr[k++]; A.entCnt = (int *) ptr[k++];
+    A.tail = (Tail *) ptr[k++]; A.waitHead = (int *) ptr[k++]; A.waitTail = (int *) ptr[k++]; A.inserted = (unsigned char *) ptr[k++];
+    A.curPhase = (int *) ptr[k++]; A.remain = (double *) ptr[k++]; A.vehList[0] = (int2 *) ptr[k++]; A.vehList[1] = (int2 *) ptr[k++];
+    A.actList[0] = (int *) ptr[k++]; A.actList[1] = (int *) ptr[k++]; A.ctrl = (Ctrl *) ptr[k++];
+    A.pos = (int *) ptr[k++]; A.waitNext = (int *) ptr[k++]; A.slotInfo = (int4 *) ptr[k++]; A.slotCust = (double *) ptr[k++];
+    A.blk = (int *) ptr[k++]; A.delStep = (int *) ptr[k++];
+    return A;
+}
+
+inline void decodeImage(std::vector<unsigned char> &blob, const ImageGeometry &G, StateImage &out) {
+    const ImageArrays A = imageMap(blob.data(), blob.size(), G);
+    out = StateImage();
+    out.step = A.ctrl->step;
+    out.active = A.ctrl->active;
+    out.slotCount = A.slotCap;
+    const int lastStep = A.ctrl->step - 1;
+    out.drivables.resize(G.nDrv);
+    for (int d = 0; d < G.nDrv; ++d) {
+        const int n = A.count[d];
+        if (n < 0 || n > G.off[d + 1] - G.off[d]) throw std::runtime_error("cityflow_b200: corrupt archive (list length)");
+        out.drivables[d].resize(n);
+        for (int k = 0; k < n; ++k) {
+            const int p = G.off[d] + k;
+            StateImage::Running &r = out.drivables[d][k];
+            r.slot = A.ids[p].x; r.tmpl = A.ids[p].y; r.priority = A.ids[p].z; r.nextDrivable = A.ids[p].w;
+            r.planIdx = A.nav[p].x; r.prevDrivable = A.nav[p].y; r.blockerSlot = A.nav[p].z; r.enterLaneLinkTime = A.nav[p].w;
+            // a blocker that left the network in the last step is dropped lazily on the device (see DeviceSim::debugDump)
+            if (r.blockerSlot >= 0 && r.blockerSlot < A.slotCap && A.delStep[r.blockerSlot] == lastStep) r.blockerSlot = -1;
+            const int lp = A.leader[p];
+            r.leaderSlot = lp >= 0 ? A.ids[lp].x : -1;
+            r.dis = A.kin[p].x; r.speed = A.kin[p].y;
+            r.gap = lp >= 0 ? A.gap[p] : 0.0;
+            r.len = 0;
+        }
+    }
+    out.waiting.resize(G.nLanes);
+    for (int l = 0; l < G.nLanes; ++l) {
+        int guard = 0;
+        for (int s = A.waitHead[l]; s >= 0; s = A.waitNext[s]) {
+            if (s >= A.slotCap || ++guard > A.slotCap) throw std::runtime_error("cityflow_b200: corrupt archive (waiting queue)");
+            out.waiting[l].push_back(StateImage::Waiting{s, A.slotInfo[s].x, A.slotInfo[s].y, A.slotInfo[s].z});
+        }
+    }
+    out.curPhase.assign(A.curPhase, A.curPhase + G.nInter);
+    out.remain.assign(A.remain, A.remain + G.nInter);
+}
+
+inline void encodeImage(const StateImage &in, const ImageGeometry &G, std::vector<unsigned char> &blob) {
+    if ((int) in.drivables.size() != G.nDrv || (int) in.waiting.size() != G.nLanes || (int) in.curPhase.size() != G.nInter ||
+        (int) in.remain.size() != G.nInter)
+        throw std::runtime_error("cityflow_b200: archive does not match this road network");
+    const size_t S = (size_t) std::max(in.slotCount, 1);
+    const std::vector<size_t> bytes = imageRegionBytes(G, S);
+    std::vector<long long> hdr = {IMAGE_MAGIC, in.step, (long long) S, (long long) bytes.size()};
+    size_t total = 0;
+    for (size_t b : bytes) { hdr.push_back((long long) b); total += imagePad(b); }
+    blob.assign(hdr.size() * sizeof(long long) + total, 0);
+    memcpy(blob.data(), hdr.data(), hdr.size() * sizeof(long long));
+    ImageArrays A = imageMap(blob.data(), blob.size(), G);
+    const int par = (int) (in.step & 1);
+    for (size_t p = 0; p < G.P; ++p) { A.leader[p] = -1; A.cust[p] = NAN; }
+    for (size_t s = 0; s < S; ++s) { A.pos[s] = -1; A.waitNext[s] = -1; A.slotCust[s] = NAN; A.blk[s] = -1; A.delStep[s] = INT_MIN; }
+    Ctrl c{};
+    c.step = (int) in.step;
+    c.epoch = (int) in.step;
+    c.active = in.active;
+    auto slotOk = [&](int s) { return s >= 0 && (size_t) s < S; };
+    for (int d = 0; d < G.nDrv; ++d) {
+        const auto &L = in.drivables[d];
+        const int n = (int) L.size();
+        if (n > G.off[d + 1] - G.off[d]) throw std::runtime_error("cityflow_b200: more vehicles on a drivable than its bucket holds");
+        A.count[d] = n;
+        Tail t{};
+        t.pos = -1; t.prev = -1;
+        for (int k = 0; k < n; ++k) {
+            const StateImage::Running &r = L[k];
+            const int p = G.off[d] + k;
+            if (!slotOk(r.slot) || A.pos[r.slot] >= 0) throw std::runtime_error("cityflow_b200: corrupt archive (vehicle listed twice)");
+            A.pos[r.slot] = p;
+            A.kin[p] = make_double2(r.dis, r.speed);
+            A.ids[p] = make_int4(r.slot, r.tmpl, r.priority, r.nextDrivable);
+            A.nav[p] = make_int4(r.planIdx, r.prevDrivable, slotOk(r.blockerSlot) ? r.blockerSlot : -1, r.enterLaneLinkTime);
+            A.blk[r.slot] = A.nav[p].z;
+            A.vehList[par][c.nVeh[par]++] = make_int2(p, k == 0 ? (d | HEAD_BIT) : d);
+            if (k == n - 1) { t.dis = r.dis; t.speed = r.speed; t.len = r.len; t.pos = p; t.prev = r.prevDrivable; }
+        }
+        A.tail[d] = t;
+        if (n > 0) A.actList[par][c.nAct[par]++] = d;
+    }
+    for (int d = 0; d < G.nDrv; ++d)   // leaders by position, now that every vehicle has one
+        for (size_t k = 0; k < in.drivables[d].size(); ++k) {
+            const StateImage::Running &r = in.drivables[d][k];
+            const int p = G.off[d] + (int) k;
+            if (slotOk(r.leaderSlot) && A.pos[r.leaderSlot] >= 0) { A.leader[p] = A.pos[r.leaderSlot]; A.gap[p] = r.gap; }
+        }
+    for (int l = 0; l < G.nLanes; ++l) {
+        int tail = -1;
+        for (const StateImage::Waiting &w : in.waiting[l]) {
+            if (!slotOk(w.slot) || A.pos[w.slot] >= 0) throw std::runtime_error("cityflow_b200: corrupt archive (waiting vehicle)");
+            A.slotInfo[w.slot] = make_int4(w.tmpl, w.priority, w.plan, 0);
+            if (tail < 0) A.waitHead[l] = w.slot; else A.waitNext[tail] = w.slot;
+            tail = w.slot;
+        }
+        if (tail < 0) A.waitHead[l] = -1;
+        A.waitTail[l] = tail;
+    }
+    if (G.nLanes == 0) { A.waitHead[0] = -1; A.waitTail[0] = -1; }
+    for (int i = 0; i < G.nInter; ++i) { A.curPhase[i] = in.curPhase[i]; A.remain[i] = in.remain[i]; }
+    *A.ctrl = c;
+}
+
+}  // namespace cfb

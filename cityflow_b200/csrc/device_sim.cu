@@ -61,6 +61,7 @@ namespace cg = cooperative_groups;
 
 }  // namespace cfb
 #include "device_view.cuh"
+#include "device_image.cuh"
 namespace cfb {
 
 }  // namespace cfb
@@ -1649,29 +1650,18 @@ struct DeviceSim::Snapshot {
     size_t total = 0;
 };
 
-static std::vector<std::pair<void *, size_t>> snapshotRegions(DeviceSim::Impl &I) {
-    const View &V = I.V;
-    const size_t P = (size_t) I.P, S = (size_t) I.slotCap;
-    return {
-        {V.kin, P * sizeof(double2)}, {V.gap, P * sizeof(double)}, {V.leader, P * sizeof(int)},
-        {V.ids, P * sizeof(int4)}, {V.nav, P * sizeof(int4)}, {V.cust, P * sizeof(double)},
-        {V.count, (size_t) V.nDrv * sizeof(int)}, {V.entCnt, (size_t) V.nDrv * sizeof(int)},
-        {V.tail, (size_t) V.nDrv * sizeof(Tail)},
-        {V.waitHead, (size_t) std::max(V.nLanes, 1) * sizeof(int)}, {V.waitTail, (size_t) std::max(V.nLanes, 1) * sizeof(int)},
-        {V.inserted, (size_t) std::max(V.nLanes, 1)},
-        {V.curPhase, (size_t) V.nInter * sizeof(int)}, {V.remain, (size_t) V.nInter * sizeof(double)},
-        {V.vehList[0], P * sizeof(int2)}, {V.vehList[1], P * sizeof(int2)},
-        {V.actList[0], (size_t) V.nDrv * sizeof(int)}, {V.actList[1], (size_t) V.nDrv * sizeof(int)},
-        {V.ctrl, sizeof(Ctrl)},
-        // slot-indexed arrays last (their size may differ between snapshot and restore time)
-        {V.pos, S * sizeof(int)}, {V.waitNext, S * sizeof(int)}, {V.slotInfo, S * sizeof(int4)}, {V.slotCust, S * sizeof(double)},
-        {V.blk, S * sizeof(int)}, {V.delStep, S * sizeof(int)},
-    };
+static std::vector<std::pair<void *, size_t>> snapshotRegions(DeviceSim::Impl &I) {   // device_image.cuh
+    return snapshotRegions(I.V, (size_t) I.P, (size_t) I.slotCap);
 }
 
 DeviceSim::Snapshot *DeviceSim::snapshot() {
     Impl &I = *impl_;
     CFB_CUDA(cudaStreamSynchronize(I.stream));
+    if (I.phaseDirty && I.V.nInter) {   // set_tl_phase calls not sent up yet are part of the state (trafficlight.cpp:39-41 acts at once)
+        CFB_CUDA(cudaMemcpyAsync(I.V.curPhase, I.hPhase.data(), I.V.nInter * sizeof(int), cudaMemcpyHostToDevice, I.stream));
+        CFB_CUDA(cudaStreamSynchronize(I.stream));
+        I.phaseDirty = false;
+    }
     auto regs = snapshotRegions(I);
     Snapshot *s = new Snapshot();
     for (auto &r : regs) { s->regions.push_back({r.second}); s->total += (r.second + 255) & ~(size_t) 255; }
@@ -1725,6 +1715,21 @@ void DeviceSim::restore(const Snapshot *s) {
 }
 
 void DeviceSim::freeSnapshot(Snapshot *s) { delete s; }
+
+// The image in decoded form (device_image.cuh): the reference-schema JSON archive of host_engine.cpp goes through these.
+static ImageGeometry imageGeometry(DeviceSim::Impl &I) {
+    return ImageGeometry{I.offHost.data(), I.V.nDrv, I.V.nLanes, I.V.nInter, (size_t) I.P};
+}
+void DeviceSim::decodeSnapshot(const Snapshot *s, StateImage &out) {
+    std::vector<unsigned char> blob;
+    snapshotToHost(s, blob);
+    decodeImage(blob, imageGeometry(*impl_), out);
+}
+DeviceSim::Snapshot *DeviceSim::encodeSnapshot(const StateImage &in) {
+    std::vector<unsigned char> blob;
+    encodeImage(in, imageGeometry(*impl_), blob);
+    return snapshotFromHost(blob.data(), blob.size());
+}
 
 void DeviceSim::snapshotToHost(const Snapshot *s, std::vector<unsigned char> &out) {
     // header: magic, steps, slotCap, #regions, region sizes; then the blob

@@ -42,6 +42,31 @@ struct DebugRec {      // full per-vehicle state for parity tests (cfb_debug_veh
     double dis, speed, gap;
 };
 
+// The dynamic state at a step boundary in decoded form: what Archive::dump writes per vehicle, drivable and
+// traffic light (archive.cpp:179-343).  Vehicles are named by slot; DeviceSim::decodeSnapshot / encodeSnapshot
+// translate between this and the device image (device_image.cuh).
+struct StateImage {
+    struct Running {
+        int32_t slot, tmpl, priority;
+        int32_t planIdx;            // absolute index into the plan table of the vehicle's current drivable
+        int32_t nextDrivable;       // plan[planIdx + 1] (PLAN_END / PLAN_DEAD past the last road)
+        int32_t prevDrivable;       // -1 none
+        int32_t blockerSlot;        // -1 none
+        int32_t leaderSlot;         // -1 none
+        int32_t enterLaneLinkTime;
+        double dis, speed, gap;     // gap: meaningful with a leader
+        double len;                 // of the vehicle's template (encode only: the drivable's tail record)
+    };
+    struct Waiting { int32_t slot, tmpl, priority, plan; };
+    std::vector<std::vector<Running>> drivables;   // per drivable, list order (front first)
+    std::vector<std::vector<Waiting>> waiting;     // per lane, queue order
+    std::vector<int32_t> curPhase;                 // per intersection
+    std::vector<double> remain;
+    long long step = 0;
+    int active = 0;
+    int slotCount = 0;             // slots in use: 0 .. slotCount-1
+};
+
 enum DeviceError : int {
     ERR_BUCKET_OVERFLOW = 1,    // more vehicles on a drivable than its bucket holds
     ERR_ENTRANT_OVERFLOW = 2,   // more vehicles entering one drivable in one step than staged
@@ -178,6 +203,9 @@ public:
     static void freeSnapshot(Snapshot *s);
     static void snapshotToHost(const Snapshot *s, std::vector<unsigned char> &out);
     static Snapshot *snapshotFromHost(const unsigned char *data, size_t n);
+    // the image in decoded form (the reference's JSON archive, host_engine.cpp); not with lane change
+    void decodeSnapshot(const Snapshot *s, StateImage &out);
+    Snapshot *encodeSnapshot(const StateImage &in);
 
     // Measurement support for bench.py / profiles (CUDA-event timing of one kernel across launches).
     struct KernelTimes { double ingest = 0, notify = 0, control = 0, move = 0, leader = 0; long long launches = 0; };

@@ -98,11 +98,12 @@ int Routing::chooseLink(int lane, const std::vector<int> &roads, int r) const {
     return best < 0 ? PLAN_DEAD : best;
 }
 
-int Routing::buildPlan(const std::vector<int> &roads, int startLane, int roadPos, int routeId) {
+int Routing::buildPlan(const std::vector<int> &roads, int startLane, int roadPos, int routeId, const std::vector<int> &prefix) {
     const int id = (int) planBeg_.size();
     planBeg_.push_back((int) planData_.size());
     planRoute_.push_back(routeId);
     planRoadPos_.push_back(roadPos);
+    planData_.insert(planData_.end(), prefix.begin(), prefix.end());   // planFrom(): drivables before the sequential part
     int lane = startLane;
     for (int r = roadPos;; ++r) {
         planData_.push_back(lane);
@@ -120,6 +121,44 @@ int Routing::buildPlan(const std::vector<int> &roads, int startLane, int roadPos
         lane = net_.llEndLane[ll];
     }
     return id;
+}
+
+int Routing::planFrom(int routeId, int drivable) {
+    const auto key = std::make_pair(routeId, drivable);
+    auto it = planFrom_.find(key);
+    if (it != planFrom_.end()) return it->second;
+    const Route &rt = routes_[routeId];
+    if (!rt.valid) return -1;
+    const std::vector<int> roads = rt.roads;   // (buildPlan grows the tables: no references into them)
+    auto firstVisit = [&roads](int road) {
+        for (size_t r = 0; r < roads.size(); ++r)
+            if (roads[r] == road) return (int) r;
+        return -1;
+    };
+    const int nL = net_.nLanes();
+    int plan = -1;
+    if (drivable >= nL) {   // on a laneLink: its end lane, looked up from the start of the route
+        const int lane = net_.llEndLane[drivable - nL];
+        const int pos = firstVisit(net_.laneRoad[lane]);
+        if (pos < 0) return -1;
+        plan = buildPlan(roads, lane, pos, routeId, {drivable});
+    } else {
+        const int pos = firstVisit(net_.laneRoad[drivable]);
+        if (pos < 0) return -1;
+        const int ll = chooseLink(drivable, roads, pos);
+        const int pos2 = ll >= 0 ? firstVisit(roads[pos + 1]) : -1;
+        if (ll >= 0 && pos2 != pos + 1) {
+            // the next road was visited before: the router takes that visit for the current one once the vehicle is there
+            plan = buildPlan(roads, net_.llEndLane[ll], pos2, routeId, {drivable, nL + ll});
+        } else {
+            if (pos == 0)
+                for (size_t k = 0; k < rt.startLanes.size(); ++k)
+                    if (rt.startLanes[k] == drivable) plan = rt.planOfStartLane[k];
+            if (plan < 0) plan = buildPlan(roads, drivable, pos, routeId);
+        }
+    }
+    planFrom_[key] = plan;
+    return plan;
 }
 
 int Routing::intern(const std::vector<int> &anchors) {

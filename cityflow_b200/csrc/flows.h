@@ -75,6 +75,14 @@ public:
     int lanePlan(int routeId, int roadPos, int laneIdx) const {
         return lanePlanId_[lanePlanBeg_[lanePlanRoad_[routeId] + roadPos] + laneIdx];
     }
+    // Plan of a vehicle picked up mid-route on `drivable` (a reference-schema archive, archive.cpp:378-385 + :433): the
+    // sequence the reference's router yields from there.  A loaded Router starts with iCurRoad = route.begin()
+    // (router.cpp:16-21), so on a route that visits a road twice it takes the FIRST visit for the current one: the
+    // current lane's road is looked up from the start of the route (router.cpp:49-57), and so is the road of the first
+    // lane the vehicle moves on to (Router::update advances iCurRoad from where it stood, router.cpp:78-94) -- only
+    // from there on the pointer follows the route.  A vehicle on a laneLink continues on that link's end lane
+    // (router.cpp:44-45).  -1: the drivable's road is not on the route.
+    int planFrom(int routeId, int drivable);
     int planRoute(int plan) const { return planRoute_[plan]; }      // route a plan belongs to
     int planRoadPos(int plan) const { return planRoadPos_[plan]; }  // position in that route of the plan's first road
     const std::vector<int> &lanePlanRoadTable() const { return lanePlanRoad_; }
@@ -85,7 +93,9 @@ public:
 
 private:
     bool dijkstra(int start, int end, std::vector<int> &buffer) const;
-    int buildPlan(const std::vector<int> &roads, int startLane, int roadPos = 0, int routeId = -1);
+    int buildPlan(const std::vector<int> &roads, int startLane, int roadPos = 0, int routeId = -1,
+                  const std::vector<int> &prefix = std::vector<int>());
+    std::map<std::pair<int, int>, int> planFrom_;
     const RoadNet &net_;
     std::vector<Route> routes_;
     std::map<std::vector<int>, int> byAnchors_;

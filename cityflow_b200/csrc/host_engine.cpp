@@ -880,6 +880,289 @@ public:
         finishedDirty = false;
     }
 
+    // ---- Archive in the reference's JSON schema: Archive::dump (archive.cpp:153-343) and the file loader
+    // Archive::Archive(Engine &, filename) (archive.cpp:345-550).  The device half goes through the decoded image
+    // (StateImage, device_image.cuh); vehicles are named as the reference names them, so a file written here loads
+    // in the reference and the other way round.  Not with laneChange (shadow vehicles, signals); the lanes'
+    // speed history (Lane::history, read only by RouterType::DURATION routing) is written empty and ignored. ----
+    std::string vehicleName(const SlotInfo &s) const {
+        return s.flow == -2 ? "manually_pushed_" + std::to_string(s.index) : "flow_" + std::to_string(s.flow) + "_" + std::to_string(s.index);
+    }
+    std::string drivableName(int d) const {   // Lane::getId roadnet.h:323, LaneLink::getId roadnet.h:478
+        if (d < net.nLanes()) return net.laneName(d);
+        const int k = d - net.nLanes();
+        return net.laneName(net.llStartLane[k]) + "_TO_" + net.laneName(net.llEndLane[k]);
+    }
+
+    void writeReferenceArchive(const HostState &hs, const StateImage &img, std::string &o) const {
+        if (laneChange) throw std::runtime_error("an archive in the reference's JSON schema is not written with laneChange on (use the binary form)");
+        if (!laneLocal.empty()) throw std::runtime_error("an archive in the reference's JSON schema is not written by one rank of a sharded engine");
+        if (!hs.pending.empty()) throw std::runtime_error("archive taken in the middle of a step");
+        const int nL = net.nLanes();
+        struct Ref { int priority, slot, drivable; const StateImage::Running *run; };
+        std::vector<Ref> refs;
+        for (int d = 0; d < (int) img.drivables.size(); ++d)
+            for (const auto &r : img.drivables[d]) refs.push_back(Ref{r.priority, r.slot, d, &r});
+        for (int l = 0; l < (int) img.waiting.size(); ++l)
+            for (const auto &w : img.waiting[l]) refs.push_back(Ref{w.priority, w.slot, l, nullptr});
+        std::sort(refs.begin(), refs.end(), [](const Ref &a, const Ref &b) { return a.priority < b.priority; });   // vehiclePool is a std::map
+        auto nameOf = [&](int slot) {
+            if (slot < 0 || (size_t) slot >= hs.slots.size() || !hs.slots[slot].live) throw std::runtime_error("corrupt archive (unknown vehicle)");
+            return vehicleName(hs.slots[slot]);
+        };
+        auto key = [&o](const char *k) { o.push_back('"'); o += k; o += "\":"; };
+        auto num = [&](const char *k, double v) { key(k); putJsonNumberLikeRapidjson(o, v); o.push_back(','); };
+        o.clear();
+        o.reserve(refs.size() * 1100 + 4096);
+        o += "{\"step\":" + std::to_string(hs.step) + ",\"activeVehicleCount\":" + std::to_string(img.active) + ",\"rnd\":";
+        { std::ostringstream r; r << hs.rnd; putJsonString(o, r.str()); }
+        o += ",\"vehicles\":[";
+        bool first = true;
+        for (const Ref &v : refs) {
+            const SlotInfo &si = hs.slots.at(v.slot);
+            if (si.shadow) throw std::runtime_error("archive holds lane-change state");
+            const VehicleTemplate &t = hs.templates.at(si.tmplId);
+            if (!first) o.push_back(',');
+            first = false;
+            o += "{\"priority\":" + std::to_string(v.priority) + ",\"id\":";
+            putJsonString(o, vehicleName(si));
+            o.push_back(',');
+            num("enterTime", si.enterTime);
+            num("speed", v.run ? v.run->speed : t.speed);   // VehicleInfo::speed is the live speed (vehicle.cpp:119)
+            num("len", t.len); num("width", t.width); num("maxPosAcc", t.maxPosAcc); num("maxNegAcc", t.maxNegAcc);
+            num("usualPosAcc", t.usualPosAcc); num("usualNegAcc", t.usualNegAcc); num("minGap", t.minGap); num("maxSpeed", t.maxSpeed);
+            num("headwayTime", t.headwayTime); num("yieldDistance", t.yieldDistance); num("turnSpeed", t.turnSpeed);
+            key("route");
+            o.push_back('[');
+            const Route &rt = routing->route(si.routeId);
+            for (size_t k = 0; k < rt.roads.size(); ++k) { if (k) o.push_back(','); putJsonString(o, net.roadId[rt.roads[k]]); }
+            o += "],";
+            num("dis", v.run ? v.run->dis : 0.0);
+            key("drivable"); putJsonString(o, drivableName(v.drivable)); o.push_back(',');
+            if (v.run && v.run->prevDrivable >= 0) { key("prevDrivable"); putJsonString(o, drivableName(v.run->prevDrivable)); o.push_back(','); }
+            num("approachingIntersectionDistance", t.maxSpeed * t.maxSpeed / t.usualNegAcc / 2 + t.maxSpeed * interval * 2);   // vehicle.cpp:27-28
+            num("gap", v.run ? v.run->gap : 0.0);
+            key("enterLaneLinkTime"); o += std::to_string((unsigned) (v.run ? v.run->enterLaneLinkTime : INT_MAX)); o.push_back(',');
+            if (v.run && v.run->leaderSlot >= 0) { key("leader"); putJsonString(o, nameOf(v.run->leaderSlot)); o.push_back(','); }
+            if (v.run && v.run->blockerSlot >= 0) { key("blocker"); putJsonString(o, nameOf(v.run->blockerSlot)); o.push_back(','); }
+            o += "\"end\":false,\"running\":";
+            o += v.run ? "true" : "false";
+            o += ",\"partnerType\":0,\"offset\":0.0,\"laneChangeWaitingTime\":0.0,\"laneChanging\":false,\"laneChangeLastTime\":0.0}";
+        }
+        o += "],\"drivables\":{";
+        for (int d = 0; d < (int) img.drivables.size(); ++d) {
+            if (d) o.push_back(',');
+            putJsonString(o, drivableName(d));
+            o += ":{\"vehicles\":[";
+            for (size_t k = 0; k < img.drivables[d].size(); ++k) { if (k) o.push_back(','); putJsonString(o, nameOf(img.drivables[d][k].slot)); }
+            o.push_back(']');
+            if (d < nL) {
+                o += ",\"waitingBuffer\":[";
+                for (size_t k = 0; k < img.waiting[d].size(); ++k) { if (k) o.push_back(','); putJsonString(o, nameOf(img.waiting[d][k].slot)); }
+                o += "],\"history\":[],\"historyVehicleNum\":0,\"historyAverageSpeed\":0.0";
+            }
+            o.push_back('}');
+        }
+        o += "},\"flows\":{";
+        for (size_t i = 0; i < flows.size(); ++i) {
+            if (i) o.push_back(',');
+            putJsonString(o, flows[i].def.id);
+            o += ":{";
+            num("nowTime", hs.flowNow.at(i)); num("currentTime", hs.flowCur.at(i));
+            o += "\"cnt\":" + std::to_string((unsigned) hs.flowCnt.at(i)) + "}";
+        }
+        o += "},\"trafficLights\":{";
+        for (int i = 0; i < net.nInter(); ++i) {
+            if (i) o.push_back(',');
+            putJsonString(o, net.interId[i]);
+            o += ":{";
+            num("remainDuration", net.interVirtual[i] ? 0.0 : img.remain.at(i));
+            o += "\"curPhaseIndex\":" + std::to_string((unsigned) (net.interVirtual[i] ? 0 : img.curPhase.at(i))) + "}";
+        }
+        o += "},\"finishedVehicleCnt\":" + std::to_string(hs.finishedCnt) + ",";
+        key("cumulativeTravelTime");
+        putJsonNumberLikeRapidjson(o, hs.cumulativeTravelTime);
+        o += "}";
+    }
+
+    void readReferenceArchive(const Json &root, HostState &hs, StateImage &img) {
+        if (laneChange) throw std::runtime_error("an archive in the reference's JSON schema is not read with laneChange on");
+        if (!laneLocal.empty()) throw std::runtime_error("an archive in the reference's JSON schema is not read by one rank of a sharded engine");
+        if (!root.isObject()) throw std::runtime_error("archive file: expected a JSON object");
+        auto member = [](const Json &o, const char *name) -> const Json & {
+            const Json *v = o.find(name);
+            if (!v) throw std::runtime_error(std::string(name) + " is required but missing in json file");   // utility.h:113-127
+            return *v;
+        };
+        auto dbl = [&](const Json &o, const char *name) {
+            const Json &v = member(o, name);
+            if (!v.isNumber()) throw std::runtime_error(std::string(name) + ": expected a number");
+            return v.asDouble();
+        };
+        auto integer = [&](const Json &o, const char *name) -> long long {
+            const Json &v = member(o, name);
+            if (!v.isNumber() || v.kind == Json::Double) throw std::runtime_error(std::string(name) + ": expected an integer");
+            return (v.kind == Json::Int || v.kind == Json::Int64) ? (long long) v.i : (long long) v.u;
+        };
+        auto str = [&](const Json &o, const char *name) -> const std::string & {
+            const Json &v = member(o, name);
+            if (!v.isString()) throw std::runtime_error(std::string(name) + ": expected a string");
+            return v.s;
+        };
+        auto optStr = [](const Json &o, const char *name) -> const std::string * {
+            const Json *v = o.find(name);
+            return v && v->isString() ? &v->s : nullptr;
+        };
+        hs = HostState();
+        img = StateImage();
+        { std::istringstream r(str(root, "rnd")); r >> hs.rnd; if (!r) throw std::runtime_error("rnd: not a std::mt19937 state"); }
+        hs.step = (size_t) integer(root, "step");
+        img.step = (long long) hs.step;
+        img.active = (int) integer(root, "activeVehicleCount");
+        const Json &vehicles = member(root, "vehicles");
+        if (!vehicles.isArray()) throw std::runtime_error("vehicles: expected an array");
+        const int nL = net.nLanes(), nD = net.nDrivables(), n = (int) vehicles.arr.size();
+        std::unordered_map<std::string, int> drvIndex, slotOfName;
+        for (int d = 0; d < nD; ++d) drvIndex.emplace(drivableName(d), d);
+        auto drivableOf = [&](const std::string &id) {
+            auto it = drvIndex.find(id);
+            if (it == drvIndex.end()) throw std::runtime_error("No such drivable: " + id);
+            return it->second;
+        };
+        hs.slots.assign(n, SlotInfo());
+        std::vector<double> speed(n);
+        std::vector<char> running(n);
+        for (int k = 0; k < n; ++k) {
+            const Json &v = vehicles.arr[k];
+            if (!v.isObject()) throw std::runtime_error("vehicles: expected objects");
+            SlotInfo &si = hs.slots[k];
+            const std::string &id = str(v, "id");
+            {   // flow_<flow>_<index> (flow.cpp:14) / manually_pushed_<index> (engine.cpp:700)
+                char *end = nullptr;
+                if (id.compare(0, 16, "manually_pushed_") == 0) {
+                    si.flow = -2;
+                    si.index = (int) strtol(id.c_str() + 16, &end, 10);
+                } else if (id.compare(0, 5, "flow_") == 0) {
+                    si.flow = (int) strtol(id.c_str() + 5, &end, 10);
+                    if (*end != '_' || si.flow < 0 || si.flow >= (int) flows.size()) throw std::runtime_error("vehicle id not understood: " + id);
+                    si.index = (int) strtol(end + 1, &end, 10);
+                }
+                if (!end || *end != 0) throw std::runtime_error("vehicle id not understood: " + id + (id.find("shadow") != std::string::npos ? " (lane-change state is not read)" : ""));
+            }
+            if (!slotOfName.emplace(id, k).second) throw std::runtime_error("vehicle listed twice: " + id);
+            if (integer(v, "partnerType") != 0) throw std::runtime_error("archive holds lane-change state (partner vehicles): not read");
+            si.priority = (int) integer(v, "priority");
+            si.enterTime = dbl(v, "enterTime");
+            si.spawnStep = (int32_t) std::llround(si.enterTime / interval);
+            const Json &rn = member(v, "running");
+            if (!rn.isBool()) throw std::runtime_error("running: expected a bool");
+            running[k] = rn.asBool();
+            speed[k] = dbl(v, "speed");
+            VehicleTemplate t;
+            t.speed = running[k] ? 0.0 : speed[k];   // a running vehicle's initial speed is never read again
+            t.len = dbl(v, "len"); t.width = dbl(v, "width"); t.maxPosAcc = dbl(v, "maxPosAcc"); t.maxNegAcc = dbl(v, "maxNegAcc");
+            t.usualPosAcc = dbl(v, "usualPosAcc"); t.usualNegAcc = dbl(v, "usualNegAcc"); t.minGap = dbl(v, "minGap");
+            t.maxSpeed = dbl(v, "maxSpeed"); t.headwayTime = dbl(v, "headwayTime"); t.yieldDistance = dbl(v, "yieldDistance");
+            t.turnSpeed = dbl(v, "turnSpeed");
+            si.tmplId = internTemplate(t);
+            const Json &rj = member(v, "route");
+            if (!rj.isArray()) throw std::runtime_error("route: expected an array");
+            std::vector<int> roads;
+            for (const Json &r : rj.arr) {
+                if (!r.isString()) throw std::runtime_error("route: expected strings");
+                auto it = net.roadIndex.find(r.s);
+                if (it == net.roadIndex.end()) throw std::runtime_error("No such road: " + r.s);
+                roads.push_back(it->second);
+            }
+            si.routeId = routing->intern(roads);
+            if (!routing->route(si.routeId).valid || routing->route(si.routeId).roads != roads)
+                throw std::runtime_error("route of vehicle " + id + " is not a path of this road network");
+            si.live = true;
+        }
+        auto slotOf = [&](const std::string *id) {
+            if (!id) return -1;
+            auto it = slotOfName.find(*id);
+            if (it == slotOfName.end()) throw std::runtime_error("No such vehicle: " + *id);
+            return it->second;
+        };
+        const Json &drivables = member(root, "drivables");
+        if (!drivables.isObject()) throw std::runtime_error("drivables: expected an object");
+        std::unordered_map<std::string, const Json *> drvJson;
+        for (const auto &kv : drivables.obj) drvJson.emplace(kv.first, &kv.second);
+        img.drivables.assign(nD, {});
+        img.waiting.assign(nL, {});
+        std::vector<char> placed(n, 0);
+        int runningCount = 0;
+        for (int d = 0; d < nD; ++d) {
+            auto dj = drvJson.find(drivableName(d));
+            if (dj == drvJson.end()) throw std::runtime_error(drivableName(d) + " is required but missing in json file");
+            const Json &list = member(*dj->second, "vehicles");
+            if (!list.isArray()) throw std::runtime_error("vehicles: expected an array");
+            for (const Json &e : list.arr) {
+                if (!e.isString()) throw std::runtime_error("vehicles: expected strings");
+                const int k = slotOf(&e.s);
+                const Json &v = vehicles.arr[k];
+                if (placed[k]++ || !running[k] || drivableOf(str(v, "drivable")) != d) throw std::runtime_error("vehicle " + e.s + " is listed on a drivable it is not on");
+                const SlotInfo &si = hs.slots[k];
+                StateImage::Running r{};
+                r.slot = k; r.tmpl = si.tmplId; r.priority = si.priority;
+                const int plan = routing->planFrom(si.routeId, d);
+                if (plan < 0) throw std::runtime_error("vehicle " + e.s + " is on a road that is not on its route");
+                r.planIdx = routing->planBeg()[plan];
+                r.nextDrivable = routing->planData()[r.planIdx + 1];
+                const std::string *prev = optStr(v, "prevDrivable");
+                r.prevDrivable = prev ? drivableOf(*prev) : -1;
+                r.blockerSlot = slotOf(optStr(v, "blocker"));
+                r.leaderSlot = slotOf(optStr(v, "leader"));
+                const long long ell = integer(v, "enterLaneLinkTime");   // written as unsigned (archive.cpp:219-220); INT_MAX on a lane (engine.cpp:489)
+                r.enterLaneLinkTime = ell < 0 || ell > INT_MAX ? INT_MAX : (int) ell;
+                r.dis = dbl(v, "dis"); r.speed = speed[k]; r.gap = dbl(v, "gap");
+                r.len = templates[si.tmplId].len;
+                img.drivables[d].push_back(r);
+                ++runningCount;
+            }
+            if (d < nL) {
+                const Json &wb = member(*dj->second, "waitingBuffer");
+                if (!wb.isArray()) throw std::runtime_error("waitingBuffer: expected an array");
+                for (const Json &e : wb.arr) {
+                    if (!e.isString()) throw std::runtime_error("waitingBuffer: expected strings");
+                    const int k = slotOf(&e.s);
+                    if (placed[k]++ || running[k]) throw std::runtime_error("vehicle " + e.s + " is listed twice");
+                    SlotInfo &si = hs.slots[k];
+                    const int plan = routing->planFrom(si.routeId, d);
+                    if (plan < 0) throw std::runtime_error("vehicle " + e.s + " waits on a road that is not on its route");
+                    si.firstLane = d;
+                    img.waiting[d].push_back(StateImage::Waiting{k, si.tmplId, si.priority, plan});
+                }
+            }
+        }
+        for (int k = 0; k < n; ++k) if (!placed[k]) throw std::runtime_error("vehicle " + vehicleName(hs.slots[k]) + " is on no drivable");
+        if (runningCount != img.active) throw std::runtime_error("activeVehicleCount does not match the drivables' lists");
+        img.slotCount = n;
+        const Json &fl = member(root, "flows");
+        for (size_t i = 0; i < flows.size(); ++i) {
+            const Json &f = member(fl, flows[i].def.id.c_str());
+            hs.flowNow.push_back(dbl(f, "nowTime")); hs.flowCur.push_back(dbl(f, "currentTime")); hs.flowCnt.push_back((int) integer(f, "cnt"));
+            hs.flowValid.push_back((uint8_t) hot[i].valid);     // not archived by the reference: the engine's stays
+        }
+        const Json &tl = member(root, "trafficLights");
+        img.curPhase.assign(net.nInter(), 0);
+        img.remain.assign(net.nInter(), 0.0);
+        for (int i = 0; i < net.nInter(); ++i) {
+            const Json &t = member(tl, net.interId[i].c_str());
+            if (net.interVirtual[i]) continue;                  // TrafficLight::init leaves a virtual intersection's light alone (trafficlight.cpp:11)
+            img.remain[i] = dbl(t, "remainDuration");
+            const long long ph = integer(t, "curPhaseIndex");
+            if (ph < 0 || ph >= net.interPhaseBeg[i + 1] - net.interPhaseBeg[i]) throw std::runtime_error("curPhaseIndex out of range");
+            img.curPhase[i] = (int) ph;
+        }
+        hs.finishedCnt = (int) integer(root, "finishedVehicleCnt");
+        hs.cumulativeTravelTime = dbl(root, "cumulativeTravelTime");
+        hs.manuallyPushCnt = manuallyPushCnt;                   // not archived by the reference either
+        for (int r = 0; r < routing->numRoutes(); ++r) hs.routeAnchors.push_back(routing->anchorsOf(r));
+        hs.templates = templates;
+    }
+
     cfb_vehicle_ref refOf(int slot) const { return cfb_vehicle_ref{slots[slot].flow, slots[slot].index}; }
 };
 
@@ -887,7 +1170,27 @@ public:
 
 // ------------------------------------------------------------------------------------------
 // C ABI
+namespace {
+// Engines alive in this process.  A snapshot remembers the engine it was taken from (a JSON dump needs its road network
+// for names); dumping after that engine was destroyed must fail cleanly, not touch freed memory.
+std::mutex g_liveMutex;
+std::map<const cfb_engine *, uint64_t> g_live;
+uint64_t g_nextSerial = 1;
+}  // namespace
+
 struct cfb_engine {
+    cfb_engine() {
+        std::lock_guard<std::mutex> lock(g_liveMutex);
+        serial = g_nextSerial++;
+        g_live[this] = serial;
+    }
+    ~cfb_engine() {
+        std::lock_guard<std::mutex> lock(g_liveMutex);
+        g_live.erase(this);
+    }
+    cfb_engine(const cfb_engine &) = delete;
+    cfb_engine &operator=(const cfb_engine &) = delete;
+    uint64_t serial = 0;
     cfb::HostEngine h;
     std::string lastError;
     std::vector<cfb::SpeedRec> recs;
@@ -1445,6 +1748,13 @@ extern "C" int64_t cfb_debug_arrays(cfb_engine *e, uint32_t *cyc, uint32_t *path
 struct cfb_archive {
     cfb::HostEngine::HostState host;
     cfb::DeviceSim::Snapshot *dev = nullptr;
+    cfb_engine *owner = nullptr;     // the engine the snapshot was taken from: its road network names what a JSON dump lists
+    uint64_t ownerSerial = 0;
+    bool ownerAlive() const {
+        std::lock_guard<std::mutex> lock(g_liveMutex);
+        auto it = g_live.find(owner);
+        return it != g_live.end() && it->second == ownerSerial;
+    }
     ~cfb_archive() { if (dev) cfb::DeviceSim::freeSnapshot(dev); }
 };
 
@@ -1470,6 +1780,8 @@ cfb_archive *cfb_snapshot(cfb_engine *e) {
         cfb_archive *a = new cfb_archive();
         e->h.saveHost(a->host);
         a->dev = e->h.dev->snapshot();
+        a->owner = e;
+        a->ownerSerial = e->serial;
         return a;
     } catch (const std::exception &ex) {
         e->lastError = ex.what();
@@ -1488,8 +1800,30 @@ int cfb_load(cfb_engine *e, const cfb_archive *a) {
     return CFB_OK;
 }
 
+static bool endsWithJson(const char *path) {
+    const size_t n = strlen(path);
+    return n >= 5 && strcmp(path + n - 5, ".json") == 0;
+}
+
 int cfb_archive_dump(const cfb_archive *a, const char *path) {
     try {
+        if (endsWithJson(path)) {   // the reference's schema (Archive::dump archive.cpp:153-177): interchangeable with it
+            if (!a->owner || !a->ownerAlive()) return CFB_ERR_UNSUPPORTED;
+            DeviceGuard guard(a->owner);
+            cfb::StateImage img;
+            a->owner->h.dev->decodeSnapshot(a->dev, img);
+            std::string text;
+            try {
+                a->owner->h.writeReferenceArchive(a->host, img, text);
+            } catch (const std::exception &ex) {
+                a->owner->lastError = ex.what();
+                return CFB_ERR_UNSUPPORTED;
+            }
+            std::ofstream o(path, std::ios::binary);   // writeJsonToFile utility.cpp:103-112
+            if (!o) return CFB_ERR_ARGUMENT;
+            o.write(text.data(), (std::streamsize) text.size());
+            return o ? CFB_OK : CFB_ERR_ARGUMENT;
+        }
         std::ofstream o(path, std::ios::binary);
         if (!o) return CFB_ERR_ARGUMENT;
         const auto &s = a->host;
@@ -1523,13 +1857,34 @@ int cfb_archive_dump(const cfb_archive *a, const char *path) {
     }
 }
 
+// Engine::loadFromFile engine.cpp:822-825.  The file is either this engine's binary image or the reference's JSON
+// (Archive(Engine &, file) archive.cpp:345-550), told apart by the first bytes; reading the JSON interns the routes and
+// vehicle templates it lists (loadHost uploads the grown tables) and rebuilds the device image from the decoded state.
 int cfb_load_from_file(cfb_engine *e, const char *path) {
     CFB_TRY(e,
         std::ifstream i(path, std::ios::binary);
         if (!i) throw std::runtime_error(std::string("cannot open archive file ") + path);
         uint64_t magic = 0;
         i.read((char *) &magic, 8);
-        if (magic != 0x3242464341ULL) throw std::runtime_error("not an archive written by cityflow_b200 (the reference's JSON archive format is not supported)");
+        if (magic != 0x3242464341ULL) {
+            i.clear();
+            i.seekg(0);
+            int c = i.get();
+            while (c == ' ' || c == '\n' || c == '\r' || c == '\t') c = i.get();
+            if (c != '{') throw std::runtime_error("not an archive: neither this engine's binary image nor the reference's JSON");
+            i.close();
+            const cfb::Json root = cfb::Json::parseFile(path);
+            cfb_archive a;
+            cfb::StateImage img;
+            e->h.dev->synchronize();
+            e->h.cancelAhead();
+            e->h.drain();
+            e->h.readReferenceArchive(root, a.host, img);
+            e->h.loadHost(a.host);
+            a.dev = e->h.dev->encodeSnapshot(img);
+            e->h.dev->restore(a.dev);
+            return CFB_OK;
+        }
         cfb_archive a;
         auto &s = a.host;
         std::vector<char> rv;

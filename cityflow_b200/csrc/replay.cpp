@@ -17,55 +17,11 @@ inline double norm(Pt a) { return std::sqrt(a.x * a.x + a.y * a.y); }          /
 inline Pt unit(Pt a) { const double l = norm(a); return Pt{a.x / l, a.y / l}; }  // Point::unit
 inline double cross2(Pt a, Pt b) { return a.x * b.y - a.y * b.x; }              // crossMultiply
 
-// Shortest digit string that parses back to v (std::to_chars), laid out the way the reference's
-// printer lays numbers out (dtoa_milo.h Prettify: "2.0", "12.34", "0.001234", "1.234e33").
-void put(std::string &s, double v) {
-    if (v == 0) { s += "0.0"; return; }
-    if (v < 0) { s.push_back('-'); v = -v; }
-    char buf[40];
-    const auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
-    char digits[24];
-    int length = 0, expo = 0;
-    const char *q = buf;
-    for (; q < r.ptr && *q != 'e'; ++q)
-        if (*q != '.') digits[length++] = *q;
-    if (q < r.ptr) {
-        ++q;
-        const bool neg = *q == '-';
-        if (*q == '-' || *q == '+') ++q;
-        for (; q < r.ptr; ++q) expo = expo * 10 + (*q - '0');
-        if (neg) expo = -expo;
-    }
-    const int kk = expo + 1;   // 10^(kk-1) <= v < 10^kk
-    if (length <= kk && kk <= 21) {
-        s.append(digits, length);
-        s.append((size_t) (kk - length), '0');
-        s += ".0";
-    } else if (0 < kk && kk <= 21) {
-        s.append(digits, kk);
-        s.push_back('.');
-        s.append(digits + kk, length - kk);
-    } else if (-6 < kk && kk <= 0) {
-        s += "0.";
-        s.append((size_t) -kk, '0');
-        s.append(digits, length);
-    } else {
-        s.push_back(digits[0]);
-        if (length > 1) { s.push_back('.'); s.append(digits + 1, length - 1); }
-        s.push_back('e');
-        s += std::to_string(kk - 1);
-    }
-}
+}  // namespace
 
-void putJsonString(std::string &s, const std::string &v) {
-    s.push_back('"');
-    for (unsigned char c : v) {
-        if (c == '"' || c == '\\') { s.push_back('\\'); s.push_back((char) c); }
-        else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04X", c); s.append(b); }
-        else s.push_back((char) c);
-    }
-    s.push_back('"');
-}
+namespace {
+
+inline void put(std::string &s, double v) { putJsonNumber(s, v); }
 
 // getPointByDistance(points, dis)  roadnet.cpp:17-28 (+ getLengthOfPoints :30-35)
 Pt pointAt(const std::vector<Pt> &p, double dis) {

@@ -28,6 +28,13 @@ struct ReplayVehicle {
     double len, width;   // VehicleInfo len / width
 };
 
+// JSON output pieces (json_write.cpp).  putJsonNumber: the shortest digit string that parses back to `v`, laid out like
+// the reference's printer ("2.0", "12.34", "1.234e33").  putJsonNumberLikeRapidjson: the digits rapidjson's writer
+// (Grisu2) emits -- the archive writer uses it so that the reference reads back the doubles it would from its own file.
+void putJsonNumber(std::string &s, double v);
+void putJsonNumberLikeRapidjson(std::string &s, double v);
+void putJsonString(std::string &s, const std::string &v);
+
 class ReplayWriter {
 public:
     explicit ReplayWriter(const RoadNet &net);

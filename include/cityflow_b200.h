@@ -138,8 +138,18 @@ int64_t cfb_get_vehicle_info(cfb_engine *e, cfb_vehicle_ref vehicle, char *out, 
 /* Archive.  Engine::snapshot() / Engine::load(archive) engine.h:176-177, Archive::dump
  * archive.cpp:153-177, Engine::loadFromFile engine.cpp:822-825.  A snapshot is a device-resident
  * image of the whole dynamic state plus the host bookkeeping (RNG, flows, id tables); it can be
- * restored into the engine that made it or into another engine built from the same config.  The
- * file written by cfb_archive_dump is this engine's own binary image, not the reference's JSON. */
+ * restored into the engine that made it or into another engine built from the same config.
+ * cfb_archive_dump writes one of two forms, chosen by the file name: a path ending in ".json" (what the
+ * reference's users pass, tests/python/test_archive.py:99) gets the reference's JSON schema
+ * (archive.cpp:153-343) -- same members, vehicle / drivable / flow / intersection names, numbers in
+ * rapidjson's own spelling -- which the reference's loadFromFile reads; any other name gets this
+ * engine's binary image (exact, and ~50x smaller and faster).  cfb_load_from_file accepts both and
+ * tells them apart by the first bytes, so a JSON archive written by the reference loads here
+ * (archive.cpp:345-550).  JSON form: not with laneChange; the engine the snapshot was taken from must
+ * still exist when it is dumped (its road network names the drivables), CFB_ERR_UNSUPPORTED otherwise.
+ * Note that the JSON round trip is lossy IN THE REFERENCE (its parser returns some 17-digit numbers
+ * one ulp off): an engine that loads a JSON file follows the trajectory of the reference loading that
+ * file, not the uninterrupted one -- tests/archive_checks.py. */
 typedef struct cfb_archive cfb_archive;
 cfb_archive *cfb_snapshot(cfb_engine *e);
 void cfb_archive_destroy(cfb_archive *a);

@@ -240,6 +240,18 @@ class RefDump:
             return parse_run(f.name, n_inter, n_drivables)
 
     @staticmethod
+    def archive(config: str, steps: int, out_json: str, threads: int = 1) -> None:
+        """The reference's own JSON archive (Archive::dump) after `steps` steps."""
+        subprocess.check_call([REFDUMP, "archive", config, str(steps), str(threads), out_json], timeout=REF_TIMEOUT)
+
+    @staticmethod
+    def resume(config: str, archive_json: str, steps: int, threads: int = 1, every: int = 1, *, n_inter: int, n_drivables: int):
+        """Engine::loadFromFile(archive_json) in the reference, then `steps` steps dumped like run()."""
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            subprocess.check_call([REFDUMP, "resume", config, archive_json, str(steps), str(threads), f.name, str(every)], timeout=REF_TIMEOUT)
+            return parse_run(f.name, n_inter, n_drivables)
+
+    @staticmethod
     def runlc(config: str, steps: int, every: int = 1, *, n_inter: int, n_drivables: int, patched: bool = True, threads: int = 1):
         """laneChange=true run of the reference with the priority-ordered worker set (`patched`,
         oracle/lc_order_patch.sh) or of the unmodified build; states incl. shadows."""

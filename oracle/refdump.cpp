@@ -10,6 +10,10 @@
 //   refdump run <config.json> <steps> <threads> <out.bin> [every]
 //       per-step dynamic state of every running vehicle (raw IEEE-754 bits) ->
 //       the parity oracle for tests/ and for generating tests/golden/.
+//   refdump archive <config.json> <steps> <threads> <out.json>
+//       the reference's JSON archive (Archive::dump) after <steps> steps;
+//   refdump resume <config.json> <archive.json> <steps> <threads> <out.bin> [every]
+//       Engine::loadFromFile(<archive.json>), then as `run` -> archives interchange with cityflow_b200's in both directions.
 //   refdump runlc <config.json> <steps> <threads> <out.bin> [every]
 //       the same for laneChange=true runs: every running vehicle including shadows, keyed by
 //       priority, with the lane-change state (partner, offset, changing, waiting time).
@@ -36,6 +40,7 @@
 #include <deque>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <list>
 #include <map>
 #include <memory>
@@ -161,8 +166,9 @@ int dumpStatic(const char *cfg, const char *outPath) {
     return 0;
 }
 
-int dumpRun(const char *cfg, int steps, int threads, const char *outPath, int every) {
+int dumpRun(const char *cfg, int steps, int threads, const char *outPath, int every, const char *resumeFrom = nullptr) {
     Engine e(cfg, threads);
+    if (resumeFrom) e.loadFromFile(resumeFrom);   // Engine::loadFromFile engine.cpp:822-825: a JSON archive (its own or one written by cityflow_b200)
     Index ix(e);
     Out o(outPath);
     const auto &lanes = e.roadnet.getLanes();
@@ -218,6 +224,26 @@ int dumpRun(const char *cfg, int steps, int threads, const char *outPath, int ev
     o.close();
     fflush(stdout);
     _exit(0);
+    return 0;
+}
+
+// The reference's own JSON archive after `steps` steps (Engine::snapshot + Archive::dump, archive.cpp:153-177).
+// Two members of Vehicle::ControllerInfo have no initialiser (vehicle.h:85-86) and are dumped as they are: `gap` until the
+// vehicle first has a leader, `enterLaneLinkTime` until it first changes drivable.  Neither is read in that state, but a
+// `gap` that happens to be NaN / infinite makes rapidjson's writer stop (the file is cut at a 64 KiB flush) and an
+// `enterLaneLinkTime` above INT_MAX makes the reference refuse its own file -- both seen here, depending on what the heap
+// held.  So the harness (not the engine) gives the two members defined values first: what cityflow_b200 writes for them.
+int writeArchive(const char *cfg, int steps, int threads, const char *outPath) {
+    Engine e(cfg, threads);
+    for (int s = 0; s < steps; ++s) e.nextStep();
+    for (auto &vp : e.vehiclePool) {
+        Vehicle *v = vp.second.first;
+        if (!v->controllerInfo.leader) v->controllerInfo.gap = 0.0;
+        if (!v->controllerInfo.prevDrivable) v->controllerInfo.enterLaneLinkTime = (size_t) std::numeric_limits<int>::max();
+    }
+    e.snapshot().dump(outPath);
+    fflush(stdout);
+    _exit(0);   // (no ~Engine, see dumpRun)
     return 0;
 }
 
@@ -393,6 +419,9 @@ int main(int argc, char **argv) {
     if (argc >= 4 && !strcmp(argv[1], "static")) return dumpStatic(argv[2], argv[3]);
     if (argc >= 6 && !strcmp(argv[1], "run"))
         return dumpRun(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
+    if (argc >= 6 && !strcmp(argv[1], "archive")) return writeArchive(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
+    if (argc >= 7 && !strcmp(argv[1], "resume"))
+        return dumpRun(argv[2], atoi(argv[4]), atoi(argv[5]), argv[6], argc >= 8 ? atoi(argv[7]) : 1, argv[3]);
     if (argc >= 6 && !strcmp(argv[1], "runlc"))
         return dumpRunLC(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5], argc >= 7 ? atoi(argv[6]) : 1);
     if (argc >= 6 && !strcmp(argv[1], "counts"))
@@ -400,6 +429,6 @@ int main(int argc, char **argv) {
     if (argc >= 5 && !strcmp(argv[1], "bench"))
         return bench(argv[2], atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0, argc >= 7 ? argv[6] : nullptr);
     if (argc >= 6 && !strcmp(argv[1], "sweep")) return sweep(argv[2], atoi(argv[3]), atoi(argv[4]), argv[5]);
-    fprintf(stderr, "usage: refdump static|run|runlc|counts|sweep|bench ...\n");
+    fprintf(stderr, "usage: refdump static|run|runlc|counts|sweep|bench|archive|resume ...\n");
     return 64;
 }

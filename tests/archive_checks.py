@@ -1,0 +1,118 @@
+"""Checks of the reference-schema JSON archive (Archive::dump archive.cpp:153-343, the file loader :345-550) shared by the
+CPU test (the real host engine over the emulated device, tests/test_cpu.py) and the GPU test (tests/test_gpu_zarchive.py).
+TEST INFRASTRUCTURE: the checker is the UNMODIFIED reference, compiled in oracle/_ref/refdump (modes `archive`, `resume`).
+
+What "equal" means here.  The reference's own file round trip is lossy: its JSON parser (rapidjson without
+kParseFullPrecisionFlag) returns some 17-digit numbers one ulp off, so an engine that loads a file does NOT continue the
+uninterrupted trajectory -- in the reference itself.  The parity target is therefore the reference LOADING THE SAME FILE:
+this engine's loader parses numbers the way rapidjson does (csrc/json_min.h), and must then move every vehicle exactly
+as the reference does after its loadFromFile()."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from oracle import harness as H   # noqa: E402
+
+STATE_FIELDS = ("flow", "cnt", "priority", "drivable", "dis", "speed", "leader_flow", "leader_cnt", "blocker_flow", "blocker_cnt", "gap")
+
+
+def compare_archives(ours: dict, ref: dict):
+    """Every member of every vehicle, drivable, flow and light.  (`refdump archive` first gives the two members the
+    reference leaves uninitialised -- `gap` without a leader, `enterLaneLinkTime` before the first change of drivable --
+    the values this engine writes, see oracle/refdump.cpp; the lanes' speed history is written empty here: it is read
+    only by RouterType::DURATION routing, which nothing in the engine selects.)"""
+    assert sorted(ours) == sorted(ref)
+    for k in ("step", "activeVehicleCount", "rnd", "finishedVehicleCnt", "cumulativeTravelTime", "flows", "trafficLights"):
+        assert ours[k] == ref[k], k
+    assert [v["id"] for v in ours["vehicles"]] == [v["id"] for v in ref["vehicles"]]      # priority order
+    checked = 0
+    for a, b in zip(ours["vehicles"], ref["vehicles"]):
+        assert sorted(a) == sorted(b), (a["id"], sorted(a), sorted(b))
+        for k in a:
+            assert a[k] == b[k], (a["id"], k, a[k], b[k])
+            checked += 1
+    assert sorted(ours["drivables"]) == sorted(ref["drivables"])
+    for d, x in ours["drivables"].items():
+        y = ref["drivables"][d]
+        assert sorted(x) == sorted(y), d
+        assert x["vehicles"] == y["vehicles"], d
+        assert x.get("waitingBuffer") == y.get("waitingBuffer"), d
+    return checked
+
+
+def follow(eng, states, tag):
+    """`eng` steps along the reference's dumped states: every running vehicle equal in every field."""
+    g = None
+    for st in states:
+        eng.next_step()
+        assert eng.vehicle_count() == st.vehicle_count, (tag, st.step)
+        assert np.array_equal(eng.lane_vehicle_count(), st.lane_count), (tag, st.step)
+        assert np.array_equal(eng.lane_waiting_count(), st.lane_waiting), (tag, st.step)
+        g = np.sort(eng.debug_vehicles(), order=["flow", "cnt"])
+        o = np.sort(st.vehicles, order=["flow", "cnt"])
+        assert len(g) == len(o), (tag, st.step)
+        for f in STATE_FIELDS:
+            assert np.array_equal(g[f], o[f]), (tag, st.step, f)
+    return g
+
+
+def check_json_interchange(make_engine, cfg: str, tmp: str, n0: int, n1: int):
+    """Both directions at step `n0`, followed for `n1` steps:
+    (1) this engine's dump equals the reference's own dump field by field, and the reference loads it and then moves as it
+        does from its own file; (2) this engine loads the reference's file -- over an unrelated state -- and then moves
+        exactly as the reference does from that file, travel-time statistics included; (3) the file written here loads back
+        here to the same trajectory as (2)."""
+    ours_path, ref_path = os.path.join(tmp, "ours.json"), os.path.join(tmp, "ref.json")
+    eng = make_engine(cfg)
+    eng.next_step(n0)
+    eng.dump(ours_path)
+    H.RefDump.archive(cfg, n0, ref_path)
+    checked = compare_archives(json.load(open(ours_path)), json.load(open(ref_path)))
+    assert checked > 20000
+    kw = dict(n_inter=eng.n_inter, n_drivables=eng.n_drivables)
+    from_ref = H.RefDump.resume(cfg, ref_path, n1, **kw)
+    from_ours = H.RefDump.resume(cfg, ours_path, n1, **kw)
+    for a, b in zip(from_ref, from_ours):
+        assert a.vehicle_count == b.vehicle_count and a.finished == b.finished and a.cum_travel_time == b.cum_travel_time
+        assert a.vehicles.tobytes() == b.vehicles.tobytes(), a.step
+    # (2) the reference's file into an engine that is somewhere else entirely
+    other = make_engine(cfg)
+    other.next_step(17)
+    other.load_from_file(ref_path)
+    g = follow(other, from_ref, "reference file")
+    assert len(g) > 300
+    # (3) our own file back into the first engine (it has moved on in the meantime)
+    eng.next_step(5)
+    eng.load_from_file(ours_path)
+    follow(eng, from_ref, "own file")
+    assert eng.average_travel_time() == other.average_travel_time()
+    return from_ref
+
+
+def check_json_with_rl_phases(make_engine, cfg: str, tmp: str):
+    """rlTrafficLight mode, phases set right before the snapshot (not yet sent to the device when it is taken): the file
+    carries them, the reference resuming from it shows them and moves the vehicles as this engine does after loading the
+    same file."""
+    roadnet = json.load(open(json.load(open(cfg))["dir"] + json.load(open(cfg))["roadnetFile"]))
+    real = [k for k, i in enumerate(roadnet["intersections"]) if not i["virtual"]]
+    eng = make_engine(cfg)
+    eng.next_step(90)
+    want = {k: (3 * n + 1) % 8 for n, k in enumerate(real)}
+    for k, ph in want.items():
+        eng.set_tl_phase(k, ph)
+    path = os.path.join(tmp, "rl.json")
+    eng.dump(path)
+    doc = json.load(open(path))
+    assert doc["step"] == 90 and doc["activeVehicleCount"] == eng.vehicle_count()
+    for k, ph in want.items():
+        assert doc["trafficLights"][roadnet["intersections"][k]["id"]]["curPhaseIndex"] == ph
+    ref = H.RefDump.resume(cfg, path, 40, n_inter=eng.n_inter, n_drivables=eng.n_drivables)
+    assert [int(p) for p in ref[-1].phases if p >= 0] == [want[k] for k in real]
+    other = make_engine(cfg)
+    other.load_from_file(path)
+    follow(other, ref, "rl file")

@@ -9,9 +9,10 @@
 // 32-fiber warp -- about a thousand times slower than the GPU.
 //
 // Implemented: what the single-GPU engine uses (step, lane-change step halves, observations, debug dumps,
-// phases, custom speed, plans, reset).  Not emulated (throw): sharding, snapshots, device-resident
-// observations / actions, timing.
+// phases, custom speed, plans, reset, snapshots in the product's image format) and the peer-memory seam protocol of
+// a loop-back group.  Not emulated (throw): NCCL sharding, device-resident observations / actions, timing.
 #include "device_hostsim.h"
+#include "device_image.cuh"
 #include "partition.h"
 
 #include <stdexcept>
@@ -449,11 +450,70 @@ void DeviceSim::shardWaitingCounts(ShardTransport *, int32_t *) { notEmulated("s
 void DeviceSim::shardGatherFinished(ShardTransport *, std::vector<FinRec> &) { notEmulated("sharding"); }
 DeviceObs DeviceSim::observeOnDevice(void *) { notEmulated("device-resident observations"); return DeviceObs(); }
 void DeviceSim::setPhasesFromDevice(const int32_t *, void *) { notEmulated("device-resident actions"); }
-DeviceSim::Snapshot *DeviceSim::snapshot() { notEmulated("snapshots"); return nullptr; }
-void DeviceSim::restore(const Snapshot *) { notEmulated("snapshots"); }
-void DeviceSim::freeSnapshot(Snapshot *) {}
-void DeviceSim::snapshotToHost(const Snapshot *, std::vector<unsigned char> &) { notEmulated("snapshots"); }
-DeviceSim::Snapshot *DeviceSim::snapshotFromHost(const unsigned char *, size_t) { notEmulated("snapshots"); return nullptr; }
+// ---- snapshots: the serialised image of device_sim.cu (device_image.cuh), kept on the host ----
+struct DeviceSim::Snapshot { std::vector<unsigned char> bytes; };
+DeviceSim::Snapshot *DeviceSim::snapshot() {
+    Impl &I = *impl_;
+    HostSim &H = I.H;
+    if (I.phaseDirty) { for (int i = 0; i < H.V.nInter; ++i) H.curPhase[i] = I.hPhase[i]; I.phaseDirty = false; }
+    const auto regs = snapshotRegions(H.V, (size_t) H.P, (size_t) H.slotCap);
+    std::vector<long long> hdr = {IMAGE_MAGIC, steps_, (long long) H.slotCap, (long long) regs.size()};
+    size_t total = 0;
+    for (auto &r : regs) { hdr.push_back((long long) r.second); total += imagePad(r.second); }
+    Snapshot *s = new Snapshot();
+    s->bytes.assign(hdr.size() * sizeof(long long) + total, 0);
+    memcpy(s->bytes.data(), hdr.data(), hdr.size() * sizeof(long long));
+    size_t off = hdr.size() * sizeof(long long);
+    for (auto &r : regs) { if (r.second) memcpy(s->bytes.data() + off, r.first, r.second); off += imagePad(r.second); }
+    return s;
+}
+void DeviceSim::restore(const Snapshot *s) {
+    Impl &I = *impl_;
+    HostSim &H = I.H;
+    const long long *h = reinterpret_cast<const long long *>(s->bytes.data());
+    const int slotCap = (int) h[2];
+    ensureSlotCapacity(slotCap);
+    const auto regs = snapshotRegions(H.V, (size_t) H.P, (size_t) H.slotCap);
+    if ((size_t) h[3] != regs.size()) throw std::runtime_error("cityflow_b200: archive does not match this engine");
+    std::fill(H.pos.begin(), H.pos.end(), -1); std::fill(H.waitNext.begin(), H.waitNext.end(), -1);
+    std::fill(H.slotCust.begin(), H.slotCust.end(), NAN); std::fill(H.blk.begin(), H.blk.end(), -1);
+    std::fill(H.delStep.begin(), H.delStep.end(), INT_MIN);
+    size_t off = (4 + regs.size()) * sizeof(long long);
+    for (size_t k = 0; k < regs.size(); ++k) {
+        const size_t bytes = (size_t) h[4 + k];
+        if (bytes > regs[k].second) throw std::runtime_error("cityflow_b200: archive does not match this engine (region size)");
+        if (k + IMAGE_SLOT_REGIONS < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
+        if (bytes) memcpy(regs[k].first, s->bytes.data() + off, bytes);
+        off += imagePad(bytes);
+    }
+    for (int i = 0; i < H.V.nInter; ++i) I.hPhase[i] = H.curPhase[i];
+    I.phaseDirty = false;
+    for (auto &n : H.notify) n = Notify{0.0, 0, 0};
+    std::fill(H.foeMask.begin(), H.foeMask.end(), 0u);
+    steps_ = h[1];
+}
+void DeviceSim::freeSnapshot(Snapshot *s) { delete s; }
+void DeviceSim::snapshotToHost(const Snapshot *s, std::vector<unsigned char> &out) { out = s->bytes; }
+DeviceSim::Snapshot *DeviceSim::snapshotFromHost(const unsigned char *data, size_t n) {
+    if (n < 4 * sizeof(long long) || reinterpret_cast<const long long *>(data)[0] != IMAGE_MAGIC)
+        throw std::runtime_error("cityflow_b200: not an archive of this engine");
+    Snapshot *s = new Snapshot();
+    s->bytes.assign(data, data + n);
+    return s;
+}
+static ImageGeometry imageGeometry(DeviceSim::Impl &I) {
+    return ImageGeometry{I.offHost.data(), I.H.V.nDrv, I.H.V.nLanes, I.H.V.nInter, (size_t) I.H.P};
+}
+void DeviceSim::decodeSnapshot(const Snapshot *s, StateImage &out) {
+    std::vector<unsigned char> blob;
+    snapshotToHost(s, blob);
+    decodeImage(blob, imageGeometry(*impl_), out);
+}
+DeviceSim::Snapshot *DeviceSim::encodeSnapshot(const StateImage &in) {
+    std::vector<unsigned char> blob;
+    encodeImage(in, imageGeometry(*impl_), blob);
+    return snapshotFromHost(blob.data(), blob.size());
+}
 void DeviceSim::enableKernelTiming(bool) {}
 void DeviceSim::flushL2() {}
 void DeviceSim::markTimed() {}
