@@ -116,3 +116,23 @@ def check_json_with_rl_phases(make_engine, cfg: str, tmp: str):
     other = make_engine(cfg)
     other.load_from_file(path)
     follow(other, ref, "rl file")
+
+
+def check_reference_disk_io_tests(make_engine, cfg: str, tmp: str, record):
+    """The reference's own tests/python/test_archive.py:95-119 (test_save_to_file, test_multi_save_to_file), file name
+    included: dump("save.json") after 100 steps, 100 more -> record, load_from_file("save.json"), 100 steps -> the
+    same record (lane vehicle counts + average travel time), twice over.  `cfg` must be a scenario whose routes visit
+    no road twice: on other routes the reference's reloaded router deviates (see Routing::planFrom) and its own test
+    would fail."""
+    path = os.path.join(tmp, "save.json")
+    eng = make_engine(cfg)
+    for _ in range(2):
+        eng.next_step(100)
+        eng.dump(path)
+        assert open(path).read(1) == "{"
+        eng.next_step(100)
+        want = record(eng)
+        for _ in range(2):
+            eng.load_from_file(path)
+            eng.next_step(100)
+            assert record(eng) == want

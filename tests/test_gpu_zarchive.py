@@ -45,3 +45,25 @@ def test_json_archive_through_the_python_module(cfg_3x3_dense, tmp_path):
     assert eng2.get_current_time() == 80.0 and eng2.get_vehicle_count() == eng.get_vehicle_count()
     assert sorted(eng2.get_vehicles(include_waiting=True)) == sorted(eng.get_vehicles(include_waiting=True))
     assert eng2.get_lane_vehicle_count() == eng.get_lane_vehicle_count()
+
+
+def test_reference_disk_io_archive_tests(cfg_6x6, tmp_path):
+    """tests/python/test_archive.py:95-119 of the reference through the drop-in module, "save.json" and all."""
+    import cityflow
+
+    class Eng:
+        def __init__(self, cfg):
+            self.e = cityflow.Engine(cfg, thread_num=4)
+
+        def next_step(self, n=1):
+            for _ in range(n):
+                self.e.next_step()
+
+        def dump(self, path):
+            self.e.snapshot().dump(path)
+
+        def load_from_file(self, path):
+            self.e.load_from_file(path)
+
+    archive_checks.check_reference_disk_io_tests(Eng, cfg_6x6, str(tmp_path),
+                                                 lambda x: (x.e.get_lane_vehicle_count(), x.e.get_average_travel_time()))
