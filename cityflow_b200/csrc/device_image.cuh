@@ -19,11 +19,13 @@ struct ImageGeometry {
 };
 
 // (pointer, bytes) of every array a snapshot carries, in image order; slot-indexed arrays last (their size may differ
-// between the time a snapshot is taken and the time it is restored)
-constexpr size_t IMAGE_SLOT_REGIONS = 6;
+// between the time a snapshot is taken and the time it is restored).  With lane change on, the per-slot lane-change
+// state (LaneChangeInfo + LaneChange, device_lc_types.cuh) is one more of them; everything else of that path is
+// rebuilt every step.
+inline size_t imageSlotRegions(const View &V) { return V.lcOn ? 7 : 6; }
 inline std::vector<std::pair<void *, size_t>> snapshotRegions(const View &V, size_t P, size_t S) {
     const size_t nL = (size_t) std::max(V.nLanes, 1);
-    return {
+    std::vector<std::pair<void *, size_t>> regs = {
         {V.kin, P * sizeof(double2)}, {V.gap, P * sizeof(double)}, {V.leader, P * sizeof(int)},
         {V.ids, P * sizeof(int4)}, {V.nav, P * sizeof(int4)}, {V.cust, P * sizeof(double)},
         {V.count, (size_t) V.nDrv * sizeof(int)}, {V.entCnt, (size_t) V.nDrv * sizeof(int)},
@@ -37,6 +39,8 @@ inline std::vector<std::pair<void *, size_t>> snapshotRegions(const View &V, siz
         {V.pos, S * sizeof(int)}, {V.waitNext, S * sizeof(int)}, {V.slotInfo, S * sizeof(int4)}, {V.slotCust, S * sizeof(double)},
         {V.blk, S * sizeof(int)}, {V.delStep, S * sizeof(int)},
     };
+    if (V.lcOn) regs.push_back({V.lc.slot, S * sizeof(LcSlot)});
+    return regs;
 }
 
 // The serialised image (snapshotToHost): {magic, steps, slotCap, #regions, region bytes...} as long long, then the

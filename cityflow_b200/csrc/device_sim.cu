@@ -1690,7 +1690,7 @@ void DeviceSim::restore(const Snapshot *s) {
     for (size_t k = 0; k < regs.size(); ++k) {
         const size_t bytes = s->regions[k].bytes;
         if (bytes > regs[k].second) throw std::runtime_error("cityflow_b200: archive does not match this engine (region size)");
-        if (k + 6 < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
+        if (k + imageSlotRegions(I.V) < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
         if (bytes) CFB_CUDA(cudaMemcpyAsync(regs[k].first, s->blob.p + off, bytes, cudaMemcpyDeviceToDevice, I.stream));
         off += (bytes + 255) & ~(size_t) 255;
     }

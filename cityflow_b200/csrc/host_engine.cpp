@@ -895,7 +895,7 @@ public:
     }
 
     void writeReferenceArchive(const HostState &hs, const StateImage &img, std::string &o) const {
-        if (laneChange) throw std::runtime_error("an archive in the reference's JSON schema is not written with laneChange on (use the binary form)");
+        if (laneChange) throw std::runtime_error("an archive in the reference's JSON schema is not written with laneChange on (any other file name gets the binary form)");
         if (!laneLocal.empty()) throw std::runtime_error("an archive in the reference's JSON schema is not written by one rank of a sharded engine");
         if (!hs.pending.empty()) throw std::runtime_error("archive taken in the middle of a step");
         const int nL = net.nLanes();
@@ -1810,6 +1810,10 @@ int cfb_archive_dump(const cfb_archive *a, const char *path) {
         if (endsWithJson(path)) {   // the reference's schema (Archive::dump archive.cpp:153-177): interchangeable with it
             if (!a->owner || !a->ownerAlive()) return CFB_ERR_UNSUPPORTED;
             DeviceGuard guard(a->owner);
+            if (a->owner->h.laneChange) {
+                a->owner->lastError = "an archive in the reference's JSON schema is not written with laneChange on (any other file name gets the binary form)";
+                return CFB_ERR_UNSUPPORTED;
+            }
             cfb::StateImage img;
             a->owner->h.dev->decodeSnapshot(a->dev, img);
             std::string text;

@@ -136,3 +136,46 @@ def check_reference_disk_io_tests(make_engine, cfg: str, tmp: str, record):
             eng.load_from_file(path)
             eng.next_step(100)
             assert record(eng) == want
+
+
+def lc_vehicles(eng):
+    """cfb_debug_lc_vehicles: every running vehicle incl. shadows with its lane-change state."""
+    import ctypes
+    lib = eng.lib
+    lib.cfb_debug_lc_vehicles.restype = ctypes.c_int64
+    lib.cfb_debug_lc_vehicles.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    n = int(lib.cfb_debug_lc_vehicles(eng.h, None, 0))
+    got = np.zeros(n, H.LC_DTYPE)
+    if n:
+        lib.cfb_debug_lc_vehicles(eng.h, got.ctypes.data, n)
+    return got
+
+
+def check_lane_change_snapshot(make_engine, cfg: str, tmp: str):
+    """laneChange = true: the binary archive carries the per-vehicle lane-change state (partners, offsets, signals,
+    waiting times).  Taken while shadows are on the road, loaded into the same and into a fresh engine: the
+    uninterrupted run, every field of every vehicle and shadow, 60 steps.  The JSON form is refused with laneChange."""
+    eng = make_engine(cfg)
+    eng.next_step(100)
+    for _ in range(200):
+        if (lc_vehicles(eng)["partner_type"] == 2).sum() >= 2:
+            break
+        eng.next_step()
+    assert (lc_vehicles(eng)["partner_type"] == 2).sum() >= 2
+    path = os.path.join(tmp, "lc.bin")
+    eng.dump(path)
+    want = []
+    for _ in range(60):
+        eng.next_step()
+        want.append((eng.vehicle_count(), lc_vehicles(eng).tobytes()))
+    fresh = make_engine(cfg)
+    for e in (eng, fresh):
+        e.load_from_file(path)
+        for k in range(60):
+            e.next_step()
+            assert (e.vehicle_count(), lc_vehicles(e).tobytes()) == want[k], k
+    try:
+        eng.dump(os.path.join(tmp, "lc.json"))
+        raise AssertionError("the JSON form must be refused with laneChange on")
+    except RuntimeError as ex:
+        assert "laneChange" in str(ex)

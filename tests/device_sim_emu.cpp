@@ -482,7 +482,7 @@ void DeviceSim::restore(const Snapshot *s) {
     for (size_t k = 0; k < regs.size(); ++k) {
         const size_t bytes = (size_t) h[4 + k];
         if (bytes > regs[k].second) throw std::runtime_error("cityflow_b200: archive does not match this engine (region size)");
-        if (k + IMAGE_SLOT_REGIONS < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
+        if (k + imageSlotRegions(H.V) < regs.size() && bytes != regs[k].second) throw std::runtime_error("cityflow_b200: archive was taken on a different road network");
         if (bytes) memcpy(regs[k].first, s->bytes.data() + off, bytes);
         off += imagePad(bytes);
     }

@@ -67,3 +67,10 @@ def test_reference_disk_io_archive_tests(cfg_6x6, tmp_path):
 
     archive_checks.check_reference_disk_io_tests(Eng, cfg_6x6, str(tmp_path),
                                                  lambda x: (x.e.get_lane_vehicle_count(), x.e.get_average_travel_time()))
+
+
+def test_lane_change_snapshot(tmp_path):
+    """snapshot / dump / load_from_file with laneChange = true: the per-vehicle lane-change state travels in the image."""
+    from cityflow_b200 import scenario
+    cfg = scenario.make_grid_scenario(str(tmp_path), 3, 3, dense=dict(frac=1.0, interval=3.0, seed=3), name="s33lc", lane_change=True)
+    archive_checks.check_lane_change_snapshot(_engine, cfg, str(tmp_path))
