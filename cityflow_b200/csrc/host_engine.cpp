@@ -1791,8 +1791,15 @@ cfb_archive *cfb_snapshot(cfb_engine *e) {
 
 void cfb_archive_destroy(cfb_archive *a) { delete a; }
 
+// (Not on one rank of a sharded engine: the seam mailboxes and their flags are stamped with the engine's own count of
+// completed steps, which an image taken at another time would rewind.)
+static void refuseShardedLoad(const cfb_engine *e) {
+    if (!e->h.laneLocal.empty()) throw std::runtime_error("load / load_from_file: not supported on one rank of a sharded engine");
+}
+
 int cfb_load(cfb_engine *e, const cfb_archive *a) {
     CFB_TRY(e,
+        refuseShardedLoad(e);
         e->h.dev->synchronize();
         e->h.loadHost(a->host);          // (re-interns routes / templates first: may re-upload tables)
         e->h.dev->restore(a->dev);
@@ -1866,6 +1873,7 @@ int cfb_archive_dump(const cfb_archive *a, const char *path) {
 // vehicle templates it lists (loadHost uploads the grown tables) and rebuilds the device image from the decoded state.
 int cfb_load_from_file(cfb_engine *e, const char *path) {
     CFB_TRY(e,
+        refuseShardedLoad(e);
         std::ifstream i(path, std::ios::binary);
         if (!i) throw std::runtime_error(std::string("cannot open archive file ") + path);
         uint64_t magic = 0;
