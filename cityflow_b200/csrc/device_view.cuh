@@ -1,6 +1,6 @@
 // device_view.cuh -- device-side data layout (View) and the scalar helpers of the step kernels.
 // Part of device_sim.cu (included there, inside namespace cfb's translation unit); a header only so that
-// tests/lc_device_probe.cpp can compile the lane-change draft's device functions for the host.
+// tests/lc_device_probe.cpp can compile the device functions for the host.
 #pragma once
 
 namespace cfb {

@@ -66,7 +66,7 @@ public:
     int numPlans() const { return (int) planBeg_.size(); }
     // next laneLink for a vehicle on `lane` whose route continues with roads[r+1] (, roads[r+2])
     int chooseLink(int lane, const std::vector<int> &roads, int r) const;
-    // Lane change (not enabled by the engine yet): a shadow vehicle continues its
+    // Lane change: a shadow vehicle continues its
     // parent's route from the lane it was inserted into, so every lane of every road of a route gets
     // a plan.  Must be switched on before the first intern().
     void enableLanePlans() { lanePlans_ = true; }

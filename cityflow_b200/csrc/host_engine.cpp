@@ -65,7 +65,7 @@ struct SlotInfo {
     int32_t routeId = -1;            // resolved route (Routing::route), for get_vehicle_info / set_vehicle_route
     int32_t firstLane = -1;          // lane whose waiting queue the vehicle was put in
     int32_t tmplId = -1;             // vehicle template (length / width for the replay log)
-    bool shadow = false;             // lane-change draft: a shadow vehicle (Vehicle::isReal() == false)
+    bool shadow = false;             // lane change: a shadow vehicle (Vehicle::isReal() == false)
     bool live = false;
 };
 
@@ -280,7 +280,7 @@ public:
             if (replaced[k]) {
                 SlotInfo &s = slots[fin[k].slot];
                 if (!s.live) continue;
-                for (SlotInfo &o : slots)   // its shadow: same name, live, flagged (rare event: linear search is fine in the draft)
+                for (SlotInfo &o : slots)   // its shadow: same name, live, flagged (rare event: a linear search)
                     if (o.live && o.shadow && o.flow == s.flow && o.index == s.index) { o.shadow = false; break; }
                 if (pool.get(s.priority) == fin[k].slot) pool.erase(s.priority);
                 s.live = false;

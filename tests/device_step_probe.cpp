@@ -1,8 +1,8 @@
 // CPU probe: the WHOLE device step on the host.  TEST INFRASTRUCTURE ONLY.
 //
 // The bodies of all five step kernels (csrc/device_phases_a.cuh: k_ingest, k_notify; device_control.cuh:
-// k_control; device_phases_b.cuh: k_move, k_leader) and, with laneChange, the kernels of the lane-change
-// draft (csrc/device_lc.cuh) run on an emulated warp (tests/device_emu.h: 32 lock-stepped fibers) over
+// k_control; device_phases_b.cuh: k_move, k_leader) and, with laneChange, the lane-change kernels
+// (csrc/device_lc.cuh) run on an emulated warp (tests/device_emu.h: 32 lock-stepped fibers) over
 // persistent lane-bucket arrays laid out like DeviceSim's.  The emulated engine gets the same spawn events as
 // the restatement (oracle/cityflow_oracle.cpp) and evolves ON ITS OWN; after every step its full state --
 // list order, distance, speed, leader, gap, blocker, enterLaneLinkTime of every vehicle, vehicle counts,
@@ -129,7 +129,7 @@ void deviceStep(Oracle &o) {
             Veh *parent = vehOfSlot[H.shadowLog[k].x];
             int pr = INT_MIN;
             for (auto &sp : o.shadowsThisStep) if (sp.first == parent) pr = sp.second;
-            CHECK(pr != INT_MIN, "the draft created a shadow for prio %d, the restatement did not", parent ? parent->priority : 0);
+            CHECK(pr != INT_MIN, "the device created a shadow for prio %d, the restatement did not", parent ? parent->priority : 0);
             H.prio[k] = pr;
             // the restatement's shadow object, if it survived its first step (it may have aborted at once)
             auto it = pr != INT_MIN ? o.pool.find(pr) : o.pool.end();
@@ -140,8 +140,8 @@ void deviceStep(Oracle &o) {
                 vehOfSlot[sh] = it->second;
             }
         }
-        CHECK(ns == (int) o.shadowsThisStep.size(), "shadows created: restatement %zu, draft %d", o.shadowsThisStep.size(), ns);
-        for (auto &sp : o.shadowsThisStep) {   // diagnostics: a parent the draft did not serve
+        CHECK(ns == (int) o.shadowsThisStep.size(), "shadows created: restatement %zu, device %d", o.shadowsThisStep.size(), ns);
+        for (auto &sp : o.shadowsThisStep) {   // diagnostics: a parent the device did not serve
             Veh *pv = sp.first;
             const int ps = slotOf.at(pv);
             bool found = false;
@@ -189,7 +189,7 @@ void deviceStep(Oracle &o) {
 void compare(Oracle &o, std::vector<Veh *> &removedThisStep) {
     HostSim &H = *S;
     View &V = H.V;
-    // shadows created this step: map the restatement's object to the draft's slot (through the parent)
+    // shadows created this step: map the restatement's object to the device's slot (through the parent)
     for (auto &kv : o.pool) {
         Veh *v = kv.second;
         if (!v->running || slotOf.count(v)) continue;

@@ -42,7 +42,7 @@ namespace {
 
 using namespace cfb;
 
-struct Soa {   // the arrays the draft's functions touch, sized for this step
+struct Soa {   // the arrays the device functions touch, sized for this step
     std::vector<int> off, count, pos, leader, laneOutBeg, laneOutLinks, planBeg, planData, segIdx, posDrv, segBeg,
         laneIdx, laneRoadN, planRoute, planRoadPos, lpRoad, lpBeg, lpId, cand, involved, spare, act[2], blk, extra, entCnt, ent;
     std::vector<double> drvLength, gap, cust, segStart, laneWidth, drvMaxSpeed, lcDist;
@@ -295,7 +295,7 @@ void after(Oracle &o) {
     const int epoch = S.epoch;
     ++g_steps;
     CHECK(S.lcCtrl.error == 0, "capacity error %d", S.lcCtrl.error);
-    // shadows: the restatement's new shadows <-> the draft's, by parent
+    // shadows: the restatement's new shadows <-> the device's, by parent
     int newShadows = 0;
     for (auto &kv : o.pool) {
         Veh *v = kv.second;
@@ -304,14 +304,14 @@ void after(Oracle &o) {
         CHECK(v->partnerType == 2 && v->partner && S.slotOf.count(v->partner), "new vehicle that is not a shadow");
         const int ps = S.slotOf.at(v->partner);
         const int sh = S.slot[ps].partner;
-        CHECK(sh >= 0 && S.slot[ps].type == 1 && S.slot[sh].type == 2 && S.slot[sh].partner == ps, "parent %d has no shadow in the draft", v->partner->priority);
+        CHECK(sh >= 0 && S.slot[ps].type == 1 && S.slot[sh].type == 2 && S.slot[sh].partner == ps, "parent %d has no shadow on the device", v->partner->priority);
         if (sh >= 0) { S.slotOf[v] = sh; if ((int) S.vehOfSlot.size() <= sh) S.vehOfSlot.resize(sh + 1, nullptr); S.vehOfSlot[sh] = v; }
     }
-    CHECK(newShadows == S.lcCtrl.nShadows, "shadows: restatement %d draft %d", newShadows, S.lcCtrl.nShadows);
+    CHECK(newShadows == S.lcCtrl.nShadows, "shadows: restatement %d device %d", newShadows, S.lcCtrl.nShadows);
     g_shadows += newShadows;
     // the log must be in the restatement's creation order (= RNG order): ascending shadow creation is the
     // order of priorities drawn, which the restatement recorded implicitly in its own draws; compare by
-    // walking the draft's log and checking each parent got its shadow
+    // walking the device's log and checking each parent got its shadow
     for (int k = 0; k < S.lcCtrl.nShadows; ++k) CHECK(S.slot[S.shadowLog[k].x].partner == S.shadowLog[k].y, "shadow log entry %d inconsistent", k);
     // lists: same vehicles in the same order on every drivable
     for (int d = 0; d < V.nDrv; ++d) {
@@ -361,7 +361,7 @@ void after(Oracle &o) {
             CHECK(S.ids[p].w == want || (S.ids[p].w < 0 && want < 0), "shadow prio %d: next drivable %d vs %d", v->priority, S.ids[p].w, want);
         }
     }
-    CHECK(cands == S.lcCtrl.nCand, "candidates: restatement %d draft %d", cands, S.lcCtrl.nCand);
+    CHECK(cands == S.lcCtrl.nCand, "candidates: restatement %d device %d", cands, S.lcCtrl.nCand);
     g_candidates += cands;
 }
 
