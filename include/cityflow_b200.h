@@ -143,7 +143,7 @@ int64_t cfb_get_vehicle_info(cfb_engine *e, cfb_vehicle_ref vehicle, char *out, 
  * reference's users pass, tests/python/test_archive.py:99) gets the reference's JSON schema
  * (archive.cpp:153-343) -- same members, vehicle / drivable / flow / intersection names, numbers in
  * rapidjson's own spelling -- which the reference's loadFromFile reads; any other name gets this
- * engine's binary image (exact, and ~50x smaller and faster).  cfb_load_from_file accepts both and
+ * engine's binary image (exact; its size follows the engine's capacity, not the vehicle count).  cfb_load_from_file accepts both and
  * tells them apart by the first bytes, so a JSON archive written by the reference loads here
  * (archive.cpp:345-550).  JSON form: not with laneChange; the engine the snapshot was taken from must
  * still exist when it is dumped (its road network names the drivables), CFB_ERR_UNSUPPORTED otherwise.
