@@ -179,3 +179,63 @@ def check_lane_change_snapshot(make_engine, cfg: str, tmp: str):
         raise AssertionError("the JSON form must be refused with laneChange on")
     except RuntimeError as ex:
         assert "laneChange" in str(ex)
+
+
+def check_damaged_json_is_refused(make_engine, cfg: str, tmp: str, rounds: int = 150, seed: int = 1):
+    """load_from_file on damaged input: a valid archive with random structural damage (members removed or retyped, list
+    entries removed / duplicated / replaced, truncation).  Every file is either refused with an error or accepted and
+    steppable, never a crash, and the engine loads the intact file afterwards."""
+    import copy
+    import random
+    rng = random.Random(seed)
+    eng = make_engine(cfg)
+    eng.next_step(80)
+    good, bad = os.path.join(tmp, "good.json"), os.path.join(tmp, "bad.json")
+    eng.dump(good)
+    doc = json.load(open(good))
+
+    def mutate(x, depth=0):
+        if isinstance(x, dict) and x:
+            k = rng.choice(list(x))
+            r = rng.random()
+            if r < 0.25 or depth > 3:
+                del x[k]
+            elif r < 0.5:
+                x[k] = rng.choice([None, -1, 1e308, "zzz", [], {}, True, 2 ** 40, -2 ** 40, "road_0_0_0", 1.5])
+            elif not mutate(x[k], depth + 1):
+                x[k] = rng.choice([None, -5, "x", [], {}])
+            return True
+        if isinstance(x, list) and x:
+            i = rng.randrange(len(x))
+            r = rng.random()
+            if r < 0.2:
+                del x[i]
+            elif r < 0.4:
+                x.append(copy.deepcopy(x[i]))
+            elif r < 0.6:
+                x[i] = rng.choice([None, 7, "flow_0_0", "nope", {}, []])
+            elif not mutate(x[i], depth + 1):
+                x[i] = rng.choice([None, -5, "x"])
+            return True
+        return False
+
+    refused = 0
+    for _ in range(rounds):
+        m = copy.deepcopy(doc)
+        for _ in range(rng.choice([1, 1, 1, 2, 3])):
+            mutate(m)
+        text = json.dumps(m)
+        if rng.random() < 0.1:
+            text = text[:rng.randrange(len(text))]
+        with open(bad, "w") as f:
+            f.write(text)
+        try:
+            eng.load_from_file(bad)
+            eng.next_step(2)
+        except RuntimeError:
+            refused += 1
+        eng.load_from_file(good)
+        eng.next_step(1)
+        assert eng.vehicle_count() == doc["activeVehicleCount"] or eng.vehicle_count() > 0
+    assert refused > rounds // 2
+    return refused
