@@ -96,7 +96,10 @@ DeviceSim::DeviceSim(const RoadNet &net, const std::vector<VehicleTemplate> &tem
     uploadTemplates(templates);
     uploadPlans(routing);
 }
-DeviceSim::~DeviceSim() { delete impl_; }
+DeviceSim::~DeviceSim() {
+    g_shardEmu.erase(this);   // (a later engine at the same address must not inherit this one's mailboxes and flags)
+    delete impl_;
+}
 
 void DeviceSim::uploadTemplates(const std::vector<VehicleTemplate> &templates) {
     HostSim &H = impl_->H;
