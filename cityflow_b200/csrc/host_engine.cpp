@@ -356,36 +356,54 @@ public:
         }
     };
     std::unique_ptr<Workers> workers;
-    // Used for steps that spawn at least this many vehicles (CITYFLOW_B200_PARALLEL_SPAWN_MIN; 0 = never): in practice the
-    // ranks of a 4- or 8-GPU run, which replicate 725 / 1451 creations per step; the single-GPU and 2-GPU workloads stay
-    // on the sequential loop.  Measured on a B200 host (4 ranks, 30x120, profiles/r02i): spawn generation 147 -> 95 us per
-    // step, end to end 0.260 -> 0.161 ms per step, parity_check equal.  The RNG, the slot hand-out and the flow clocks stay
-    // sequential.
+    // Used for steps that spawn at least this many vehicles (CITYFLOW_B200_PARALLEL_SPAWN_MIN; 0 = never).  The bench flows
+    // spawn in bursts (every flow every 10 s), so this is every tenth step of any bench run: 1 800 creations on one GPU,
+    // 14 400 on every rank of the 8-GPU run (a sharded run replicates the whole network's spawns).  Measured on a B200 host
+    // (4 ranks, 30x120, profiles/r02i): spawn generation 147 -> 95 us per step, end to end 0.260 -> 0.161 ms per step,
+    // parity_check equal; reworked after that (thread-local vectors, one buffer of draws: DESIGN.md section 8), measured in
+    // the kernel-free spawner mode of the test build only: 170 -> 120 us per step at the 8-GPU population.  The RNG, the slot
+    // hand-out and the flow clocks stay sequential.
     int parallelSpawnMin = 512;
     std::vector<int> parSlot, parIndex;
 
     std::vector<uint32_t> parMine[Workers::T];
     std::vector<uint32_t> parInserted[Workers::T];
-    // Creates the vehicles due[from .. n), whose slots / indices are in parSlot / parIndex and whose draws -- with the RNG at
-    // its current position -- are predicted[from .. n); returns the index of the first hit (n: none).  Vehicles before the hit
-    // are complete, the RNG stands behind their draws.
+    // The creation phase's share of the RNG stream, taken from the engine RNG itself before the vehicles are made (every
+    // value is consumed below, in order, so the RNG ends where the sequential loop would leave it): vehicle k's priority
+    // is rawDraws[2 k + drawShift], the value after it its thread index (engine.cpp:601-606); drawShift counts the
+    // redraws of vehicles that hit a priority in use (each moves everybody behind it one value on).
+    std::vector<uint32_t> rawDraws;
+    size_t drawShift = 0, drawPos = 0;
+    bool drawFromBuffer = false;
+    uint32_t nextDraw() {
+        if (!drawFromBuffer) return (uint32_t) rnd();
+        if (drawPos == rawDraws.size()) rawDraws.push_back((uint32_t) rnd());
+        return rawDraws[drawPos++];
+    }
+    int plannedKey(size_t k) const { return (int) rawDraws[2 * k + drawShift]; }
+    // Creates the vehicles due[from .. n), whose slots / indices are in parSlot / parIndex and whose draws are plannedKey(k);
+    // returns the index of the first hit (n: none).  Vehicles before the hit are complete.
     size_t createParallel(size_t from, size_t n) {
         std::atomic<size_t> firstHit{n};
         const double enter = currentTime();
         const int32_t spawnStep = (int32_t) step;
         workers->run([&](int w) {
             PriorityMap &M = pool.sub(w);
-            std::vector<uint32_t> &mine = parMine[w], &ins = parInserted[w];
+            // (the vectors' control blocks sit side by side in the member arrays: a thread works on locals and hands them back
+            // at the end, or every push_back takes the cache line away from the other three -- measured 3x on the job)
+            std::vector<uint32_t> mine, ins;
+            mine.swap(parMine[w]);
+            ins.swap(parInserted[w]);
             mine.clear(); ins.clear();
-            for (size_t k = from; k < n; ++k) if (PriorityMap4::part(predicted[k]) == w) mine.push_back((uint32_t) k);
+            for (size_t k = from; k < n; ++k) if (PriorityMap4::part(plannedKey(k)) == w) mine.push_back((uint32_t) k);
             constexpr size_t PF = 12;
-            auto pf = [&](size_t j) { M.prefetch(predicted[mine[j]]); __builtin_prefetch(&slots[parSlot[mine[j]]], 1); };
+            auto pf = [&](size_t j) { M.prefetch(plannedKey(mine[j])); __builtin_prefetch(&slots[parSlot[mine[j]]], 1); };
             for (size_t j = 0; j < std::min(PF, mine.size()); ++j) pf(j);
             for (size_t j = 0; j < mine.size(); ++j) {
                 if (j + PF < mine.size()) pf(j + PF);
                 const size_t k = mine[j];
                 if (k >= firstHit.load(std::memory_order_relaxed)) break;
-                const int key = predicted[k];
+                const int key = plannedKey(k);
                 if (M.get(key) >= 0) {   // in use (or drawn twice this step): from here on the sequential code decides
                     size_t cur = firstHit.load();
                     while (k < cur && !firstHit.compare_exchange_weak(cur, k)) {}
@@ -398,18 +416,19 @@ public:
                 s.flow = due[k]; s.index = parIndex[k]; s.priority = key; s.enterTime = enter; s.spawnStep = spawnStep;
                 s.routeId = fs.routeId; s.firstLane = -1; s.tmplId = fs.tmplId; s.shadow = false; s.live = true;
             }
+            mine.swap(parMine[w]);
+            ins.swap(parInserted[w]);
         });
         const size_t c = firstHit.load();
         for (int w = 0; w < Workers::T; ++w)     // what the other threads created beyond the hit is taken back
             for (size_t j = parInserted[w].size(); j-- > 0 && parInserted[w][j] > c;) {
                 const size_t k = parInserted[w][j];
-                pool.erase(predicted[k]);
+                pool.erase(plannedKey(k));
                 slots[parSlot[k]].live = false;
             }
-        rnd.discard(2 * (c - from));             // priority + thread index per vehicle (engine.cpp:601-606)
         for (size_t k = from; k < c; ++k) {
             const FlowStatic &fs = flowStatic[due[k]];
-            if (undoLog) { undo.inserted.push_back(predicted[k]); undo.allocated.push_back(parSlot[k]); }
+            if (undoLog) { undo.inserted.push_back(plannedKey(k)); undo.allocated.push_back(parSlot[k]); }
             pending.push_back({parSlot[k], fs.firstRoad, fs.routeId, fs.tmplId, due[k]});
         }
         idMapValid = false;
@@ -430,7 +449,7 @@ public:
     int createVehicle(int flow, int index, int routeId, int tmplId, int firstRoad, int slotGiven = -1) {
         int priority;
         for (;;) {
-            priority = (int) rnd();
+            priority = (int) nextDraw();
             const int other = pool.get(priority);
             if (other < 0) break;
             // The holder of this priority may have left the network on the device already (the host
@@ -444,7 +463,7 @@ public:
                 break;
             }
         }
-        (void) rnd();  // threadIndex = rnd() % threadNum (engine.cpp:606): drawn, not needed here
+        (void) nextDraw();  // threadIndex = rnd() % threadNum (engine.cpp:606): drawn, not needed here
         const int slot = slotGiven >= 0 ? slotGiven : allocSlot();
         SlotInfo &s = slots[slot];
         s.flow = flow;
@@ -506,7 +525,8 @@ public:
         // line fills, so issuing all of a step's prefetches up front drops most of them (measured: 285 -> see profiles/).
         const size_t nDue = due.size();
         constexpr size_t PF = 12;
-        if (nDue >= 8) {
+        const bool parallel = parallelSpawnMin > 0 && nDue >= (size_t) parallelSpawnMin;
+        if (nDue >= 8 && !parallel) {
             std::mt19937 ahead = rnd;
             predicted.resize(nDue);
             for (size_t k = 0; k < nDue; ++k) { predicted[k] = (int) ahead(); (void) ahead(); }
@@ -517,20 +537,33 @@ public:
             if (k < nFree) __builtin_prefetch(&slots[freeSlots[nFree - 1 - k]], 1);
         };
         size_t done = 0;
-        if (parallelSpawnMin > 0 && nDue >= (size_t) parallelSpawnMin) {
+        if (parallel) {
             if (!workers) { workers.reset(new Workers()); workers->start(); }
             parSlot.resize(nDue); parIndex.resize(nDue);
-            for (size_t k = 0; k < nDue; ++k) { parIndex[k] = H[due[k]].cnt++; parSlot[k] = allocSlot(); }   // same order as the sequential loop
+            for (size_t k = 0; k < nDue; ++k) parIndex[k] = H[due[k]].cnt++;
+            {   // allocSlot() nDue times, in the sequential loop's order: the free list from its end, then new slots
+                const size_t reuse = std::min(nDue, freeSlots.size()), nF = freeSlots.size();
+                for (size_t k = 0; k < reuse; ++k) parSlot[k] = freeSlots[nF - 1 - k];
+                freeSlots.resize(nF - reuse);
+                for (size_t k = reuse; k < nDue; ++k) { slots.emplace_back(); parSlot[k] = (int) slots.size() - 1; }
+            }
+            rawDraws.resize(2 * nDue);
+            for (size_t i = 0; i < 2 * nDue; ++i) rawDraws[i] = (uint32_t) rnd();
+            drawShift = 0;
             while (done < nDue) {
                 done = createParallel(done, nDue);
                 if (done == nDue) break;
-                // a hit: this one vehicle goes through the sequential code (device query, redraws), then the draws of the rest
-                // are predicted again from where the RNG stands now
+                // a hit: this one vehicle goes through the sequential code (device query, redraws) reading the same stream; each
+                // redraw moves the draws of everybody behind it one value on
                 const FlowStatic &fs = flowStatic[due[done]];
-                createVehicle(due[done], parIndex[done], fs.routeId, fs.tmplId, fs.firstRoad, parSlot[done]);
+                drawPos = 2 * done + drawShift;
+                {
+                    struct FromBuffer { bool &f; explicit FromBuffer(bool &b) : f(b) { f = true; } ~FromBuffer() { f = false; } } guard(drawFromBuffer);
+                    createVehicle(due[done], parIndex[done], fs.routeId, fs.tmplId, fs.firstRoad, parSlot[done]);
+                }
+                drawShift = drawPos - 2 * (done + 1);
                 ++done;
-                std::mt19937 ahead = rnd;
-                for (size_t k = done; k < nDue; ++k) { predicted[k] = (int) ahead(); (void) ahead(); }
+                while (rawDraws.size() < 2 * nDue + drawShift) rawDraws.push_back((uint32_t) rnd());
             }
         }
         if (done < nDue && nDue >= 8) for (size_t k = 0; k < std::min(PF, nDue); ++k) prefetchFor(k);
